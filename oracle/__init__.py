@@ -1,0 +1,19 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+A restatement of the reference's algorithm for the SuperPoint x2 + LightGlue stereo front-end hot
+path, used as the parity checker.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this package; the product path (superslam_b200/) never does and
+fails loudly when the CUDA library is missing.
+
+Pinning status:
+  * SuperPoint dense network  — PINNED: checked against outputs of the reference's own torch module
+    (utils/convert_superpoint_to_onnx.py, weights/superpoint_v1.pth) run in the authoring container;
+    fixtures in tests/golden/ made by tests/golden/make_golden.py.
+  * keypoint select / descriptor gather / stereo post-filter / FreeList — restated line by line from
+    the reference C++ (cited per function); the reference has no golden vectors for them beyond
+    tests/test_stereo_frontend.cc and tests/test_descriptor_pool.cc, which are re-expressed in tests/.
+  * LightGlue — PARITY UNPINNED: the arithmetic lives in the un-vendored, un-pinned third-party
+    package cvg/LightGlue and no weights are available offline.  The restatement follows the
+    published model (lightglue/lightglue.py) and is cross-checked against the independent
+    HuggingFace port shipped in this image (transformers 5.5, models/lightglue) with shared weights.
+"""

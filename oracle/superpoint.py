@@ -1,0 +1,137 @@
+"""Oracle: SuperPoint dense network + host keypoint selection + descriptor gather (fp32, CPU).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows, line by line:
+  * network          /root/reference/utils/convert_superpoint_to_onnx.py:38-64 (encoder), :72-90 (heads,
+                     softmax, dustbin drop, depth-to-space, 9x9 NMS, descriptor L2 norm)
+  * preprocess       /root/reference/src/SuperPoint.cc:768-778 (gray u8 -> f32 * (1/255))
+  * select           /root/reference/src/SuperPoint.cc:696-719 (threshold, borders, sort, top-K, cells)
+  * gather+normalise /root/reference/src/DescriptorGather.cu:14-56 (fp16 grid, fp32 tree sum, fp16 rows)
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from superslam_b200.weights_io import load_archive
+
+ENCODER = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]
+POOL_AFTER = {"conv1b", "conv2b", "conv3b"}
+NMS_RADIUS = 4  # baked at export time: convert_superpoint_to_onnx.py:97
+DESC_DIM = 256
+
+
+def load_weights(path: str) -> "OrderedDict[str, torch.Tensor]":
+    return OrderedDict((k, torch.from_numpy(v)) for k, v in load_archive(path).items())
+
+
+def _q16(x: torch.Tensor) -> torch.Tensor:
+    """Round to fp16 and back (models fp16 storage with fp32 arithmetic)."""
+    return x.half().float()
+
+
+def preprocess(images_u8: np.ndarray) -> torch.Tensor:
+    """[B,H,W] u8 -> [B,1,H,W] f32, value * float32(1/255) (cv::Mat::convertTo, SuperPoint.cc:776)."""
+    x = torch.from_numpy(np.ascontiguousarray(images_u8)).float() * np.float32(1.0 / 255.0)
+    return x[:, None]
+
+
+def dense_forward(images_u8: np.ndarray, w, fp16_storage: bool = False):
+    """Dense SuperPoint graph.  Returns (scores [B,8Hc,8Wc] f32 after NMS, descriptor grid
+    [B,256,Hc,Wc] f32 L2-normalised over channels, raw softmax scores before NMS).
+
+    fp16_storage=False is the reference graph in fp32 (the ground truth).  fp16_storage=True models
+    the precision plan of the CUDA path: conv1a in fp32 on fp32 weights, every other layer on
+    fp16-rounded weights, activations rounded to fp16 wherever they are stored (after every
+    bias+ReLU(+pool)); accumulation, softmax, NMS and the channel norm stay fp32.
+    """
+    q = _q16 if fp16_storage else (lambda t: t)
+    x = preprocess(images_u8)
+    with torch.no_grad():
+        for name in ENCODER:
+            wt = w[name + ".weight"] if name == "conv1a" else q(w[name + ".weight"])
+            x = F.relu(F.conv2d(x, wt, w[name + ".bias"], padding=1))
+            if name in POOL_AFTER:
+                x = F.max_pool2d(x, 2, 2)
+            x = q(x)
+        pa = q(F.relu(F.conv2d(x, q(w["convPa.weight"]), w["convPa.bias"], padding=1)))
+        logits = F.conv2d(pa, q(w["convPb.weight"]), w["convPb.bias"])
+        prob = F.softmax(logits, 1)[:, :-1]
+        b, _, hc, wc = prob.shape
+        s = prob.permute(0, 2, 3, 1).reshape(b, hc, wc, 8, 8)
+        s = s.permute(0, 1, 3, 2, 4).reshape(b, hc * 8, wc * 8)
+        raw = s
+        r = NMS_RADIUS
+        s4 = s.unsqueeze(1)
+        pooled = F.max_pool2d(s4, 2 * r + 1, stride=1, padding=r)
+        scores = torch.where(s4 == pooled, s4, torch.zeros_like(s4)).squeeze(1)
+        da = q(F.relu(F.conv2d(x, q(w["convDa.weight"]), w["convDa.bias"], padding=1)))
+        d = F.conv2d(da, q(w["convDb.weight"]), w["convDb.bias"])
+        d = F.normalize(d, p=2, dim=1)
+    return scores.numpy(), d.numpy(), raw.numpy()
+
+
+def select_keypoints(scores: np.ndarray, input_h: int, input_w: int, max_keypoints: int,
+                     keypoint_threshold: float, remove_borders: int, desc_h: int, desc_w: int):
+    """Host half of SuperPoint::select_and_gather (SuperPoint.cc:696-719) for one image.
+
+    scores: [H', W'] f32.  Returns dict(xy [n,2] f32, score [n] f32, hw [n,2] i32, cell [n,2] i32).
+    Order: score descending, ties by row descending then column descending (std::greater on
+    pair<float,pair<int,int>>).  The threshold compare is float-promoted-to-double > double.
+    """
+    sh, sw = scores.shape
+    rb = remove_borders
+    hs, ws = np.nonzero(scores.astype(np.float64) > float(keypoint_threshold))
+    keep = (hs >= rb) & (hs < sh - rb) & (ws >= rb) & (ws < sw - rb)
+    hs, ws = hs[keep], ws[keep]
+    sc = scores[hs, ws]
+    # lexsort: last key is primary.  Descending on all three.
+    order = np.lexsort((-ws, -hs, -sc.astype(np.float64)))
+    order = order[:max_keypoints]
+    hs, ws, sc = hs[order].astype(np.int32), ws[order].astype(np.int32), sc[order].astype(np.float32)
+    scale_x = np.float32(input_w) / np.float32(sw)
+    scale_y = np.float32(input_h) / np.float32(sh)
+    xy = np.stack([ws.astype(np.float32) * scale_x, hs.astype(np.float32) * scale_y], 1).astype(np.float32)
+    cell = np.stack([np.minimum(hs // 8, desc_h - 1), np.minimum(ws // 8, desc_w - 1)], 1).astype(np.int32)
+    return dict(xy=xy.reshape(-1, 2), score=sc, hw=np.stack([hs, ws], 1).reshape(-1, 2), cell=cell.reshape(-1, 2))
+
+
+def gather_normalize(grid_f16: np.ndarray, cell: np.ndarray) -> np.ndarray:
+    """gather_normalize_kernel (DescriptorGather.cu:14-56).  grid_f16 [256,Hc,Wc] fp16, cell [n,2]
+    (row, col).  fp32 sum of squares in the kernel's 256-wide tree order (strides 128..1),
+    rsqrtf(sum + 1e-12f), output fp16 (round-to-nearest) rows [n,256]."""
+    n = cell.shape[0]
+    if n == 0:
+        return np.zeros((0, grid_f16.shape[0]), np.float16)
+    v = grid_f16[:, cell[:, 0], cell[:, 1]].T.astype(np.float32)  # [n,256]
+    p = (v * v).astype(np.float32)
+    stride = p.shape[1] // 2
+    while stride > 0:
+        p = (p[:, :stride] + p[:, stride:2 * stride]).astype(np.float32)
+        stride //= 2
+    inv = (np.float32(1.0) / np.sqrt(p[:, 0] + np.float32(1e-12), dtype=np.float32)).astype(np.float32)
+    return (v * inv[:, None]).astype(np.float32).astype(np.float16)
+
+
+def extract(images_u8: np.ndarray, w, max_keypoints: int, keypoint_threshold: float = 0.005,
+            remove_borders: int = 4, fp16_storage: bool = False):
+    """Full IFeatureExtractor::extract / extract_stereo restatement for a batch of same-size images.
+    Returns a list (one per image) of dicts with xy, score, hw, cell, desc (fp16 [n,256]), plus the
+    dense outputs for inspection."""
+    b, h, wd = images_u8.shape
+    scores, grid, raw = dense_forward(images_u8, w, fp16_storage)
+    grid16 = grid.astype(np.float16)  # engine binding is fp16 (scripts/rebuild_engines.sh:92)
+    out = []
+    for i in range(b):
+        k = select_keypoints(scores[i], h, wd, max_keypoints, keypoint_threshold, remove_borders,
+                             grid.shape[2], grid.shape[3])
+        k["desc"] = gather_normalize(grid16[i], k["cell"])
+        k["scores_map"] = scores[i]
+        k["grid_f16"] = grid16[i]
+        k["raw_map"] = raw[i]
+        out.append(k)
+    return out

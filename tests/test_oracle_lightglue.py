@@ -1,0 +1,133 @@
+"""LightGlue oracle: cross-check the restatement against the independent HuggingFace port that ships in
+this image (transformers/models/lightglue/modeling_lightglue.py) with shared weights, and check the
+assignment / filter logic on hand-made cases.  (Parity with the reference's TensorRT engine is unpinned:
+no weights and no cvg/LightGlue source offline - see oracle/__init__.py.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend as ofe
+from oracle import lightglue as olg
+
+
+def _inputs(n0, n1, seed=0):
+    rng = np.random.default_rng(seed)
+    k0 = rng.uniform(-1, 1, (n0, 2)).astype(np.float32)
+    k1 = rng.uniform(-1, 1, (n1, 2)).astype(np.float32)
+    d0 = rng.normal(size=(n0, 256)).astype(np.float32)
+    d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+    perm = rng.permutation(max(n0, n1))[:n1] % n0
+    d1 = d0[perm] + 0.05 * rng.normal(size=(n1, 256)).astype(np.float32)
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+    return k0, d0.astype(np.float16), k1, d1.astype(np.float16)
+
+
+def test_against_huggingface_port(lg_weights):
+    hf = pytest.importorskip("transformers.models.lightglue.modeling_lightglue")
+    from transformers.models.lightglue.configuration_lightglue import LightGlueConfig
+
+    cfg = LightGlueConfig()
+    cfg._attn_implementation = "eager"
+    w = lg_weights
+    n = 96
+    k0, d0, k1, d1 = _inputs(n, n)
+    pe = hf.LightGluePositionalEncoder(cfg)
+    pe.projector.weight.data = w["posenc.Wr.weight"].clone()
+    layers = [hf.LightGlueTransformerLayer(cfg, i).eval() for i in range(cfg.num_hidden_layers)]
+
+    def split_qkv(wt, b):  # cvg layout (head, dim, 3) -> separate q/k/v [256,256]
+        wt = wt.view(4, 64, 3, 256)
+        b = b.view(4, 64, 3)
+        return [(wt[:, :, j].reshape(256, 256).clone(), b[:, :, j].reshape(256).clone()) for j in range(3)]
+
+    for i, L in enumerate(layers):
+        p = f"transformers.{i}.self_attn."
+        (qw, qb), (kw, kb), (vw, vb) = split_qkv(w[p + "Wqkv.weight"], w[p + "Wqkv.bias"])
+        a = L.self_attention
+        a.q_proj.weight.data, a.q_proj.bias.data = qw, qb
+        a.k_proj.weight.data, a.k_proj.bias.data = kw, kb
+        a.v_proj.weight.data, a.v_proj.bias.data = vw, vb
+        a.o_proj.weight.data, a.o_proj.bias.data = w[p + "out_proj.weight"].clone(), w[p + "out_proj.bias"].clone()
+        for mlp, q in ((L.self_mlp, p + "ffn."), (L.cross_mlp, f"transformers.{i}.cross_attn.ffn.")):
+            mlp.fc1.weight.data, mlp.fc1.bias.data = w[q + "0.weight"].clone(), w[q + "0.bias"].clone()
+            mlp.layer_norm.weight.data, mlp.layer_norm.bias.data = w[q + "1.weight"].clone(), w[q + "1.bias"].clone()
+            mlp.fc2.weight.data, mlp.fc2.bias.data = w[q + "3.weight"].clone(), w[q + "3.bias"].clone()
+        p = f"transformers.{i}.cross_attn."
+        c = L.cross_attention
+        c.q_proj.weight.data, c.q_proj.bias.data = w[p + "to_qk.weight"].clone(), w[p + "to_qk.bias"].clone()
+        c.k_proj.weight.data, c.k_proj.bias.data = w[p + "to_qk.weight"].clone(), w[p + "to_qk.bias"].clone()
+        c.v_proj.weight.data, c.v_proj.bias.data = w[p + "to_v.weight"].clone(), w[p + "to_v.bias"].clone()
+        c.o_proj.weight.data, c.o_proj.bias.data = w[p + "to_out.weight"].clone(), w[p + "to_out.bias"].clone()
+    ma = hf.LightGlueMatchAssignmentLayer(cfg).eval()
+    p = "log_assignment.8."
+    ma.final_projection.weight.data, ma.final_projection.bias.data = w[p + "final_proj.weight"].clone(), w[p + "final_proj.bias"].clone()
+    ma.matchability.weight.data, ma.matchability.bias.data = w[p + "matchability.weight"].clone(), w[p + "matchability.bias"].clone()
+
+    with torch.no_grad():
+        kp = torch.from_numpy(np.stack([k0, k1]))
+        x = torch.from_numpy(np.stack([d0, d1]).astype(np.float32))
+        enc = pe(kp)[0]
+        for L in layers:
+            x = L(x, enc, None)[0]
+        scores = ma(x, None)  # [1, n+1, n+1]
+        hf_m, hf_s = hf.get_matches_from_scores(scores, 0.1)
+    m0, ms0, inter = olg.match(w, k0, d0, k1, d1, return_intermediates=True)
+    assert np.abs(inter["cross8"][0] - x[0].numpy()).max() < 2e-4
+    assert np.abs(inter["scores"] - scores[0, :-1, :-1].numpy()).max() < 2e-3
+    assert np.array_equal(m0, hf_m[0].numpy().astype(np.int32))
+    assert np.abs(ms0 - hf_s[0].numpy()).max() < 1e-4
+    assert (m0 >= 0).sum() > 10
+
+
+def test_filter_matches_mutual_threshold():
+    s = torch.full((3, 4), -9.0)
+    s[0, 1] = np.log(0.9)   # mutual, above threshold
+    s[1, 1] = np.log(0.5)   # row 1 prefers col 1 but col 1 prefers row 0 -> not mutual
+    s[2, 3] = np.log(0.05)  # mutual but exp(score) <= 0.1
+    m0, ms0 = olg.filter_matches(s)
+    assert m0.tolist() == [1, -1, -1]
+    assert abs(float(ms0[0]) - 0.9) < 1e-6 and float(ms0[1]) == 0.0 and abs(float(ms0[2]) - 0.05) < 1e-6
+
+
+def test_ragged_counts_and_single_keypoint(lg_weights):
+    k0, d0, k1, d1 = _inputs(37, 5, seed=3)
+    m0, ms0 = olg.match(lg_weights, k0, d0, k1, d1)
+    assert m0.shape == (37,) and ms0.shape == (37,) and m0.max() < 5
+    m0, ms0 = olg.match(lg_weights, k0[:1], d0[:1], k1, d1)
+    assert m0.shape == (1,)
+
+
+def test_normalize_keypoints_uses_yaml_size():
+    xy = np.array([[0, 0], [1241, 376], [620.5, 188]], np.float32)
+    out = olg.normalize_keypoints(xy, 1241, 376)
+    assert np.allclose(out, [[-1, -188 / 620.5], [1, 188 / 620.5], [0, 0]], atol=1e-6)
+
+
+def test_dmatches_and_stereo_postfilter():
+    # re-expresses /root/reference/tests/test_stereo_frontend.cc:49-73 against the restated filter
+    xl = np.array([[100, 50], [200, 80]], np.float32)
+    xr = xl - np.array([[10, 0]], np.float32)
+    q, t, dist = ofe.dmatches(np.array([0, 1], np.int32), np.array([1.0, 0.75], np.float32))
+    assert q.tolist() == [0, 1] and t.tolist() == [0, 1] and dist.tolist() == [0.0, 0.25]
+    st, hd = ofe.stereo_postfilter(xl, xr, q, t)
+    assert hd.tolist() == [1, 1] and st[0].tolist() == [100.0, 90.0, 50.0]
+    st, hd = ofe.stereo_postfilter(xl, xl, q, t)  # zero disparity rejected
+    assert hd.tolist() == [0, 0] and np.isnan(st[0, 1]) and st[0, 0] == 100.0
+    st, hd = ofe.stereo_postfilter(xl, xr + np.array([[0, 2.5]], np.float32), q, t)  # row check
+    assert hd.tolist() == [0, 0]
+    q, t, _ = ofe.dmatches(np.array([-1, 0, -1], np.int32), np.zeros(3, np.float32))
+    assert q.tolist() == [1] and t.tolist() == [0]
+
+
+def test_free_list_semantics():
+    # re-expresses /root/reference/tests/test_descriptor_pool.cc:7-29
+    f = ofe.FreeList(3)
+    a, b, c = f.acquire(), f.acquire(), f.acquire()
+    assert min(a, b, c) >= 0 and f.acquire() == -1 and f.in_use() == 3
+    f.release(b)
+    assert f.in_use() == 2 and f.acquire() == b
+    f = ofe.FreeList(2)
+    assert f.in_use() == 0
+    a, b = f.acquire(), f.acquire()
+    f.release(a), f.release(b)
+    assert f.in_use() == 0
