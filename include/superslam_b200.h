@@ -1,0 +1,133 @@
+/* superslam_b200 — C ABI of the B200-native SuperPoint + LightGlue stereo front-end.
+ *
+ * This is the drop-in boundary behind SuperSLAM's inference interfaces
+ * (reference include/InferenceInterfaces.h:27-59).  Every entry point takes plain pointers and sizes,
+ * returns an int status (0 = ok) and never throws; ssb_last_error() describes the last failure on the
+ * calling thread.  The C++ adapter include/superslam_b200_adapter.hpp wraps these calls into
+ * superslam::IFeatureExtractor / superslam::IFeatureMatcher; INTEGRATION.md shows the wiring.
+ *
+ * Conventions shared with the reference:
+ *   - images: 8-bit gray (channels = 1) or BGR (channels = 3), row-major, `row_stride` bytes per row
+ *   - keypoints: pixel coordinates (x, y) float32, x = w * (W / score_W)   (src/SuperPoint.cc:708-716)
+ *   - descriptors: fp16 [count, 256] row-major in DEVICE memory, L2-normalised rows
+ *     (include/DescriptorPool.h:13-20, src/DescriptorGather.cu:14-56)
+ *   - matches0[i] = index into set 1 or -1, mscores0[i] float32         (src/LightGlue.cc:326-363)
+ */
+#ifndef SUPERSLAM_B200_H_
+#define SUPERSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_OK 0
+#define SSB_ERR_INVALID 1
+#define SSB_ERR_CUDA 2
+#define SSB_ERR_IO 3
+#define SSB_ERR_EXHAUSTED 4 /* descriptor pool has no free slot (src/SuperPoint.cc:724-727) */
+#define SSB_ERR_NODEVICE 5
+
+typedef struct ssb_superpoint ssb_superpoint;
+typedef struct ssb_lightglue ssb_lightglue;
+typedef struct ssb_frontend ssb_frontend;
+
+const char* ssb_last_error(void);
+int ssb_version(void);
+/* Number of sm_100 devices visible to the process, or a negative status. */
+int ssb_device_count(void);
+
+/* ---- SuperPoint: replaces class SuperPoint (include/SuperPoint.h:37-52) ------------------------ */
+
+/* SuperPoint(engine_file, max_keypoints, keypoint_threshold, remove_borders) + initialize()
+ * (include/SuperPoint.h:39-44, src/SuperPoint.cc:41-63).  `weights_path` is an SSBW archive made by
+ * tools/convert_superpoint_weights.py.  `num_slots` <= 0 selects the reference's 8 descriptor slots
+ * (include/SuperPoint.h:86-87). */
+int ssb_sp_create(const char* weights_path, int max_keypoints, double keypoint_threshold,
+                  int remove_borders, int num_slots, int device_id, ssb_superpoint** out);
+void ssb_sp_destroy(ssb_superpoint* sp);
+
+/* IFeatureExtractor::extract (batch = 1, src/SuperPoint.cc:894-899) and ::extract_stereo (batch = 2,
+ * src/SuperPoint.cc:901-907, one batched {2,1,H,W} pass); larger batches are a throughput extension.
+ * For image i: xy[i] receives count[i] (x, y) pairs, score[i] the responses (arrays sized
+ * max_keypoints), desc_dev[i] the device pointer of the fp16 [count, 256] rows, slot[i] the pool slot
+ * that owns them (-1 when the pool is exhausted: SSB_ERR_EXHAUSTED is returned and that image has no
+ * descriptors, like the reference's empty handle).  A slot starts with one reference. */
+int ssb_sp_extract(ssb_superpoint* sp, const uint8_t* const* images, int batch, int height, int width,
+                   int row_stride, int channels, float* const* xy, float* const* score, int* count,
+                   void** desc_dev, int* slot);
+
+/* DeviceDescriptors::slot_ref (include/DescriptorPool.h:62-76): copies share the slot, the last
+ * release returns it to the LIFO free list. */
+int ssb_sp_slot_retain(ssb_superpoint* sp, int slot);
+int ssb_sp_slot_release(ssb_superpoint* sp, int slot);
+int ssb_sp_slots_in_use(ssb_superpoint* sp); /* DescriptorPool::in_use() */
+int ssb_sp_max_keypoints(ssb_superpoint* sp);
+/* Test hook: copy an intermediate device buffer ("conv1a" ... "scores", "grid") to the host. */
+int ssb_sp_debug_read(ssb_superpoint* sp, const char* what, void* dst, size_t bytes);
+
+/* ---- LightGlue: replaces class LightGlue (include/LightGlue.h:33-57) --------------------------- */
+
+/* LightGlue(engine_file, image_width, image_height) + initialize() (include/LightGlue.h:36).
+ * `weights_path`: SSBW archive with cvg/LightGlue state-dict names (tools/convert_lightglue_weights.py).
+ * `max_keypoints` sizes the workspace (the reference engine profile tops out at 1024). */
+int ssb_lg_create(const char* weights_path, int image_width, int image_height, int max_keypoints,
+                  int device_id, ssb_lightglue** out);
+/* LightGlue(shared_engine, w, h) (include/LightGlue.h:39-44, src/SuperSLAM.cc:129-133): shares the
+ * immutable weights, owns its stream and workspace; use one context per thread. */
+int ssb_lg_clone_context(ssb_lightglue* src, int image_width, int image_height, ssb_lightglue** out);
+void ssb_lg_destroy(ssb_lightglue* lg);
+
+/* IFeatureMatcher::match(kp0, DeviceDescriptors, kp1, DeviceDescriptors) (src/LightGlue.cc:377-457).
+ * xy*: host pixel keypoints [n, 2]; desc*_dev: device fp16 [n, 256].  matches0 / mscores0: host
+ * arrays of n0 entries.  n0 == 0 or n1 == 0 yields no matches and SSB_OK. */
+int ssb_lg_match_device(ssb_lightglue* lg, const float* xy0, int n0, const void* desc0_dev,
+                        const float* xy1, int n1, const void* desc1_dev, int32_t* matches0,
+                        float* mscores0);
+/* IFeatureMatcher::match(kp0, cv::Mat, kp1, cv::Mat) (src/LightGlue.cc:285-324): host fp32 [n, 256]. */
+int ssb_lg_match_host(ssb_lightglue* lg, const float* xy0, int n0, const float* desc0_f32,
+                      const float* xy1, int n1, const float* desc1_f32, int32_t* matches0,
+                      float* mscores0);
+/* IFeatureMatcher::descriptors_to_host (src/LightGlue.cc:460-475): blocking D2H, fp16 -> fp32. */
+int ssb_desc_to_host_f32(int device_id, const void* desc_dev_f16, int count, int dim, float* out);
+int ssb_lg_debug_read(ssb_lightglue* lg, const char* what, void* dst, size_t bytes);
+
+/* ---- Frame-pair front end (throughput path; not in the reference API) --------------------------
+ * SuperPoint x2 + LightGlue + the StereoFrontEnd disparity / row filter (src/StereoFrontEnd.cc:35-47)
+ * for `pairs` stereo pairs per call, chained on one stream with device-resident keypoint counts: one
+ * host synchronisation per call.  Image 2p is the left, 2p+1 the right image of pair p. */
+int ssb_fe_create(const char* sp_weights, const char* lg_weights, int max_keypoints,
+                  double keypoint_threshold, int remove_borders, int lg_image_width, int lg_image_height,
+                  float min_disparity, int max_pairs, int device_id, ssb_frontend** out);
+void ssb_fe_destroy(ssb_frontend* fe);
+/* Host images in (gray u8, 2*pairs pointers), host results out.  Any output pointer may be NULL.
+ *   count      [2*pairs]            keypoints per image
+ *   xy         [2*pairs][K][2]      score [2*pairs][K]
+ *   matches0   [pairs][K]           mscores0 [pairs][K]
+ *   stereo_ur  [pairs][K]           right-image u of the accepted match, NaN otherwise
+ *   has_depth  [pairs][K]           1 where the match passed the disparity and row checks */
+int ssb_fe_process(ssb_frontend* fe, const uint8_t* const* images, int pairs, int height, int width,
+                   int row_stride, int* count, float* xy, float* score, int32_t* matches0,
+                   float* mscores0, float* stereo_ur, uint8_t* has_depth);
+/* Same pipeline on images already resident on the device ([2*pairs][H][W] u8 contiguous); enqueue
+ * only, results stay on the device until ssb_fe_fetch.  Used for the HBM-resident throughput number. */
+int ssb_fe_enqueue_device(ssb_frontend* fe, const uint8_t* images_dev, int pairs, int height, int width);
+int ssb_fe_fetch(ssb_frontend* fe, int pairs, int* count, float* xy, float* score, int32_t* matches0,
+                 float* mscores0, float* stereo_ur, uint8_t* has_depth);
+int ssb_fe_sync(ssb_frontend* fe);
+/* CUDA-event timing on the front end's own stream (torch.cuda.Event only sees torch's stream). */
+int ssb_fe_event_record(ssb_frontend* fe, int index /* 0..15 */);
+int ssb_fe_event_elapsed_ms(ssb_frontend* fe, int start_index, int stop_index, float* ms);
+/* Device buffer helpers for callers without a CUDA runtime binding of their own. */
+int ssb_fe_upload_images(ssb_frontend* fe, const uint8_t* const* images, int count, int height, int width,
+                         int row_stride, uint8_t** images_dev_out);
+int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs);
+ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe);
+ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERSLAM_B200_H_ */

@@ -34,59 +34,7 @@ HEAD_DIM = 64
 FILTER_THRESHOLD = 0.1
 
 
-def normalise_keys(sd):
-    out = OrderedDict()
-    for k, v in sd.items():
-        k = re.sub(r"^matcher\.", "", k)
-        m = re.match(r"^(self_attn|cross_attn)\.(\d+)\.(.*)$", k)
-        if m:
-            k = f"transformers.{m.group(2)}.{m.group(1)}.{m.group(3)}"
-        out[k] = v
-    return out
-
-
-def make_random_weights(seed: int = 7, sharpen: float = 6.0, matchability_bias: float = 3.0):
-    """Seeded synthetic weights with torch.nn.Linear's default init (U(-1/sqrt(in), 1/sqrt(in))),
-    LayerNorm weight 1 / bias 0, posenc.Wr ~ N(0,1) (gamma = 1.0).
-
-    Two deliberate departures from a plain random init, so the assignment stage exercises matched,
-    unmatched and thresholded branches instead of returning all -1: the last layer's final_proj is
-    scaled by `sharpen` (peaked double softmax) and its matchability bias is raised to
-    `matchability_bias` (logsigmoid ~ 0).  The real checkpoint needs neither.
-    """
-    g = torch.Generator().manual_seed(seed)
-
-    def lin(out_f, in_f, bias=True):
-        b = 1.0 / math.sqrt(in_f)
-        wt = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * b
-        bs = (torch.rand(out_f, generator=g) * 2 - 1) * b if bias else None
-        return wt, bs
-
-    sd = OrderedDict()
-    sd["posenc.Wr.weight"] = torch.randn(HEAD_DIM // 2, 2, generator=g)
-    for i in range(N_LAYERS):
-        p = f"transformers.{i}.self_attn."
-        sd[p + "Wqkv.weight"], sd[p + "Wqkv.bias"] = lin(3 * DIM, DIM)
-        sd[p + "out_proj.weight"], sd[p + "out_proj.bias"] = lin(DIM, DIM)
-        for blk in ("self_attn", "cross_attn"):
-            q = f"transformers.{i}.{blk}.ffn."
-            sd[q + "0.weight"], sd[q + "0.bias"] = lin(2 * DIM, 2 * DIM)
-            sd[q + "1.weight"] = torch.ones(2 * DIM) + 0.1 * torch.randn(2 * DIM, generator=g)
-            sd[q + "1.bias"] = 0.1 * torch.randn(2 * DIM, generator=g)
-            sd[q + "3.weight"], sd[q + "3.bias"] = lin(DIM, 2 * DIM)
-        p = f"transformers.{i}.cross_attn."
-        sd[p + "to_qk.weight"], sd[p + "to_qk.bias"] = lin(DIM, DIM)
-        sd[p + "to_v.weight"], sd[p + "to_v.bias"] = lin(DIM, DIM)
-        sd[p + "to_out.weight"], sd[p + "to_out.bias"] = lin(DIM, DIM)
-        p = f"log_assignment.{i}."
-        sd[p + "matchability.weight"], sd[p + "matchability.bias"] = lin(1, DIM)
-        sd[p + "final_proj.weight"], sd[p + "final_proj.bias"] = lin(DIM, DIM)
-    last = f"log_assignment.{N_LAYERS - 1}."
-    sd[last + "final_proj.weight"] = sd[last + "final_proj.weight"] * sharpen
-    sd[last + "final_proj.bias"] = sd[last + "final_proj.bias"] * sharpen
-    sd[last + "matchability.bias"] = sd[last + "matchability.bias"] + matchability_bias
-    # reorder keys so that weight/bias pairs are adjacent and deterministic
-    return OrderedDict((k, v.contiguous()) for k, v in sd.items())
+from superslam_b200.lightglue_weights import make_random_weights, normalise_keys  # noqa: F401,E402
 
 
 def normalize_keypoints(xy: np.ndarray, image_width: int, image_height: int) -> np.ndarray:
@@ -134,6 +82,28 @@ def _self_block(w, i, x, enc):
     ctx = torch.einsum("hij,hjd->hid", attn, v)
     msg = F.linear(ctx.transpose(0, 1).flatten(-2), w[p + "out_proj.weight"], w[p + "out_proj.bias"])
     return x + _ffn(w, p + "ffn.", torch.cat([x, msg], -1))
+
+
+def self_block_debug(w, i, kpts, desc):
+    """Every intermediate of SelfBlock i for one image (numpy), in the layouts the CUDA path stores:
+    q (rotary applied, pre-scaled by 1/8) / k / v [H,N,64], logits S [H,N,N], ctx [N,256], msg [N,256],
+    h1 = GELU(LayerNorm(fc1(cat[x,msg]))) [N,512], out x [N,256]."""
+    w = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(v)) for k, v in w.items()}
+    x = torch.from_numpy(np.asarray(desc).astype(np.float32))
+    enc = _posenc(w, torch.from_numpy(np.asarray(kpts, np.float32)))
+    p = f"transformers.{i}.self_attn."
+    with torch.no_grad():
+        qkv = F.linear(x, w[p + "Wqkv.weight"], w[p + "Wqkv.bias"]).unflatten(-1, (N_HEADS, HEAD_DIM, 3)).transpose(0, 1)
+        q, k, v = _rope(enc, qkv[..., 0]), _rope(enc, qkv[..., 1]), qkv[..., 2]
+        S = torch.einsum("hid,hjd->hij", q, k) * HEAD_DIM ** -0.5
+        ctx = torch.einsum("hij,hjd->hid", F.softmax(S, -1), v).transpose(0, 1).flatten(-2)
+        msg = F.linear(ctx, w[p + "out_proj.weight"], w[p + "out_proj.bias"])
+        cat = torch.cat([x, msg], -1)
+        h1 = F.linear(cat, w[p + "ffn.0.weight"], w[p + "ffn.0.bias"])
+        h1 = F.gelu(F.layer_norm(h1, (512,), w[p + "ffn.1.weight"], w[p + "ffn.1.bias"], 1e-5))
+        out = x + F.linear(h1, w[p + "ffn.3.weight"], w[p + "ffn.3.bias"])
+    return dict(q=(q * 0.125).numpy(), k=k.numpy(), v=v.numpy(), S=S.numpy(), ctx=ctx.numpy(), msg=msg.numpy(),
+                h1=h1.numpy(), x=out.numpy(), cos=enc[0].numpy(), sin=enc[1].numpy())
 
 
 def _cross_block(w, i, x0, x1):

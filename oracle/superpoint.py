@@ -75,6 +75,46 @@ def dense_forward(images_u8: np.ndarray, w, fp16_storage: bool = False):
     return scores.numpy(), d.numpy(), raw.numpy()
 
 
+def dense_intermediates(images_u8: np.ndarray, w, fp16_storage: bool = True):
+    """Per-layer activations of dense_forward (NHWC numpy, as the CUDA path stores them), for
+    layer-by-layer parity checks.  Keys: conv1a..conv4b, convPa, convDa, logits, raw, grid."""
+    q = _q16 if fp16_storage else (lambda t: t)
+    x = preprocess(images_u8)
+    out = {}
+    with torch.no_grad():
+        for name in ENCODER:
+            wt = w[name + ".weight"] if name == "conv1a" else q(w[name + ".weight"])
+            x = F.relu(F.conv2d(x, wt, w[name + ".bias"], padding=1))
+            if name in POOL_AFTER:
+                x = F.max_pool2d(x, 2, 2)
+            x = q(x)
+            out[name] = x.permute(0, 2, 3, 1).numpy().copy()
+        pa = q(F.relu(F.conv2d(x, q(w["convPa.weight"]), w["convPa.bias"], padding=1)))
+        da = q(F.relu(F.conv2d(x, q(w["convDa.weight"]), w["convDa.bias"], padding=1)))
+        out["convPa"] = pa.permute(0, 2, 3, 1).numpy().copy()
+        out["convDa"] = da.permute(0, 2, 3, 1).numpy().copy()
+        logits = F.conv2d(pa, q(w["convPb.weight"]), w["convPb.bias"])
+        out["logits"] = logits.permute(0, 2, 3, 1).numpy().copy()
+        prob = F.softmax(logits, 1)[:, :-1]
+        b, _, hc, wc = prob.shape
+        s = prob.permute(0, 2, 3, 1).reshape(b, hc, wc, 8, 8).permute(0, 1, 3, 2, 4).reshape(b, hc * 8, wc * 8)
+        out["raw"] = s.numpy().copy()
+        d = F.normalize(F.conv2d(da, q(w["convDb.weight"]), w["convDb.bias"]), p=2, dim=1)
+        out["grid"] = d.permute(0, 2, 3, 1).numpy().copy()
+    return out
+
+
+def nms_select(raw: np.ndarray, input_h: int, input_w: int, max_keypoints: int, keypoint_threshold: float,
+               remove_borders: int):
+    """9x9 NMS (convert_superpoint_to_onnx.py:82-87) on a given raw heat map [H',W'] followed by
+    select_keypoints: the exact index work the CUDA nms/select kernels must reproduce bit for bit."""
+    s4 = torch.from_numpy(raw)[None, None]
+    pooled = F.max_pool2d(s4, 2 * NMS_RADIUS + 1, stride=1, padding=NMS_RADIUS)
+    scores = torch.where(s4 == pooled, s4, torch.zeros_like(s4))[0, 0].numpy()
+    return select_keypoints(scores, input_h, input_w, max_keypoints, keypoint_threshold, remove_borders,
+                            raw.shape[0] // 8, raw.shape[1] // 8)
+
+
 def select_keypoints(scores: np.ndarray, input_h: int, input_w: int, max_keypoints: int,
                      keypoint_threshold: float, remove_borders: int, desc_h: int, desc_w: int):
     """Host half of SuperPoint::select_and_gather (SuperPoint.cc:696-719) for one image.

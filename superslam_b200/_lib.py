@@ -1,0 +1,93 @@
+"""ctypes binding of libsuperslam_b200.so (the C-ABI declared in include/superslam_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module raises,
+and every wrapper raises SsbError on a non-zero status from the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsuperslam_b200.so")
+
+
+class SsbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"superslam_b200 status {status}: {message}")
+        self.status = status
+
+
+SSB_OK, SSB_ERR_INVALID, SSB_ERR_CUDA, SSB_ERR_IO, SSB_ERR_EXHAUSTED, SSB_ERR_NODEVICE = range(6)
+
+# Every symbol include/superslam_b200.h declares: (name, restype, argtypes)
+_u8pp = C.POINTER(C.POINTER(C.c_uint8))
+_fpp = C.POINTER(C.POINTER(C.c_float))
+_vp = C.c_void_p
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+
+SYMBOLS = [
+    ("ssb_last_error", C.c_char_p, []),
+    ("ssb_version", C.c_int, []),
+    ("ssb_device_count", C.c_int, []),
+    ("ssb_sp_create", C.c_int, [C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_sp_destroy", None, [_vp]),
+    ("ssb_sp_extract", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fpp, _fpp, _ip,
+                                 C.POINTER(_vp), _ip]),
+    ("ssb_sp_slot_retain", C.c_int, [_vp, C.c_int]),
+    ("ssb_sp_slot_release", C.c_int, [_vp, C.c_int]),
+    ("ssb_sp_slots_in_use", C.c_int, [_vp]),
+    ("ssb_sp_max_keypoints", C.c_int, [_vp]),
+    ("ssb_sp_debug_read", C.c_int, [_vp, C.c_char_p, _vp, C.c_size_t]),
+    ("ssb_lg_create", C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_lg_clone_context", C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_lg_destroy", None, [_vp]),
+    ("ssb_lg_match_device", C.c_int, [_vp, _fp, C.c_int, _vp, _fp, C.c_int, _vp, _i32p, _fp]),
+    ("ssb_lg_match_host", C.c_int, [_vp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, _i32p, _fp]),
+    ("ssb_desc_to_host_f32", C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _fp]),
+    ("ssb_lg_debug_read", C.c_int, [_vp, C.c_char_p, _vp, C.c_size_t]),
+    ("ssb_fe_create", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                C.c_float, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_fe_destroy", None, [_vp]),
+    ("ssb_fe_process", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp, _i32p, _fp, _fp,
+                                 _u8p]),
+    ("ssb_fe_enqueue_device", C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    ("ssb_fe_fetch", C.c_int, [_vp, C.c_int, _ip, _fp, _fp, _i32p, _fp, _fp, _u8p]),
+    ("ssb_fe_sync", C.c_int, [_vp]),
+    ("ssb_fe_event_record", C.c_int, [_vp, C.c_int]),
+    ("ssb_fe_event_elapsed_ms", C.c_int, [_vp, C.c_int, C.c_int, _fp]),
+    ("ssb_fe_upload_images", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_fe_kernel_launches_per_call", C.c_int, [_vp, C.c_int]),
+    ("ssb_fe_superpoint", _vp, [_vp]),
+    ("ssb_fe_lightglue", _vp, [_vp]),
+    ("ssb_kernel_launch_count", C.c_longlong, []),
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises OSError with build instructions if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C superslam_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != SSB_OK:
+        msg = load().ssb_last_error()
+        raise SsbError(status, msg.decode() if msg else "")

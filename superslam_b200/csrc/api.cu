@@ -1,0 +1,397 @@
+// C-ABI of the library (include/superslam_b200.h): opaque handles over ssb::SuperPoint / ssb::LightGlue
+// plus the chained frame-pair front end.  No exception and no C++ type crosses this boundary.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "../../include/superslam_b200.h"
+#include "lightglue.cuh"
+#include "superpoint.cuh"
+
+struct ssb_superpoint {
+  ssb::SuperPoint impl;
+};
+struct ssb_lightglue {
+  ssb::LightGlue impl;
+};
+
+namespace ssb {
+
+// StereoFrontEnd::process post-filter (src/StereoFrontEnd.cc:22-47) on the device: default
+// (uL, NaN, v) / has_depth 0; a match is kept iff uL-uR >= min_disparity and |vL-vR| <= 2.
+__global__ void stereo_postfilter_kernel(const float* __restrict__ kp_xy, int K, const int* __restrict__ cnt,
+                                         const int32_t* __restrict__ matches0, int kp, float min_disp,
+                                         float* __restrict__ ur, uint8_t* __restrict__ has_depth) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const size_t o = static_cast<size_t>(pair) * K + i;
+  float u = nanf("");
+  uint8_t hd = 0;
+  const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
+  if (i < n0) {
+    const int j = matches0[static_cast<size_t>(pair) * kp + i];
+    if (j >= 0 && j < n1) {
+      const float* l = kp_xy + (static_cast<size_t>(2 * pair) * K + i) * 2;
+      const float* r = kp_xy + (static_cast<size_t>(2 * pair + 1) * K + j) * 2;
+      if (l[0] - r[0] >= min_disp && fabsf(l[1] - r[1]) <= 2.0f) {
+        u = r[0];
+        hd = 1;
+      }
+    }
+  }
+  ur[o] = u;
+  has_depth[o] = hd;
+}
+
+class FrontEnd {
+ public:
+  ~FrontEnd() {
+    cudaSetDevice(device_);
+    for (auto& e : events_)
+      if (e) cudaEventDestroy(e);
+    if (ur_) cudaFree(ur_);
+    if (hd_) cudaFree(hd_);
+    if (img_dev_) cudaFree(img_dev_);
+    if (slot_ptrs_) cudaFree(slot_ptrs_);
+    if (host_) cudaFreeHost(host_);
+    if (host_img_) cudaFreeHost(host_img_);
+  }
+  int init(const char* spw, const char* lgw, int K, double thr, int rb, int lw, int lh, float min_disp,
+           int max_pairs, int device) {
+    SSB_CHECK(max_pairs >= 1 && max_pairs <= 32, SSB_ERR_INVALID, "max_pairs out of range (1..32)");
+    device_ = device;
+    K_ = K;
+    pairs_ = max_pairs;
+    min_disp_ = min_disp;
+    SSB_RETURN_IF(sp.impl.init(spw, K, thr, rb, 2 * max_pairs, device));
+    auto w = std::make_shared<LgWeights>();
+    SSB_RETURN_IF(w->load(lgw, device));
+    SSB_RETURN_IF(lg.impl.init(w, lw, lh, K, max_pairs));
+    stream_ = sp.impl.stream();
+    // fixed descriptor slots: image i of a call always lands in slot i
+    std::vector<void*> ptrs;
+    for (int i = 0; i < 2 * max_pairs; ++i) {
+      const int s = sp.impl.pool().acquire();
+      SSB_CHECK(s >= 0, SSB_ERR_EXHAUSTED, "front end could not reserve descriptor slots");
+      ptrs.push_back(sp.impl.pool().slot_ptr(s));
+    }
+    SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&slot_ptrs_), ptrs.size() * sizeof(void*)));
+    SSB_CUDA_CHECK(cudaMemcpy(slot_ptrs_, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ur_), static_cast<size_t>(max_pairs) * K * 4));
+    SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&hd_), static_cast<size_t>(max_pairs) * K));
+    host_bytes_ = result_bytes(max_pairs);
+    SSB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_), host_bytes_));
+    for (auto& e : events_) SSB_CUDA_CHECK(cudaEventCreate(&e));
+    return SSB_OK;
+  }
+  // pinned result block: count | xy | score | matches | mscores | ur | has_depth
+  size_t result_bytes(int pairs) const {
+    const size_t P = pairs, K = K_;
+    return 2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 64;
+  }
+  int enqueue_device(const uint8_t* images_dev, int pairs, int h, int w) {
+    SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
+    SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
+    stereo_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
+        sp.impl.kp_xy(), K_, sp.impl.kp_count(), lg.impl.matches_dev(), lg.impl.kp(), min_disp_, ur_, hd_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return SSB_OK;
+  }
+  int fetch(int pairs, int* count, float* xy, float* score, int32_t* matches0, float* mscores0, float* ur,
+            uint8_t* hd) {
+    SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    const size_t P = pairs, K = K_, KP = lg.impl.kp();
+    uint8_t* h = host_;
+    int* h_cnt = reinterpret_cast<int*>(h);
+    float* h_xy = reinterpret_cast<float*>(h + 2 * P * 4);
+    float* h_sc = h_xy + 2 * P * K * 2;
+    int32_t* h_m = reinterpret_cast<int32_t*>(h_sc + 2 * P * K);
+    float* h_ms = reinterpret_cast<float*>(h_m + P * K);
+    float* h_ur = h_ms + P * K;
+    uint8_t* h_hd = reinterpret_cast<uint8_t*>(h_ur + P * K);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(h_cnt, sp.impl.kp_count(), 2 * P * 4, cudaMemcpyDeviceToHost, stream_));
+    if (xy) SSB_CUDA_CHECK(cudaMemcpyAsync(h_xy, sp.impl.kp_xy(), 2 * P * K * 8, cudaMemcpyDeviceToHost, stream_));
+    if (score) SSB_CUDA_CHECK(cudaMemcpyAsync(h_sc, sp.impl.kp_score(), 2 * P * K * 4, cudaMemcpyDeviceToHost, stream_));
+    if (matches0)
+      SSB_CUDA_CHECK(cudaMemcpy2DAsync(h_m, K * 4, lg.impl.matches_dev(), KP * 4, K * 4, P, cudaMemcpyDeviceToHost, stream_));
+    if (mscores0)
+      SSB_CUDA_CHECK(cudaMemcpy2DAsync(h_ms, K * 4, lg.impl.mscores_dev(), KP * 4, K * 4, P, cudaMemcpyDeviceToHost, stream_));
+    if (ur) SSB_CUDA_CHECK(cudaMemcpyAsync(h_ur, ur_, P * K * 4, cudaMemcpyDeviceToHost, stream_));
+    if (hd) SSB_CUDA_CHECK(cudaMemcpyAsync(h_hd, hd_, P * K, cudaMemcpyDeviceToHost, stream_));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (count) std::memcpy(count, h_cnt, 2 * P * 4);
+    if (xy) std::memcpy(xy, h_xy, 2 * P * K * 8);
+    if (score) std::memcpy(score, h_sc, 2 * P * K * 4);
+    if (matches0) std::memcpy(matches0, h_m, P * K * 4);
+    if (mscores0) std::memcpy(mscores0, h_ms, P * K * 4);
+    if (ur) std::memcpy(ur, h_ur, P * K * 4);
+    if (hd) std::memcpy(hd, h_hd, P * K);
+    return SSB_OK;
+  }
+  int stage_images(const uint8_t* const* images, int count, int h, int w, int row_stride, bool own_copy,
+                   uint8_t** out) {
+    SSB_CHECK(images != nullptr && row_stride >= w, SSB_ERR_INVALID, "bad image arguments");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    const size_t bytes = static_cast<size_t>(count) * h * w;
+    if (bytes > host_img_bytes_) {
+      SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if (host_img_) cudaFreeHost(host_img_);
+      if (img_dev_) cudaFree(img_dev_);
+      host_img_ = nullptr, img_dev_ = nullptr;
+      SSB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_img_), bytes));
+      SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&img_dev_), bytes));
+      host_img_bytes_ = bytes;
+    }
+    for (int i = 0; i < count; ++i) {
+      SSB_CHECK(images[i] != nullptr, SSB_ERR_INVALID, "image %d is null", i);
+      for (int y = 0; y < h; ++y)
+        std::memcpy(host_img_ + (static_cast<size_t>(i) * h + y) * w, images[i] + static_cast<size_t>(y) * row_stride, w);
+    }
+    uint8_t* dst = img_dev_;
+    if (own_copy) {  // caller keeps it (bench: inputs resident in HBM); freed with the process
+      SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dst), bytes));
+    }
+    SSB_CUDA_CHECK(cudaMemcpyAsync(dst, host_img_, bytes, cudaMemcpyHostToDevice, stream_));
+    if (own_copy) SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    *out = dst;
+    return SSB_OK;
+  }
+
+  ssb_superpoint sp;
+  ssb_lightglue lg;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t events_[16] = {};
+  int device_ = 0, K_ = 0, pairs_ = 0;
+  float min_disp_ = 1.0f;
+  void** slot_ptrs_ = nullptr;
+  float* ur_ = nullptr;
+  uint8_t* hd_ = nullptr;
+  uint8_t* host_ = nullptr;
+  size_t host_bytes_ = 0;
+  uint8_t* host_img_ = nullptr;
+  uint8_t* img_dev_ = nullptr;
+  size_t host_img_bytes_ = 0;
+};
+
+}  // namespace ssb
+
+struct ssb_frontend {
+  ssb::FrontEnd impl;
+};
+
+using namespace ssb;
+
+#define SSB_API_BEGIN try {
+#define SSB_API_END                                                  \
+  }                                                                  \
+  catch (const std::bad_alloc&) {                                    \
+    ssb::set_last_error("out of host memory");                       \
+    return SSB_ERR_INVALID;                                          \
+  }                                                                  \
+  catch (...) {                                                      \
+    ssb::set_last_error("unexpected C++ exception");                 \
+    return SSB_ERR_INVALID;                                          \
+  }
+
+extern "C" {
+
+const char* ssb_last_error(void) { return ssb::last_error(); }
+int ssb_version(void) { return 100; }
+long long ssb_kernel_launch_count(void) { return ssb::launch_count(); }
+
+int ssb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    ssb::set_last_error("cudaGetDeviceCount failed (no driver / no device)");
+    cudaGetLastError();
+    return -SSB_ERR_NODEVICE;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int ssb_sp_create(const char* weights_path, int max_keypoints, double keypoint_threshold, int remove_borders,
+                  int num_slots, int device_id, ssb_superpoint** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  std::unique_ptr<ssb_superpoint> h(new ssb_superpoint);
+  SSB_RETURN_IF(h->impl.init(weights_path, max_keypoints, keypoint_threshold, remove_borders, num_slots, device_id));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_sp_destroy(ssb_superpoint* sp) { delete sp; }
+
+int ssb_sp_extract(ssb_superpoint* sp, const uint8_t* const* images, int batch, int height, int width,
+                   int row_stride, int channels, float* const* xy, float* const* score, int* count,
+                   void** desc_dev, int* slot) {
+  SSB_API_BEGIN
+  SSB_CHECK(sp != nullptr, SSB_ERR_INVALID, "sp is null");
+  return sp->impl.extract(images, batch, height, width, row_stride, channels, xy, score, count, desc_dev, slot);
+  SSB_API_END
+}
+int ssb_sp_slot_retain(ssb_superpoint* sp, int slot) {
+  SSB_CHECK(sp != nullptr, SSB_ERR_INVALID, "sp is null");
+  return sp->impl.pool().retain(slot);
+}
+int ssb_sp_slot_release(ssb_superpoint* sp, int slot) {
+  SSB_CHECK(sp != nullptr, SSB_ERR_INVALID, "sp is null");
+  return sp->impl.pool().release(slot);
+}
+int ssb_sp_slots_in_use(ssb_superpoint* sp) { return sp ? sp->impl.pool().in_use() : -1; }
+int ssb_sp_max_keypoints(ssb_superpoint* sp) { return sp ? sp->impl.max_keypoints() : -1; }
+int ssb_sp_debug_read(ssb_superpoint* sp, const char* what, void* dst, size_t bytes) {
+  SSB_CHECK(sp != nullptr && dst != nullptr, SSB_ERR_INVALID, "null argument");
+  return sp->impl.debug_read(what, dst, bytes);
+}
+
+int ssb_lg_create(const char* weights_path, int image_width, int image_height, int max_keypoints,
+                  int device_id, ssb_lightglue** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  SSB_CUDA_CHECK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  SSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_id));
+  SSB_CHECK(prop.major == 10, SSB_ERR_NODEVICE, "device %d is sm_%d%d; this library needs sm_100", device_id,
+            prop.major, prop.minor);
+  auto w = std::make_shared<ssb::LgWeights>();
+  SSB_RETURN_IF(w->load(weights_path, device_id));
+  std::unique_ptr<ssb_lightglue> h(new ssb_lightglue);
+  SSB_RETURN_IF(h->impl.init(w, image_width, image_height, max_keypoints, 1));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+int ssb_lg_clone_context(ssb_lightglue* src, int image_width, int image_height, ssb_lightglue** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(src != nullptr && out != nullptr, SSB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::unique_ptr<ssb_lightglue> h(new ssb_lightglue);
+  SSB_RETURN_IF(h->impl.init(src->impl.weights(), image_width, image_height, src->impl.max_keypoints(), 1));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_lg_destroy(ssb_lightglue* lg) { delete lg; }
+
+int ssb_lg_match_device(ssb_lightglue* lg, const float* xy0, int n0, const void* desc0_dev, const float* xy1,
+                        int n1, const void* desc1_dev, int32_t* matches0, float* mscores0) {
+  SSB_API_BEGIN
+  SSB_CHECK(lg != nullptr, SSB_ERR_INVALID, "lg is null");
+  return lg->impl.match_device(xy0, n0, desc0_dev, xy1, n1, desc1_dev, matches0, mscores0);
+  SSB_API_END
+}
+int ssb_lg_match_host(ssb_lightglue* lg, const float* xy0, int n0, const float* desc0_f32, const float* xy1,
+                      int n1, const float* desc1_f32, int32_t* matches0, float* mscores0) {
+  SSB_API_BEGIN
+  SSB_CHECK(lg != nullptr, SSB_ERR_INVALID, "lg is null");
+  return lg->impl.match_host(xy0, n0, desc0_f32, xy1, n1, desc1_f32, matches0, mscores0);
+  SSB_API_END
+}
+int ssb_desc_to_host_f32(int device_id, const void* desc_dev_f16, int count, int dim, float* out) {
+  SSB_API_BEGIN
+  if (desc_dev_f16 == nullptr || count <= 0) return SSB_OK;  // empty handle -> empty Mat
+  SSB_CHECK(out != nullptr && dim > 0, SSB_ERR_INVALID, "bad arguments");
+  SSB_CUDA_CHECK(cudaSetDevice(device_id));
+  const size_t n = static_cast<size_t>(count) * dim;
+  std::vector<__half> tmp(n);
+  SSB_CUDA_CHECK(cudaMemcpy(tmp.data(), desc_dev_f16, n * sizeof(__half), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) out[i] = __half2float(tmp[i]);
+  return SSB_OK;
+  SSB_API_END
+}
+int ssb_lg_debug_read(ssb_lightglue* lg, const char* what, void* dst, size_t bytes) {
+  SSB_CHECK(lg != nullptr && dst != nullptr, SSB_ERR_INVALID, "null argument");
+  return lg->impl.debug_read(what, dst, bytes);
+}
+
+int ssb_fe_create(const char* sp_weights, const char* lg_weights, int max_keypoints, double keypoint_threshold,
+                  int remove_borders, int lg_image_width, int lg_image_height, float min_disparity,
+                  int max_pairs, int device_id, ssb_frontend** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  std::unique_ptr<ssb_frontend> h(new ssb_frontend);
+  SSB_RETURN_IF(h->impl.init(sp_weights, lg_weights, max_keypoints, keypoint_threshold, remove_borders,
+                             lg_image_width, lg_image_height, min_disparity, max_pairs, device_id));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_fe_destroy(ssb_frontend* fe) { delete fe; }
+
+int ssb_fe_process(ssb_frontend* fe, const uint8_t* const* images, int pairs, int height, int width,
+                   int row_stride, int* count, float* xy, float* score, int32_t* matches0, float* mscores0,
+                   float* stereo_ur, uint8_t* has_depth) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  uint8_t* dev = nullptr;
+  SSB_RETURN_IF(fe->impl.stage_images(images, 2 * pairs, height, width, row_stride, false, &dev));
+  SSB_RETURN_IF(fe->impl.enqueue_device(dev, pairs, height, width));
+  return fe->impl.fetch(pairs, count, xy, score, matches0, mscores0, stereo_ur, has_depth);
+  SSB_API_END
+}
+int ssb_fe_enqueue_device(ssb_frontend* fe, const uint8_t* images_dev, int pairs, int height, int width) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr && images_dev != nullptr, SSB_ERR_INVALID, "null argument");
+  return fe->impl.enqueue_device(images_dev, pairs, height, width);
+  SSB_API_END
+}
+int ssb_fe_fetch(ssb_frontend* fe, int pairs, int* count, float* xy, float* score, int32_t* matches0,
+                 float* mscores0, float* stereo_ur, uint8_t* has_depth) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.fetch(pairs, count, xy, score, matches0, mscores0, stereo_ur, has_depth);
+  SSB_API_END
+}
+int ssb_fe_sync(ssb_frontend* fe) {
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  SSB_CUDA_CHECK(cudaSetDevice(fe->impl.device_));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(fe->impl.stream_));
+  return SSB_OK;
+}
+int ssb_fe_event_record(ssb_frontend* fe, int index) {
+  SSB_CHECK(fe != nullptr && index >= 0 && index < 16, SSB_ERR_INVALID, "bad event index");
+  SSB_CUDA_CHECK(cudaSetDevice(fe->impl.device_));
+  SSB_CUDA_CHECK(cudaEventRecord(fe->impl.events_[index], fe->impl.stream_));
+  return SSB_OK;
+}
+int ssb_fe_event_elapsed_ms(ssb_frontend* fe, int start_index, int stop_index, float* ms) {
+  SSB_CHECK(fe != nullptr && ms != nullptr && start_index >= 0 && start_index < 16 && stop_index >= 0 &&
+                stop_index < 16,
+            SSB_ERR_INVALID, "bad arguments");
+  SSB_CUDA_CHECK(cudaSetDevice(fe->impl.device_));
+  SSB_CUDA_CHECK(cudaEventSynchronize(fe->impl.events_[stop_index]));
+  SSB_CUDA_CHECK(cudaEventElapsedTime(ms, fe->impl.events_[start_index], fe->impl.events_[stop_index]));
+  return SSB_OK;
+}
+int ssb_fe_upload_images(ssb_frontend* fe, const uint8_t* const* images, int count, int height, int width,
+                         int row_stride, uint8_t** images_dev_out) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr && images_dev_out != nullptr, SSB_ERR_INVALID, "null argument");
+  return fe->impl.stage_images(images, count, height, width, row_stride, true, images_dev_out);
+  SSB_API_END
+}
+int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
+  (void)fe;
+  (void)pairs;
+  // conv1a + 10 tcgen05 convs + memset-free: nms, select, gather | prepare + 9 x 15 + 8 | postfilter
+  return 14 + 1 + 9 * 16 + 8 + 1;
+}
+ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe) { return fe ? &fe->impl.sp : nullptr; }
+ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe) { return fe ? &fe->impl.lg : nullptr; }
+
+}  // extern "C"

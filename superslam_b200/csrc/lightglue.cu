@@ -1,0 +1,951 @@
+// LightGlue on sm_100a.  Every dense contraction (QKV / out / FFN / final projections, Q*K^T, P*V,
+// the assignment similarity) runs on tcgen05 through umma_core.cuh; rotary embedding, LayerNorm+GELU,
+// the residual update and the hi/lo split of the final projection are fused into the TMEM epilogues.
+// Softmax, log-sum-exp, arg-max and the mutual check are warp-per-row SIMT kernels (HBM/L2 bound).
+//
+// Model (cvg/LightGlue lightglue.py, restated in oracle/lightglue.py):
+//   posenc   cos/sin(Wr * kpt) repeat-interleaved to 64, rotary on q,k of self-attention only
+//   self     Wqkv (head, dim, 3) -> rotary -> softmax(q k^T / 8) v -> out_proj -> ffn(cat[x, msg]) + x
+//   cross    shared to_qk, to_v; sim = qk0 qk1^T / 8; m0 = softmax_row(sim) v1, m1 = softmax_row(sim^T) v0
+//   assign   final_proj / 4, sim = md0 md1^T, log_softmax rows + cols + logsigmoid(matchability)
+//   filter   row/col arg-max, mutual, exp(score) > 0.1
+// Host contract (cite /root/reference): keypoint normalisation src/LightGlue.cc:241-251, device path
+// :377-457, host path :285-324, outputs matches0 int32 / mscores0 fp32 :326-363.
+#include "lightglue.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "umma_core.cuh"
+
+namespace ssb {
+
+// =================================================================================================
+// SIMT kernels
+// =================================================================================================
+
+// One warp per keypoint row: copy the fp16 descriptor row into the fp16/fp32 residual stream (zero the
+// padding rows), normalise the pixel keypoint exactly like LightGlue::store_keypoints and evaluate
+// the learnable Fourier encoding (lane f owns frequency f).
+__global__ void __launch_bounds__(256)
+lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __restrict__ kp_count,
+                  void* const* __restrict__ desc_ptrs, const float* __restrict__ wr, float cx, float cy,
+                  float scale, int kp, __half* __restrict__ x16, float* __restrict__ x32,
+                  float* __restrict__ cs, float* __restrict__ sn) {
+  const int z = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= kp) return;
+  const int n = kp_count[z];
+  const size_t o = (static_cast<size_t>(z) * kp + row) * kLgDim + lane * 8;
+  if (row >= n || desc_ptrs[z] == nullptr) {
+    *reinterpret_cast<uint4*>(x16 + o) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<float4*>(x32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(x32 + o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const __half* d = static_cast<const __half*>(desc_ptrs[z]) + static_cast<size_t>(row) * kLgDim + lane * 8;
+  const uint4 raw = *reinterpret_cast<const uint4*>(d);
+  *reinterpret_cast<uint4*>(x16 + o) = raw;
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+  const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
+               e = __half22float2(h2[3]);
+  *reinterpret_cast<float4*>(x32 + o) = make_float4(a.x, a.y, b.x, b.y);
+  *reinterpret_cast<float4*>(x32 + o + 4) = make_float4(c.x, c.y, e.x, e.y);
+  const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
+  const float nx = (xy[0] - cx) / scale;
+  const float ny = (xy[1] - cy) / scale;
+  const float proj = wr[lane * 2 + 0] * nx + wr[lane * 2 + 1] * ny;
+  const size_t t = (static_cast<size_t>(z) * kp + row) * 32 + lane;
+  cs[t] = cosf(proj);
+  sn[t] = sinf(proj);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// Row softmax of the attention logits: S fp32 [z][kp][kp] -> P fp16, zero-padded up to the next
+// multiple of 64 keys (the P*V K-loop runs in 64-key chunks).  img = z/4; keys come from img ^ key_xor.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, __half* __restrict__ P, int kp,
+                    const int* __restrict__ cnt, int key_xor) {
+  const int z = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int img = z >> 2;
+  if (row >= cnt[img]) return;
+  const int nk = cnt[img ^ key_xor];
+  const float* s = S + (static_cast<size_t>(z) * kp + row) * kp;
+  __half* p = P + (static_cast<size_t>(z) * kp + row) * kp;
+  float m = -INFINITY;
+  for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
+  m = warp_max(m);
+  const float l2e = 1.4426950408889634f;
+  float sum = 0.f;
+  for (int j = lane; j < nk; j += 32) sum += exp2f((s[j] - m) * l2e);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  const int npad = (nk + 63) & ~63;
+  for (int j = lane; j < npad; j += 32)
+    p[j] = __float2half(j < nk ? exp2f((s[j] - m) * l2e) * inv : 0.f);
+}
+
+// logsigmoid(matchability(x)) per keypoint, fp32 on the fp32 residual stream.
+__global__ void __launch_bounds__(256)
+matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, float b, int kp,
+                    const int* __restrict__ cnt, float* __restrict__ lz) {
+  const int z = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= cnt[z]) return;
+  const float* x = x32 + (static_cast<size_t>(z) * kp + row) * kLgDim;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc = fmaf(x[lane + 32 * j], w[lane + 32 * j], acc);
+  acc = warp_sum(acc) + b;
+  if (lane == 0) lz[static_cast<size_t>(z) * kp + row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
+}
+
+// Row log-sum-exp of sim (pass 0: z = pair, rows of image 2z over columns of image 2z+1; pass 1 on
+// sim^T gives the column log-sum-exp).  blockIdx.y = pair*2 + pass.
+__global__ void __launch_bounds__(256)
+lse_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp, const int* __restrict__ cnt,
+                float* __restrict__ lse) {
+  const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int nr = cnt[2 * pair + pass], nc = cnt[2 * pair + (pass ^ 1)];
+  if (row >= nr) return;
+  const float* s = sim + pass * pass_stride + (static_cast<size_t>(pair) * kp + row) * kp;
+  float m = -INFINITY;
+  for (int j = lane; j < nc; j += 32) m = fmaxf(m, s[j]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < nc; j += 32) sum += expf(s[j] - m);
+  sum = warp_sum(sum);
+  if (lane == 0) lse[(static_cast<size_t>(2 * pair + pass)) * kp + row] = m + logf(sum);
+}
+
+// Row arg-max of the assignment scores
+//   score(i,j) = ((sim - lse_row0[i]) + (sim - lse_col1[j])) + (lz0[i] + lz1[j])
+// evaluated with the same association on sim (pass 0, gives matches0 candidates and their score) and
+// on sim^T (pass 1, gives the column arg-max), so both passes see bit-identical values.
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp,
+                   const int* __restrict__ cnt, const float* __restrict__ lse,
+                   const float* __restrict__ lz, float* __restrict__ max0, int* __restrict__ arg0,
+                   int* __restrict__ arg1) {
+  const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int nr = cnt[2 * pair + pass], nc = cnt[2 * pair + (pass ^ 1)];
+  if (row >= nr) return;
+  const float* s = sim + pass * pass_stride + (static_cast<size_t>(pair) * kp + row) * kp;
+  const float* lse0 = lse + static_cast<size_t>(2 * pair) * kp;
+  const float* lse1 = lse0 + kp;
+  const float* lz0 = lz + static_cast<size_t>(2 * pair) * kp;
+  const float* lz1 = lz0 + kp;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < nc; j += 32) {
+    const float v = s[j];
+    const int i0 = pass == 0 ? row : j;  // index into image 0
+    const int i1 = pass == 0 ? j : row;  // index into image 1
+    const float val = ((v - lse0[i0]) + (v - lse1[i1])) + (lz0[i0] + lz1[i1]);
+    if (val > best) {
+      best = val;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    if (pass == 0) {
+      max0[static_cast<size_t>(pair) * kp + row] = best;
+      arg0[static_cast<size_t>(pair) * kp + row] = bi;
+    } else {
+      arg1[static_cast<size_t>(pair) * kp + row] = bi;
+    }
+  }
+}
+
+// filter_matches: mutual nearest neighbours, score = exp(max) if mutual else 0, valid iff > 0.1.
+__global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* __restrict__ arg0,
+                                     const int* __restrict__ arg1, const int* __restrict__ cnt, int kp,
+                                     float threshold, int32_t* __restrict__ matches0,
+                                     float* __restrict__ mscores0) {
+  const int pair = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kp) return;
+  const size_t o = static_cast<size_t>(pair) * kp + i;
+  const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
+  if (i >= n0 || n1 <= 0) {
+    matches0[o] = -1;
+    mscores0[o] = 0.f;
+    return;
+  }
+  const int j = arg0[o];
+  const bool mutual = arg1[static_cast<size_t>(pair) * kp + j] == i;
+  const float ms = mutual ? expf(max0[o]) : 0.f;
+  matches0[o] = (mutual && ms > threshold) ? j : -1;
+  mscores0[o] = ms;
+}
+
+// =================================================================================================
+// TMEM epilogues
+// =================================================================================================
+
+// Fused QKV projection epilogue (self attention).  Tile n0 = 0 / 256 / 512 holds q / k / v for all
+// four heads.  q,k: rotary  t*cos + rotate_half(t)*sin  with rotate_half((a,b)) = (-b,a); stored
+// head-major [z*4+h][kp][64].  v: stored transposed [z*4+h][64][kp] (K-major B operand of P*V).
+struct EpiQkvRope {
+  const float* bias;
+  const float* cs;
+  const float* sn;
+  __half* q;
+  __half* k;
+  __half* vt;
+  int kp;
+  int rope;  // 1: self attention (n0 0/256 = q/k with rotary, 512 = v); 0: cross (n0 0 = qk, 256 = v)
+  __device__ void operator()(const EpiCtx& c, bool) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    const int which = c.n0 >> 8;
+    const bool is_v = rope ? (which == 2) : (which == 1);
+    for (int col = 0; col < 256; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+      const int head = col >> 6, d0 = col & 63;
+      const size_t zh = static_cast<size_t>(c.z) * kLgHeads + head;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
+      if (!is_v) {
+        if (rope && valid) {
+          const float* cr = cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
+          const float* sr = sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float co = cr[i], si = sr[i];
+            const float a = v[2 * i], b = v[2 * i + 1];
+            v[2 * i] = a * co - b * si;
+            v[2 * i + 1] = b * co + a * si;
+          }
+        }
+        __half* dstp = (which == 0 ? q : k) + (zh * kp + row) * kLgHeadDim + d0;
+        uint4* dst = reinterpret_cast<uint4*>(dstp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          dst[j] = o;
+        }
+      } else {
+        __half* base = vt + (zh * kLgHeadDim + d0) * kp + row;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) base[static_cast<size_t>(j) * kp] = __float2half(v[j]);
+      }
+    }
+  }
+};
+
+// bias -> fp16 rows [z][kp][256] (out_proj / to_out); padding rows inside the tile are zeroed.
+struct EpiBias16 {
+  const float* bias;
+  __half* out;
+  int kp;
+  __device__ void operator()(const EpiCtx& c, bool) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    for (int col = 0; col < 256; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(c.z) * kp + row) * kLgDim + c.n0 + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        dst[j] = o;
+      }
+    }
+  }
+};
+
+// FFN first half: Linear(512->512) + LayerNorm(512, eps 1e-5) + exact GELU -> fp16 [z][kp][512].
+// The thread owns its whole 512-wide row in TMEM, so mean / variance / normalise are three cheap
+// passes over tcgen05.ld.
+struct EpiLnGelu {
+  const float* bias;
+  const float* g;
+  const float* b;
+  __half* out;
+  int kp;
+  __device__ void operator()(const EpiCtx& c, bool) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    float sum = 0.f;
+    for (int col = 0; col < 512; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j] + __ldg(bias + col + j);
+    }
+    const float mean = sum * (1.0f / 512.0f);
+    float sq = 0.f;
+    for (int col = 0; col < 512; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] + __ldg(bias + col + j) - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+    const float rstd = rsqrtf(sq * (1.0f / 512.0f) + 1e-5f);
+    for (int col = 0; col < 512; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float y = (v[j] + __ldg(bias + col + j) - mean) * rstd * __ldg(g + col + j) + __ldg(b + col + j);
+        y = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
+        v[j] = valid ? y : 0.f;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(c.z) * kp + row) * 512 + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        dst[j] = o;
+      }
+    }
+  }
+};
+
+// FFN second half: Linear(512->256) + bias + residual; writes the fp32 master and its fp16 copy.
+struct EpiResidual {
+  const float* bias;
+  float* x32;
+  __half* x16;
+  int kp;
+  __device__ void operator()(const EpiCtx& c, bool) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    for (int col = 0; col < 256; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+      const size_t o = (static_cast<size_t>(c.z) * kp + row) * kLgDim + col;
+      float4* xr = reinterpret_cast<float4*>(x32 + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = valid ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x.x = valid ? x.x + (v[4 * j + 0] + __ldg(bias + col + 4 * j + 0)) : 0.f;
+        x.y = valid ? x.y + (v[4 * j + 1] + __ldg(bias + col + 4 * j + 1)) : 0.f;
+        x.z = valid ? x.z + (v[4 * j + 2] + __ldg(bias + col + 4 * j + 2)) : 0.f;
+        x.w = valid ? x.w + (v[4 * j + 3] + __ldg(bias + col + 4 * j + 3)) : 0.f;
+        xr[j] = x;
+        v[4 * j + 0] = x.x, v[4 * j + 1] = x.y, v[4 * j + 2] = x.z, v[4 * j + 3] = x.w;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(x16 + o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        w.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        w.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        w.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        dst[j] = w;
+      }
+    }
+  }
+};
+
+// fp32 logits: out[z_off + z*z_stride + row*ld + n0 + col] = acc * scale (valid rows only).
+struct EpiStoreF32 {
+  float* out;
+  int ld;
+  size_t z_stride;
+  float scale;
+  int block_n;
+  __device__ void operator()(const EpiCtx& c, bool has_acc) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    for (int col = 0; col < block_n; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(c.z) * z_stride +
+                                                static_cast<size_t>(row) * ld + c.n0 + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = has_acc ? make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale,
+                                         v[4 * j + 3] * scale)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+};
+
+// P*V epilogue: heads are concatenated back into [img][kp][256] fp16 (z = img*4 + head).
+struct EpiCtx16 {
+  __half* ctx;
+  int kp;
+  __device__ void operator()(const EpiCtx& c, bool has_acc) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    const int img = c.z >> 2, head = c.z & 3;
+    for (int col = 0; col < 64; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (valid && has_acc) ? v[j] : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(img) * kp + row) * kLgDim +
+                                            head * kLgHeadDim + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        dst[j] = o;
+      }
+    }
+  }
+};
+
+// final_proj epilogue: md = (acc + bias) / 256^(1/4); split md = hi + lo (two fp16) so the fp16
+// tensor-core similarity recovers ~fp32 accuracy: sim = hi0.hi1 + hi0.lo1 + lo0.hi1 as one K=768
+// product of A-form [hi|hi|lo] with B-form [hi|lo|hi].
+struct EpiSplit {
+  const float* bias;
+  __half* mda;
+  __half* mdb;
+  int kp;
+  __device__ void operator()(const EpiCtx& c, bool) const {
+    const int row = c.px;
+    const bool valid = row < c.m_valid;
+    for (int col = 0; col < 256; col += 32) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + col, v);
+      tmem_ld_wait();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = valid ? (v[2 * j] + __ldg(bias + col + 2 * j)) * 0.25f : 0.f;
+        const float b = valid ? (v[2 * j + 1] + __ldg(bias + col + 2 * j + 1)) * 0.25f : 0.f;
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = pack_half2(a - hf.x, b - hf.y);
+      }
+      const size_t o = (static_cast<size_t>(c.z) * kp + row) * 768 + col;
+      uint4* a0 = reinterpret_cast<uint4*>(mda + o);
+      uint4* a1 = reinterpret_cast<uint4*>(mda + o + 256);
+      uint4* a2 = reinterpret_cast<uint4*>(mda + o + 512);
+      uint4* b0 = reinterpret_cast<uint4*>(mdb + o);
+      uint4* b1 = reinterpret_cast<uint4*>(mdb + o + 256);
+      uint4* b2 = reinterpret_cast<uint4*>(mdb + o + 512);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 H = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        const uint4 L = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        a0[j] = H, a1[j] = H, a2[j] = L;
+        b0[j] = H, b1[j] = L, b2[j] = H;
+      }
+    }
+  }
+};
+
+// =================================================================================================
+// weights
+// =================================================================================================
+LgWeights::~LgWeights() {
+  cudaSetDevice(device);
+  for (void* p : owned)
+    if (p) cudaFree(p);
+}
+
+static int upload(LgWeights* W, const void* src, size_t bytes, void** dst) {
+  SSB_CUDA_CHECK(cudaMalloc(dst, bytes));
+  W->owned.push_back(*dst);
+  SSB_CUDA_CHECK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+  return SSB_OK;
+}
+
+static int make_linear(LgWeights* W, LgLinear* L, const std::vector<float>& w, const std::vector<float>& b,
+                       int n, int k) {
+  L->n = n;
+  L->k = k;
+  std::vector<__half> hw(w.size());
+  for (size_t i = 0; i < w.size(); ++i) hw[i] = __float2half(w[i]);
+  SSB_RETURN_IF(upload(W, hw.data(), hw.size() * sizeof(__half), reinterpret_cast<void**>(&L->w)));
+  SSB_RETURN_IF(upload(W, b.data(), b.size() * sizeof(float), reinterpret_cast<void**>(&L->bias)));
+  uint64_t dims[3] = {static_cast<uint64_t>(k), static_cast<uint64_t>(n), 1};
+  uint64_t strides[2] = {static_cast<uint64_t>(k) * 2, static_cast<uint64_t>(n) * k * 2};
+  uint32_t box[3] = {64, static_cast<uint32_t>(n > 256 ? 256 : n), 1};
+  return encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box);
+}
+
+int LgWeights::load(const char* path, int dev) {
+  device = dev;
+  SSB_CUDA_CHECK(cudaSetDevice(dev));
+  WeightArchive ar;
+  SSB_RETURN_IF(load_archive(path, &ar));
+  // accept upstream checkpoint naming (self_attn.{i}.* / cross_attn.{i}.*) as well
+  auto key = [&](int i, const char* blk, const char* rest) -> std::string {
+    std::string a = "transformers." + std::to_string(i) + "." + blk + "." + rest;
+    if (ar.has(a)) return a;
+    return std::string(blk) + "." + std::to_string(i) + "." + rest;
+  };
+  auto need = [&](const std::string& name, std::initializer_list<int> dims) { return ar.get(name, dims); };
+  const HostTensor* wr_t = need("posenc.Wr.weight", {32, 2});
+  if (!wr_t) return SSB_ERR_IO;
+  SSB_RETURN_IF(upload(this, wr_t->data.data(), 64 * sizeof(float), reinterpret_cast<void**>(&wr)));
+  auto ffn = [&](int i, const char* blk, LgBlockFfn* F) -> int {
+    const HostTensor* w0 = need(key(i, blk, "ffn.0.weight"), {512, 512});
+    const HostTensor* b0 = need(key(i, blk, "ffn.0.bias"), {512});
+    const HostTensor* g = need(key(i, blk, "ffn.1.weight"), {512});
+    const HostTensor* be = need(key(i, blk, "ffn.1.bias"), {512});
+    const HostTensor* w3 = need(key(i, blk, "ffn.3.weight"), {256, 512});
+    const HostTensor* b3 = need(key(i, blk, "ffn.3.bias"), {256});
+    if (!w0 || !b0 || !g || !be || !w3 || !b3) return SSB_ERR_IO;
+    SSB_RETURN_IF(make_linear(this, &F->fc1, w0->data, b0->data, 512, 512));
+    SSB_RETURN_IF(make_linear(this, &F->fc2, w3->data, b3->data, 256, 512));
+    SSB_RETURN_IF(upload(this, g->data.data(), 512 * sizeof(float), reinterpret_cast<void**>(&F->ln_g)));
+    SSB_RETURN_IF(upload(this, be->data.data(), 512 * sizeof(float), reinterpret_cast<void**>(&F->ln_b)));
+    return SSB_OK;
+  };
+  for (int i = 0; i < kLgLayers; ++i) {
+    LgLayer& L = layers[i];
+    const HostTensor* wq = need(key(i, "self_attn", "Wqkv.weight"), {768, 256});
+    const HostTensor* bq = need(key(i, "self_attn", "Wqkv.bias"), {768});
+    const HostTensor* wo = need(key(i, "self_attn", "out_proj.weight"), {256, 256});
+    const HostTensor* bo = need(key(i, "self_attn", "out_proj.bias"), {256});
+    if (!wq || !bq || !wo || !bo) return SSB_ERR_IO;
+    // cvg layout: output feature = head*192 + dim*3 + {q,k,v}  ->  [which][head][dim]; the softmax
+    // scale 1/sqrt(64) = 1/8 is folded into q (a power of two: exact in every precision).
+    std::vector<float> w(768 * 256), b(768);
+    for (int which = 0; which < 3; ++which)
+      for (int h = 0; h < 4; ++h)
+        for (int d = 0; d < 64; ++d) {
+          const int src = h * 192 + d * 3 + which, dst = which * 256 + h * 64 + d;
+          const float sc = which == 0 ? 0.125f : 1.0f;
+          b[dst] = bq->data[src] * sc;
+          for (int kk = 0; kk < 256; ++kk) w[static_cast<size_t>(dst) * 256 + kk] = wq->data[static_cast<size_t>(src) * 256 + kk] * sc;
+        }
+    SSB_RETURN_IF(make_linear(this, &L.qkv, w, b, 768, 256));
+    SSB_RETURN_IF(make_linear(this, &L.out, wo->data, bo->data, 256, 256));
+    SSB_RETURN_IF(ffn(i, "self_attn", &L.sffn));
+    const HostTensor* wqk = need(key(i, "cross_attn", "to_qk.weight"), {256, 256});
+    const HostTensor* bqk = need(key(i, "cross_attn", "to_qk.bias"), {256});
+    const HostTensor* wv = need(key(i, "cross_attn", "to_v.weight"), {256, 256});
+    const HostTensor* bv = need(key(i, "cross_attn", "to_v.bias"), {256});
+    const HostTensor* wto = need(key(i, "cross_attn", "to_out.weight"), {256, 256});
+    const HostTensor* bto = need(key(i, "cross_attn", "to_out.bias"), {256});
+    if (!wqk || !bqk || !wv || !bv || !wto || !bto) return SSB_ERR_IO;
+    std::vector<float> wc(wqk->data), bc(bqk->data);
+    wc.insert(wc.end(), wv->data.begin(), wv->data.end());
+    bc.insert(bc.end(), bv->data.begin(), bv->data.end());
+    SSB_RETURN_IF(make_linear(this, &L.qkv_c, wc, bc, 512, 256));
+    SSB_RETURN_IF(make_linear(this, &L.to_out, wto->data, bto->data, 256, 256));
+    SSB_RETURN_IF(ffn(i, "cross_attn", &L.cffn));
+  }
+  const std::string la = "log_assignment." + std::to_string(kLgLayers - 1) + ".";
+  const HostTensor* wf = need(la + "final_proj.weight", {256, 256});
+  const HostTensor* bf = need(la + "final_proj.bias", {256});
+  const HostTensor* wm = need(la + "matchability.weight", {1, 256});
+  const HostTensor* bm = need(la + "matchability.bias", {1});
+  if (!wf || !bf || !wm || !bm) return SSB_ERR_IO;
+  SSB_RETURN_IF(make_linear(this, &final_proj, wf->data, bf->data, 256, 256));
+  SSB_RETURN_IF(upload(this, wm->data.data(), 256 * sizeof(float), reinterpret_cast<void**>(&match_w)));
+  match_b = bm->data[0];
+  return SSB_OK;
+}
+
+// =================================================================================================
+// context
+// =================================================================================================
+LightGlue::~LightGlue() {
+  cudaSetDevice(device_);
+  void* bufs[] = {kp_xy_, kp_count_, desc_ptrs_, desc_stage_, cs_, sn_, x32_, x16_, q_, k_, vt_, s_, p_,
+                  ctx_, msg_, h1_, mda_, mdb_, lz_, lse_, max0_, arg0_, arg1_, matches_, mscores_};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  if (host_io_) cudaFreeHost(host_io_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+static int tm_rows4(CUtensorMap* tm, const void* base, int cols, int rows, int batch) {
+  uint64_t dims[4] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows), 1, static_cast<uint64_t>(batch)};
+  uint64_t strides[3] = {static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(rows) * cols * 2,
+                         static_cast<uint64_t>(rows) * cols * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return encode_tmap_f16(tm, base, 4, dims, strides, box);
+}
+static int tm_rows3(CUtensorMap* tm, const void* base, int cols, int rows, int batch, int box_rows) {
+  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows), static_cast<uint64_t>(batch)};
+  uint64_t strides[2] = {static_cast<uint64_t>(cols) * 2, static_cast<uint64_t>(rows) * cols * 2};
+  uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return encode_tmap_f16(tm, base, 3, dims, strides, box);
+}
+
+int LightGlue::alloc_workspace() {
+  const size_t P2 = static_cast<size_t>(pairs_) * 2, Z = P2 * kLgHeads, KP = kp_;
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    SSB_CUDA_CHECK(cudaMalloc(p, bytes + 65536));
+    SSB_CUDA_CHECK(cudaMemset(*p, 0, bytes + 65536));
+    return SSB_OK;
+  };
+#define A(ptr, bytes) SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&ptr), (bytes)))
+  A(kp_xy_, P2 * KP * 2 * 4);
+  A(kp_count_, P2 * 4);
+  A(desc_ptrs_, P2 * sizeof(void*));
+  A(desc_stage_, 2 * KP * kLgDim * 2);
+  A(cs_, P2 * KP * 32 * 4);
+  A(sn_, P2 * KP * 32 * 4);
+  A(x32_, P2 * KP * kLgDim * 4);
+  A(x16_, P2 * KP * kLgDim * 2);
+  A(q_, Z * KP * kLgHeadDim * 2);
+  A(k_, Z * KP * kLgHeadDim * 2);
+  A(vt_, Z * KP * kLgHeadDim * 2);
+  A(s_, Z * KP * KP * 4);
+  A(p_, Z * KP * KP * 2);
+  A(ctx_, P2 * KP * kLgDim * 2);
+  A(msg_, P2 * KP * kLgDim * 2);
+  A(h1_, P2 * KP * 512 * 2);
+  A(mda_, P2 * KP * 768 * 2);
+  A(mdb_, P2 * KP * 768 * 2);
+  A(lz_, P2 * KP * 4);
+  A(lse_, P2 * KP * 4);
+  A(max0_, static_cast<size_t>(pairs_) * KP * 4);
+  A(arg0_, static_cast<size_t>(pairs_) * KP * 4);
+  A(arg1_, static_cast<size_t>(pairs_) * KP * 4);
+  A(matches_, static_cast<size_t>(pairs_) * KP * 4);
+  A(mscores_, static_cast<size_t>(pairs_) * KP * 4);
+#undef A
+  const int p2 = static_cast<int>(P2), z = static_cast<int>(Z);
+  SSB_RETURN_IF(tm_rows4(&tm_x16_, x16_, 256, kp_, p2));
+  SSB_RETURN_IF(tm_rows4(&tm_msg_, msg_, 256, kp_, p2));
+  SSB_RETURN_IF(tm_rows4(&tm_ctx_, ctx_, 256, kp_, p2));
+  SSB_RETURN_IF(tm_rows4(&tm_h1_, h1_, 512, kp_, p2));
+  SSB_RETURN_IF(tm_rows4(&tm_q_a_, q_, 64, kp_, z));
+  SSB_RETURN_IF(tm_rows3(&tm_q_b_, q_, 64, kp_, z, 256));
+  SSB_RETURN_IF(tm_rows3(&tm_k_b_, k_, 64, kp_, z, 256));
+  SSB_RETURN_IF(tm_rows4(&tm_p_a_, p_, kp_, kp_, z));
+  SSB_RETURN_IF(tm_rows3(&tm_vt_b_, vt_, kp_, 64, z, 64));
+  SSB_RETURN_IF(tm_rows4(&tm_mda_a_, mda_, 768, kp_, p2));
+  SSB_RETURN_IF(tm_rows4(&tm_mdb_a_, mdb_, 768, kp_, p2));
+  SSB_RETURN_IF(tm_rows3(&tm_mda_b_, mda_, 768, kp_, p2, 256));
+  SSB_RETURN_IF(tm_rows3(&tm_mdb_b_, mdb_, 768, kp_, p2, 256));
+  return SSB_OK;
+}
+
+int LightGlue::init(std::shared_ptr<LgWeights> weights, int image_width, int image_height,
+                    int max_keypoints, int max_pairs) {
+  SSB_CHECK(weights != nullptr, SSB_ERR_INVALID, "null weights");
+  SSB_CHECK(max_keypoints >= 1 && max_keypoints <= 8192, SSB_ERR_INVALID, "max_keypoints out of range");
+  SSB_CHECK(max_pairs >= 1 && max_pairs <= 64, SSB_ERR_INVALID, "max_pairs out of range (1..64)");
+  SSB_CHECK(image_width > 0 && image_height > 0, SSB_ERR_INVALID, "bad image size");
+  w_ = std::move(weights);
+  device_ = w_->device;
+  img_w_ = image_width;
+  img_h_ = image_height;
+  kmax_ = max_keypoints;
+  kp_ = (max_keypoints + 255) / 256 * 256;  // whole 256-column N tiles for the logits
+  pairs_ = max_pairs;
+  SSB_CUDA_CHECK(cudaSetDevice(device_));
+  SSB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  SSB_RETURN_IF(alloc_workspace());
+  host_io_bytes_ = static_cast<size_t>(kp_) * (4 * 4 + 8) + 64;
+  SSB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&host_io_), host_io_bytes_));
+  return SSB_OK;
+}
+
+int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* kp_count_dev,
+                   void* const* desc_ptrs_dev, cudaStream_t stream) {
+  SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
+  SSB_CUDA_CHECK(cudaSetDevice(device_));
+  const int P2 = pairs * 2, Z = P2 * kLgHeads, KP = kp_;
+  const int tiles = KP / 128;
+  const int* cnt = kp_count_dev;
+  {
+    const float scale = static_cast<float>(std::max(img_w_, img_h_)) / 2.0f;
+    const float cx = img_w_ / 2.0f, cy = img_h_ / 2.0f;
+    lg_prepare_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
+                                                            w_->wr, cx, cy, scale, KP, x16_, x32_, cs_, sn_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+    count_launch();
+  }
+  auto lin = [&](int kc0, int kc1, int block_n) {
+    CoreParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.taps_h = p.taps_w = 1;
+    p.kc0 = kc0;
+    p.kc1 = kc1;
+    p.tile_w = 128;
+    p.tile_h = 1;
+    p.tiles_w = tiles;
+    p.block_n = block_n;
+    p.a_z_mul = 1;
+    p.m_valid = dev_count(cnt);
+    return p;
+  };
+  auto ffn = [&](const LgBlockFfn& F) -> int {
+    {
+      CoreParams p = lin(4, 4, 512);
+      EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, h1_, KP};
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
+    }
+    {
+      CoreParams p = lin(8, 0, 256);
+      EpiResidual e{F.fc2.bias, x32_, x16_, KP};
+      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
+    }
+    return SSB_OK;
+  };
+  // logits -> probabilities -> context, shared by self (key_xor 0) and cross (key_xor 1) attention
+  auto attention = [&](const CUtensorMap& tmKeys, int key_xor, float scale) -> int {
+    {
+      CoreParams p = lin(1, 0, 256);
+      p.b_z_xor = key_xor ? kLgHeads : 0;
+      p.b_z_mul = 1;
+      p.m_valid = dev_count(cnt, kLgHeads);
+      p.n_valid = dev_count(cnt, kLgHeads, key_xor);
+      EpiStoreF32 e{s_, KP, static_cast<size_t>(KP) * KP, scale, 256};
+      SSB_RETURN_IF(launch_core(tm_q_a_, tm_q_a_, tmKeys, p, e, dim3(tiles, KP / 256, Z), stream));
+    }
+    softmax_rows_kernel<<<dim3(KP / 8, Z), 256, 0, stream>>>(s_, p_, KP, cnt, key_xor);
+    SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+    count_launch();
+    {
+      CoreParams p = lin(KP / 64, 0, 64);
+      p.b_z_xor = key_xor ? kLgHeads : 0;
+      p.b_z_mul = 1;
+      p.m_valid = dev_count(cnt, kLgHeads);
+      p.k_valid = dev_count(cnt, kLgHeads, key_xor);
+      EpiCtx16 e{ctx_, KP};
+      SSB_RETURN_IF(launch_core(tm_p_a_, tm_p_a_, tm_vt_b_, p, e, dim3(tiles, 1, Z), stream));
+    }
+    return SSB_OK;
+  };
+
+  // test hook: SSB_LG_STOP_AFTER=n returns after n half-blocks (self = odd, cross = even) so the
+  // residual stream can be compared with the oracle layer by layer (tools/gpu_diag.py)
+  int stop_after = -1, blocks = 0;
+  if (const char* e = std::getenv("SSB_LG_STOP_AFTER")) stop_after = std::atoi(e);
+  for (int i = 0; i < kLgLayers; ++i) {
+    const LgLayer& L = w_->layers[i];
+    // ---- self block ----
+    {
+      CoreParams p = lin(4, 0, 256);
+      EpiQkvRope e{L.qkv.bias, cs_, sn_, q_, k_, vt_, KP, 1};
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
+    }
+    SSB_RETURN_IF(attention(tm_k_b_, 0, 1.0f));
+    {
+      CoreParams p = lin(4, 0, 256);
+      EpiBias16 e{L.out.bias, msg_, KP};
+      SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
+    }
+    SSB_RETURN_IF(ffn(L.sffn));
+    if (++blocks == stop_after) return SSB_OK;
+    // ---- cross block ----
+    {
+      CoreParams p = lin(4, 0, 256);
+      EpiQkvRope e{L.qkv_c.bias, cs_, sn_, q_, k_, vt_, KP, 0};
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
+    }
+    SSB_RETURN_IF(attention(tm_q_b_, 1, 0.125f));
+    {
+      CoreParams p = lin(4, 0, 256);
+      EpiBias16 e{L.to_out.bias, msg_, KP};
+      SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));
+    }
+    SSB_RETURN_IF(ffn(L.cffn));
+    if (++blocks == stop_after) return SSB_OK;
+  }
+  // ---- assignment ----
+  {
+    CoreParams p = lin(4, 0, 256);
+    EpiSplit e{w_->final_proj.bias, mda_, mdb_, KP};
+    SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
+  }
+  matchability_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(x32_, w_->match_w, w_->match_b, KP, cnt, lz_);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  const size_t pass_stride = static_cast<size_t>(pairs) * KP * KP;
+  {
+    CoreParams p = lin(12, 0, 256);  // sim[pair] = A-form(img 2p) x B-form(img 2p+1)
+    p.a_z_mul = 2;
+    p.b_z_mul = 2;
+    p.b_z_add = 1;
+    p.m_valid = dev_count(cnt, 1, 0, 2, 0);
+    p.n_valid = dev_count(cnt, 1, 0, 2, 1);
+    EpiStoreF32 e{s_, KP, static_cast<size_t>(KP) * KP, 1.0f, 256};
+    SSB_RETURN_IF(launch_core(tm_mda_a_, tm_mda_a_, tm_mdb_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
+  }
+  {
+    CoreParams p = lin(12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
+    p.a_z_mul = 2;
+    p.a_z_add = 1;
+    p.b_z_mul = 2;
+    p.m_valid = dev_count(cnt, 1, 0, 2, 1);
+    p.n_valid = dev_count(cnt, 1, 0, 2, 0);
+    EpiStoreF32 e{s_ + pass_stride, KP, static_cast<size_t>(KP) * KP, 1.0f, 256};
+    SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
+  }
+  lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  argmax_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_, lz_, max0_,
+                                                                 arg0_, arg1_);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  mutual_filter_kernel<<<dim3((KP + 255) / 256, pairs), 256, 0, stream>>>(max0_, arg0_, arg1_, cnt, KP, 0.1f,
+                                                                         matches_, mscores_);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SSB_OK;
+}
+
+int LightGlue::match_common(int n0, int n1, int32_t* matches0, float* mscores0) {
+  SSB_RETURN_IF(run(1, kp_xy_, kp_, kp_count_, desc_ptrs_, stream_));
+  int32_t* mh = reinterpret_cast<int32_t*>(host_io_);
+  float* sh = host_io_ + kp_;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(mh, matches_, static_cast<size_t>(n0) * 4, cudaMemcpyDeviceToHost, stream_));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(sh, mscores_, static_cast<size_t>(n0) * 4, cudaMemcpyDeviceToHost, stream_));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::memcpy(matches0, mh, static_cast<size_t>(n0) * 4);
+  if (mscores0) std::memcpy(mscores0, sh, static_cast<size_t>(n0) * 4);
+  (void)n1;
+  return SSB_OK;
+}
+
+int LightGlue::match_device(const float* xy0, int n0, const void* desc0_dev, const float* xy1, int n1,
+                            const void* desc1_dev, int32_t* matches0, float* mscores0) {
+  SSB_CHECK(n0 >= 0 && n1 >= 0 && n0 <= kmax_ && n1 <= kmax_, SSB_ERR_INVALID,
+            "keypoint counts (%d, %d) exceed max_keypoints %d", n0, n1, kmax_);
+  SSB_CHECK(matches0 != nullptr || n0 == 0, SSB_ERR_INVALID, "matches0 is null");
+  if (n0 == 0 || n1 == 0) {  // src/LightGlue.cc:386-387: empty result, not an error
+    for (int i = 0; i < n0; ++i) {
+      matches0[i] = -1;
+      if (mscores0) mscores0[i] = 0.f;
+    }
+    return SSB_OK;
+  }
+  SSB_CHECK(xy0 && xy1 && desc0_dev && desc1_dev, SSB_ERR_INVALID, "null input");
+  SSB_CUDA_CHECK(cudaSetDevice(device_));
+  // pinned staging layout: [xy0 (kp*2) | xy1 (kp*2)] floats, then counts, then pointer table
+  float* h = host_io_;
+  std::memcpy(h, xy0, static_cast<size_t>(n0) * 8);
+  std::memcpy(h + static_cast<size_t>(kp_) * 2, xy1, static_cast<size_t>(n1) * 8);
+  int* hc = reinterpret_cast<int*>(h + static_cast<size_t>(kp_) * 4);
+  hc[0] = n0;
+  hc[1] = n1;
+  void** hp = reinterpret_cast<void**>(hc + 2);
+  hp[0] = const_cast<void*>(desc0_dev);
+  hp[1] = const_cast<void*>(desc1_dev);
+  SSB_CUDA_CHECK(cudaMemcpyAsync(kp_xy_, h, static_cast<size_t>(n0) * 8, cudaMemcpyHostToDevice, stream_));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(kp_xy_ + static_cast<size_t>(kp_) * 2, h + static_cast<size_t>(kp_) * 2,
+                                 static_cast<size_t>(n1) * 8, cudaMemcpyHostToDevice, stream_));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(kp_count_, hc, 8, cudaMemcpyHostToDevice, stream_));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(desc_ptrs_, hp, 2 * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+  return match_common(n0, n1, matches0, mscores0);
+}
+
+int LightGlue::match_host(const float* xy0, int n0, const float* desc0, const float* xy1, int n1,
+                          const float* desc1, int32_t* matches0, float* mscores0) {
+  SSB_CHECK(n0 >= 0 && n1 >= 0 && n0 <= kmax_ && n1 <= kmax_, SSB_ERR_INVALID,
+            "keypoint counts (%d, %d) exceed max_keypoints %d", n0, n1, kmax_);
+  if (n0 == 0 || n1 == 0) {
+    for (int i = 0; i < n0; ++i) {
+      matches0[i] = -1;
+      if (mscores0) mscores0[i] = 0.f;
+    }
+    return SSB_OK;
+  }
+  SSB_CHECK(desc0 && desc1, SSB_ERR_INVALID, "null descriptors");
+  SSB_CUDA_CHECK(cudaSetDevice(device_));
+  // store_floats (src/LightGlue.cc:229-238): fp32 -> fp16 round-to-nearest on the host, then H2D
+  std::vector<__half> tmp(static_cast<size_t>(n0 + n1) * kLgDim);
+  for (size_t i = 0; i < static_cast<size_t>(n0) * kLgDim; ++i) tmp[i] = __float2half(desc0[i]);
+  for (size_t i = 0; i < static_cast<size_t>(n1) * kLgDim; ++i)
+    tmp[static_cast<size_t>(n0) * kLgDim + i] = __float2half(desc1[i]);
+  __half* d0 = desc_stage_;
+  __half* d1 = desc_stage_ + static_cast<size_t>(kp_) * kLgDim;
+  SSB_CUDA_CHECK(cudaMemcpyAsync(d0, tmp.data(), static_cast<size_t>(n0) * kLgDim * 2, cudaMemcpyHostToDevice, stream_));
+  SSB_CUDA_CHECK(cudaMemcpyAsync(d1, tmp.data() + static_cast<size_t>(n0) * kLgDim,
+                                 static_cast<size_t>(n1) * kLgDim * 2, cudaMemcpyHostToDevice, stream_));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));  // tmp is pageable and dies at scope exit
+  return match_device(xy0, n0, d0, xy1, n1, d1, matches0, mscores0);
+}
+
+int LightGlue::debug_read(const char* what, void* dst, size_t bytes) {
+  SSB_CUDA_CHECK(cudaSetDevice(device_));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  const std::string k(what ? what : "");
+  const size_t P2 = static_cast<size_t>(pairs_) * 2, KP = kp_;
+  struct Ent {
+    const char* name;
+    const void* ptr;
+    size_t bytes;
+  } tab[] = {
+      {"x32", x32_, P2 * KP * 256 * 4},   {"x16", x16_, P2 * KP * 256 * 2}, {"sim", s_, pairs_ * KP * KP * 4},
+      {"lse", lse_, P2 * KP * 4},         {"lz", lz_, P2 * KP * 4},         {"cos", cs_, P2 * KP * 32 * 4},
+      {"sin", sn_, P2 * KP * 32 * 4},     {"msg", msg_, P2 * KP * 256 * 2}, {"ctx", ctx_, P2 * KP * 256 * 2},
+      {"h1", h1_, P2 * KP * 512 * 2},     {"q", q_, P2 * 4 * KP * 64 * 2},  {"k", k_, P2 * 4 * KP * 64 * 2},
+      {"vt", vt_, P2 * 4 * KP * 64 * 2},  {"max0", max0_, pairs_ * KP * 4}, {"arg0", arg0_, pairs_ * KP * 4},
+      {"arg1", arg1_, pairs_ * KP * 4},
+  };
+  for (const Ent& e : tab) {
+    if (k == e.name) {
+      SSB_CHECK(bytes <= e.bytes, SSB_ERR_INVALID, "debug_read: '%s' holds %zu bytes, asked %zu", what,
+                e.bytes, bytes);
+      SSB_CUDA_CHECK(cudaMemcpy(dst, e.ptr, bytes, cudaMemcpyDeviceToHost));
+      return SSB_OK;
+    }
+  }
+  set_last_error("debug_read: unknown buffer '%s'", what);
+  return SSB_ERR_INVALID;
+}
+
+}  // namespace ssb

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's inference interfaces over the C-ABI.
+
+Same names, argument meaning and error behaviour as /root/reference/include/InferenceInterfaces.h:
+  SuperPoint.extract / extract_stereo        IFeatureExtractor      (:27-36)
+  LightGlue.match / descriptors_to_host      IFeatureMatcher        (:41-59)
+  Features / DeviceDescriptors / MatchResult                        (:12-24, DescriptorPool.h:13-20)
+  StereoFrontEnd.process                     src/StereoFrontEnd.cc:10-49
+The interface methods never raise on a failed inference: like the reference they log and return an
+empty Features / MatchResult (src/SuperPoint.cc:895-899, src/LightGlue.cc:381-390).  Constructors do
+raise (the reference's initialize() returns false and the facade carries on broken).
+Keypoints are numpy arrays instead of cv::KeyPoint: xy float32 [n,2] (pt.x, pt.y) and response [n];
+size = 1 and angle = -1 are constants in the reference (src/SuperPoint.cc:716).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+log = logging.getLogger("superslam_b200")
+DESC_DIM = 256
+
+
+class _Slot:
+    """shared_ptr<void> slot_ref (DescriptorPool.h:19,62-76): the last owner returns the slot."""
+
+    def __init__(self, owner: "SuperPoint", slot: int):
+        self.owner, self.slot = owner, slot
+
+    def __del__(self):
+        try:
+            if self.slot >= 0 and self.owner._h:
+                _lib.load().ssb_sp_slot_release(self.owner._h, self.slot)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+@dataclass
+class DeviceDescriptors:
+    data: int = 0          # device pointer (fp16 [count, dim] row-major)
+    count: int = 0
+    dim: int = 0
+    slot: int = -1
+    slot_ref: object = None
+    device: int = 0
+
+    def empty(self) -> bool:
+        return self.data == 0 or self.count == 0
+
+
+@dataclass
+class Features:
+    keypoints: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.float32))
+    responses: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.float32))
+    descriptors: DeviceDescriptors = field(default_factory=DeviceDescriptors)
+
+
+@dataclass
+class MatchResult:
+    """matches: rows (queryIdx, trainIdx); distance = 1 - mscore (src/LightGlue.cc:352-361)."""
+    query: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.int32))
+    train: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.int32))
+    distance: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.float32))
+    matches0: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.int32))
+    mscores0: np.ndarray = field(default_factory=lambda: np.zeros((0,), np.float32))
+
+
+def _as_gray_or_bgr(img: np.ndarray):
+    img = np.asarray(img)
+    if img.dtype != np.uint8:
+        raise TypeError("images must be uint8")
+    if img.ndim == 2:
+        ch = 1
+    elif img.ndim == 3 and img.shape[2] in (1, 3):
+        ch = img.shape[2]
+    else:
+        raise ValueError("image must be HxW or HxWx3 (BGR)")
+    if img.strides[-1] != 1 or (img.ndim == 3 and img.strides[1] != ch):
+        img = np.ascontiguousarray(img)
+    return img, ch
+
+
+class SuperPoint:
+    """IFeatureExtractor over ssb_sp_* (reference class SuperPoint, include/SuperPoint.h:37-52)."""
+
+    def __init__(self, weights_path: str, max_keypoints: int, keypoint_threshold: float = 0.005,
+                 remove_borders: int = 4, num_slots: int = 8, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = device
+        self.max_keypoints = max_keypoints
+        _lib.check(self._lib.ssb_sp_create(weights_path.encode(), max_keypoints, float(keypoint_threshold),
+                                           remove_borders, num_slots, device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_sp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def slots_in_use(self) -> int:
+        return self._lib.ssb_sp_slots_in_use(self._h)
+
+    def _extract(self, images):
+        prepared = [_as_gray_or_bgr(i) for i in images]
+        h, w = prepared[0][0].shape[:2]
+        ch = prepared[0][1]
+        for im, c in prepared:
+            if im.shape[:2] != (h, w) or c != ch:
+                log.error("SuperPoint: stereo pair must share resolution (rectified)")
+                return [Features() for _ in images]
+        b = len(prepared)
+        K = self.max_keypoints
+        ptrs = (C.POINTER(C.c_uint8) * b)(*[im.ctypes.data_as(C.POINTER(C.c_uint8)) for im, _ in prepared])
+        xy = [np.zeros((K, 2), np.float32) for _ in range(b)]
+        sc = [np.zeros((K,), np.float32) for _ in range(b)]
+        xyp = (C.POINTER(C.c_float) * b)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in xy])
+        scp = (C.POINTER(C.c_float) * b)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in sc])
+        cnt = (C.c_int * b)()
+        desc = (C.c_void_p * b)()
+        slot = (C.c_int * b)()
+        st = self._lib.ssb_sp_extract(self._h, ptrs, b, h, w, prepared[0][0].strides[0], ch, xyp, scp, cnt, desc, slot)
+        if st not in (_lib.SSB_OK, _lib.SSB_ERR_EXHAUSTED):
+            log.error("SuperPoint: extract failed: %s", self._lib.ssb_last_error().decode())
+            return [Features() for _ in images]
+        out = []
+        for i in range(b):
+            n = cnt[i]
+            d = DeviceDescriptors(device=self.device)
+            if slot[i] >= 0:
+                d = DeviceDescriptors(data=desc[i] or 0, count=n, dim=DESC_DIM, slot=slot[i],
+                                      slot_ref=_Slot(self, slot[i]), device=self.device)
+            else:
+                log.error("SuperPoint: descriptor pool exhausted (no free slot)")
+            out.append(Features(keypoints=xy[i][:n].copy(), responses=sc[i][:n].copy(), descriptors=d))
+        return out
+
+    def extract(self, image) -> Features:
+        return self._extract([image])[0]
+
+    def extract_stereo(self, left, right):
+        l, r = self._extract([left, right])
+        return l, r
+
+    def debug_read(self, what: str, shape, dtype):
+        out = np.empty(shape, dtype)
+        _lib.check(self._lib.ssb_sp_debug_read(self._h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+
+class LightGlue:
+    """IFeatureMatcher over ssb_lg_* (reference class LightGlue, include/LightGlue.h:33-57)."""
+
+    def __init__(self, weights_path: str | None, image_width: int, image_height: int, max_keypoints: int = 1024,
+                 device: int = 0, _shared: "LightGlue | None" = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = device
+        self.image_width, self.image_height = image_width, image_height
+        if _shared is not None:
+            _lib.check(self._lib.ssb_lg_clone_context(_shared._h, image_width, image_height, C.byref(self._h)))
+            self.max_keypoints = _shared.max_keypoints
+        else:
+            _lib.check(self._lib.ssb_lg_create(weights_path.encode(), image_width, image_height, max_keypoints,
+                                               device, C.byref(self._h)))
+            self.max_keypoints = max_keypoints
+
+    def shared_context(self, image_width=None, image_height=None) -> "LightGlue":
+        """LightGlue(shared_engine(), w, h): same weights, own stream/workspace (src/SuperSLAM.cc:129-133)."""
+        return LightGlue(None, image_width or self.image_width, image_height or self.image_height,
+                         device=self.device, _shared=self)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_lg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @staticmethod
+    def _result(m0, ms0) -> MatchResult:
+        q = np.nonzero(m0 >= 0)[0].astype(np.int32)
+        return MatchResult(query=q, train=m0[q].astype(np.int32), distance=(np.float32(1.0) - ms0[q]).astype(np.float32),
+                           matches0=m0, mscores0=ms0)
+
+    def match(self, kp0, d0, kp1, d1) -> MatchResult:
+        """Device path when d0/d1 are DeviceDescriptors, host path when they are float arrays [n,256]."""
+        kp0 = np.ascontiguousarray(kp0, np.float32).reshape(-1, 2)
+        kp1 = np.ascontiguousarray(kp1, np.float32).reshape(-1, 2)
+        n0, n1 = len(kp0), len(kp1)
+        m0 = np.full((n0,), -1, np.int32)
+        ms0 = np.zeros((n0,), np.float32)
+        fp = C.POINTER(C.c_float)
+        if isinstance(d0, DeviceDescriptors):
+            if d0.empty() or d1.empty() or n0 == 0 or n1 == 0:
+                return MatchResult()
+            st = self._lib.ssb_lg_match_device(self._h, kp0.ctypes.data_as(fp), n0, C.c_void_p(d0.data),
+                                               kp1.ctypes.data_as(fp), n1, C.c_void_p(d1.data),
+                                               m0.ctypes.data_as(C.POINTER(C.c_int32)), ms0.ctypes.data_as(fp))
+        else:
+            if n0 == 0 or n1 == 0:
+                return MatchResult()
+            a = np.ascontiguousarray(d0, np.float32)
+            b = np.ascontiguousarray(d1, np.float32)
+            st = self._lib.ssb_lg_match_host(self._h, kp0.ctypes.data_as(fp), n0, a.ctypes.data_as(fp),
+                                             kp1.ctypes.data_as(fp), n1, b.ctypes.data_as(fp),
+                                             m0.ctypes.data_as(C.POINTER(C.c_int32)), ms0.ctypes.data_as(fp))
+        if st != _lib.SSB_OK:
+            log.error("LightGlue: match failed: %s", self._lib.ssb_last_error().decode())
+            return MatchResult()
+        return self._result(m0, ms0)
+
+    def descriptors_to_host(self, d: DeviceDescriptors) -> np.ndarray:
+        """CV_32F [count, dim]; empty handle -> empty array (src/LightGlue.cc:460-475)."""
+        if d.empty():
+            return np.zeros((0, 0), np.float32)
+        out = np.empty((d.count, d.dim), np.float32)
+        st = self._lib.ssb_desc_to_host_f32(d.device, C.c_void_p(d.data), d.count, d.dim,
+                                            out.ctypes.data_as(C.POINTER(C.c_float)))
+        if st != _lib.SSB_OK:
+            log.error("LightGlue: descriptors_to_host D2H failed")
+            return np.zeros((0, 0), np.float32)
+        return out
+
+    def debug_read(self, what: str, shape, dtype):
+        out = np.empty(shape, dtype)
+        _lib.check(self._lib.ssb_lg_debug_read(self._h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+
+@dataclass
+class StereoFrame:
+    timestamp: float = 0.0
+    keypoints_left: np.ndarray = None
+    descriptors_left: DeviceDescriptors = None
+    stereo: np.ndarray = None     # [n,3] float64 (uL, uR, v); uR = NaN if no stereo
+    has_depth: np.ndarray = None  # [n] int8
+
+
+class StereoFrontEnd:
+    """src/StereoFrontEnd.cc:10-49 over any extractor/matcher with the interface methods above."""
+
+    def __init__(self, ext, matcher, min_disparity: float = 1.0):
+        self.ext, self.matcher, self.min_disparity = ext, matcher, np.float32(min_disparity)
+
+    def process(self, left, right, timestamp: float = 0.0) -> StereoFrame:
+        L, R = self.ext.extract_stereo(left, right)
+        n = len(L.keypoints)
+        stereo = np.empty((n, 3), np.float64)
+        if n:
+            stereo[:, 0], stereo[:, 1], stereo[:, 2] = L.keypoints[:, 0], np.nan, L.keypoints[:, 1]
+        has_depth = np.zeros((n,), np.int8)
+        m = self.matcher.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
+        for i, j in zip(m.query.tolist(), m.train.tolist()):
+            if i < 0 or j < 0 or i >= n or j >= len(R.keypoints):
+                continue
+            uL, v, uR = L.keypoints[i, 0], L.keypoints[i, 1], R.keypoints[j, 0]
+            if np.float32(uL - uR) < self.min_disparity:
+                continue
+            if abs(np.float32(L.keypoints[i, 1] - R.keypoints[j, 1])) > np.float32(2.0):
+                continue
+            stereo[i] = (uL, uR, v)
+            has_depth[i] = 1
+        return StereoFrame(timestamp, L.keypoints, L.descriptors, stereo, has_depth)
+
+
+class FramePairPipeline:
+    """Throughput path (ssb_fe_*): SP x2 + LG + stereo post-filter for `pairs` pairs per call."""
+
+    def __init__(self, sp_weights: str, lg_weights: str, max_keypoints: int, lg_image_width: int,
+                 lg_image_height: int, keypoint_threshold: float = 0.005, remove_borders: int = 4,
+                 min_disparity: float = 1.0, max_pairs: int = 1, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.K, self.max_pairs, self.device = max_keypoints, max_pairs, device
+        _lib.check(self._lib.ssb_fe_create(sp_weights.encode(), lg_weights.encode(), max_keypoints,
+                                           float(keypoint_threshold), remove_borders, lg_image_width,
+                                           lg_image_height, float(min_disparity), max_pairs, device,
+                                           C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_fe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _outputs(self, pairs):
+        K = self.K
+        return dict(count=np.zeros((2 * pairs,), np.int32), xy=np.zeros((2 * pairs, K, 2), np.float32),
+                    score=np.zeros((2 * pairs, K), np.float32), matches0=np.zeros((pairs, K), np.int32),
+                    mscores0=np.zeros((pairs, K), np.float32), stereo_ur=np.zeros((pairs, K), np.float32),
+                    has_depth=np.zeros((pairs, K), np.uint8))
+
+    @staticmethod
+    def _ptrs(o):
+        fp, ip, i32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        return (o["count"].ctypes.data_as(ip), o["xy"].ctypes.data_as(fp), o["score"].ctypes.data_as(fp),
+                o["matches0"].ctypes.data_as(i32p), o["mscores0"].ctypes.data_as(fp),
+                o["stereo_ur"].ctypes.data_as(fp), o["has_depth"].ctypes.data_as(u8p))
+
+    def process(self, images):
+        """images: list of 2*pairs gray u8 arrays (left0, right0, left1, ...). One sync per call."""
+        images = [np.ascontiguousarray(i, np.uint8) for i in images]
+        pairs = len(images) // 2
+        h, w = images[0].shape
+        ptrs = (C.POINTER(C.c_uint8) * len(images))(*[i.ctypes.data_as(C.POINTER(C.c_uint8)) for i in images])
+        o = self._outputs(pairs)
+        _lib.check(self._lib.ssb_fe_process(self._h, ptrs, pairs, h, w, w, *self._ptrs(o)))
+        return o
+
+    def upload(self, images) -> int:
+        images = [np.ascontiguousarray(i, np.uint8) for i in images]
+        h, w = images[0].shape
+        ptrs = (C.POINTER(C.c_uint8) * len(images))(*[i.ctypes.data_as(C.POINTER(C.c_uint8)) for i in images])
+        dev = C.c_void_p()
+        _lib.check(self._lib.ssb_fe_upload_images(self._h, ptrs, len(images), h, w, w, C.byref(dev)))
+        return dev.value
+
+    def enqueue_device(self, images_dev: int, pairs: int, h: int, w: int):
+        _lib.check(self._lib.ssb_fe_enqueue_device(self._h, C.c_void_p(images_dev), pairs, h, w))
+
+    def fetch(self, pairs: int):
+        o = self._outputs(pairs)
+        _lib.check(self._lib.ssb_fe_fetch(self._h, pairs, *self._ptrs(o)))
+        return o
+
+    def sync(self):
+        _lib.check(self._lib.ssb_fe_sync(self._h))
+
+    def event_record(self, idx: int):
+        _lib.check(self._lib.ssb_fe_event_record(self._h, idx))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _lib.check(self._lib.ssb_fe_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def lightglue_debug_read(self, what, shape, dtype):
+        out = np.empty(shape, dtype)
+        h = self._lib.ssb_fe_lightglue(self._h)
+        _lib.check(self._lib.ssb_lg_debug_read(C.c_void_p(h), what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def superpoint_debug_read(self, what, shape, dtype):
+        out = np.empty(shape, dtype)
+        h = self._lib.ssb_fe_superpoint(self._h)
+        _lib.check(self._lib.ssb_sp_debug_read(C.c_void_p(h), what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().ssb_kernel_launch_count())

@@ -1,0 +1,93 @@
+"""LightGlue weight handling for the host side: key normalisation for cvg/LightGlue checkpoints,
+conversion to the SSBW archive the C++ runtime loads, and seeded synthetic weights.
+
+The reference ships no LightGlue weights (they are fetched by the un-vendored `lightglue` package,
+/root/reference/utils/convert_lightglue_to_onnx.py:69); until a real checkpoint is dropped in
+(tools/convert_lightglue_weights.py), tests and the benchmark run the correct architecture on the
+synthetic weights below - throughput does not depend on the values.
+"""
+from __future__ import annotations
+
+import math
+import re
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .weights_io import save_archive
+
+N_LAYERS = 9
+DIM = 256
+HEAD_DIM = 64
+
+
+def normalise_keys(sd):
+    """Accept both the in-memory names (transformers.{i}.self_attn.*) and the checkpoint-file names
+    (self_attn.{i}.*, cross_attn.{i}.*), with or without a leading 'matcher.'."""
+    out = OrderedDict()
+    for k, v in sd.items():
+        k = re.sub(r"^matcher\.", "", k)
+        m = re.match(r"^(self_attn|cross_attn)\.(\d+)\.(.*)$", k)
+        if m:
+            k = f"transformers.{m.group(2)}.{m.group(1)}.{m.group(3)}"
+        out[k] = v
+    return out
+
+
+def make_random_weights(seed: int = 7, sharpen: float = 6.0, matchability_bias: float = 3.0):
+    """Seeded synthetic weights with torch.nn.Linear's default init (U(-1/sqrt(in), 1/sqrt(in))),
+    LayerNorm weight ~1 / bias ~0, posenc.Wr ~ N(0,1) (gamma = 1.0).
+
+    Two deliberate departures from a plain random init, so the assignment stage exercises matched,
+    unmatched and thresholded branches instead of returning all -1: the last layer's final_proj is
+    scaled by `sharpen` (peaked double softmax) and its matchability bias is raised by
+    `matchability_bias` (logsigmoid ~ 0).  A real checkpoint needs neither.
+    """
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(out_f, in_f):
+        b = 1.0 / math.sqrt(in_f)
+        wt = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * b
+        bs = (torch.rand(out_f, generator=g) * 2 - 1) * b
+        return wt, bs
+
+    sd = OrderedDict()
+    sd["posenc.Wr.weight"] = torch.randn(HEAD_DIM // 2, 2, generator=g)
+    for i in range(N_LAYERS):
+        p = f"transformers.{i}.self_attn."
+        sd[p + "Wqkv.weight"], sd[p + "Wqkv.bias"] = lin(3 * DIM, DIM)
+        sd[p + "out_proj.weight"], sd[p + "out_proj.bias"] = lin(DIM, DIM)
+        for blk in ("self_attn", "cross_attn"):
+            q = f"transformers.{i}.{blk}.ffn."
+            sd[q + "0.weight"], sd[q + "0.bias"] = lin(2 * DIM, 2 * DIM)
+            sd[q + "1.weight"] = torch.ones(2 * DIM) + 0.1 * torch.randn(2 * DIM, generator=g)
+            sd[q + "1.bias"] = 0.1 * torch.randn(2 * DIM, generator=g)
+            sd[q + "3.weight"], sd[q + "3.bias"] = lin(DIM, 2 * DIM)
+        p = f"transformers.{i}.cross_attn."
+        sd[p + "to_qk.weight"], sd[p + "to_qk.bias"] = lin(DIM, DIM)
+        sd[p + "to_v.weight"], sd[p + "to_v.bias"] = lin(DIM, DIM)
+        sd[p + "to_out.weight"], sd[p + "to_out.bias"] = lin(DIM, DIM)
+        p = f"log_assignment.{i}."
+        sd[p + "matchability.weight"], sd[p + "matchability.bias"] = lin(1, DIM)
+        sd[p + "final_proj.weight"], sd[p + "final_proj.bias"] = lin(DIM, DIM)
+    last = f"log_assignment.{N_LAYERS - 1}."
+    sd[last + "final_proj.weight"] = sd[last + "final_proj.weight"] * sharpen
+    sd[last + "final_proj.bias"] = sd[last + "final_proj.bias"] * sharpen
+    sd[last + "matchability.bias"] = sd[last + "matchability.bias"] + matchability_bias
+    return OrderedDict((k, v.contiguous()) for k, v in sd.items())
+
+
+def save_state_dict(sd, path: str) -> None:
+    """Write a (normalised) LightGlue state dict as an SSBW archive; token_confidence.* (unused with
+    early exit disabled) and non-final log_assignment layers are dropped."""
+    sd = normalise_keys(sd)
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.startswith("token_confidence."):
+            continue
+        m = re.match(r"^log_assignment\.(\d+)\.", k)
+        if m and int(m.group(1)) != N_LAYERS - 1:
+            continue
+        out[k] = (v.detach().cpu().float().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, np.float32))
+    save_archive(path, out)
