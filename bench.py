@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: stereo frame-pairs/sec (SuperPoint x2 + LightGlue, 1024 keypoints,
+640x480) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1     # CPU restatement of the reference path
+
+A "step" is one pass of the whole hot path (conv trunk, heads, NMS, top-K, gather, 9 LightGlue layers,
+assignment, stereo post-filter) over one batch of `--pairs` synthetic stereo pairs per GPU.
+  value   whole-job pairs/s with the input images already resident in HBM (CUDA events on the
+          pipeline's own stream, per step, L2 flushed between steps, max over ranks)
+  e2e     the same metric through the public call (FramePairPipeline.process: host u8 images in,
+          host keypoints / matches out, H2D + D2H inside the timed region)
+  roofline  the dominant tcgen05 kernel, timed live with CUDA events during the timed steps
+  cpu_baseline  the oracle (reference restated in fp32 torch) on this box's host cores, bounded sample
+Pairs shard across ranks with no data-path collective (weak scaling); rank 0 gathers per-rank
+match counts with one NCCL all_gather after the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, K = 480, 640, 1024
+SPW = os.path.join(ROOT, "superslam_b200", "weights", "superpoint_v1.ssbw")
+METRIC = "stereo frame-pairs/sec (SPx2+LG, 1024 kpts, 640x480)"
+
+# 2*MAC counts of the dense contractions
+SP_LAYER_GF = {"sp.conv1b": 22.65, "sp.conv2a": 5.66, "sp.conv2b": 5.66, "sp.conv3a": 2.83, "sp.conv3b": 5.66,
+               "sp.conv4a": 1.42, "sp.conv4b": 1.42, "sp.convPaDa": 5.66, "sp.convPb": 0.16, "sp.convDb": 0.63}
+
+
+def lg_weights_path(rank: int) -> str:
+    from superslam_b200.lightglue_weights import make_random_weights, save_state_dict
+
+    p = f"/tmp/ssb_bench_lightglue_r{rank}.ssbw"
+    save_state_dict(make_random_weights(7), p)
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_pair_seconds(n_iters: int, warmup: int):
+    """One stereo pair through the CPU oracle (fp32 torch restatement of the reference graph +
+    restated host logic), all host threads.  Returns (median seconds per pair, threads)."""
+    import torch
+
+    from oracle import frontend as ofe
+    from oracle import lightglue as olg
+    from oracle import superpoint as osp
+    from superslam_b200.lightglue_weights import make_random_weights
+    from superslam_b200.synth import synth_pair
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    wsp = osp.load_weights(SPW)
+    wlg = make_random_weights(7)
+    l, r = synth_pair(H, W, 1234)
+    times = []
+    for it in range(warmup + n_iters):
+        t = time.perf_counter()
+        res = osp.extract(np.stack([l, r]), wsp, K)
+        m0, ms0 = olg.match(wlg, olg.normalize_keypoints(res[0]["xy"], W, H), res[0]["desc"],
+                            olg.normalize_keypoints(res[1]["xy"], W, H), res[1]["desc"])
+        q, tr, _ = ofe.dmatches(m0, ms0)
+        ofe.stereo_postfilter(res[0]["xy"], res[1]["xy"], q, tr)
+        if it >= warmup:
+            times.append(time.perf_counter() - t)
+    return float(np.median(times)), torch.get_num_threads()
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    sec, threads = oracle_pair_seconds(max(1, args.steps), args.warmup)
+    v = 1.0 / sec
+    line = {
+        "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "C2: 1 stereo pair 640x480, K=1024, LightGlue 9 layers (seeded synthetic weights)",
+                   "pairs_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} pair(s) after {args.warmup} warm-up; oracle = reference's torch "
+                                   "graph + restated host logic (the reference itself has no CPU path, TensorRT only)"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=8, help="stereo pairs per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5  # bounded sample: ~1.5 s of CPU work per pair
+        run_reference(args, rank)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from superslam_b200 import _lib
+    from superslam_b200 import frontend as fe
+    from superslam_b200.synth import synth_pair
+
+    lib = _lib.load()
+    lib.ssb_profile_enable.argtypes = [C.c_int]
+    lib.ssb_profile_report.argtypes = [C.c_char_p, C.c_size_t]
+    P = args.pairs
+    pipe = fe.FramePairPipeline(SPW, lg_weights_path(rank), K, W, H, max_pairs=P, device=local)
+    images = []
+    for i in range(P):
+        l, r = synth_pair(H, W, 1234 + rank * P + i)
+        images += [l, r]
+    dev_images = pipe.upload(images)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(max(3, args.warmup)):
+        pipe.enqueue_device(dev_images, P, H, W)
+    pipe.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    lib.ssb_profile_enable(1)
+    launches0 = fe.kernel_launch_count()
+    step_ms = []
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        pipe.event_record(0)
+        pipe.enqueue_device(dev_images, P, H, W)
+        pipe.event_record(1)
+        pipe.sync()
+        step_ms.append(pipe.event_elapsed_ms(0, 1))
+        lib.ssb_profile_collect()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    launches = fe.kernel_launch_count() - launches0
+    lib.ssb_profile_enable(0)
+    clocks = sampler.stop()
+    buf = C.create_string_buffer(1 << 16)
+    lib.ssb_profile_report(buf, len(buf))
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, ms = ln.split()
+        prof[name] = (int(cnt), float(ms))
+    out = pipe.fetch(P)
+
+    dev_total_ms = float(sum(step_ms))
+    t = torch.tensor([dev_total_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * P * args.steps / (max_ms / 1e3)
+
+    # ---- end to end through the public call, host buffers in / out ----
+    for _ in range(2):
+        pipe.process(images)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pipe.process(images)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * P * args.steps / float(t.item())
+    h2d = 2 * P * H * W
+    d2h = sum(v.nbytes for v in res.values())
+
+    # result gather (the only collective on the path): per-rank match counts
+    matches = torch.tensor([int((out["matches0"] >= 0).sum()), int(out["has_depth"].sum()), int(out["count"].sum())],
+                           dtype=torch.int64, device=f"cuda:{local}")
+    gathered = [matches]
+    if dist is not None:
+        gathered = [torch.zeros_like(matches) for _ in range(world)]
+        dist.all_gather(gathered, matches)
+
+    if rank == 0:
+        # roofline of the dominant tensor-core kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+        total_prof_ms = sum(ms for _, ms in prof.values()) or 1.0
+        dom = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+        roof = None
+        if dom is not None:
+            cnt, ms = prof[dom]
+            avg_ms = ms / max(1, cnt)
+            if dom in SP_LAYER_GF:
+                gf = SP_LAYER_GF[dom] * 2 * P  # per launch: 2*P images
+                roof = {"kernel": dom, "bound": "tensor", "achieved": gf / avg_ms, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": gf / avg_ms / peak_tf, "traffic": None, "avg_launch_ms": avg_ms,
+                        "share_of_step": ms / total_prof_ms, "peak_source": peak_src,
+                        "algorithmic_gflop_per_launch": gf}
+            else:
+                roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": float(peaks.get("hbm_gbs", 6650.0)),
+                        "unit": "GB/s", "frac": None, "traffic": None, "avg_launch_ms": avg_ms,
+                        "share_of_step": ms / total_prof_ms, "peak_source": peak_src}
+        shares = {k: round(v[1] / total_prof_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            sec, threads = oracle_pair_seconds(3, 1)
+            cpu = {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
+                   "sample": "3 pairs after 1 warm-up of the same C2 workload through oracle/ (fp32 torch restatement)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "C2: stereo pairs 640x480, K=1024, LightGlue 9 layers (seeded synthetic LightGlue "
+                                   "weights: none ship with the reference); SuperPoint weights = reference checkpoint",
+                       "pairs_per_step_per_gpu": P, "l2": "flushed between steps (256 MiB memset)",
+                       "timing": "CUDA events per step on the pipeline stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_time_shares": shares,
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+            "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,13 @@ int ssb_fe_event_elapsed_ms(ssb_frontend* fe, int start_index, int stop_index, f
 int ssb_fe_upload_images(ssb_frontend* fe, const uint8_t* const* images, int count, int height, int width,
                          int row_stride, uint8_t** images_dev_out);
 int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs);
+/* Process-wide instrumentation used by bench.py: kernels launched so far, and optional CUDA-event
+ * timing of every kernel on its launching stream (enable, run steps, collect after each sync, report as
+ * "label count total_ms" lines). */
+long long ssb_kernel_launch_count(void);
+void ssb_profile_enable(int on);
+void ssb_profile_collect(void);
+int ssb_profile_report(char* buf, size_t bytes);
 ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe);
 ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe);
 

@@ -1,0 +1,175 @@
+// Drop-in adapter: implements SuperSLAM's inference interfaces on top of the C-ABI.
+//
+// Compile this header inside the reference tree (it needs the reference's own
+// include/InferenceInterfaces.h, include/DescriptorPool.h and OpenCV core) and link
+// libsuperslam_b200.so.  It replaces the reference's TensorRT-backed classes one for one:
+//
+//   reference (include/SuperPoint.h:37-52, include/LightGlue.h:33-57)   this header
+//   ------------------------------------------------------------------  ---------------------------
+//   SuperPoint(engine, max_kp, thresh, borders) + initialize()          superslam_b200::SuperPointB200
+//   LightGlue(engine, w, h) + initialize()                              superslam_b200::LightGlueB200
+//   LightGlue(shared_engine(), w, h)                                    LightGlueB200(other, w, h)
+//
+// Error behaviour is the reference's: interface methods never throw; failure -> empty Features /
+// MatchResult (src/SuperPoint.cc:895-899, src/LightGlue.cc:381-390); initialize() returns bool.
+// Keypoints are built exactly like src/SuperPoint.cc:716 (size 1, angle -1, response = score) and
+// matches like src/LightGlue.cc:352-361 (increasing queryIdx, distance = 1 - score).
+#pragma once
+
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "InferenceInterfaces.h"  // reference header: superslam::IFeatureExtractor / IFeatureMatcher
+#include "superslam_b200.h"
+
+namespace superslam_b200 {
+
+class SuperPointB200 : public superslam::IFeatureExtractor {
+ public:
+  SuperPointB200(std::string weights_file, int max_keypoints, double keypoint_threshold, int remove_borders,
+                 int device_id = 0)
+      : weights_(std::move(weights_file)), max_kp_(max_keypoints), thresh_(keypoint_threshold),
+        borders_(remove_borders), device_(device_id) {}
+  ~SuperPointB200() override { ssb_sp_destroy(sp_); }
+
+  bool initialize() {
+    return ssb_sp_create(weights_.c_str(), max_kp_, thresh_, borders_, /*num_slots=*/8, device_, &sp_) == SSB_OK;
+  }
+
+  superslam::Features extract(const cv::Mat& image) override {
+    std::vector<superslam::Features> f = run({&image});
+    return f.empty() ? superslam::Features{} : std::move(f[0]);
+  }
+  std::pair<superslam::Features, superslam::Features> extract_stereo(const cv::Mat& left,
+                                                                    const cv::Mat& right) override {
+    if (left.rows != right.rows || left.cols != right.cols || left.channels() != right.channels())
+      return {};  // "stereo pair must share resolution" (src/SuperPoint.cc:761-764)
+    std::vector<superslam::Features> f = run({&left, &right});
+    if (f.size() != 2) return {};
+    return {std::move(f[0]), std::move(f[1])};
+  }
+
+ private:
+  std::vector<superslam::Features> run(std::vector<const cv::Mat*> imgs) {
+    std::vector<superslam::Features> out;
+    if (!sp_ || imgs.empty() || imgs[0]->empty() || imgs[0]->depth() != CV_8U) return out;
+    const int b = static_cast<int>(imgs.size());
+    const int h = imgs[0]->rows, w = imgs[0]->cols, ch = imgs[0]->channels();
+    std::vector<const uint8_t*> ptr(b);
+    for (int i = 0; i < b; ++i) {
+      if (imgs[i]->step[0] != imgs[0]->step[0]) return out;
+      ptr[i] = imgs[i]->data;
+    }
+    std::vector<std::vector<float>> xy(b, std::vector<float>(2 * max_kp_)), sc(b, std::vector<float>(max_kp_));
+    std::vector<float*> xyp(b), scp(b);
+    for (int i = 0; i < b; ++i) xyp[i] = xy[i].data(), scp[i] = sc[i].data();
+    std::vector<int> count(b, 0), slot(b, -1);
+    std::vector<void*> desc(b, nullptr);
+    const int st = ssb_sp_extract(sp_, ptr.data(), b, h, w, static_cast<int>(imgs[0]->step[0]), ch, xyp.data(),
+                                  scp.data(), count.data(), desc.data(), slot.data());
+    if (st != SSB_OK && st != SSB_ERR_EXHAUSTED) return out;
+    out.resize(b);
+    for (int i = 0; i < b; ++i) {
+      superslam::Features& f = out[i];
+      f.keypoints.reserve(count[i]);
+      for (int k = 0; k < count[i]; ++k)
+        f.keypoints.emplace_back(xy[i][2 * k], xy[i][2 * k + 1], 1.0f, -1, sc[i][k]);
+      f.descriptors.count = count[i];
+      f.descriptors.dim = 256;
+      f.descriptors.slot = slot[i];
+      if (slot[i] >= 0) {  // DescriptorPool::make (include/DescriptorPool.h:62-76)
+        f.descriptors.data = desc[i];
+        ssb_superpoint* sp = sp_;
+        const int s = slot[i];
+        f.descriptors.slot_ref = std::shared_ptr<void>(desc[i], [sp, s](void*) { ssb_sp_slot_release(sp, s); });
+      }
+    }
+    return out;
+  }
+
+  std::string weights_;
+  int max_kp_;
+  double thresh_;
+  int borders_, device_;
+  ssb_superpoint* sp_ = nullptr;
+};
+
+class LightGlueB200 : public superslam::IFeatureMatcher {
+ public:
+  LightGlueB200(std::string weights_file, int image_width, int image_height, int max_keypoints = 1024,
+                int device_id = 0)
+      : weights_(std::move(weights_file)), w_(image_width), h_(image_height), max_kp_(max_keypoints),
+        device_(device_id) {}
+  // Shared-weights context for a second thread (loop closure): src/SuperSLAM.cc:129-133.
+  LightGlueB200(const LightGlueB200& primary, int image_width, int image_height)
+      : w_(image_width), h_(image_height), max_kp_(primary.max_kp_), device_(primary.device_), shared_(primary.lg_) {}
+  ~LightGlueB200() override { ssb_lg_destroy(lg_); }
+
+  bool initialize() {
+    if (shared_) return ssb_lg_clone_context(shared_, w_, h_, &lg_) == SSB_OK;
+    return ssb_lg_create(weights_.c_str(), w_, h_, max_kp_, device_, &lg_) == SSB_OK;
+  }
+
+  MatchResult match(const std::vector<cv::KeyPoint>& kp0, const cv::Mat& d0, const std::vector<cv::KeyPoint>& kp1,
+                    const cv::Mat& d1) override {
+    MatchResult r;
+    if (!lg_ || kp0.empty() || kp1.empty()) return r;
+    cv::Mat a = d0, b = d1;
+    if (a.type() != CV_32F) d0.convertTo(a, CV_32F);
+    if (b.type() != CV_32F) d1.convertTo(b, CV_32F);
+    if (!a.isContinuous()) a = a.clone();
+    if (!b.isContinuous()) b = b.clone();
+    const std::vector<float> x0 = flatten(kp0), x1 = flatten(kp1);
+    std::vector<int32_t> m(kp0.size());
+    std::vector<float> s(kp0.size());
+    if (ssb_lg_match_host(lg_, x0.data(), static_cast<int>(kp0.size()), a.ptr<float>(), x1.data(),
+                          static_cast<int>(kp1.size()), b.ptr<float>(), m.data(), s.data()) != SSB_OK)
+      return r;
+    fill(m, s, &r);
+    return r;
+  }
+  MatchResult match(const std::vector<cv::KeyPoint>& kp0, const superslam::DeviceDescriptors& d0,
+                    const std::vector<cv::KeyPoint>& kp1, const superslam::DeviceDescriptors& d1) override {
+    MatchResult r;
+    if (!lg_ || d0.empty() || d1.empty() || kp0.empty() || kp1.empty()) return r;
+    const std::vector<float> x0 = flatten(kp0), x1 = flatten(kp1);
+    std::vector<int32_t> m(kp0.size());
+    std::vector<float> s(kp0.size());
+    if (ssb_lg_match_device(lg_, x0.data(), static_cast<int>(kp0.size()), d0.data, x1.data(),
+                            static_cast<int>(kp1.size()), d1.data, m.data(), s.data()) != SSB_OK)
+      return r;
+    fill(m, s, &r);
+    return r;
+  }
+  cv::Mat descriptors_to_host(const superslam::DeviceDescriptors& d) override {
+    if (d.empty()) return cv::Mat();
+    cv::Mat out(d.count, d.dim, CV_32F);
+    if (ssb_desc_to_host_f32(device_, d.data, d.count, d.dim, out.ptr<float>()) != SSB_OK) return cv::Mat();
+    return out;
+  }
+
+ private:
+  static std::vector<float> flatten(const std::vector<cv::KeyPoint>& kp) {
+    std::vector<float> v(kp.size() * 2);
+    for (size_t i = 0; i < kp.size(); ++i) v[2 * i] = kp[i].pt.x, v[2 * i + 1] = kp[i].pt.y;
+    return v;
+  }
+  static void fill(const std::vector<int32_t>& m, const std::vector<float>& s, MatchResult* r) {
+    for (int i = 0; i < static_cast<int>(m.size()); ++i) {
+      if (m[i] < 0) continue;  // unmatched query keypoint (src/LightGlue.cc:353-355)
+      cv::DMatch dm;
+      dm.queryIdx = i;
+      dm.trainIdx = m[i];
+      dm.distance = 1.0f - s[i];
+      r->matches.push_back(dm);
+    }
+  }
+  std::string weights_;
+  int w_, h_, max_kp_, device_;
+  ssb_lightglue* shared_ = nullptr;
+  ssb_lightglue* lg_ = nullptr;
+};
+
+}  // namespace superslam_b200

@@ -64,6 +64,9 @@ SYMBOLS = [
     ("ssb_fe_superpoint", _vp, [_vp]),
     ("ssb_fe_lightglue", _vp, [_vp]),
     ("ssb_kernel_launch_count", C.c_longlong, []),
+    ("ssb_profile_enable", None, [C.c_int]),
+    ("ssb_profile_collect", None, []),
+    ("ssb_profile_report", C.c_int, [C.c_char_p, C.c_size_t]),
 ]
 
 _lib = None

@@ -95,12 +95,14 @@ class FrontEnd {
   int enqueue_device(const uint8_t* images_dev, int pairs, int h, int w) {
     SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
     SSB_CUDA_CHECK(cudaSetDevice(device_));
+    prof_begin(stream_);
     SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
     SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
     stereo_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
         sp.impl.kp_xy(), K_, sp.impl.kp_count(), lg.impl.matches_dev(), lg.impl.kp(), min_disp_, ur_, hd_);
     SSB_CUDA_CHECK(cudaGetLastError());
     count_launch();
+    prof_mark(stream_, "fe.postfilter");
     return SSB_OK;
   }
   int fetch(int pairs, int* count, float* xy, float* score, int32_t* matches0, float* mscores0, float* ur,
@@ -205,6 +207,9 @@ extern "C" {
 const char* ssb_last_error(void) { return ssb::last_error(); }
 int ssb_version(void) { return 100; }
 long long ssb_kernel_launch_count(void) { return ssb::launch_count(); }
+void ssb_profile_enable(int on) { ssb::prof_enable(on != 0); }
+void ssb_profile_collect(void) { ssb::prof_collect(); }
+int ssb_profile_report(char* buf, size_t bytes) { return ssb::prof_report(buf, bytes); }
 
 int ssb_device_count(void) {
   int n = 0;

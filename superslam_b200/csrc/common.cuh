@@ -31,6 +31,15 @@ void set_last_error(const char* fmt, ...);
 // Number of kernels this library has launched in this process (bench.py reports the delta).
 void count_launch(int n = 1);
 long long launch_count();
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg):
+// prof_begin() marks the start of a step, prof_mark() is called after every kernel launch with that
+// kernel's label, prof_collect() (after a stream sync) folds event deltas into per-label totals.
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_begin(cudaStream_t stream);
+void prof_mark(cudaStream_t stream, const char* label);
+void prof_collect();
+int prof_report(char* buf, size_t bytes);
 const char* last_error();
 
 #define SSB_CUDA_CHECK(expr)                                                                  \

@@ -711,12 +711,13 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     lg_prepare_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
                                                             w_->wr, cx, cy, scale, KP, x16_, x32_, cs_, sn_);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "lg.prepare");
   }
-  auto lin = [&](int kc0, int kc1, int block_n) {
+  auto lin = [&](const char* label, int kc0, int kc1, int block_n) {
     CoreParams p;
     std::memset(&p, 0, sizeof(p));
+    p.label = label;
     p.taps_h = p.taps_w = 1;
     p.kc0 = kc0;
     p.kc1 = kc1;
@@ -730,12 +731,12 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   };
   auto ffn = [&](const LgBlockFfn& F) -> int {
     {
-      CoreParams p = lin(4, 4, 512);
+      CoreParams p = lin("lg.ffn1", 4, 4, 512);
       EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, h1_, KP};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     {
-      CoreParams p = lin(8, 0, 256);
+      CoreParams p = lin("lg.ffn2", 8, 0, 256);
       EpiResidual e{F.fc2.bias, x32_, x16_, KP};
       SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -744,7 +745,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   // logits -> probabilities -> context, shared by self (key_xor 0) and cross (key_xor 1) attention
   auto attention = [&](const CUtensorMap& tmKeys, int key_xor, float scale) -> int {
     {
-      CoreParams p = lin(1, 0, 256);
+      CoreParams p = lin(key_xor ? "lg.qk_cross" : "lg.qk_self", 1, 0, 256);
       p.b_z_xor = key_xor ? kLgHeads : 0;
       p.b_z_mul = 1;
       p.m_valid = dev_count(cnt, kLgHeads);
@@ -754,10 +755,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     }
     softmax_rows_kernel<<<dim3(KP / 8, Z), 256, 0, stream>>>(s_, p_, KP, cnt, key_xor);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "lg.softmax");
     {
-      CoreParams p = lin(KP / 64, 0, 64);
+      CoreParams p = lin("lg.pv", KP / 64, 0, 64);
       p.b_z_xor = key_xor ? kLgHeads : 0;
       p.b_z_mul = 1;
       p.m_valid = dev_count(cnt, kLgHeads);
@@ -776,13 +777,13 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     const LgLayer& L = w_->layers[i];
     // ---- self block ----
     {
-      CoreParams p = lin(4, 0, 256);
+      CoreParams p = lin("lg.qkv", 4, 0, 256);
       EpiQkvRope e{L.qkv.bias, cs_, sn_, q_, k_, vt_, KP, 1};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k_b_, 0, 1.0f));
     {
-      CoreParams p = lin(4, 0, 256);
+      CoreParams p = lin("lg.out_proj", 4, 0, 256);
       EpiBias16 e{L.out.bias, msg_, KP};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -790,13 +791,13 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     if (++blocks == stop_after) return SSB_OK;
     // ---- cross block ----
     {
-      CoreParams p = lin(4, 0, 256);
+      CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, q_, k_, vt_, KP, 0};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q_b_, 1, 0.125f));
     {
-      CoreParams p = lin(4, 0, 256);
+      CoreParams p = lin("lg.to_out", 4, 0, 256);
       EpiBias16 e{L.to_out.bias, msg_, KP};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -805,16 +806,17 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   }
   // ---- assignment ----
   {
-    CoreParams p = lin(4, 0, 256);
+    CoreParams p = lin("lg.final_proj", 4, 0, 256);
     EpiSplit e{w_->final_proj.bias, mda_, mdb_, KP};
     SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }
   matchability_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(x32_, w_->match_w, w_->match_b, KP, cnt, lz_);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  prof_mark(stream, "lg.matchability");
   const size_t pass_stride = static_cast<size_t>(pairs) * KP * KP;
   {
-    CoreParams p = lin(12, 0, 256);  // sim[pair] = A-form(img 2p) x B-form(img 2p+1)
+    CoreParams p = lin("lg.sim", 12, 0, 256);  // sim[pair] = A-form(img 2p) x B-form(img 2p+1)
     p.a_z_mul = 2;
     p.b_z_mul = 2;
     p.b_z_add = 1;
@@ -824,7 +826,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     SSB_RETURN_IF(launch_core(tm_mda_a_, tm_mda_a_, tm_mdb_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
   }
   {
-    CoreParams p = lin(12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
+    CoreParams p = lin("lg.simT", 12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
     p.a_z_mul = 2;
     p.a_z_add = 1;
     p.b_z_mul = 2;
@@ -836,14 +838,17 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  prof_mark(stream, "lg.lse");
   argmax_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_, lz_, max0_,
                                                                  arg0_, arg1_);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  prof_mark(stream, "lg.argmax");
   mutual_filter_kernel<<<dim3((KP + 255) / 256, pairs), 256, 0, stream>>>(max0_, arg0_, arg1_, cnt, KP, 0.1f,
                                                                          matches_, mscores_);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  prof_mark(stream, "lg.mutual");
   return SSB_OK;
 }
 

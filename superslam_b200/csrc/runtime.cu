@@ -3,7 +3,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -22,6 +25,78 @@ const char* last_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> label;
+  size_t n = 0;
+  std::map<std::string, std::pair<double, long long>> acc;
+  std::mutex mu;
+};
+Prof& prof() {
+  static Prof p;
+  return p;
+}
+cudaEvent_t prof_event(Prof& p) {
+  if (p.n >= p.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p.ev.push_back(e);
+    p.label.push_back(nullptr);
+  }
+  return p.ev[p.n];
+}
+}  // namespace
+
+void prof_enable(bool on) {
+  std::lock_guard<std::mutex> g(prof().mu);
+  prof().on = on;
+}
+bool prof_enabled() { return prof().on; }
+void prof_begin(cudaStream_t stream) {
+  Prof& p = prof();
+  if (!p.on) return;
+  std::lock_guard<std::mutex> g(p.mu);
+  cudaEventRecord(prof_event(p), stream);
+  p.label[p.n++] = nullptr;  // nullptr = step start marker
+}
+void prof_mark(cudaStream_t stream, const char* label) {
+  Prof& p = prof();
+  if (!p.on) return;
+  std::lock_guard<std::mutex> g(p.mu);
+  cudaEventRecord(prof_event(p), stream);
+  p.label[p.n++] = label ? label : "?";
+}
+void prof_collect() {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  for (size_t i = 1; i < p.n; ++i) {
+    if (p.label[i] == nullptr) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.ev[i - 1], p.ev[i]) == cudaSuccess) {
+      auto& a = p.acc[p.label[i]];
+      a.first += ms;
+      a.second += 1;
+    }
+  }
+  p.n = 0;
+}
+int prof_report(char* buf, size_t bytes) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  std::string out;
+  char line[256];
+  for (auto& kv : p.acc) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.second, kv.second.first);
+    out += line;
+  }
+  p.acc.clear();
+  if (out.size() + 1 > bytes) return SSB_ERR_INVALID;
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return SSB_OK;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

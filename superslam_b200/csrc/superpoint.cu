@@ -725,32 +725,35 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     dim3 g((w + 31) / 32, (h + 7) / 8, B);
     conv1a_kernel<<<g, 256, 0, stream>>>(images_dev, h, w, w1a_, b1a_, a1a_);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "sp.conv1a");
   }
-  auto conv = [&](const CUtensorMap& tmA, const ConvLayer& L, int H, int W, __half* out, int Ho, int Wo,
-                  int block_n, int pool) -> int {
+  auto conv = [&](const char* label, const CUtensorMap& tmA, const ConvLayer& L, int H, int W, __half* out,
+                  int Ho, int Wo, int block_n, int pool) -> int {
     CoreParams p = conv_params(L.taps, L.cin, L.cout_pad, block_n, W);
+    p.label = label;
     EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, block_n};
     dim3 g(p.tiles_w * ((H + 7) / 8), L.cout / block_n, B);
     return launch_core(tmA, tmA, L.tmB, p, e, g, stream);
   };
-  SSB_RETURN_IF(conv(tm_a1a_, l1b_, h, w, a1b_, h2_, w2_, 64, 1));
-  SSB_RETURN_IF(conv(tm_a1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 64, 0));
-  SSB_RETURN_IF(conv(tm_a2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 64, 1));
-  SSB_RETURN_IF(conv(tm_a2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 128, 0));
-  SSB_RETURN_IF(conv(tm_a3a_, l3b_, h4_, w4_, a3b_, hc_, wc_, 128, 1));
-  SSB_RETURN_IF(conv(tm_a3b_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv(tm_a4a_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv(tm_a4b_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));
+  SSB_RETURN_IF(conv("sp.conv1b", tm_a1a_, l1b_, h, w, a1b_, h2_, w2_, 64, 1));
+  SSB_RETURN_IF(conv("sp.conv2a", tm_a1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 64, 0));
+  SSB_RETURN_IF(conv("sp.conv2b", tm_a2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 64, 1));
+  SSB_RETURN_IF(conv("sp.conv3a", tm_a2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 128, 0));
+  SSB_RETURN_IF(conv("sp.conv3b", tm_a3a_, l3b_, h4_, w4_, a3b_, hc_, wc_, 128, 1));
+  SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
+  SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
+  SSB_RETURN_IF(conv("sp.convPaDa", tm_a4b_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));
   {
     CoreParams p = conv_params(1, 256, lpb_.cout_pad, lpb_.cout_pad, wc_);
+    p.label = "sp.convPb";
     EpiScores e{lpb_.bias, scores_, hc_, wc_, hs_, ws_};
     dim3 g(p.tiles_w * ((hc_ + 7) / 8), 1, B);
     SSB_RETURN_IF(launch_core(tm_apa_, tm_apa_, lpb_.tmB, p, e, g, stream));
   }
   {
     CoreParams p = conv_params(1, 256, ldb_.cout_pad, 256, wc_);
+    p.label = "sp.convDb";
     EpiDescNorm e{ldb_.bias, grid_, hc_, wc_};
     dim3 g(p.tiles_w * ((hc_ + 7) / 8), 1, B);
     SSB_RETURN_IF(launch_core(tm_ada_, tm_ada_, ldb_.tmB, p, e, g, stream));
@@ -761,8 +764,8 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     nms_candidates_kernel<<<g, dim3(32, 16), 0, stream>>>(scores_, hs_, ws_, remove_borders_, threshold_,
                                                           cand_, cand_cap_, cand_count_);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "sp.nms");
   }
   {
     int sort_cap = 1;
@@ -779,16 +782,16 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     select_topk_kernel<<<B, 1024, smem, stream>>>(cand_, cand_cap_, cand_count_, max_kpts_, sort_cap, ws_,
                                                   hc_, wc_, sx, sy, kp_xy_, kp_score_, kp_cell_, kp_count_);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "sp.select");
   }
   if (desc_out != nullptr) {
     dim3 g((max_kpts_ + 7) / 8, B);
     gather_normalize_kernel<<<g, 256, 0, stream>>>(grid_, hc_ * wc_, kp_cell_, kp_count_, max_kpts_,
                                                    desc_out);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream, "sp.gather");
   }
   return SSB_OK;
 }
@@ -825,8 +828,8 @@ int SuperPoint::extract(const uint8_t* const* images, int batch, int h, int w, i
     const size_t n = static_cast<size_t>(batch) * h * w;
     bgr_to_gray_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream_>>>(ds, img_, n);
     SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
     count_launch();
+    prof_mark(stream_, "sp.bgr2gray");
   }
   // descriptor slots (DescriptorPool::make, SuperPoint.cc:721-727): exhaustion -> no descriptors
   std::vector<void*> ptrs(batch, nullptr);

@@ -56,6 +56,7 @@ struct CoreParams {
   // without a host round trip): tiles whose first row >= m_valid or first column >= n_valid exit,
   // rows >= m_valid are masked by the epilogues, K chunks beyond ceil(k_valid / 64) are not issued.
   DevCount m_valid, n_valid, k_valid;
+  const char* label;   // host-only: kernel name for the event profiler
 };
 
 struct EpiCtx {
@@ -249,6 +250,7 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   umma_core_kernel<Epi><<<grid, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
+  prof_mark(stream, p.label);
   return SSB_OK;
 }
 

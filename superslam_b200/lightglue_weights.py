@@ -35,7 +35,7 @@ def normalise_keys(sd):
     return out
 
 
-def make_random_weights(seed: int = 7, sharpen: float = 6.0, matchability_bias: float = 3.0):
+def make_random_weights(seed: int = 7, sharpen: float = 2.0, matchability_bias: float = 3.0):
     """Seeded synthetic weights with torch.nn.Linear's default init (U(-1/sqrt(in), 1/sqrt(in))),
     LayerNorm weight ~1 / bias ~0, posenc.Wr ~ N(0,1) (gamma = 1.0).
 

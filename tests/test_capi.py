@@ -1,0 +1,65 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol the header declares,
+and fails loudly (status + message, no fallback) when there is no sm_100 device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, SP_WEIGHTS
+
+HEADER = os.path.join(ROOT, "include", "superslam_b200.h")
+
+
+def _header_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from superslam_b200 import _lib
+
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in bound, f"{name} declared in the header but not bound in _lib.SYMBOLS"
+
+
+def test_no_gpu_fails_loudly_without_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from superslam_b200 import _lib, frontend
+
+    assert _lib.load().ssb_device_count() < 0
+    with pytest.raises(_lib.SsbError):
+        frontend.SuperPoint(SP_WEIGHTS, 64)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "superslam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_weight_archive_roundtrip(tmp_path):
+    import numpy as np
+
+    from superslam_b200.weights_io import load_archive, save_archive
+
+    a = {"x.weight": np.arange(24, dtype=np.float32).reshape(2, 3, 4), "y": np.array([1.5], np.float32)}
+    p = str(tmp_path / "t.ssbw")
+    save_archive(p, a)
+    b = load_archive(p)
+    assert list(b) == list(a) and all(np.array_equal(a[k], b[k]) for k in a)
+    sp = load_archive(SP_WEIGHTS)
+    assert sp["conv1a.weight"].shape == (64, 1, 3, 3) and sp["convPb.weight"].shape == (65, 256, 1, 1)
+    assert sum(v.size for v in sp.values()) == 1300865
