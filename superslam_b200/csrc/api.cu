@@ -1,6 +1,7 @@
 // C-ABI of the library (include/superslam_b200.h): opaque handles over ssb::SuperPoint / ssb::LightGlue
 // plus the chained frame-pair front end.  No exception and no C++ type crosses this boundary.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -50,6 +51,7 @@ class FrontEnd {
  public:
   ~FrontEnd() {
     cudaSetDevice(device_);
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
     for (auto& e : events_)
       if (e) cudaEventDestroy(e);
     if (ur_) cudaFree(ur_);
@@ -92,9 +94,47 @@ class FrontEnd {
     const size_t P = pairs, K = K_;
     return 2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 64;
   }
+  // The whole pair pipeline (~120 kernels, no host dependency thanks to device-side counts) is
+  // captured into a CUDA graph the second time a (images, pairs, h, w) combination is seen and
+  // replayed afterwards; SSB_NO_GRAPH=1 or an active event profiler falls back to eager launches.
   int enqueue_device(const uint8_t* images_dev, int pairs, int h, int w) {
     SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
     SSB_CUDA_CHECK(cudaSetDevice(device_));
+    static const bool no_graph = std::getenv("SSB_NO_GRAPH") != nullptr;
+    if (no_graph || prof_enabled()) return enqueue_eager(images_dev, pairs, h, w);
+    const bool same = images_dev == g_img_ && pairs == g_pairs_ && h == g_h_ && w == g_w_;
+    if (same && graph_exec_ != nullptr) {
+      SSB_CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+      count_launch(graph_kernels_);
+      return SSB_OK;
+    }
+    if (!same) {  // first sighting: run eagerly (allocations, function attributes), remember the key
+      if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+      graph_exec_ = nullptr;
+      g_img_ = images_dev, g_pairs_ = pairs, g_h_ = h, g_w_ = w;
+      return enqueue_eager(images_dev, pairs, h, w);
+    }
+    SSB_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    const long long before = launch_count();
+    const int st = enqueue_eager(images_dev, pairs, h, w);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
+    if (st != SSB_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g_img_ = nullptr;  // do not try again for this key
+      if (st != SSB_OK) return st;
+      set_last_error("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+      return SSB_ERR_CUDA;
+    }
+    graph_kernels_ = static_cast<int>(launch_count() - before);
+    const cudaError_t ie = cudaGraphInstantiate(&graph_exec_, graph, 0);
+    cudaGraphDestroy(graph);
+    SSB_CHECK(ie == cudaSuccess, SSB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    SSB_CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+    return SSB_OK;
+  }
+  int enqueue_eager(const uint8_t* images_dev, int pairs, int h, int w) {
     prof_begin(stream_);
     SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
     SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
@@ -168,6 +208,9 @@ class FrontEnd {
 
   ssb_superpoint sp;
   ssb_lightglue lg;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const uint8_t* g_img_ = nullptr;
+  int g_pairs_ = 0, g_h_ = 0, g_w_ = 0, graph_kernels_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t events_[16] = {};
   int device_ = 0, K_ = 0, pairs_ = 0;

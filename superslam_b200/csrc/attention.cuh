@@ -1,0 +1,269 @@
+// Fused attention for LightGlue on sm_100a (flash-attention style, one CTA per 128-query tile):
+//   S = Q K^T        tcgen05.mma, fp32 accumulator in TMEM (never leaves the SM)
+//   P = exp2(S*c - m) online softmax by 128 threads (one query row each), fp16 P written straight into
+//                    the 128B-swizzled shared-memory layout the next MMA reads as its A operand
+//   O += P V         tcgen05.mma with V as an MN-major B operand (V rows = keys, as stored by the QKV
+//                    epilogue; no transposed copy of V exists)
+// The N x M logits of the reference graph (softmax(q k^T / 8) v for self attention, both directions of
+// the bidirectional cross attention: oracle/lightglue.py _self_block/_cross_block) are therefore never
+// written to HBM.  The running max is only refreshed when it grows by more than 2^8 (the O rescale is
+// skipped otherwise), which keeps P <= 256 in fp16 and is exact after the final division by the row sum.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = softmax + epilogue (TMEM lane quadrant = warp % 4).
+#pragma once
+
+#include "common.cuh"
+#include "umma_core.cuh"
+
+namespace ssb {
+
+constexpr int kFaThreads = 192;
+constexpr int kFaBlockKeys = 128;
+constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 1024 + 256;
+
+struct FaParams {
+  const int* cnt;      // per-image keypoint counts
+  int heads;           // z = img * heads + head
+  int key_xor;         // keys / values come from image (img ^ key_xor)
+  float scale_log2;    // logits scale * log2(e)
+  __half* ctx;         // [img][kp][heads*64]
+  int kp;
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// tmQ: 4-D (64, kp, 1, Z) box (64,128,1,1).  tmK, tmV: 3-D (64, kp, Z) box (64,128,1).
+__global__ void __launch_bounds__(kFaThreads)
+flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;            // 2 stages
+  uint8_t* sV = smem + 16384 + 32768;    // 2 stages
+  uint8_t* sP = smem + 16384 + 65536;    // 128 x 128 fp16 = two [128 x 64] slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int img = z / p.heads, head = z % p.heads;
+  const int q0 = blockIdx.x * 128;
+  const int nq = p.cnt[img];
+  if (q0 >= nq) return;
+  const int nk = p.cnt[img ^ p.key_xor];
+  const int zk = (img ^ p.key_xor) * p.heads + head;
+  const int nblk = (nk + kFaBlockKeys - 1) / kFaBlockKeys;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;        // 128 columns
+  const uint32_t tO = tmem + 128;  // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 16384);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[s], 32768);
+        tma_load_3d(sK + s * 16384, &tmK, &kv_full[s], 0, j * kFaBlockKeys, zk);
+        tma_load_3d(sV + s * 16384, &tmV, &kv_full[s], 0, j * kFaBlockKeys, zk);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
+      const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
+      mbar_wait(q_full, 0);
+      const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t kdesc = make_smem_desc_k_sw128(smem_u32(sK + s * 16384), 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+        mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
+        tc_fence_after();
+        const uint32_t vbase = smem_u32(sV + s * 16384);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
+          const uint64_t pdesc = make_smem_desc_k_sw128(smem_u32(sP + (k >> 2) * 16384), 1024) + 2 * (k & 3);
+          const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
+          umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
+      tc_fence_after();
+      const int kvalid = min(kFaBlockKeys, nk - j * kFaBlockKeys);
+      // pass 1: block max (log2 domain)
+      float bm = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tS + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kvalid) bm = fmaxf(bm, v[i] * p.scale_log2);
+      }
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = bm;
+      } else if (bm > m_used + 8.0f) {
+        alpha = exp2f(m_used - bm);
+        m_used = bm;
+        need = true;
+      }
+      // P and O are still being read / written by the previous P*V until pv_done fires
+      if (j > 0) {
+        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        l *= alpha;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          float o[32];
+          tmem_ld_32x32(tO + lane_off + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= alpha;
+          tmem_st_32x32(tO + lane_off + c, o);
+        }
+        tmem_st_wait();
+      }
+      // pass 2: probabilities -> fp16 -> swizzled A-operand layout
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tS + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = (c + i < kvalid) ? exp2f(v[i] * p.scale_log2 - m_used) : 0.f;
+          // accumulate the row sum from the values the tensor core will actually see (fp16-rounded)
+          const float er = __half2float(__float2half(e));
+          l += er;
+          v[i] = er;
+        }
+        uint8_t* slab = sP + (c >> 6) * 16384 + row * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = ((c & 63) >> 3) + u;
+          uint4 w;
+          w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
+          w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
+          w.z = pack_half2(v[8 * u + 4], v[8 * u + 5]);
+          w.w = pack_half2(v[8 * u + 6], v[8 * u + 7]);
+          *reinterpret_cast<uint4*>(slab + ((unit ^ (row & 7)) << 4)) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive_cta(p_full);
+    }
+    // epilogue: O / l -> fp16 context rows (heads concatenated)
+    mbar_wait(pv_done, static_cast<uint32_t>(nblk - 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const bool valid = (q0 + row) < nq;
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      float o[32];
+      tmem_ld_32x32(tO + lane_off + c, o);
+      tmem_ld_wait();
+      uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(img) * p.kp + q0 + row) * (p.heads * 64) +
+                                            head * 64 + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
+        w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
+        w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
+        w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
+        dst[u] = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                  const FaParams& p, int q_tiles, int z, cudaStream_t stream, const char* label) {
+  static bool configured = false;
+  if (!configured) {
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFaSmemBytes));
+    configured = true;
+  }
+  flash_attention_kernel<<<dim3(q_tiles, 1, z), kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  prof_mark(stream, label);
+  return SSB_OK;
+}
+
+}  // namespace ssb

@@ -1,0 +1,169 @@
+// 3x3 convolution as an implicit GEMM with *halo reuse*: the (16+2) x (8b+2) pixel input patch of a
+// 16 x 8b output tile is brought into shared memory ONCE by TMA (128B swizzle, zero-filled padding) and
+// all nine filter taps read it in place: the A-operand descriptor of each tcgen05.mma simply starts at
+// pixel (kh, 8s+kw) of the patch, with the stride between 8-pixel row groups (SBO) equal to the patch
+// pitch.  tcgen05 applies the 128B swizzle on absolute shared-memory address bits, so a start address
+// shifted by whole 128-byte pixels needs no base-offset (verified on hardware: tools/umma_probe.cu,
+// profiles/umma_probe_r01.txt).  Compared with re-loading a shifted box per tap (umma_core.cuh) this
+// cuts A traffic from 9 x 128 B to ~1.27 x 128 B per output pixel; weights stream through a small
+// TMA ring.  One MMA covers 16 rows x 8 pixels (M = 128); sub-tile s of the CTA owns TMEM columns
+// [s*N, (s+1)*N).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue.
+#pragma once
+
+#include "common.cuh"
+#include "umma_core.cuh"
+
+namespace ssb {
+
+struct HaloParams {
+  int slabs;       // Cin / 64
+  int subtiles;    // b: output tile is 16 rows x 8b pixels
+  int block_n;     // output channels per CTA
+  int cout_rows;   // rows per tap in the weight matrix
+  int tiles_w;     // tiles along W
+  int stages;      // weight ring depth
+  int tmem_cols;
+  int slab_bytes;  // halo bytes per 64-channel slab, rounded up to 1024
+  const char* label;
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(kCoreThreads)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const HaloParams p, const Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int pw = 8 * p.subtiles + 2;           // patch pitch in pixels
+  const int wstage = p.block_n * 128;          // one tap x one slab of weights
+  uint8_t* s_halo = smem;
+  uint8_t* s_w = smem + p.slabs * p.slab_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + p.stages * wstage);
+  uint64_t* halo_full = bars;                  // [2]
+  uint64_t* w_full = bars + 2;                 // [stages]
+  uint64_t* w_empty = w_full + p.stages;       // [stages]
+  uint64_t* accum_bar = w_empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int w0 = (blockIdx.x % p.tiles_w) * 8 * p.subtiles;
+  const int h0 = (blockIdx.x / p.tiles_w) * 16;
+  const int n0 = blockIdx.y * p.block_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    mbar_init(&halo_full[0], 1);
+    mbar_init(&halo_full[1], 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_w = p.slabs * 9;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t halo_tx = static_cast<uint32_t>(18 * pw * 128);
+      for (int s = 0; s < p.slabs; ++s) {
+        mbar_arrive_expect_tx(&halo_full[s], halo_tx);
+        tma_load_4d(s_halo + s * p.slab_bytes, &tmA, &halo_full[s], s * 64, w0 - 1, h0 - 1, z);
+      }
+      for (int it = 0; it < num_w; ++it) {
+        const int slab = it / 9, tap = it % 9;
+        const int st = it % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+        mbar_wait(&w_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&w_full[st], static_cast<uint32_t>(wstage));
+        tma_load_3d(s_w + st * wstage, &tmB, &w_full[st], slab * 64, tap * p.cout_rows + n0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.block_n));
+      const uint32_t sbo = static_cast<uint32_t>(pw * 128);
+      for (int it = 0; it < num_w; ++it) {
+        const int slab = it / 9, tap = it % 9;
+        const int kh = tap / 3, kw = tap % 3;
+        const int st = it % p.stages;
+        if (tap == 0) {
+          mbar_wait(&halo_full[slab], 0);
+        }
+        mbar_wait(&w_full[st], static_cast<uint32_t>(it / p.stages) & 1u);
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(s_w + st * wstage), 1024);
+        const uint32_t a_tap = smem_u32(s_halo + slab * p.slab_bytes) + static_cast<uint32_t>((kh * pw + kw) * 128);
+        for (int sub = 0; sub < p.subtiles; ++sub) {
+          const uint64_t adesc = make_smem_desc_k_sw128(a_tap + sub * 8 * 128, sbo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + sub * p.block_n, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&w_empty[st]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    EpiCtx c;
+    c.row = q * 32 + lane;
+    c.lane = lane;
+    c.z = z;
+    c.n0 = n0;
+    c.m_valid = 0x7fffffff;
+    c.py = h0 + (c.row >> 3);
+    for (int sub = 0; sub < p.subtiles; ++sub) {
+      c.px = w0 + sub * 8 + (c.row & 7);
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * p.block_n;
+      epi(c, true);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+inline int halo_slab_bytes(int subtiles) { return (18 * (8 * subtiles + 2) * 128 + 1023) / 1024 * 1024; }
+
+template <class Epi>
+int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, HaloParams p, const Epi& epi, int W, int H,
+                     int batch, int n_tiles, cudaStream_t stream) {
+  p.tiles_w = (W + 8 * p.subtiles - 1) / (8 * p.subtiles);
+  const int tiles_h = (H + 15) / 16;
+  p.slab_bytes = halo_slab_bytes(p.subtiles);
+  p.tmem_cols = core_tmem_cols(p.subtiles * p.block_n);
+  if (p.subtiles * p.block_n > 512 || p.slabs < 1 || p.slabs > 2 || p.block_n % 16 != 0) {
+    set_last_error("launch_conv_halo: unsupported configuration");
+    return SSB_ERR_INVALID;
+  }
+  if (p.stages <= 0) p.stages = 4;
+  const int smem = p.slabs * p.slab_bytes + p.stages * p.block_n * 128 + 1024 + 256;
+  static int configured = 0;
+  if (smem > configured) {
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  conv_halo_kernel<Epi><<<dim3(p.tiles_w * tiles_h, n_tiles, batch), kCoreThreads, smem, stream>>>(tmA, tmB, p, epi);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  prof_mark(stream, p.label);
+  return SSB_OK;
+}
+
+}  // namespace ssb

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <string>
 
+#include "attention.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -73,32 +74,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
-}
-
-// Row softmax of the attention logits: S fp32 [z][kp][kp] -> P fp16, zero-padded up to the next
-// multiple of 64 keys (the P*V K-loop runs in 64-key chunks).  img = z/4; keys come from img ^ key_xor.
-__global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ S, __half* __restrict__ P, int kp,
-                    const int* __restrict__ cnt, int key_xor) {
-  const int z = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  const int img = z >> 2;
-  if (row >= cnt[img]) return;
-  const int nk = cnt[img ^ key_xor];
-  const float* s = S + (static_cast<size_t>(z) * kp + row) * kp;
-  __half* p = P + (static_cast<size_t>(z) * kp + row) * kp;
-  float m = -INFINITY;
-  for (int j = lane; j < nk; j += 32) m = fmaxf(m, s[j]);
-  m = warp_max(m);
-  const float l2e = 1.4426950408889634f;
-  float sum = 0.f;
-  for (int j = lane; j < nk; j += 32) sum += exp2f((s[j] - m) * l2e);
-  sum = warp_sum(sum);
-  const float inv = 1.0f / sum;
-  const int npad = (nk + 63) & ~63;
-  for (int j = lane; j < npad; j += 32)
-    p[j] = __float2half(j < nk ? exp2f((s[j] - m) * l2e) * inv : 0.f);
 }
 
 // logsigmoid(matchability(x)) per keypoint, fp32 on the fp32 residual stream.
@@ -214,15 +189,15 @@ __global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* 
 // =================================================================================================
 
 // Fused QKV projection epilogue (self attention).  Tile n0 = 0 / 256 / 512 holds q / k / v for all
-// four heads.  q,k: rotary  t*cos + rotate_half(t)*sin  with rotate_half((a,b)) = (-b,a); stored
-// head-major [z*4+h][kp][64].  v: stored transposed [z*4+h][64][kp] (K-major B operand of P*V).
+// four heads.  q,k: rotary  t*cos + rotate_half(t)*sin  with rotate_half((a,b)) = (-b,a).  q, k and v are
+// all stored head-major [z*4+h][kp][64]; the attention kernel reads V as an MN-major B operand.
 struct EpiQkvRope {
   const float* bias;
   const float* cs;
   const float* sn;
   __half* q;
   __half* k;
-  __half* vt;
+  __half* v_out;
   int kp;
   int rope;  // 1: self attention (n0 0/256 = q/k with rotary, 512 = v); 0: cross (n0 0 = qk, 256 = v)
   __device__ void operator()(const EpiCtx& c, bool) const {
@@ -238,33 +213,27 @@ struct EpiQkvRope {
       const size_t zh = static_cast<size_t>(c.z) * kLgHeads + head;
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
-      if (!is_v) {
-        if (rope && valid) {
-          const float* cr = cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
-          const float* sr = sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
+      if (!is_v && rope && valid) {
+        const float* cr = cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
+        const float* sr = sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float co = cr[i], si = sr[i];
-            const float a = v[2 * i], b = v[2 * i + 1];
-            v[2 * i] = a * co - b * si;
-            v[2 * i + 1] = b * co + a * si;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const float co = cr[i], si = sr[i];
+          const float a = v[2 * i], b = v[2 * i + 1];
+          v[2 * i] = a * co - b * si;
+          v[2 * i + 1] = b * co + a * si;
         }
-        __half* dstp = (which == 0 ? q : k) + (zh * kp + row) * kLgHeadDim + d0;
-        uint4* dst = reinterpret_cast<uint4*>(dstp);
+      }
+      __half* dstp = (is_v ? v_out : (which == 0 ? q : k)) + (zh * kp + row) * kLgHeadDim + d0;
+      uint4* dst = reinterpret_cast<uint4*>(dstp);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-          dst[j] = o;
-        }
-      } else {
-        __half* base = vt + (zh * kLgHeadDim + d0) * kp + row;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) base[static_cast<size_t>(j) * kp] = __float2half(v[j]);
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        dst[j] = o;
       }
     }
   }
@@ -416,35 +385,6 @@ struct EpiStoreF32 {
           dst[j] = has_acc ? make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale,
                                          v[4 * j + 3] * scale)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-};
-
-// P*V epilogue: heads are concatenated back into [img][kp][256] fp16 (z = img*4 + head).
-struct EpiCtx16 {
-  __half* ctx;
-  int kp;
-  __device__ void operator()(const EpiCtx& c, bool has_acc) const {
-    const int row = c.px;
-    const bool valid = row < c.m_valid;
-    const int img = c.z >> 2, head = c.z & 3;
-    for (int col = 0; col < 64; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (valid && has_acc) ? v[j] : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(img) * kp + row) * kLgDim +
-                                            head * kLgHeadDim + col);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        dst[j] = o;
       }
     }
   }
@@ -604,7 +544,7 @@ int LgWeights::load(const char* path, int dev) {
 // =================================================================================================
 LightGlue::~LightGlue() {
   cudaSetDevice(device_);
-  void* bufs[] = {kp_xy_, kp_count_, desc_ptrs_, desc_stage_, cs_, sn_, x32_, x16_, q_, k_, vt_, s_, p_,
+  void* bufs[] = {kp_xy_, kp_count_, desc_ptrs_, desc_stage_, cs_, sn_, x32_, x16_, q_, k_, v_, s_,
                   ctx_, msg_, h1_, mda_, mdb_, lz_, lse_, max0_, arg0_, arg1_, matches_, mscores_};
   for (void* p : bufs)
     if (p) cudaFree(p);
@@ -644,9 +584,8 @@ int LightGlue::alloc_workspace() {
   A(x16_, P2 * KP * kLgDim * 2);
   A(q_, Z * KP * kLgHeadDim * 2);
   A(k_, Z * KP * kLgHeadDim * 2);
-  A(vt_, Z * KP * kLgHeadDim * 2);
-  A(s_, Z * KP * KP * 4);
-  A(p_, Z * KP * KP * 2);
+  A(v_, Z * KP * kLgHeadDim * 2);
+  A(s_, P2 * KP * KP * 4);  // sim and sim^T per pair
   A(ctx_, P2 * KP * kLgDim * 2);
   A(msg_, P2 * KP * kLgDim * 2);
   A(h1_, P2 * KP * 512 * 2);
@@ -666,10 +605,9 @@ int LightGlue::alloc_workspace() {
   SSB_RETURN_IF(tm_rows4(&tm_ctx_, ctx_, 256, kp_, p2));
   SSB_RETURN_IF(tm_rows4(&tm_h1_, h1_, 512, kp_, p2));
   SSB_RETURN_IF(tm_rows4(&tm_q_a_, q_, 64, kp_, z));
-  SSB_RETURN_IF(tm_rows3(&tm_q_b_, q_, 64, kp_, z, 256));
-  SSB_RETURN_IF(tm_rows3(&tm_k_b_, k_, 64, kp_, z, 256));
-  SSB_RETURN_IF(tm_rows4(&tm_p_a_, p_, kp_, kp_, z));
-  SSB_RETURN_IF(tm_rows3(&tm_vt_b_, vt_, kp_, 64, z, 64));
+  SSB_RETURN_IF(tm_rows3(&tm_q3_, q_, 64, kp_, z, 128));
+  SSB_RETURN_IF(tm_rows3(&tm_k3_, k_, 64, kp_, z, 128));
+  SSB_RETURN_IF(tm_rows3(&tm_v3_, v_, 64, kp_, z, 128));
   SSB_RETURN_IF(tm_rows4(&tm_mda_a_, mda_, 768, kp_, p2));
   SSB_RETURN_IF(tm_rows4(&tm_mdb_a_, mdb_, 768, kp_, p2));
   SSB_RETURN_IF(tm_rows3(&tm_mda_b_, mda_, 768, kp_, p2, 256));
@@ -742,31 +680,17 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     }
     return SSB_OK;
   };
-  // logits -> probabilities -> context, shared by self (key_xor 0) and cross (key_xor 1) attention
+  // fused attention (S, softmax and P*V never leave the SM): self (key_xor 0) and cross (key_xor 1)
   auto attention = [&](const CUtensorMap& tmKeys, int key_xor, float scale) -> int {
-    {
-      CoreParams p = lin(key_xor ? "lg.qk_cross" : "lg.qk_self", 1, 0, 256);
-      p.b_z_xor = key_xor ? kLgHeads : 0;
-      p.b_z_mul = 1;
-      p.m_valid = dev_count(cnt, kLgHeads);
-      p.n_valid = dev_count(cnt, kLgHeads, key_xor);
-      EpiStoreF32 e{s_, KP, static_cast<size_t>(KP) * KP, scale, 256};
-      SSB_RETURN_IF(launch_core(tm_q_a_, tm_q_a_, tmKeys, p, e, dim3(tiles, KP / 256, Z), stream));
-    }
-    softmax_rows_kernel<<<dim3(KP / 8, Z), 256, 0, stream>>>(s_, p_, KP, cnt, key_xor);
-    SSB_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    prof_mark(stream, "lg.softmax");
-    {
-      CoreParams p = lin("lg.pv", KP / 64, 0, 64);
-      p.b_z_xor = key_xor ? kLgHeads : 0;
-      p.b_z_mul = 1;
-      p.m_valid = dev_count(cnt, kLgHeads);
-      p.k_valid = dev_count(cnt, kLgHeads, key_xor);
-      EpiCtx16 e{ctx_, KP};
-      SSB_RETURN_IF(launch_core(tm_p_a_, tm_p_a_, tm_vt_b_, p, e, dim3(tiles, 1, Z), stream));
-    }
-    return SSB_OK;
+    FaParams fp;
+    fp.cnt = cnt;
+    fp.heads = kLgHeads;
+    fp.key_xor = key_xor;
+    fp.scale_log2 = scale * 1.4426950408889634f;
+    fp.ctx = ctx_;
+    fp.kp = KP;
+    return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
+                                  key_xor ? "lg.attn_cross" : "lg.attn_self");
   };
 
   // test hook: SSB_LG_STOP_AFTER=n returns after n half-blocks (self = odd, cross = even) so the
@@ -778,10 +702,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
-      EpiQkvRope e{L.qkv.bias, cs_, sn_, q_, k_, vt_, KP, 1};
+      EpiQkvRope e{L.qkv.bias, cs_, sn_, q_, k_, v_, KP, 1};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
-    SSB_RETURN_IF(attention(tm_k_b_, 0, 1.0f));
+    SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     {
       CoreParams p = lin("lg.out_proj", 4, 0, 256);
       EpiBias16 e{L.out.bias, msg_, KP};
@@ -792,10 +716,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
-      EpiQkvRope e{L.qkv_c.bias, cs_, sn_, q_, k_, vt_, KP, 0};
+      EpiQkvRope e{L.qkv_c.bias, cs_, sn_, q_, k_, v_, KP, 0};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
-    SSB_RETURN_IF(attention(tm_q_b_, 1, 0.125f));
+    SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     {
       CoreParams p = lin("lg.to_out", 4, 0, 256);
       EpiBias16 e{L.to_out.bias, msg_, KP};
@@ -934,11 +858,11 @@ int LightGlue::debug_read(const char* what, void* dst, size_t bytes) {
     const void* ptr;
     size_t bytes;
   } tab[] = {
-      {"x32", x32_, P2 * KP * 256 * 4},   {"x16", x16_, P2 * KP * 256 * 2}, {"sim", s_, pairs_ * KP * KP * 4},
+      {"x32", x32_, P2 * KP * 256 * 4},   {"x16", x16_, P2 * KP * 256 * 2}, {"sim", s_, static_cast<size_t>(pairs_) * KP * KP * 4},
       {"lse", lse_, P2 * KP * 4},         {"lz", lz_, P2 * KP * 4},         {"cos", cs_, P2 * KP * 32 * 4},
       {"sin", sn_, P2 * KP * 32 * 4},     {"msg", msg_, P2 * KP * 256 * 2}, {"ctx", ctx_, P2 * KP * 256 * 2},
       {"h1", h1_, P2 * KP * 512 * 2},     {"q", q_, P2 * 4 * KP * 64 * 2},  {"k", k_, P2 * 4 * KP * 64 * 2},
-      {"vt", vt_, P2 * 4 * KP * 64 * 2},  {"max0", max0_, pairs_ * KP * 4}, {"arg0", arg0_, pairs_ * KP * 4},
+      {"v", v_, P2 * 4 * KP * 64 * 2},   {"max0", max0_, pairs_ * KP * 4}, {"arg0", arg0_, pairs_ * KP * 4},
       {"arg1", arg1_, pairs_ * KP * 4},
   };
   for (const Ent& e : tab) {

@@ -102,9 +102,8 @@ class LightGlue {
   float* x32_ = nullptr;        // [2P][kp][256] residual stream (fp32 master)
   __half* x16_ = nullptr;       // [2P][kp][256] fp16 copy (GEMM operand)
   __half *q_ = nullptr, *k_ = nullptr;  // [2P*4][kp][64]
-  __half* vt_ = nullptr;        // [2P*4][64][kp]
-  float* s_ = nullptr;          // [2P*4][kp][kp] attention logits; reused for sim / sim^T
-  __half* p_ = nullptr;         // [2P*4][kp][kp] attention probabilities
+  __half* v_ = nullptr;         // [2P*4][kp][64]
+  float* s_ = nullptr;          // [2P][kp][kp] assignment similarity sim / sim^T (fp32)
   __half *ctx_ = nullptr, *msg_ = nullptr;  // [2P][kp][256]
   __half* h1_ = nullptr;        // [2P][kp][512]
   __half *mda_ = nullptr, *mdb_ = nullptr;  // [2P][kp][768] split-precision final projections
@@ -117,7 +116,7 @@ class LightGlue {
   float* host_io_ = nullptr;    // pinned staging for match_* (xy in, matches/scores out)
   size_t host_io_bytes_ = 0;
 
-  CUtensorMap tm_x16_, tm_msg_, tm_ctx_, tm_h1_, tm_q_a_, tm_q_b_, tm_k_b_, tm_p_a_, tm_vt_b_, tm_mda_a_,
+  CUtensorMap tm_x16_, tm_msg_, tm_ctx_, tm_h1_, tm_q_a_, tm_q3_, tm_k3_, tm_v3_, tm_mda_a_,
       tm_mdb_b_, tm_mdb_a_, tm_mda_b_;
 };
 

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 
+#include "conv_halo.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -148,6 +149,7 @@ struct EpiConvRelu {
   int H, W;        // conv output extent (masking when not pooling)
   int pool;
   int block_n;
+  int row_xor;     // lane distance between vertically adjacent pixels: 16 (16x8 tiles) or 8 (16 rows x 8 px)
   __device__ void operator()(const EpiCtx& c, bool has_acc) const {
     for (int col = 0; col < block_n; col += 32) {
       float v[32];
@@ -162,9 +164,9 @@ struct EpiConvRelu {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 16));
+          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], row_xor));
         }
-        writer = ((c.lane & 17) == 0);
+        writer = ((c.lane & (1 | row_xor)) == 0);
         oy >>= 1;
         ox >>= 1;
         writer = writer && oy < Ho && ox < Wo;
@@ -613,12 +615,18 @@ void SuperPoint::free_shape() {
   cap_batch_ = 0;
 }
 
-static int make_act_tmap(CUtensorMap* tm, const __half* base, int C, int Cpitch, int W, int H, int B) {
+static int make_act_tmap(CUtensorMap* tm, const __half* base, int C, int Cpitch, int W, int H, int B,
+                         int box_w = 16, int box_h = 8);
+static int make_halo_tmap(CUtensorMap* tm, const __half* base, int C, int W, int H, int B, int subtiles) {
+  return make_act_tmap(tm, base, C, C, W, H, B, 8 * subtiles + 2, 18);
+}
+static int make_act_tmap(CUtensorMap* tm, const __half* base, int C, int Cpitch, int W, int H, int B, int box_w,
+                         int box_h) {
   uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                       static_cast<uint64_t>(B)};
   uint64_t strides[3] = {static_cast<uint64_t>(Cpitch) * 2, static_cast<uint64_t>(W) * Cpitch * 2,
                          static_cast<uint64_t>(H) * W * Cpitch * 2};
-  uint32_t box[4] = {64, 16, 8, 1};
+  uint32_t box[4] = {64, static_cast<uint32_t>(box_w), static_cast<uint32_t>(box_h), 1};
   return encode_tmap_f16(tm, base, 4, dims, strides, box);
 }
 
@@ -667,6 +675,11 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_act_tmap(&tm_a3b_, a3b_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4a_, a4a_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4b_, a4b_, 128, 128, wc_, hc_, nb));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h1a_, a1a_, 64, w, h, nb, 4));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h1b_, a1b_, 64, w2_, h2_, nb, 4));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h2a_, a2a_, 64, w2_, h2_, nb, 4));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h2b_, a2b_, 64, w4_, h4_, nb, 2));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h3a_, a3a_, 128, w4_, h4_, nb, 2));
   SSB_RETURN_IF(make_act_tmap(&tm_apa_, apd_, 256, 512, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_ada_, apd_ + 256, 256, 512, wc_, hc_, nb));
   const size_t need = B * (static_cast<size_t>(max_kpts_) * 3 + 1) * sizeof(float);
@@ -732,15 +745,29 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
                   int Ho, int Wo, int block_n, int pool) -> int {
     CoreParams p = conv_params(L.taps, L.cin, L.cout_pad, block_n, W);
     p.label = label;
-    EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, block_n};
+    EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, block_n, 16};
     dim3 g(p.tiles_w * ((H + 7) / 8), L.cout / block_n, B);
     return launch_core(tmA, tmA, L.tmB, p, e, g, stream);
   };
-  SSB_RETURN_IF(conv("sp.conv1b", tm_a1a_, l1b_, h, w, a1b_, h2_, w2_, 64, 1));
-  SSB_RETURN_IF(conv("sp.conv2a", tm_a1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 64, 0));
-  SSB_RETURN_IF(conv("sp.conv2b", tm_a2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 64, 1));
-  SSB_RETURN_IF(conv("sp.conv3a", tm_a2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 128, 0));
-  SSB_RETURN_IF(conv("sp.conv3b", tm_a3a_, l3b_, h4_, w4_, a3b_, hc_, wc_, 128, 1));
+  // the five large layers (82 % of the trunk FLOPs) reuse one shared-memory halo for all nine taps
+  auto hconv = [&](const char* label, const CUtensorMap& tmH, const ConvLayer& L, int H, int W, __half* out,
+                   int Ho, int Wo, int subtiles, int pool) -> int {
+    HaloParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.slabs = L.cin / 64;
+    p.subtiles = subtiles;
+    p.block_n = L.cout;
+    p.cout_rows = L.cout_pad;
+    p.stages = 4;
+    p.label = label;
+    EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, L.cout, 8};
+    return launch_conv_halo(tmH, L.tmB, p, e, W, H, B, 1, stream);
+  };
+  SSB_RETURN_IF(hconv("sp.conv1b", tm_h1a_, l1b_, h, w, a1b_, h2_, w2_, 4, 1));
+  SSB_RETURN_IF(hconv("sp.conv2a", tm_h1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 4, 0));
+  SSB_RETURN_IF(hconv("sp.conv2b", tm_h2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 4, 1));
+  SSB_RETURN_IF(hconv("sp.conv3a", tm_h2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 2, 0));
+  SSB_RETURN_IF(hconv("sp.conv3b", tm_h3a_, l3b_, h4_, w4_, a3b_, hc_, wc_, 2, 1));
   SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
   SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
   SSB_RETURN_IF(conv("sp.convPaDa", tm_a4b_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));

@@ -100,8 +100,8 @@ def main():
     print(f"lg cos maxabs {np.abs(cs - dbg['cos'][:, ::2]).max()}")
     q = lg.debug_read("q", (8, kp, 64), np.float16).astype(np.float32)[:4, :n0]
     k_ = lg.debug_read("k", (8, kp, 64), np.float16).astype(np.float32)[:4, :n0]
-    vt = lg.debug_read("vt", (8, 64, kp), np.float16).astype(np.float32)[:4, :, :n0]
-    print(f"lg q {rel(q, dbg['q'])} k {rel(k_, dbg['k'])} v {rel(vt.transpose(0, 2, 1), dbg['v'])}")
+    v_ = lg.debug_read("v", (8, kp, 64), np.float16).astype(np.float32)[:4, :n0]
+    print(f"lg q {rel(q, dbg['q'])} k {rel(k_, dbg['k'])} v {rel(v_, dbg['v'])}")
     ctx = lg.debug_read("ctx", (2, kp, 256), np.float16).astype(np.float32)[0, :n0]
     msg = lg.debug_read("msg", (2, kp, 256), np.float16).astype(np.float32)[0, :n0]
     h1 = lg.debug_read("h1", (2, kp, 512), np.float16).astype(np.float32)[0, :n0]
