@@ -41,6 +41,16 @@ METRIC = "stereo frame-pairs/sec (SPx2+LG, 1024 kpts, 640x480)"
 # 2*MAC counts of the dense contractions
 SP_LAYER_GF = {"sp.conv1b": 22.65, "sp.conv2a": 5.66, "sp.conv2b": 5.66, "sp.conv3a": 2.83, "sp.conv3b": 5.66,
                "sp.conv4a": 1.42, "sp.conv4b": 1.42, "sp.convPaDa": 5.66, "sp.convPb": 0.16, "sp.convDb": 0.63}
+# LightGlue, per launch and per PAIR at N = M = 1024 (one launch covers both images of every pair)
+_N = 1024
+LG_LAUNCH_GF = {
+    "lg.qkv": 2 * 2 * _N * 256 * 768 / 1e9, "lg.out_proj": 2 * 2 * _N * 256 * 256 / 1e9,
+    "lg.ffn1": 2 * 2 * _N * 512 * 512 / 1e9, "lg.ffn2": 2 * 2 * _N * 512 * 256 / 1e9,
+    "lg.qkv_cross": 2 * 2 * _N * 256 * 512 / 1e9, "lg.to_out": 2 * 2 * _N * 256 * 256 / 1e9,
+    "lg.attn_self": 2 * 2 * 2 * _N * _N * 256 / 1e9,   # 2 images x (QK^T + PV)
+    "lg.attn_cross": 3 * 2 * _N * _N * 256 / 1e9,      # sim once + two PV (SURVEY §8d counts sim once)
+    "lg.final_proj": 2 * 2 * _N * 256 * 256 / 1e9, "lg.sim": 2 * _N * _N * 256 / 1e9,
+}
 
 
 def lg_weights_path(rank: int) -> str:
@@ -279,8 +289,9 @@ def main():
         if dom is not None:
             cnt, ms = prof[dom]
             avg_ms = ms / max(1, cnt)
-            if dom in SP_LAYER_GF:
-                gf = SP_LAYER_GF[dom] * 2 * P  # per launch: 2*P images
+            if dom in SP_LAYER_GF or dom in LG_LAUNCH_GF:
+                # algorithmic GFLOP per launch: SuperPoint layers see 2*P images, LightGlue launches P pairs
+                gf = SP_LAYER_GF[dom] * 2 * P if dom in SP_LAYER_GF else LG_LAUNCH_GF[dom] * P
                 roof = {"kernel": dom, "bound": "tensor", "achieved": gf / avg_ms, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": gf / avg_ms / peak_tf, "traffic": None, "avg_launch_ms": avg_ms,
                         "share_of_step": ms / total_prof_ms, "peak_source": peak_src,
@@ -290,6 +301,12 @@ def main():
                         "unit": "GB/s", "frac": None, "traffic": None, "avg_launch_ms": avg_ms,
                         "share_of_step": ms / total_prof_ms, "peak_source": peak_src}
         shares = {k: round(v[1] / total_prof_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+        tensor_kernels = {}
+        for name, (cnt, ms) in prof.items():
+            gfl = SP_LAYER_GF[name] * 2 * P if name in SP_LAYER_GF else LG_LAUNCH_GF.get(name, 0) * P
+            if gfl > 0 and ms > 0:
+                tensor_kernels[name] = {"avg_launch_ms": round(ms / cnt, 5), "tflops": round(gfl / (ms / cnt), 1),
+                                        "frac_of_peak": round(gfl / (ms / cnt) / peak_tf, 4)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             sec, threads = oracle_pair_seconds(3, 1)
@@ -310,6 +327,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "kernel_time_shares": shares,
+            "tensor_kernels": tensor_kernels,
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
             "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},

@@ -1,7 +1,7 @@
 // Fused attention for LightGlue on sm_100a (flash-attention style, one CTA per 128-query tile):
 //   S = Q K^T        tcgen05.mma, fp32 accumulator in TMEM (never leaves the SM)
-//   P = exp2(S*c - m) online softmax by 128 threads (one query row each), fp16 P written straight into
-//                    the 128B-swizzled shared-memory layout the next MMA reads as its A operand
+//   P = exp2(S*c - m) online softmax by 256 threads (two per query row, 64 keys each), fp16 P written
+//                    straight into the 128B-swizzled shared-memory layout the next MMA reads as A
 //   O += P V         tcgen05.mma with V as an MN-major B operand (V rows = keys, as stored by the QKV
 //                    epilogue; no transposed copy of V exists)
 // The N x M logits of the reference graph (softmax(q k^T / 8) v for self attention, both directions of
@@ -9,8 +9,10 @@
 // written to HBM.  The running max is only refreshed when it grows by more than 2^8 (the O rescale is
 // skipped otherwise), which keeps P <= 256 in fp16 and is exact after the final division by the row sum.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = softmax + epilogue (TMEM lane quadrant = warp % 4).
+// Budget: 97 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's
+// exponentials (the MUFU-bound part: 16 ex2/clk/SM) overlap the other's MMAs and loads.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = softmax + epilogue (TMEM lane quadrant = warp % 4, key half = (warp-2) / 4).
 #pragma once
 
 #include "common.cuh"
@@ -18,9 +20,10 @@
 
 namespace ssb {
 
-constexpr int kFaThreads = 192;
+constexpr int kFaThreads = 320;
 constexpr int kFaBlockKeys = 128;
-constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 1024 + 256;
+constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 2048 /*xchg*/ +
+                             128 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
   const int* cnt;      // per-image keypoint counts
@@ -46,12 +49,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ void fa_pair_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 // tmQ: 4-D (64, kp, 1, Z) box (64,128,1,1).  tmK, tmV: 3-D (64, kp, Z) box (64,128,1).
-__global__ void __launch_bounds__(kFaThreads)
+__global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,16 +65,19 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;            // 2 stages
-  uint8_t* sV = smem + 16384 + 32768;    // 2 stages
-  uint8_t* sP = smem + 16384 + 65536;    // 128 x 128 fp16 = two [128 x 64] slabs
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
+  uint8_t* sV = smem + 16384 + 32768;    // 1 stage (V is only needed after the softmax of its block)
+  uint8_t* sP = smem + 16384 + 49152;    // 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
+  float* xchg = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);  // [2][128] block max
+  float* xchg_l = xchg + 256;                                             // [2][128] row sums (epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 2048);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -85,12 +94,13 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1);
-    mbar_init(&kv_empty[1], 1);
+    mbar_init(&k_full[0], 1);
+    mbar_init(&k_full[1], 1);
+    mbar_init(&k_empty[0], 1);
+    mbar_init(&k_empty[1], 1);
+    mbar_init(v_full, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -111,11 +121,12 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
       for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
-        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
-        mbar_wait(&kv_empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[s], 32768);
-        tma_load_3d(sK + s * 16384, &tmK, &kv_full[s], 0, j * kFaBlockKeys, zk);
-        tma_load_3d(sV + s * 16384, &tmV, &kv_full[s], 0, j * kFaBlockKeys, zk);
+        mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
+        mbar_arrive_expect_tx(&k_full[s], 16384);
+        tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, zk);
+        if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, zk);
       }
     }
   } else if (warp == 1) {
@@ -124,17 +135,19 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
       mbar_wait(q_full, 0);
       const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
+      const uint32_t vbase = smem_u32(sV);
       for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
-        mbar_wait(&kv_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+        mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_k_sw128(smem_u32(sK + s * 16384), 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&k_empty[s]);
         umma_commit(s_full);
+        mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
         mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
         tc_fence_after();
-        const uint32_t vbase = smem_u32(sV + s * 16384);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
@@ -142,36 +155,47 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
           umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
         umma_commit(pv_done);
       }
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;          // which 64 keys of the block / which 32 output columns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tSh = tS + lane_off + half * 64;
+    const uint32_t tOh = tO + lane_off + half * 32;
+    uint8_t* slab = sP + half * 16384 + row * 128;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
       tc_fence_after();
-      const int kvalid = min(kFaBlockKeys, nk - j * kFaBlockKeys);
-      // pass 1: block max (log2 domain)
-      float bm = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        float v[32];
-        tmem_ld_32x32(tS + lane_off + c, v);
-        tmem_ld_wait();
+      const int kvalid = min(64, nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
+      // pass 1: maximum of my 64 logits (raw; the positive scale is applied once)
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kvalid) bm = fmaxf(bm, v[i] * p.scale_log2);
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tSh + c, v);
+        tmem_ld_wait();
+        if (kvalid >= 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        }
       }
+      xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      fa_pair_sync();
+      const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
       float alpha = 1.f;
       bool need = false;
       if (j == 0) {
         m_used = bm;
       } else if (bm > m_used + 8.0f) {
-        alpha = exp2f(m_used - bm);
+        alpha = fast_exp2(m_used - bm);
         m_used = bm;
         need = true;
       }
@@ -182,35 +206,31 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       if (__any_sync(0xffffffffu, need)) {
         l *= alpha;
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          float o[32];
-          tmem_ld_32x32(tO + lane_off + c, o);
-          tmem_ld_wait();
+        float o[32];
+        tmem_ld_32x32(tOh, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] *= alpha;
-          tmem_st_32x32(tO + lane_off + c, o);
-        }
+        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+        tmem_st_32x32(tOh, o);
         tmem_st_wait();
       }
-      // pass 2: probabilities -> fp16 -> swizzled A-operand layout
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
+      // pass 2: probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
         float v[32];
-        tmem_ld_32x32(tS + lane_off + c, v);
+        tmem_ld_32x32(tSh + c, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float e = (c + i < kvalid) ? exp2f(v[i] * p.scale_log2 - m_used) : 0.f;
-          // accumulate the row sum from the values the tensor core will actually see (fp16-rounded)
-          const float er = __half2float(__float2half(e));
-          l += er;
-          v[i] = er;
+          float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+          if (kvalid < 64 && c + i >= kvalid) e = 0.f;
+          ls[i & 3] += e;
+          v[i] = e;
         }
-        uint8_t* slab = sP + (c >> 6) * 16384 + row * 128;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int unit = ((c & 63) >> 3) + u;
+          const int unit = (c >> 3) + u;
           uint4 w;
           w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
           w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
@@ -219,31 +239,31 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<uint4*>(slab + ((unit ^ (row & 7)) << 4)) = w;
         }
       }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive_cta(p_full);
+      mbar_arrive(p_full);
     }
-    // epilogue: O / l -> fp16 context rows (heads concatenated)
+    // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
+    xchg_l[half * 128 + row] = l;
+    fa_pair_sync();
+    const float inv = 1.0f / (xchg_l[row] + xchg_l[128 + row]);
     mbar_wait(pv_done, static_cast<uint32_t>(nblk - 1) & 1u);
     tc_fence_after();
-    const float inv = 1.0f / l;
     const bool valid = (q0 + row) < nq;
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      float o[32];
-      tmem_ld_32x32(tO + lane_off + c, o);
-      tmem_ld_wait();
-      uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(img) * p.kp + q0 + row) * (p.heads * 64) +
-                                            head * 64 + c);
+    float o[32];
+    tmem_ld_32x32(tOh, o);
+    tmem_ld_wait();
+    uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(img) * p.kp + q0 + row) * (p.heads * 64) +
+                                          head * 64 + half * 32);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 w;
-        w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
-        w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
-        w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
-        w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
-        dst[u] = w;
-      }
+    for (int u = 0; u < 4; ++u) {
+      uint4 w;
+      w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
+      w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
+      w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
+      w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
+      dst[u] = w;
     }
   }
   tc_fence_before();

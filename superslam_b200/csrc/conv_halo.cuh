@@ -18,6 +18,8 @@
 
 namespace ssb {
 
+constexpr int kHaloThreads = 192;
+
 struct HaloParams {
   int slabs;       // Cin / 64
   int subtiles;    // b: output tile is 16 rows x 8b pixels
@@ -31,7 +33,7 @@ struct HaloParams {
 };
 
 template <class Epi>
-__global__ void __launch_bounds__(kCoreThreads)
+__global__ void __launch_bounds__(kHaloThreads)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const HaloParams p, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,6 +129,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.z = z;
     c.n0 = n0;
     c.m_valid = 0x7fffffff;
+    c.col_begin = 0;
+    c.col_end = p.block_n;
+    c.half = 0;
+    c.xchg = nullptr;
     c.py = h0 + (c.row >> 3);
     for (int sub = 0; sub < p.subtiles; ++sub) {
       c.px = w0 + sub * 8 + (c.row & 7);
@@ -159,7 +165,7 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, HaloParams 
     SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  conv_halo_kernel<Epi><<<dim3(p.tiles_w * tiles_h, n_tiles, batch), kCoreThreads, smem, stream>>>(tmA, tmB, p, epi);
+  conv_halo_kernel<Epi><<<dim3(p.tiles_w * tiles_h, n_tiles, batch), kHaloThreads, smem, stream>>>(tmA, tmB, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, p.label);

@@ -200,12 +200,13 @@ struct EpiQkvRope {
   __half* v_out;
   int kp;
   int rope;  // 1: self attention (n0 0/256 = q/k with rotary, 512 = v); 0: cross (n0 0 = qk, 256 = v)
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
     const int which = c.n0 >> 8;
     const bool is_v = rope ? (which == 2) : (which == 1);
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -244,10 +245,11 @@ struct EpiBias16 {
   const float* bias;
   __half* out;
   int kp;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -276,20 +278,21 @@ struct EpiLnGelu {
   const float* b;
   __half* out;
   int kp;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
     float sum = 0.f;
-    for (int col = 0; col < 512; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += v[j] + __ldg(bias + col + j);
     }
-    const float mean = sum * (1.0f / 512.0f);
+    const float mean = epi_pair_sum(c, sum) * (1.0f / 512.0f);
     float sq = 0.f;
-    for (int col = 0; col < 512; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -299,8 +302,8 @@ struct EpiLnGelu {
         sq = fmaf(d, d, sq);
       }
     }
-    const float rstd = rsqrtf(sq * (1.0f / 512.0f) + 1e-5f);
-    for (int col = 0; col < 512; col += 32) {
+    const float rstd = rsqrtf(epi_pair_sum(c, sq) * (1.0f / 512.0f) + 1e-5f);
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -330,10 +333,11 @@ struct EpiResidual {
   float* x32;
   __half* x16;
   int kp;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -370,10 +374,11 @@ struct EpiStoreF32 {
   size_t z_stride;
   float scale;
   int block_n;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool has_acc) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
-    for (int col = 0; col < block_n; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -398,10 +403,11 @@ struct EpiSplit {
   __half* mda;
   __half* mdb;
   int kp;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();

@@ -150,8 +150,9 @@ struct EpiConvRelu {
   int pool;
   int block_n;
   int row_xor;     // lane distance between vertically adjacent pixels: 16 (16x8 tiles) or 8 (16 rows x 8 px)
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool has_acc) const {
-    for (int col = 0; col < block_n; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -197,6 +198,7 @@ struct EpiScores {
   const float* bias;  // [80], entries >= 65 unused
   float* scores;      // [B][hs][ws]
   int Hc, Wc, hs, ws;
+  static constexpr bool kSplit = false;  // the 65-way softmax needs the whole row in one thread
   __device__ void operator()(const EpiCtx& c, bool) const {
     float v[80];
     tmem_ld_32x32(c.tmem_row, v);
@@ -242,9 +244,10 @@ struct EpiDescNorm {
   const float* bias;
   __half* grid;
   int Hc, Wc;
+  static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     float ss = 0.f;
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
@@ -254,9 +257,10 @@ struct EpiDescNorm {
         ss = fmaf(x, x, ss);
       }
     }
+    ss = epi_pair_sum(c, ss);  // the two column halves of the row live in different warps
     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
     const bool ok = c.py < Hc && c.px < Wc;
-    for (int col = 0; col < 256; col += 32) {
+    for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
