@@ -39,7 +39,7 @@ SPW = os.path.join(ROOT, "superslam_b200", "weights", "superpoint_v1.ssbw")
 METRIC = "stereo frame-pairs/sec (SPx2+LG, 1024 kpts, 640x480)"
 
 # 2*MAC counts of the dense contractions
-SP_LAYER_GF = {"sp.conv1b": 22.65, "sp.conv2a": 5.66, "sp.conv2b": 5.66, "sp.conv3a": 2.83, "sp.conv3b": 5.66,
+SP_LAYER_GF = {"sp.conv1ab": 22.65 + 0.35, "sp.conv2a": 5.66, "sp.conv2b": 5.66, "sp.conv3a": 2.83, "sp.conv3b": 5.66,
                "sp.conv4a": 1.42, "sp.conv4b": 1.42, "sp.convPaDa": 5.66, "sp.convPb": 0.16, "sp.convDb": 0.63}
 # LightGlue, per launch and per PAIR at N = M = 1024 (one launch covers both images of every pair)
 _N = 1024

@@ -277,6 +277,9 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   if (!configured) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kFaSmemBytes));
+    // ask for the full shared-memory carveout so that two CTAs (2 x 99 KB) are co-resident per SM
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   flash_attention_kernel<<<dim3(q_tiles, 1, z), kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, p);

@@ -30,9 +30,16 @@ struct HaloParams {
   int tmem_cols;
   int slab_bytes;  // halo bytes per 64-channel slab, rounded up to 1024
   const char* label;
+  // fused first layer (kFuse1a): the halo of conv1a's OUTPUT is computed in the kernel from the u8 image
+  // (3x3, Cin = 1, fp32 math on fp32 weights, ReLU, fp16) and written straight into the swizzled A
+  // layout, so conv1a's 39 MB / image activation never exists in HBM.
+  const uint8_t* img;   // [B][img_h][img_w]
+  const float* w1a;     // [9][64]
+  const float* b1a;     // [64]
+  int img_h, img_w;
 };
 
-template <class Epi>
+template <class Epi, bool kFuse1a>
 __global__ void __launch_bounds__(kHaloThreads)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const HaloParams p, const Epi epi) {
@@ -78,10 +85,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const int num_w = p.slabs * 9;
 
+  if constexpr (kFuse1a) {
+    // conv1a on the fly: image patch (18+2) x (pw+2) -> 18 x pw halo pixels x 64 channels.
+    // Halo pixels outside the image are ZERO (they are conv1b's padding), inside pixels see conv1a's
+    // own zero padding of the image.  Same tap order / fp32 FMA chain as a stand-alone conv1a.
+    const int ppw = pw + 2;
+    float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* wsm = patch + ((20 * ppw + 3) & ~3);
+    float* bsm = wsm + 576;
+    const uint8_t* im = p.img + static_cast<size_t>(z) * p.img_h * p.img_w;
+    const float inv255 = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32F, 1.0/255.0)
+    for (int i = threadIdx.x; i < 20 * ppw; i += kHaloThreads) {
+      const int r = i / ppw, c = i % ppw;
+      const int y = h0 - 2 + r, x = w0 - 2 + c;
+      float v = 0.f;
+      if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) v = static_cast<float>(im[static_cast<size_t>(y) * p.img_w + x]) * inv255;
+      patch[i] = v;
+    }
+    for (int i = threadIdx.x; i < 576; i += kHaloThreads) wsm[i] = p.w1a[i];
+    if (threadIdx.x < 64) bsm[threadIdx.x] = p.b1a[threadIdx.x];
+    __syncthreads();
+    const int items = 18 * pw * 8;
+    for (int idx = threadIdx.x; idx < items; idx += kHaloThreads) {
+      const int px = idx >> 3, g = idx & 7;
+      const int hy = px / pw, hx = px % pw;
+      const int y = h0 - 1 + hy, x = w0 - 1 + hx;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bsm[g * 8 + j];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float v = patch[(hy + t / 3) * ppw + hx + t % 3];
+          const float4 wa = *reinterpret_cast<const float4*>(&wsm[t * 64 + g * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&wsm[t * 64 + g * 8 + 4]);
+          acc[0] = fmaf(v, wa.x, acc[0]);
+          acc[1] = fmaf(v, wa.y, acc[1]);
+          acc[2] = fmaf(v, wa.z, acc[2]);
+          acc[3] = fmaf(v, wa.w, acc[3]);
+          acc[4] = fmaf(v, wb.x, acc[4]);
+          acc[5] = fmaf(v, wb.y, acc[5]);
+          acc[6] = fmaf(v, wb.z, acc[6]);
+          acc[7] = fmaf(v, wb.w, acc[7]);
+        }
+        o.x = pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+        o.y = pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+        o.z = pack_half2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+        o.w = pack_half2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+      }
+      *reinterpret_cast<uint4*>(s_halo + px * 128 + ((g ^ (px & 7)) << 4)) = o;
+    }
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+  }
+
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t halo_tx = static_cast<uint32_t>(18 * pw * 128);
-      for (int s = 0; s < p.slabs; ++s) {
+      for (int s = 0; s < (kFuse1a ? 0 : p.slabs); ++s) {
         mbar_arrive_expect_tx(&halo_full[s], halo_tx);
         tma_load_4d(s_halo + s * p.slab_bytes, &tmA, &halo_full[s], s * 64, w0 - 1, h0 - 1, z);
       }
@@ -102,7 +164,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int slab = it / 9, tap = it % 9;
         const int kh = tap / 3, kw = tap % 3;
         const int st = it % p.stages;
-        if (tap == 0) {
+        if (!kFuse1a && tap == 0) {
           mbar_wait(&halo_full[slab], 0);
         }
         mbar_wait(&w_full[st], static_cast<uint32_t>(it / p.stages) & 1u);
@@ -147,7 +209,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 inline int halo_slab_bytes(int subtiles) { return (18 * (8 * subtiles + 2) * 128 + 1023) / 1024 * 1024; }
 
-template <class Epi>
+template <class Epi, bool kFuse1a = false>
 int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, HaloParams p, const Epi& epi, int W, int H,
                      int batch, int n_tiles, cudaStream_t stream) {
   p.tiles_w = (W + 8 * p.subtiles - 1) / (8 * p.subtiles);
@@ -159,13 +221,16 @@ int launch_conv_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, HaloParams 
     return SSB_ERR_INVALID;
   }
   if (p.stages <= 0) p.stages = 4;
-  const int smem = p.slabs * p.slab_bytes + p.stages * p.block_n * 128 + 1024 + 256;
+  const int smem = p.slabs * p.slab_bytes + p.stages * p.block_n * 128 + 1024 + 256 +
+                   (kFuse1a ? (20 * (8 * p.subtiles + 4) + 4 + 576 + 64) * 4 : 0);
   static int configured = 0;
   if (smem > configured) {
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<Epi, kFuse1a>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<Epi, kFuse1a>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
-  conv_halo_kernel<Epi><<<dim3(p.tiles_w * tiles_h, n_tiles, batch), kHaloThreads, smem, stream>>>(tmA, tmB, p, epi);
+  conv_halo_kernel<Epi, kFuse1a><<<dim3(p.tiles_w * tiles_h, n_tiles, batch), kHaloThreads, smem, stream>>>(tmA, tmB, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, p.label);

@@ -82,62 +82,6 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __r
   gray[i] = static_cast<uint8_t>((p[0] * 1868 + p[1] * 9617 + p[2] * 4899 + 8192) >> 14);
 }
 
-// conv1a: 1 -> 64 channels, 3x3, pad 1, bias, ReLU, fp32 math on fp32 weights, fp16 NHWC out.
-// Block = 8 rows x 32 columns of pixels; 8 threads per pixel, each owning 8 output channels, so a
-// warp writes 4 pixels x 128 B = 512 contiguous bytes.
-__global__ void __launch_bounds__(256)
-conv1a_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ wgt,
-              const float* __restrict__ bias, __half* __restrict__ out) {
-  __shared__ float patch[10][34];
-  __shared__ __align__(16) float wsm[9][64];
-  __shared__ __align__(16) float bsm[64];
-  const int z = blockIdx.z;
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-  const uint8_t* im = img + static_cast<size_t>(z) * H * W;
-  const float inv255 = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32F, 1.0/255.0): value * float(1/255)
-  for (int i = threadIdx.x; i < 340; i += 256) {
-    const int r = i / 34, c = i % 34;
-    const int y = y0 + r - 1, x = x0 + c - 1;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) v = static_cast<float>(im[static_cast<size_t>(y) * W + x]) * inv255;
-    patch[r][c] = v;
-  }
-  for (int i = threadIdx.x; i < 576; i += 256) wsm[i / 64][i % 64] = wgt[i];
-  if (threadIdx.x < 64) bsm[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int g = threadIdx.x & 7, p = threadIdx.x >> 3;
-  const int x = x0 + p;
-#pragma unroll 1
-  for (int r = 0; r < 8; ++r) {
-    const int y = y0 + r;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bsm[g * 8 + j];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float v = patch[r + t / 3][p + t % 3];
-      const float4 wa = *reinterpret_cast<const float4*>(&wsm[t][g * 8]);
-      const float4 wb = *reinterpret_cast<const float4*>(&wsm[t][g * 8 + 4]);
-      acc[0] = fmaf(v, wa.x, acc[0]);
-      acc[1] = fmaf(v, wa.y, acc[1]);
-      acc[2] = fmaf(v, wa.z, acc[2]);
-      acc[3] = fmaf(v, wa.w, acc[3]);
-      acc[4] = fmaf(v, wb.x, acc[4]);
-      acc[5] = fmaf(v, wb.y, acc[5]);
-      acc[6] = fmaf(v, wb.z, acc[6]);
-      acc[7] = fmaf(v, wb.w, acc[7]);
-    }
-    if (y < H && x < W) {
-      uint4 o;
-      o.x = pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-      o.y = pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-      o.z = pack_half2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-      o.w = pack_half2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(z) * H + y) * W + x) * 64 + g * 8) = o;
-    }
-  }
-}
-
 // ---- TMEM epilogues -------------------------------------------------------------------------------
 
 // bias + ReLU (+ 2x2/2 max-pool, floor) -> fp16 NHWC.  The 16x8 pixel tile puts two tile rows in each
@@ -652,7 +596,6 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
     return SSB_OK;
   };
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&img_), B * h * w));
-  SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&a1a_), B * h * w * 64 * 2));
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&a1b_), B * h2_ * w2_ * 64 * 2));
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&a2a_), B * h2_ * w2_ * 64 * 2));
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&a2b_), B * h4_ * w4_ * 64 * 2));
@@ -671,7 +614,6 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kp_score_), B * max_kpts_ * 4));
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kp_cell_), B * max_kpts_ * 4));
   SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kp_count_), B * 4));
-  SSB_RETURN_IF(make_act_tmap(&tm_a1a_, a1a_, 64, 64, w, h, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a1b_, a1b_, 64, 64, w2_, h2_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a2a_, a2a_, 64, 64, w2_, h2_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a2b_, a2b_, 64, 64, w4_, h4_, nb));
@@ -679,7 +621,6 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_act_tmap(&tm_a3b_, a3b_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4a_, a4a_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4b_, a4b_, 128, 128, wc_, hc_, nb));
-  SSB_RETURN_IF(make_halo_tmap(&tm_h1a_, a1a_, 64, w, h, nb, 4));
   SSB_RETURN_IF(make_halo_tmap(&tm_h1b_, a1b_, 64, w2_, h2_, nb, 4));
   SSB_RETURN_IF(make_halo_tmap(&tm_h2a_, a2a_, 64, w2_, h2_, nb, 4));
   SSB_RETURN_IF(make_halo_tmap(&tm_h2b_, a2b_, 64, w4_, h4_, nb, 2));
@@ -738,13 +679,6 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   SSB_CUDA_CHECK(cudaSetDevice(device_));
   SSB_RETURN_IF(ensure_shape(batch, h, w));
   const int B = batch;
-  {
-    dim3 g((w + 31) / 32, (h + 7) / 8, B);
-    conv1a_kernel<<<g, 256, 0, stream>>>(images_dev, h, w, w1a_, b1a_, a1a_);
-    SSB_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    prof_mark(stream, "sp.conv1a");
-  }
   auto conv = [&](const char* label, const CUtensorMap& tmA, const ConvLayer& L, int H, int W, __half* out,
                   int Ho, int Wo, int block_n, int pool) -> int {
     CoreParams p = conv_params(L.taps, L.cin, L.cout_pad, block_n, W);
@@ -767,7 +701,23 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, L.cout, 8};
     return launch_conv_halo(tmH, L.tmB, p, e, W, H, B, 1, stream);
   };
-  SSB_RETURN_IF(hconv("sp.conv1b", tm_h1a_, l1b_, h, w, a1b_, h2_, w2_, 4, 1));
+  {  // conv1a (Cin = 1) is evaluated inside conv1b's halo producer: its activation never touches HBM
+    HaloParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.slabs = 1;
+    p.subtiles = 4;
+    p.block_n = 64;
+    p.cout_rows = l1b_.cout_pad;
+    p.stages = 3;   // 77 KB halo + 3 x 8 KB weights + 5.4 KB image patch: two CTAs still fit one SM
+    p.label = "sp.conv1ab";
+    p.img = images_dev;
+    p.w1a = w1a_;
+    p.b1a = b1a_;
+    p.img_h = h;
+    p.img_w = w;
+    EpiConvRelu e{l1b_.bias, a1b_, h2_, w2_, 64, h, w, 1, 64, 8};
+    SSB_RETURN_IF((launch_conv_halo<EpiConvRelu, true>(l1b_.tmB, l1b_.tmB, p, e, w, h, B, 1, stream)));
+  }
   SSB_RETURN_IF(hconv("sp.conv2a", tm_h1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 4, 0));
   SSB_RETURN_IF(hconv("sp.conv2b", tm_h2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 4, 1));
   SSB_RETURN_IF(hconv("sp.conv3a", tm_h2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 2, 0));
@@ -910,7 +860,7 @@ int SuperPoint::debug_read(const char* what, void* dst, size_t bytes) {
     const void* ptr;
     size_t bytes;
   } tab[] = {
-      {"conv1a", a1a_, B * h_ * w_ * 64 * 2},       {"conv1b", a1b_, B * h2_ * w2_ * 64 * 2},
+      {"conv1b", a1b_, B * h2_ * w2_ * 64 * 2},
       {"conv2a", a2a_, B * h2_ * w2_ * 64 * 2},     {"conv2b", a2b_, B * h4_ * w4_ * 64 * 2},
       {"conv3a", a3a_, B * h4_ * w4_ * 128 * 2},    {"conv3b", a3b_, B * hc_ * wc_ * 128 * 2},
       {"conv4a", a4a_, B * hc_ * wc_ * 128 * 2},    {"conv4b", a4b_, B * hc_ * wc_ * 128 * 2},

@@ -48,7 +48,7 @@ def test_layers_scores_grid_and_exact_selection(fe, sp_weights, fixture, K):
     inter = osp.dense_intermediates(imgs, sp_weights, fp16_storage=True)
     # (1) activations: fp16 storage + fp32 accumulation on both sides; only the summation order
     # differs, so 2e-3 of the layer's dynamic range is ample (one fp16 ulp at the top of the range is 1e-3)
-    for name in ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:
+    for name in ["conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b"]:
         got = sp.debug_read(name, inter[name].shape, np.float16).astype(np.float32)
         assert _rel(got, inter[name]) < 2e-3, name
     hc, wc = inter["convPa"].shape[1:3]

@@ -46,7 +46,7 @@ def main():
     print(f"extract_stereo ok in {time.time()-t:.3f}s: n = {len(L.keypoints)}, {len(R.keypoints)}")
     inter = osp.dense_intermediates(imgs, w_sp, fp16_storage=True)
     shapes = {k: v.shape for k, v in inter.items()}
-    for name, key in [("conv1a", "conv1a"), ("conv1b", "conv1b"), ("conv2a", "conv2a"), ("conv2b", "conv2b"),
+    for name, key in [("conv1b", "conv1b"), ("conv2a", "conv2a"), ("conv2b", "conv2b"),
                       ("conv3a", "conv3a"), ("conv3b", "conv3b"), ("conv4a", "conv4a"), ("conv4b", "conv4b")]:
         got = sp.debug_read(name, shapes[key], np.float16).astype(np.float32)
         print(f"{name:8s} shape {shapes[key]} maxabs/rel {rel(got, inter[key])}")
