@@ -42,7 +42,7 @@ struct HaloParams {
 template <class Epi, bool kFuse1a>
 __global__ void __launch_bounds__(kHaloThreads)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const HaloParams p, const Epi epi) {
+                 const HaloParams p, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -105,29 +105,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = threadIdx.x; i < 576; i += kHaloThreads) wsm[i] = p.w1a[i];
     if (threadIdx.x < 64) bsm[threadIdx.x] = p.b1a[threadIdx.x];
     __syncthreads();
-    const int items = 18 * pw * 8;
-    for (int idx = threadIdx.x; idx < items; idx += kHaloThreads) {
-      const int px = idx >> 3, g = idx & 7;
-      const int hy = px / pw, hx = px % pw;
+    // thread t always owns channel group t % 8 (192 % 8 == 0): its 72 weights + 8 biases stay in registers
+    const int g = threadIdx.x & 7;
+    float wr[72], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wr[t * 8 + j] = wsm[t * 64 + g * 8 + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] = bsm[g * 8 + j];
+    const int npx = 18 * pw;
+    int px = threadIdx.x >> 3;             // 24 pixels per sweep
+    int hy = px / pw, hx = px - hy * pw;
+    for (; px < npx; px += kHaloThreads / 8) {
       const int y = h0 - 1 + hy, x = w0 - 1 + hx;
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
       if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) {
         float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = bsm[g * 8 + j];
+        for (int j = 0; j < 8; ++j) acc[j] = br[j];
+        const float* pp = patch + hy * ppw + hx;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const float v = patch[(hy + t / 3) * ppw + hx + t % 3];
-          const float4 wa = *reinterpret_cast<const float4*>(&wsm[t * 64 + g * 8]);
-          const float4 wb = *reinterpret_cast<const float4*>(&wsm[t * 64 + g * 8 + 4]);
-          acc[0] = fmaf(v, wa.x, acc[0]);
-          acc[1] = fmaf(v, wa.y, acc[1]);
-          acc[2] = fmaf(v, wa.z, acc[2]);
-          acc[3] = fmaf(v, wa.w, acc[3]);
-          acc[4] = fmaf(v, wb.x, acc[4]);
-          acc[5] = fmaf(v, wb.y, acc[5]);
-          acc[6] = fmaf(v, wb.z, acc[6]);
-          acc[7] = fmaf(v, wb.w, acc[7]);
+          const float v = pp[(t / 3) * ppw + (t % 3)];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[t * 8 + j], acc[j]);
         }
         o.x = pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
         o.y = pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
@@ -135,6 +137,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o.w = pack_half2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
       }
       *reinterpret_cast<uint4*>(s_halo + px * 128 + ((g ^ (px & 7)) << 4)) = o;
+      hx += kHaloThreads / 8;
+      while (hx >= pw) {
+        hx -= pw;
+        ++hy;
+      }
     }
     fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -195,12 +202,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.col_end = p.block_n;
     c.half = 0;
     c.xchg = nullptr;
+    // every MMA has completed (accum_bar), so the halo buffer is free: reuse it as TMA-store staging
+    c.stage = s_halo + (warp - 2) * 4096;
     c.py = h0 + (c.row >> 3);
     for (int sub = 0; sub < p.subtiles; ++sub) {
       c.px = w0 + sub * 8 + (c.row & 7);
       c.tmem_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * p.block_n;
       epi(c, true);
     }
+    stage_drain(c);
   }
   tc_fence_before();
   __syncthreads();

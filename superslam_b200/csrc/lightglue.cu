@@ -42,10 +42,12 @@ lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __r
   if (row >= kp) return;
   const int n = kp_count[z];
   const size_t o = (static_cast<size_t>(z) * kp + row) * kLgDim + lane * 8;
+  // fp32 master: tile-transposed [z][row/128][col][row%128] (see EpiResidual)
+  float* xt = x32 + (static_cast<size_t>(z) * (kp >> 7) + (row >> 7)) * (kLgDim * 128) + (row & 127);
   if (row >= n || desc_ptrs[z] == nullptr) {
     *reinterpret_cast<uint4*>(x16 + o) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<float4*>(x32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(x32 + o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = 0.f;
     return;
   }
   const __half* d = static_cast<const __half*>(desc_ptrs[z]) + static_cast<size_t>(row) * kLgDim + lane * 8;
@@ -54,8 +56,9 @@ lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __r
   const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
   const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
                e = __half22float2(h2[3]);
-  *reinterpret_cast<float4*>(x32 + o) = make_float4(a.x, a.y, b.x, b.y);
-  *reinterpret_cast<float4*>(x32 + o + 4) = make_float4(c.x, c.y, e.x, e.y);
+  const float f8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, e.x, e.y};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = f8[j];
   const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
   const float nx = (xy[0] - cx) / scale;
   const float ny = (xy[1] - cy) / scale;
@@ -76,20 +79,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// logsigmoid(matchability(x)) per keypoint, fp32 on the fp32 residual stream.
-__global__ void __launch_bounds__(256)
+// logsigmoid(matchability(x)) per keypoint, fp32 on the fp32 residual stream (tile-transposed layout:
+// one thread per row, consecutive threads read consecutive addresses).  grid (kp/128, 2P), block 128.
+__global__ void __launch_bounds__(128)
 matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, float b, int kp,
                     const int* __restrict__ cnt, float* __restrict__ lz) {
   const int z = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= cnt[z]) return;
-  const float* x = x32 + (static_cast<size_t>(z) * kp + row) * kLgDim;
+  const float* x = x32 + (static_cast<size_t>(z) * (kp >> 7) + blockIdx.x) * (kLgDim * 128) + threadIdx.x;
   float acc = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc = fmaf(x[lane + 32 * j], w[lane + 32 * j], acc);
-  acc = warp_sum(acc) + b;
-  if (lane == 0) lz[static_cast<size_t>(z) * kp + row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
+#pragma unroll 8
+  for (int c = 0; c < kLgDim; ++c) acc = fmaf(x[static_cast<size_t>(c) * 128], __ldg(w + c), acc);
+  acc += b;
+  lz[static_cast<size_t>(z) * kp + row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
 }
 
 // Row log-sum-exp of sim (pass 0: z = pair, rows of image 2z over columns of image 2z+1; pass 1 on
@@ -188,99 +191,124 @@ __global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* 
 // TMEM epilogues
 // =================================================================================================
 
-// Fused QKV projection epilogue (self attention).  Tile n0 = 0 / 256 / 512 holds q / k / v for all
-// four heads.  q,k: rotary  t*cos + rotate_half(t)*sin  with rotate_half((a,b)) = (-b,a).  q, k and v are
-// all stored head-major [z*4+h][kp][64]; the attention kernel reads V as an MN-major B operand.
+// All fp16 outputs below go registers -> swizzled staging -> one TMA store per warp and 64-column group
+// (3-D maps (cols, kp, batch), box (64, 32, 1)); rows beyond the keypoint count are written as zeros.
+
+// Fused QKV projection epilogue.  Self attention: tile n0 = 0 / 256 / 512 holds q / k / v for all four
+// heads; q,k get the rotary embedding  t*cos + rotate_half(t)*sin  with rotate_half((a,b)) = (-b,a).
+// Cross attention (rope = 0): n0 = 0 holds the shared qk projection, n0 = 256 holds v.
+// q, k and v are stored head-major [z*4+h][kp][64]; attention reads V as an MN-major B operand.
 struct EpiQkvRope {
   const float* bias;
   const float* cs;
   const float* sn;
-  __half* q;
-  __half* k;
-  __half* v_out;
+  CUtensorMap tm_q, tm_k, tm_v;   // 3-D (64, kp, Z)
   int kp;
-  int rope;  // 1: self attention (n0 0/256 = q/k with rotary, 512 = v); 0: cross (n0 0 = qk, 256 = v)
+  int rope;
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
+    const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
     const int which = c.n0 >> 8;
     const bool is_v = rope ? (which == 2) : (which == 1);
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      const int head = col >> 6, d0 = col & 63;
-      const size_t zh = static_cast<size_t>(c.z) * kLgHeads + head;
+    const CUtensorMap* tm = is_v ? &tm_v : (which == 0 ? &tm_q : &tm_k);
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
-      if (!is_v && rope && valid) {
-        const float* cr = cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
-        const float* sr = sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1);
+        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
+        if (!is_v && rope && valid) {
+          const int d0 = col & 63;
+          const float4* cr = reinterpret_cast<const float4*>(cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1));
+          const float4* sr = reinterpret_cast<const float4*>(sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float co = cr[i], si = sr[i];
-          const float a = v[2 * i], b = v[2 * i + 1];
-          v[2 * i] = a * co - b * si;
-          v[2 * i + 1] = b * co + a * si;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 co = cr[i4], si = sr[i4];
+            const float cc[4] = {co.x, co.y, co.z, co.w}, ss[4] = {si.x, si.y, si.z, si.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i = 4 * i4 + t;
+              const float a = v[2 * i], b = v[2 * i + 1];
+              v[2 * i] = a * cc[t] - b * ss[t];
+              v[2 * i + 1] = b * cc[t] + a * ss[t];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          stage_put(c, c.lane, hc * 4 + j, o);
         }
       }
-      __half* dstp = (is_v ? v_out : (which == 0 ? q : k)) + (zh * kp + row) * kLgHeadDim + d0;
-      uint4* dst = reinterpret_cast<uint4*>(dstp);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        dst[j] = o;
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(tm, c.stage, 0, row0, c.z * kLgHeads + (g0 >> 6));
+        bulk_commit();
       }
     }
   }
 };
 
-// bias -> fp16 rows [z][kp][256] (out_proj / to_out); padding rows inside the tile are zeroed.
+// bias -> fp16 rows [z][kp][256] (out_proj / to_out).
 struct EpiBias16 {
   const float* bias;
-  __half* out;
-  int kp;
+  CUtensorMap tm_out;
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
+    const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(c.z) * kp + row) * kLgDim + c.n0 + col);
+        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        dst[j] = o;
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          stage_put(c, c.lane, hc * 4 + j, o);
+        }
+      }
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(&tm_out, c.stage, c.n0 + g0, row0, c.z);
+        bulk_commit();
       }
     }
   }
 };
 
 // FFN first half: Linear(512->512) + LayerNorm(512, eps 1e-5) + exact GELU -> fp16 [z][kp][512].
-// The thread owns its whole 512-wide row in TMEM, so mean / variance / normalise are three cheap
-// passes over tcgen05.ld.
+// Each of the two warps that share a TMEM lane quadrant owns 256 of the row's 512 columns; mean and
+// variance are all-reduced across the pair through shared memory.
 struct EpiLnGelu {
   const float* bias;
   const float* g;
   const float* b;
-  __half* out;
-  int kp;
+  CUtensorMap tm_out;
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
+    const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
     float sum = 0.f;
     for (int col = c.col_begin; col < c.col_end; col += 32) {
@@ -303,65 +331,83 @@ struct EpiLnGelu {
       }
     }
     const float rstd = rsqrtf(epi_pair_sum(c, sq) * (1.0f / 512.0f) + 1e-5f);
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float y = (v[j] + __ldg(bias + col + j) - mean) * rstd * __ldg(g + col + j) + __ldg(b + col + j);
-        y = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
-        v[j] = valid ? y : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          float y = (v[j] + __ldg(bias + col + j) - mean) * rstd * __ldg(g + col + j) + __ldg(b + col + j);
+          y = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
+          v[j] = valid ? y : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          stage_put(c, c.lane, hc * 4 + j, o);
+        }
       }
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(c.z) * kp + row) * 512 + col);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        dst[j] = o;
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(&tm_out, c.stage, g0, row0, c.z);
+        bulk_commit();
       }
     }
   }
 };
 
-// FFN second half: Linear(512->256) + bias + residual; writes the fp32 master and its fp16 copy.
+// FFN second half: Linear(512->256) + bias + residual.  The fp32 master copy of the residual stream is
+// kept in a tile-transposed layout  x32[z][row/128][col][row%128]  so that the 32 lanes of a warp
+// (32 consecutive rows) read and write 128 contiguous bytes per column; the fp16 copy (GEMM operand,
+// row-major) goes out through the staged TMA store.
 struct EpiResidual {
   const float* bias;
   float* x32;
-  __half* x16;
+  CUtensorMap tm_x16;
   int kp;
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
+    const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      const size_t o = (static_cast<size_t>(c.z) * kp + row) * kLgDim + col;
-      float4* xr = reinterpret_cast<float4*>(x32 + o);
+    float* xt = x32 + (static_cast<size_t>(c.z) * (kp >> 7) + (row >> 7)) * (kLgDim * 128) + (row & 127);
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 x = valid ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-        x.x = valid ? x.x + (v[4 * j + 0] + __ldg(bias + col + 4 * j + 0)) : 0.f;
-        x.y = valid ? x.y + (v[4 * j + 1] + __ldg(bias + col + 4 * j + 1)) : 0.f;
-        x.z = valid ? x.z + (v[4 * j + 2] + __ldg(bias + col + 4 * j + 2)) : 0.f;
-        x.w = valid ? x.w + (v[4 * j + 3] + __ldg(bias + col + 4 * j + 3)) : 0.f;
-        xr[j] = x;
-        v[4 * j + 0] = x.x, v[4 * j + 1] = x.y, v[4 * j + 2] = x.z, v[4 * j + 3] = x.w;
+        for (int j = 0; j < 32; ++j) {
+          float* p = xt + static_cast<size_t>(col + j) * 128;
+          const float x = valid ? *p + (v[j] + __ldg(bias + col + j)) : 0.f;
+          *p = x;
+          v[j] = x;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          stage_put(c, c.lane, hc * 4 + j, o);
+        }
       }
-      uint4* dst = reinterpret_cast<uint4*>(x16 + o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        w.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        w.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        w.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        dst[j] = w;
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(&tm_x16, c.stage, g0, row0, c.z);
+        bulk_commit();
       }
     }
   }
@@ -397,43 +443,56 @@ struct EpiStoreF32 {
 
 // final_proj epilogue: md = (acc + bias) / 256^(1/4); split md = hi + lo (two fp16) so the fp16
 // tensor-core similarity recovers ~fp32 accuracy: sim = hi0.hi1 + hi0.lo1 + lo0.hi1 as one K=768
-// product of A-form [hi|hi|lo] with B-form [hi|lo|hi].
+// product of A-form [hi|hi|lo] with B-form [hi|lo|hi].  Each staged 64-column block is stored to all
+// the places it appears in (hi: four, lo: two).
 struct EpiSplit {
   const float* bias;
-  __half* mda;
-  __half* mdb;
-  int kp;
+  CUtensorMap tm_a, tm_b;   // 3-D (768, kp, 2P)
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
     const int row = c.px;
+    const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      uint32_t hi[16], lo[16];
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {   // 0: hi, 1: lo
+        stage_begin(c);
+#pragma unroll 1
+        for (int hc = 0; hc < 2; ++hc) {
+          const int col = g0 + hc * 32;
+          float v[32];
+          tmem_ld_32x32(c.tmem_row + col, v);
+          tmem_ld_wait();
+          uint32_t w[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float a = valid ? (v[2 * j] + __ldg(bias + col + 2 * j)) * 0.25f : 0.f;
-        const float b = valid ? (v[2 * j + 1] + __ldg(bias + col + 2 * j + 1)) * 0.25f : 0.f;
-        const __half2 h = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(h);
-        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[j] = pack_half2(a - hf.x, b - hf.y);
-      }
-      const size_t o = (static_cast<size_t>(c.z) * kp + row) * 768 + col;
-      uint4* a0 = reinterpret_cast<uint4*>(mda + o);
-      uint4* a1 = reinterpret_cast<uint4*>(mda + o + 256);
-      uint4* a2 = reinterpret_cast<uint4*>(mda + o + 512);
-      uint4* b0 = reinterpret_cast<uint4*>(mdb + o);
-      uint4* b1 = reinterpret_cast<uint4*>(mdb + o + 256);
-      uint4* b2 = reinterpret_cast<uint4*>(mdb + o + 512);
+          for (int j = 0; j < 16; ++j) {
+            const float a = valid ? (v[2 * j] + __ldg(bias + col + 2 * j)) * 0.25f : 0.f;
+            const float b = valid ? (v[2 * j + 1] + __ldg(bias + col + 2 * j + 1)) * 0.25f : 0.f;
+            const __half2 h = __floats2half2_rn(a, b);
+            if (part == 0) {
+              w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            } else {
+              const float2 hf = __half22float2(h);
+              w[j] = pack_half2(a - hf.x, b - hf.y);
+            }
+          }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 H = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        const uint4 L = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-        a0[j] = H, a1[j] = H, a2[j] = L;
-        b0[j] = H, b1[j] = L, b2[j] = H;
+          for (int j = 0; j < 4; ++j)
+            stage_put(c, c.lane, hc * 4 + j, make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+        }
+        stage_fence(c);
+        if (c.lane == 0) {
+          if (part == 0) {
+            tma_store_3d(&tm_a, c.stage, g0, row0, c.z);
+            tma_store_3d(&tm_a, c.stage, 256 + g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage, g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage, 512 + g0, row0, c.z);
+          } else {
+            tma_store_3d(&tm_a, c.stage, 512 + g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage, 256 + g0, row0, c.z);
+          }
+          bulk_commit();
+        }
       }
     }
   }
@@ -614,6 +673,15 @@ int LightGlue::alloc_workspace() {
   SSB_RETURN_IF(tm_rows3(&tm_q3_, q_, 64, kp_, z, 128));
   SSB_RETURN_IF(tm_rows3(&tm_k3_, k_, 64, kp_, z, 128));
   SSB_RETURN_IF(tm_rows3(&tm_v3_, v_, 64, kp_, z, 128));
+  // TMA-store maps: one warp's 32 rows x 64 columns
+  SSB_RETURN_IF(tm_rows3(&ts_x16_, x16_, 256, kp_, p2, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_msg_, msg_, 256, kp_, p2, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_h1_, h1_, 512, kp_, p2, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_q_, q_, 64, kp_, z, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_k_, k_, 64, kp_, z, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_v_, v_, 64, kp_, z, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_mda_, mda_, 768, kp_, p2, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_mdb_, mdb_, 768, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows4(&tm_mda_a_, mda_, 768, kp_, p2));
   SSB_RETURN_IF(tm_rows4(&tm_mdb_a_, mdb_, 768, kp_, p2));
   SSB_RETURN_IF(tm_rows3(&tm_mda_b_, mda_, 768, kp_, p2, 256));
@@ -676,12 +744,12 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   auto ffn = [&](const LgBlockFfn& F) -> int {
     {
       CoreParams p = lin("lg.ffn1", 4, 4, 512);
-      EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, h1_, KP};
+      EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, ts_h1_};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);
-      EpiResidual e{F.fc2.bias, x32_, x16_, KP};
+      EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
       SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     return SSB_OK;
@@ -708,13 +776,13 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
-      EpiQkvRope e{L.qkv.bias, cs_, sn_, q_, k_, v_, KP, 1};
+      EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     {
       CoreParams p = lin("lg.out_proj", 4, 0, 256);
-      EpiBias16 e{L.out.bias, msg_, KP};
+      EpiBias16 e{L.out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     SSB_RETURN_IF(ffn(L.sffn));
@@ -722,13 +790,13 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
-      EpiQkvRope e{L.qkv_c.bias, cs_, sn_, q_, k_, v_, KP, 0};
+      EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     {
       CoreParams p = lin("lg.to_out", 4, 0, 256);
-      EpiBias16 e{L.to_out.bias, msg_, KP};
+      EpiBias16 e{L.to_out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     SSB_RETURN_IF(ffn(L.cffn));
@@ -737,10 +805,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   // ---- assignment ----
   {
     CoreParams p = lin("lg.final_proj", 4, 0, 256);
-    EpiSplit e{w_->final_proj.bias, mda_, mdb_, KP};
+    EpiSplit e{w_->final_proj.bias, ts_mda_, ts_mdb_};
     SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }
-  matchability_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(x32_, w_->match_w, w_->match_b, KP, cnt, lz_);
+  matchability_kernel<<<dim3(KP / 128, P2), 128, 0, stream>>>(x32_, w_->match_w, w_->match_b, KP, cnt, lz_);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, "lg.matchability");

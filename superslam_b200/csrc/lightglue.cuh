@@ -99,7 +99,7 @@ class LightGlue {
   void** desc_ptrs_ = nullptr;  // [2P] device table
   __half* desc_stage_ = nullptr;  // [2][kp][256] staging for the host path
   float *cs_ = nullptr, *sn_ = nullptr;  // [2P][kp][32] cos / sin of the positional encoding
-  float* x32_ = nullptr;        // [2P][kp][256] residual stream (fp32 master)
+  float* x32_ = nullptr;        // residual stream, fp32 master, tile-transposed [2P][kp/128][256][128]
   __half* x16_ = nullptr;       // [2P][kp][256] fp16 copy (GEMM operand)
   __half *q_ = nullptr, *k_ = nullptr;  // [2P*4][kp][64]
   __half* v_ = nullptr;         // [2P*4][kp][64]
@@ -118,6 +118,7 @@ class LightGlue {
 
   CUtensorMap tm_x16_, tm_msg_, tm_ctx_, tm_h1_, tm_q_a_, tm_q3_, tm_k3_, tm_v3_, tm_mda_a_,
       tm_mdb_b_, tm_mdb_a_, tm_mda_b_;
+  CUtensorMap ts_x16_, ts_msg_, ts_h1_, ts_q_, ts_k_, ts_v_, ts_mda_, ts_mdb_;  // TMA-store maps
 };
 
 }  // namespace ssb

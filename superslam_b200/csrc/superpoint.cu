@@ -84,52 +84,59 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __r
 
 // ---- TMEM epilogues -------------------------------------------------------------------------------
 
-// bias + ReLU (+ 2x2/2 max-pool, floor) -> fp16 NHWC.  The 16x8 pixel tile puts two tile rows in each
-// epilogue warp (lane = 16*(row&1) + col), so the pool is two warp shuffles.
+// bias + ReLU (+ 2x2/2 max-pool, floor) -> fp16 NHWC, written with one TMA store per warp and 64-channel
+// group (registers -> swizzled staging -> bulk store; out-of-image pixels are clipped by the TMA unit).
+// Lane -> pixel mapping: 16x8 tiles of umma_core put two tile rows of 16 pixels in a warp
+// (row_xor = 16); conv_halo puts four rows of 8 pixels in a warp (row_xor = 8).  Either way the 2x2
+// pool is two warp shuffles.
 struct EpiConvRelu {
   const float* bias;
-  __half* out;
-  int Ho, Wo, C;   // stored tensor extent and channel pitch
-  int H, W;        // conv output extent (masking when not pooling)
+  CUtensorMap tm_out;  // 4-D (C, Wo, Ho, B); box = the warp's pixel block x 64 channels
   int pool;
-  int block_n;
-  int row_xor;     // lane distance between vertically adjacent pixels: 16 (16x8 tiles) or 8 (16 rows x 8 px)
+  int row_xor;
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool has_acc) const {
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      const float* b = bias + c.n0 + col;
+    const int px0 = __shfl_sync(0xffffffffu, c.px, 0), py0 = __shfl_sync(0xffffffffu, c.py, 0);
+    bool writer = true;
+    int srow = c.lane;
+    if (pool) {
+      writer = (c.lane & (1 | row_xor)) == 0;
+      srow = row_xor == 16 ? ((c.lane >> 1) & 7) : (((c.lane >> 4) & 1) * 4 + ((c.lane >> 1) & 3));
+    }
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
+        const float* b = bias + c.n0 + col;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf((has_acc ? v[j] : 0.f) + __ldg(b + j), 0.f);
-      int oy = c.py, ox = c.px;
-      bool writer;
-      if (pool) {
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf((has_acc ? v[j] : 0.f) + __ldg(b + j), 0.f);
+        if (pool) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], row_xor));
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], row_xor));
+          }
         }
-        writer = ((c.lane & (1 | row_xor)) == 0);
-        oy >>= 1;
-        ox >>= 1;
-        writer = writer && oy < Ho && ox < Wo;
-      } else {
-        writer = c.py < H && c.px < W;
+        if (writer) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+            o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+            stage_put(c, srow, hc * 4 + j, o);
+          }
+        }
       }
-      if (writer) {
-        uint4* dst = reinterpret_cast<uint4*>(
-            out + ((static_cast<size_t>(c.z) * Ho + oy) * Wo + ox) * C + c.n0 + col);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-          dst[j] = o;
-        }
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_4d(&tm_out, c.stage, c.n0 + g0, pool ? (px0 >> 1) : px0, pool ? (py0 >> 1) : py0, c.z);
+        bulk_commit();
       }
     }
   }
@@ -186,10 +193,10 @@ struct EpiScores {
 // [B][Hc*Wc][256] so the gather reads one contiguous 512-byte row per keypoint.
 struct EpiDescNorm {
   const float* bias;
-  __half* grid;
-  int Hc, Wc;
+  CUtensorMap tm_out;  // 4-D (256, Wc, Hc, B), box (64, 16, 2, 1)
   static constexpr bool kSplit = true;
   __device__ void operator()(const EpiCtx& c, bool) const {
+    const int px0 = __shfl_sync(0xffffffffu, c.px, 0), py0 = __shfl_sync(0xffffffffu, c.py, 0);
     float ss = 0.f;
     for (int col = c.col_begin; col < c.col_end; col += 32) {
       float v[32];
@@ -203,14 +210,14 @@ struct EpiDescNorm {
     }
     ss = epi_pair_sum(c, ss);  // the two column halves of the row live in different warps
     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-    const bool ok = c.py < Hc && c.px < Wc;
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(
-            grid + ((static_cast<size_t>(c.z) * Hc + c.py) * Wc + c.px) * kDescDim + col);
+    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
+      stage_begin(c);
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        const int col = g0 + hc * 32;
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + col, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x[8];
@@ -221,8 +228,13 @@ struct EpiDescNorm {
           o.y = pack_half2(x[2], x[3]);
           o.z = pack_half2(x[4], x[5]);
           o.w = pack_half2(x[6], x[7]);
-          dst[j] = o;
+          stage_put(c, c.lane, hc * 4 + j, o);
         }
+      }
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_4d(&tm_out, c.stage, g0, px0, py0, c.z);
+        bulk_commit();
       }
     }
   }
@@ -625,6 +637,17 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_halo_tmap(&tm_h2a_, a2a_, 64, w2_, h2_, nb, 4));
   SSB_RETURN_IF(make_halo_tmap(&tm_h2b_, a2b_, 64, w4_, h4_, nb, 2));
   SSB_RETURN_IF(make_halo_tmap(&tm_h3a_, a3a_, 128, w4_, h4_, nb, 2));
+  // store maps: one warp's pixel block x 64 channels (halo kernels: 4 rows x 8 px, pooled 2 x 4;
+  // 16x8-tile kernels: 2 rows x 16 px)
+  SSB_RETURN_IF(make_act_tmap(&ts_a1b_, a1b_, 64, 64, w2_, h2_, nb, 4, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_a2a_, a2a_, 64, 64, w2_, h2_, nb, 8, 4));
+  SSB_RETURN_IF(make_act_tmap(&ts_a2b_, a2b_, 64, 64, w4_, h4_, nb, 4, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_a3a_, a3a_, 128, 128, w4_, h4_, nb, 8, 4));
+  SSB_RETURN_IF(make_act_tmap(&ts_a3b_, a3b_, 128, 128, wc_, hc_, nb, 4, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_a4a_, a4a_, 128, 128, wc_, hc_, nb, 16, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_a4b_, a4b_, 128, 128, wc_, hc_, nb, 16, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_apd_, apd_, 512, 512, wc_, hc_, nb, 16, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_grid_, grid_, 256, 256, wc_, hc_, nb, 16, 2));
   SSB_RETURN_IF(make_act_tmap(&tm_apa_, apd_, 256, 512, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_ada_, apd_ + 256, 256, 512, wc_, hc_, nb));
   const size_t need = B * (static_cast<size_t>(max_kpts_) * 3 + 1) * sizeof(float);
@@ -679,17 +702,18 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   SSB_CUDA_CHECK(cudaSetDevice(device_));
   SSB_RETURN_IF(ensure_shape(batch, h, w));
   const int B = batch;
-  auto conv = [&](const char* label, const CUtensorMap& tmA, const ConvLayer& L, int H, int W, __half* out,
-                  int Ho, int Wo, int block_n, int pool) -> int {
+  auto conv = [&](const char* label, const CUtensorMap& tmA, const CUtensorMap& tmS, const ConvLayer& L, int H,
+                  int W, __half* out, int Ho, int Wo, int block_n, int pool) -> int {
     CoreParams p = conv_params(L.taps, L.cin, L.cout_pad, block_n, W);
     p.label = label;
-    EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, block_n, 16};
+    (void)out, (void)Ho, (void)Wo;
+    EpiConvRelu e{L.bias, tmS, pool, 16};
     dim3 g(p.tiles_w * ((H + 7) / 8), L.cout / block_n, B);
     return launch_core(tmA, tmA, L.tmB, p, e, g, stream);
   };
   // the five large layers (82 % of the trunk FLOPs) reuse one shared-memory halo for all nine taps
-  auto hconv = [&](const char* label, const CUtensorMap& tmH, const ConvLayer& L, int H, int W, __half* out,
-                   int Ho, int Wo, int subtiles, int pool) -> int {
+  auto hconv = [&](const char* label, const CUtensorMap& tmH, const CUtensorMap& tmS, const ConvLayer& L, int H,
+                   int W, int subtiles, int pool) -> int {
     HaloParams p;
     std::memset(&p, 0, sizeof(p));
     p.slabs = L.cin / 64;
@@ -698,7 +722,7 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     p.cout_rows = L.cout_pad;
     p.stages = 4;
     p.label = label;
-    EpiConvRelu e{L.bias, out, Ho, Wo, L.cout, H, W, pool, L.cout, 8};
+    EpiConvRelu e{L.bias, tmS, pool, 8};
     return launch_conv_halo(tmH, L.tmB, p, e, W, H, B, 1, stream);
   };
   {  // conv1a (Cin = 1) is evaluated inside conv1b's halo producer: its activation never touches HBM
@@ -715,16 +739,16 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     p.b1a = b1a_;
     p.img_h = h;
     p.img_w = w;
-    EpiConvRelu e{l1b_.bias, a1b_, h2_, w2_, 64, h, w, 1, 64, 8};
+    EpiConvRelu e{l1b_.bias, ts_a1b_, 1, 8};
     SSB_RETURN_IF((launch_conv_halo<EpiConvRelu, true>(l1b_.tmB, l1b_.tmB, p, e, w, h, B, 1, stream)));
   }
-  SSB_RETURN_IF(hconv("sp.conv2a", tm_h1b_, l2a_, h2_, w2_, a2a_, h2_, w2_, 4, 0));
-  SSB_RETURN_IF(hconv("sp.conv2b", tm_h2a_, l2b_, h2_, w2_, a2b_, h4_, w4_, 4, 1));
-  SSB_RETURN_IF(hconv("sp.conv3a", tm_h2b_, l3a_, h4_, w4_, a3a_, h4_, w4_, 2, 0));
-  SSB_RETURN_IF(hconv("sp.conv3b", tm_h3a_, l3b_, h4_, w4_, a3b_, hc_, wc_, 2, 1));
-  SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv("sp.convPaDa", tm_a4b_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));
+  SSB_RETURN_IF(hconv("sp.conv2a", tm_h1b_, ts_a2a_, l2a_, h2_, w2_, 4, 0));
+  SSB_RETURN_IF(hconv("sp.conv2b", tm_h2a_, ts_a2b_, l2b_, h2_, w2_, 4, 1));
+  SSB_RETURN_IF(hconv("sp.conv3a", tm_h2b_, ts_a3a_, l3a_, h4_, w4_, 2, 0));
+  SSB_RETURN_IF(hconv("sp.conv3b", tm_h3a_, ts_a3b_, l3b_, h4_, w4_, 2, 1));
+  SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, ts_a4a_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
+  SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, ts_a4b_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
+  SSB_RETURN_IF(conv("sp.convPaDa", tm_a4b_, ts_apd_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));
   {
     CoreParams p = conv_params(1, 256, lpb_.cout_pad, lpb_.cout_pad, wc_);
     p.label = "sp.convPb";
@@ -735,7 +759,7 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   {
     CoreParams p = conv_params(1, 256, ldb_.cout_pad, 256, wc_);
     p.label = "sp.convDb";
-    EpiDescNorm e{ldb_.bias, grid_, hc_, wc_};
+    EpiDescNorm e{ldb_.bias, ts_grid_};
     dim3 g(p.tiles_w * ((hc_ + 7) / 8), 1, B);
     SSB_RETURN_IF(launch_core(tm_ada_, tm_ada_, ldb_.tmB, p, e, g, stream));
   }

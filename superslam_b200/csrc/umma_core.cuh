@@ -77,7 +77,28 @@ struct EpiCtx {
                            // split the tile's columns; functors with kSplit == false get all of them)
   int half;            // 0 or 1: which of the two warps sharing this lane quadrant
   float* xchg;         // shared scratch [2][128] floats for row reductions across the two halves
+  uint8_t* stage;      // this warp's 4 KiB staging buffer (1024-byte aligned) for TMA stores
 };
+
+// ---- staged output: registers -> 128B-swizzled shared memory -> one TMA store per 32-row x 64-column
+// block.  A thread that owns a row writing 16-byte pieces straight to global memory touches 32
+// different lines per warp instruction (measured ~1 TB/s); the bulk store writes full lines.
+// All four calls are warp-collective.
+__device__ __forceinline__ void stage_begin(const EpiCtx& c) {   // previous store has drained the buffer
+  if (c.lane == 0) bulk_wait_read0();
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_put(const EpiCtx& c, int srow, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(c.stage + srow * 128 + ((chunk ^ (srow & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void stage_fence(const EpiCtx&) {
+  fence_proxy_async_smem();
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_drain(const EpiCtx& c) {   // before the buffer / CTA goes away
+  if (c.lane == 0) bulk_wait_all();
+  __syncwarp();
+}
 
 // Barrier among the 256 epilogue threads (both halves); every epilogue thread must call it.
 __device__ __forceinline__ void epi_pair_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -93,24 +114,28 @@ __device__ __forceinline__ float epi_pair_sum(const EpiCtx& c, float v) {
 
 __host__ __device__ inline int core_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
 
+constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp
+
 inline int core_smem_bytes(int block_n, int stages) {
-  return stages * core_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
+  return stages * core_stage_bytes(block_n) + kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+         1024 /*xchg*/;
 }
 
 template <class Epi>
 __global__ void __launch_bounds__(kCoreThreads, 1)
 umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const CoreParams p, const Epi epi) {
+                 const __grid_constant__ CUtensorMap tmB, const CoreParams p, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int stage_bytes = core_stage_bytes(p.block_n);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* staging = smem + p.stages * stage_bytes;   // 8 x 4 KiB, 1024-aligned (stage sizes are multiples of 1 KiB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kCoreStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* xchg = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256);
+  float* xchg = reinterpret_cast<float*>(staging + kCoreStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -251,6 +276,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       c.m_valid = m_valid;
       c.half = half;
       c.xchg = xchg;
+      c.stage = staging + ew * 4096;
       c.tmem_row = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
       if (Epi::kSplit) {
         const int hw = p.block_n / 2;
@@ -266,6 +292,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_arrive(&tmem_empty[buf]);
       ++seq;
     }
+    if (lane == 0) bulk_wait_all();   // outstanding TMA stores still read this CTA's shared memory
   }
 
   tc_fence_before();
@@ -282,7 +309,7 @@ inline int core_tmem_cols(int cols) {
 
 inline int core_pick_stages(int block_n) {
   const int sb = core_stage_bytes(block_n);
-  int st = (200 * 1024) / sb;   // one persistent CTA per SM owns the shared memory
+  int st = (190 * 1024 - kCoreStagingBytes) / sb;   // one persistent CTA per SM owns the shared memory
   if (st > 6) st = 6;
   if (st < 2) st = 2;
   return st;

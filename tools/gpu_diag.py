@@ -23,6 +23,12 @@ from superslam_b200.synth import synth_image  # noqa: E402
 SPW = os.path.join(ROOT, "superslam_b200", "weights", "superpoint_v1.ssbw")
 
 
+def read_x32(lg, kp):
+    """fp32 residual stream: tile-transposed on the device ([img][row/128][col][row%128]) -> [2, kp, 256]."""
+    raw = lg.debug_read("x32", (2, kp // 128, 256, 128), np.float32)
+    return raw.transpose(0, 1, 3, 2).reshape(2, kp, 256)
+
+
 def rel(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
@@ -106,18 +112,18 @@ def main():
     msg = lg.debug_read("msg", (2, kp, 256), np.float16).astype(np.float32)[0, :n0]
     h1 = lg.debug_read("h1", (2, kp, 512), np.float16).astype(np.float32)[0, :n0]
     print(f"lg ctx {rel(ctx, dbg['ctx'])} msg {rel(msg, dbg['msg'])} h1 {rel(h1, dbg['h1'])}")
-    x32 = lg.debug_read("x32", (2, kp, 256), np.float32)
+    x32 = read_x32(lg, kp)
     print(f"lg x after self0 {rel(x32[0, :n0], dbg['x'])}")
     for stop, key in [(2, "cross0"), (3, "self1"), (4, "cross1"), (10, "cross4")]:
         os.environ["SSB_LG_STOP_AFTER"] = str(stop)
         lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
-        x32 = lg.debug_read("x32", (2, kp, 256), np.float32)
+        x32 = read_x32(lg, kp)
         print(f"lg x after {key} img0 {rel(x32[0, :n0], inter[key][0])} img1 {rel(x32[1, :n1], inter[key][1])}")
     del os.environ["SSB_LG_STOP_AFTER"]
     t = time.time()
     m = lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
     print(f"lg.match ok in {time.time()-t:.3f}s, matches {len(m.query)}")
-    x32 = lg.debug_read("x32", (2, kp, 256), np.float32)
+    x32 = read_x32(lg, kp)
     print(f"lg x32 final img0 maxabs/rel {rel(x32[0, :n0], inter['cross8'][0])} img1 {rel(x32[1, :n1], inter['cross8'][1])}")
     sim = lg.debug_read("sim", (kp, kp), np.float32)
     print(f"lg matches0 equal {np.array_equal(m.matches0, om0)} ({(m.matches0 != om0).sum()} differ of {n0}); "
