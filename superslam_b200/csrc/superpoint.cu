@@ -16,6 +16,7 @@
 #include <string>
 
 #include "conv_halo.cuh"
+#include "conv_pipe.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -516,7 +517,9 @@ int SuperPoint::load_layer(const WeightArchive& ar, const char* name, int cin, i
   uint64_t dims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(T) * pad, 1};
   uint64_t strides[2] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(T) * pad * cin * 2};
   uint32_t box[3] = {64, static_cast<uint32_t>(n_part), 1};
-  return encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box);
+  SSB_RETURN_IF(encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box));
+  uint32_t box64[3] = {64, 64, 1};   // one 64-output-channel slice of one tap (conv_pipe.cuh)
+  return encode_tmap_f16(&L->tmB64, L->w, 3, dims, strides, box64);
 }
 
 int SuperPoint::init(const char* weights_path, int max_keypoints, double threshold, int remove_borders,
@@ -633,8 +636,8 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_act_tmap(&tm_a3b_, a3b_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4a_, a4a_, 128, 128, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_a4b_, a4b_, 128, 128, wc_, hc_, nb));
-  SSB_RETURN_IF(make_halo_tmap(&tm_h1b_, a1b_, 64, w2_, h2_, nb, 4));
-  SSB_RETURN_IF(make_halo_tmap(&tm_h2a_, a2a_, 64, w2_, h2_, nb, 4));
+  SSB_RETURN_IF(make_halo_tmap(&tm_p1b_, a1b_, 64, w2_, h2_, nb, 2));   // 18 x 18 halo boxes
+  SSB_RETURN_IF(make_halo_tmap(&tm_p2a_, a2a_, 64, w2_, h2_, nb, 2));
   SSB_RETURN_IF(make_halo_tmap(&tm_h2b_, a2b_, 64, w4_, h4_, nb, 2));
   SSB_RETURN_IF(make_halo_tmap(&tm_h3a_, a3a_, 128, w4_, h4_, nb, 2));
   // store maps: one warp's pixel block x 64 channels (halo kernels: 4 rows x 8 px, pooled 2 x 4;
@@ -725,26 +728,28 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     EpiConvRelu e{L.bias, tmS, pool, 8};
     return launch_conv_halo(tmH, L.tmB, p, e, W, H, B, 1, stream);
   };
-  {  // conv1a (Cin = 1) is evaluated inside conv1b's halo producer: its activation never touches HBM
-    HaloParams p;
+  // Cin = 64 layers: persistent warp-specialised kernel, weights resident, halo + TMEM double-buffered.
+  // conv1a (Cin = 1) is evaluated by the halo-producer warps of conv1b: its activation never touches HBM.
+  auto pconv = [&](const char* label, const CUtensorMap& tmH, const CUtensorMap& tmS, const ConvLayer& L, int H,
+                   int W, int pool, bool fuse1a) -> int {
+    PipeParams p;
     std::memset(&p, 0, sizeof(p));
-    p.slabs = 1;
-    p.subtiles = 4;
-    p.block_n = 64;
-    p.cout_rows = l1b_.cout_pad;
-    p.stages = 3;   // 77 KB halo + 3 x 8 KB weights + 5.4 KB image patch: two CTAs still fit one SM
-    p.label = "sp.conv1ab";
+    p.n_slices = L.cout / 64;
+    p.cout_rows = L.cout_pad;
+    p.label = label;
     p.img = images_dev;
     p.w1a = w1a_;
     p.b1a = b1a_;
     p.img_h = h;
     p.img_w = w;
-    EpiConvRelu e{l1b_.bias, ts_a1b_, 1, 8};
-    SSB_RETURN_IF((launch_conv_halo<EpiConvRelu, true>(l1b_.tmB, l1b_.tmB, p, e, w, h, B, 1, stream)));
-  }
-  SSB_RETURN_IF(hconv("sp.conv2a", tm_h1b_, ts_a2a_, l2a_, h2_, w2_, 4, 0));
-  SSB_RETURN_IF(hconv("sp.conv2b", tm_h2a_, ts_a2b_, l2b_, h2_, w2_, 4, 1));
-  SSB_RETURN_IF(hconv("sp.conv3a", tm_h2b_, ts_a3a_, l3a_, h4_, w4_, 2, 0));
+    EpiConvRelu e{L.bias, tmS, pool, 8};
+    if (fuse1a) return launch_conv_pipe<EpiConvRelu, true>(L.tmB64, L.tmB64, p, e, W, H, B, stream);
+    return launch_conv_pipe<EpiConvRelu, false>(tmH, L.tmB64, p, e, W, H, B, stream);
+  };
+  SSB_RETURN_IF(pconv("sp.conv1ab", tm_p1b_, ts_a1b_, l1b_, h, w, 1, true));
+  SSB_RETURN_IF(pconv("sp.conv2a", tm_p1b_, ts_a2a_, l2a_, h2_, w2_, 0, false));
+  SSB_RETURN_IF(pconv("sp.conv2b", tm_p2a_, ts_a2b_, l2b_, h2_, w2_, 1, false));
+  SSB_RETURN_IF(pconv("sp.conv3a", tm_h2b_, ts_a3a_, l3a_, h4_, w4_, 0, false));
   SSB_RETURN_IF(hconv("sp.conv3b", tm_h3a_, ts_a3b_, l3b_, h4_, w4_, 2, 1));
   SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, ts_a4a_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
   SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, ts_a4b_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
