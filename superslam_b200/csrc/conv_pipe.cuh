@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(kFuse1a ? kPipeThreadsFused : kPipeThreads, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const PipeParams p, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
+  // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = smem;
   uint8_t* s_halo = smem + kPipeWeightBytes;                  // [2]
   uint8_t* s_stage = s_halo + 2 * kPipeHaloBytes;             // 4 x 4 KiB

@@ -126,8 +126,9 @@ __global__ void __launch_bounds__(kCoreThreads, 1)
 umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const CoreParams p, const __grid_constant__ Epi epi) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
+  // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = core_stage_bytes(p.block_n);
   uint8_t* staging = smem + p.stages * stage_bytes;   // 8 x 4 KiB, 1024-aligned (stage sizes are multiples of 1 KiB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kCoreStagingBytes);
