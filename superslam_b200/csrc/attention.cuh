@@ -106,7 +106,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
     }
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -251,7 +251,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
     }
     // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
     xchg_l[half * 128 + row] = l;

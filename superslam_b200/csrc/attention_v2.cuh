@@ -1,0 +1,245 @@
+// Two-CTAs-per-SM variant of the fused attention kernel (see attention.cuh): 99 KB of shared memory and
+// 256 TMEM columns per CTA; one CTA's exponentials overlap the other's MMAs and loads.
+#pragma once
+
+#include "attention.cuh"
+
+namespace ssb {
+
+constexpr int kFaV2SmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 2048 /*xchg*/ +
+                               128 /*barriers*/ + 1024 /*align*/;
+
+// tmQ: 4-D (64, kp, 1, Z) box (64,128,1,1).  tmK, tmV: 3-D (64, kp, Z) box (64,128,1).
+__global__ void __launch_bounds__(kFaThreads, 2)
+flash_attention_kernel_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;            // 2 stages
+  uint8_t* sV = smem + 16384 + 32768;    // 1 stage (V is only needed after the softmax of its block)
+  uint8_t* sP = smem + 16384 + 49152;    // 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
+  float* xchg = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);  // [2][128] block max
+  float* xchg_l = xchg + 256;                                             // [2][128] row sums (epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 2048);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int img = z / p.heads, head = z % p.heads;
+  const int q0 = blockIdx.x * 128;
+  const int nq = p.cnt[img];
+  if (q0 >= nq) return;
+  const int nk = p.cnt[img ^ p.key_xor];
+  const int zk = (img ^ p.key_xor) * p.heads + head;
+  const int nblk = (nk + kFaBlockKeys - 1) / kFaBlockKeys;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(&k_full[0], 1);
+    mbar_init(&k_full[1], 1);
+    mbar_init(&k_empty[0], 1);
+    mbar_init(&k_empty[1], 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 8);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;        // 128 columns
+  const uint32_t tO = tmem + 128;  // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 16384);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
+        mbar_arrive_expect_tx(&k_full[s], 16384);
+        tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, zk);
+        if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, zk);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
+      const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
+      mbar_wait(q_full, 0);
+      const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
+      const uint32_t vbase = smem_u32(sV);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t kdesc = make_smem_desc_k_sw128(smem_u32(sK + s * 16384), 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&k_empty[s]);
+        umma_commit(s_full);
+        mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
+        mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
+          const uint64_t pdesc = make_smem_desc_k_sw128(smem_u32(sP + (k >> 2) * 16384), 1024) + 2 * (k & 3);
+          const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
+          umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;          // which 64 keys of the block / which 32 output columns
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tSh = tS + lane_off + half * 64;
+    const uint32_t tOh = tO + lane_off + half * 32;
+    uint8_t* slab = sP + half * 16384 + row * 128;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
+      tc_fence_after();
+      const int kvalid = min(64, nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
+      // pass 1: maximum of my 64 logits (raw; the positive scale is applied once)
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tSh + c, v);
+        tmem_ld_wait();
+        if (kvalid >= 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        }
+      }
+      xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      fa_pair_sync();
+      const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = bm;
+      } else if (bm > m_used + 8.0f) {
+        alpha = fast_exp2(m_used - bm);
+        m_used = bm;
+        need = true;
+      }
+      // P and O are still being read / written by the previous P*V until pv_done fires
+      if (j > 0) {
+        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        l *= alpha;
+        float o[32];
+        tmem_ld_32x32(tOh, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+        tmem_st_32x32(tOh, o);
+        tmem_st_wait();
+      }
+      // pass 2: probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tSh + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+          if (kvalid < 64 && c + i >= kvalid) e = 0.f;
+          ls[i & 3] += e;
+          v[i] = e;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (c >> 3) + u;
+          uint4 w;
+          w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
+          w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
+          w.z = pack_half2(v[8 * u + 4], v[8 * u + 5]);
+          w.w = pack_half2(v[8 * u + 6], v[8 * u + 7]);
+          *reinterpret_cast<uint4*>(slab + ((unit ^ (row & 7)) << 4)) = w;
+        }
+      }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
+    }
+    // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
+    xchg_l[half * 128 + row] = l;
+    fa_pair_sync();
+    const float inv = 1.0f / (xchg_l[row] + xchg_l[128 + row]);
+    mbar_wait(pv_done, static_cast<uint32_t>(nblk - 1) & 1u);
+    tc_fence_after();
+    const bool valid = (q0 + row) < nq;
+    float o[32];
+    tmem_ld_32x32(tOh, o);
+    tmem_ld_wait();
+    uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(img) * p.kp + q0 + row) * (p.heads * 64) +
+                                          head * 64 + half * 32);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint4 w;
+      w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
+      w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
+      w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
+      w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
+      dst[u] = w;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+inline int launch_flash_attention_v2(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                  const FaParams& p, int q_tiles, int z, cudaStream_t stream, const char* label) {
+  static bool configured = false;
+  if (!configured) {
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFaV2SmemBytes));
+    // ask for the full shared-memory carveout so that two CTAs (2 x 99 KB) are co-resident per SM
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel_v2, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  flash_attention_kernel_v2<<<dim3(q_tiles, 1, z), kFaThreads, kFaV2SmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  SSB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  prof_mark(stream, label);
+  return SSB_OK;
+}
+
+}  // namespace ssb

@@ -73,10 +73,10 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     mbar_init(w_full, 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&halo_full[b], kFuse1a ? 256 : 1);
+      mbar_init(&halo_full[b], kFuse1a ? 8 : 1);   // one arrival per producer warp
       mbar_init(&halo_empty[b], 1);
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_empty[b], 4);                // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -166,7 +166,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epi(c, true);
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[b]);
     }
     stage_drain(c);
   } else if (kFuse1a) {
@@ -229,7 +230,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&halo_full[hb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&halo_full[hb]);
     }
   }
   tc_fence_before();

@@ -20,6 +20,7 @@
 #include <string>
 
 #include "attention.cuh"
+#include "attention_v2.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -789,6 +790,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     fp.scale_log2 = scale * 1.4426950408889634f;
     fp.ctx = ctx_;
     fp.kp = KP;
+    static const bool v2 = std::getenv("SSB_FA_V2") != nullptr;   // A/B experiment, removed once decided
+    if (v2)
+      return launch_flash_attention_v2(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
+                                       key_xor ? "lg.attn_cross" : "lg.attn_self");
     return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
                                   key_xor ? "lg.attn_cross" : "lg.attn_self");
   };

@@ -151,7 +151,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], kCoreEpiThreads);
+      mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -290,7 +290,8 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         epi(c, num_k > 0);
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       ++seq;
     }
     if (lane == 0) bulk_wait_all();   // outstanding TMA stores still read this CTA's shared memory
