@@ -9,8 +9,9 @@
 // written to HBM.  The running max is only refreshed when it grows by more than 2^8 (the O rescale is
 // skipped otherwise), which keeps P <= 256 in fp16 and is exact after the final division by the row sum.
 //
-// Budget: 147 KB of shared memory and all 512 TMEM columns -> one CTA per SM, software-pipelined inside
-// (see the kernel) so that the exponentials (MUFU: 16 ex2/clk/SM) never wait for the tensor core.
+// Budget: 99 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's
+// exponentials (the MUFU-bound part: 16 ex2/clk/SM) overlap the other's MMAs and loads.  (A variant that
+// pipelines S/P double-buffered inside one CTA per SM measured 25 % slower: profiles/README.md.)
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = softmax + epilogue (TMEM lane quadrant = warp % 4, key half = (warp-2) / 4).
 #pragma once
@@ -22,7 +23,7 @@ namespace ssb {
 
 constexpr int kFaThreads = 320;
 constexpr int kFaBlockKeys = 128;
-constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 2 * 32768 /*P*/ + 3072 /*xchg*/ +
+constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 2048 /*xchg*/ +
                              128 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
@@ -57,32 +58,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ void fa_pair_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 // tmQ: 4-D (64, kp, 1, Z) box (64,128,1,1).  tmK, tmV: 3-D (64, kp, Z) box (64,128,1).
-//
-// Software pipeline inside the CTA (one CTA per SM, all 512 TMEM columns): S is double-buffered in TMEM
-// and P in shared memory, so the MMA thread issues S(j+1) = Q K(j+1)^T while the 256 softmax threads are
-// still exponentiating block j, and O += P(j) V(j) while they work on block j+1.  The softmax threads
-// therefore never wait for the tensor core: the kernel runs at the MUFU (exp2) rate.
-__global__ void __launch_bounds__(kFaThreads, 1)
+__global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;                     // 2 stages
-  uint8_t* sV = smem + 16384 + 32768;             // 2 stages
-  uint8_t* sP = smem + 16384 + 65536;             // 2 x (128 x 128 fp16 = two [128 x 64] slabs)
-  float* xchg = reinterpret_cast<float*>(smem + 16384 + 65536 + 65536);  // [2][2][128] block max (per parity)
-  float* xchg_l = xchg + 512;                     // [2][128] row sums (epilogue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 65536 + 3072);
+  uint8_t* sK = smem + 16384;            // 2 stages
+  uint8_t* sV = smem + 16384 + 32768;    // 1 stage (V is only needed after the softmax of its block)
+  uint8_t* sP = smem + 16384 + 49152;    // 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
+  float* xchg = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);  // [2][128] block max
+  float* xchg_l = xchg + 256;                                             // [2][128] row sums (epilogue)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 2048);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* pv_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* v_full = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -99,27 +94,26 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-    }
+    mbar_init(&k_full[0], 1);
+    mbar_init(&k_full[1], 1);
+    mbar_init(&k_empty[0], 1);
+    mbar_init(&k_empty[1], 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
     mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem;        // 2 x 128 columns
-  const uint32_t tO = tmem + 256;  // 64 columns
+  const uint32_t tS = tmem;        // 128 columns
+  const uint32_t tO = tmem + 128;  // 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -127,13 +121,12 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
       for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
-        const uint32_t ph = (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u;
-        mbar_wait(&k_empty[s], ph);      // S(j-2) has consumed the stage
+        mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
         mbar_arrive_expect_tx(&k_full[s], 16384);
         tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, zk);
-        mbar_wait(&v_empty[s], ph);      // P*V(j-2) has consumed the stage
-        mbar_arrive_expect_tx(&v_full[s], 16384);
-        tma_load_3d(sV + s * 16384, &tmV, &v_full[s], 0, j * kFaBlockKeys, zk);
+        if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
+        mbar_arrive_expect_tx(v_full, 16384);
+        tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, zk);
       }
     }
   } else if (warp == 1) {
@@ -142,37 +135,27 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
       mbar_wait(q_full, 0);
       const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
-      auto issue_s = [&](int j) {
+      const uint32_t vbase = smem_u32(sV);
+      for (int j = 0; j < nblk; ++j) {
         const int s = j & 1;
         mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
         tc_fence_after();
         const uint64_t kdesc = make_smem_desc_k_sw128(smem_u32(sK + s * 16384), 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tS + s * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&k_empty[s]);
-        umma_commit(&s_full[s]);
-      };
-      // S buffer j&1 is free again once the softmax of block j-2 has arrived on p_full, which the loop
-      // below has always waited for (PV(j-2)) before S(j) is issued.
-      issue_s(0);
-      if (nblk > 1) issue_s(1);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&v_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+        umma_commit(s_full);
+        mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
         mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
         tc_fence_after();
-        const uint32_t vbase = smem_u32(sV + s * 16384);
-        const uint32_t pbase = smem_u32(sP + s * 32768);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
-          const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
+          const uint64_t pdesc = make_smem_desc_k_sw128(smem_u32(sP + (k >> 2) * 16384), 1024) + 2 * (k & 3);
           const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
           umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&v_empty[s]);
         umma_commit(pv_done);
-        if (j + 2 < nblk) issue_s(j + 2);
       }
     }
   } else {
@@ -180,31 +163,33 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int half = (warp - 2) >> 2;          // which 64 keys of the block / which 32 output columns
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tSh = tS + lane_off + half * 64;
     const uint32_t tOh = tO + lane_off + half * 32;
+    uint8_t* slab = sP + half * 16384 + row * 128;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(&s_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
       tc_fence_after();
       const int kvalid = min(64, nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
-      // my 64 logits stay in registers between the max pass and the exp pass
-      float v[64];
-      tmem_ld_32x32(tS + s * 128 + lane_off + half * 64, v);
-      tmem_ld_32x32(tS + s * 128 + lane_off + half * 64 + 32, v + 32);
-      tmem_ld_wait();
+      // pass 1: maximum of my 64 logits (raw; the positive scale is applied once)
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (kvalid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
-      } else {
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tSh + c, v);
+        tmem_ld_wait();
+        if (kvalid >= 64) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        }
       }
-      float* xm = xchg + s * 256;              // per-parity exchange slots: no reuse hazard between blocks
-      xm[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       fa_pair_sync();
-      const float bm = fmaxf(xm[row], xm[128 + row]) * p.scale_log2;
+      const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
       float alpha = 1.f;
       bool need = false;
       if (j == 0) {
@@ -214,7 +199,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         m_used = bm;
         need = true;
       }
-      // O (rescale) and the P buffer of block j-2 are owned by the tensor core until P*V(j-1) completes
+      // P and O are still being read / written by the previous P*V until pv_done fires
       if (j > 0) {
         mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);
         tc_fence_after();
@@ -229,24 +214,30 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_st_32x32(tOh, o);
         tmem_st_wait();
       }
-      // probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
-      uint8_t* slab = sP + s * 32768 + half * 16384 + row * 128;
+      // pass 2: probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
-        if (kvalid < 64 && i >= kvalid) e = 0.f;
-        ls[i & 3] += e;
-        v[i] = e;
-      }
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tSh + c, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint4 w;
-        w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
-        w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
-        w.z = pack_half2(v[8 * u + 4], v[8 * u + 5]);
-        w.w = pack_half2(v[8 * u + 6], v[8 * u + 7]);
-        *reinterpret_cast<uint4*>(slab + ((u ^ (row & 7)) << 4)) = w;
+        for (int i = 0; i < 32; ++i) {
+          float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+          if (kvalid < 64 && c + i >= kvalid) e = 0.f;
+          ls[i & 3] += e;
+          v[i] = e;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (c >> 3) + u;
+          uint4 w;
+          w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
+          w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
+          w.z = pack_half2(v[8 * u + 4], v[8 * u + 5]);
+          w.w = pack_half2(v[8 * u + 6], v[8 * u + 7]);
+          *reinterpret_cast<uint4*>(slab + ((unit ^ (row & 7)) << 4)) = w;
+        }
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       fence_proxy_async_smem();
@@ -278,7 +269,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,

@@ -182,24 +182,46 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < 8; ++j) br[j] = s_b1a[g * 8 + j];
     const float inv255 = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32F, 1.0/255.0): value * float(1/255)
-    int seq = 0;
-    for (int t = first; t < total; t += stride, ++seq) {
-      const int hb = seq & 1;
+    // image patch (20 x 20 pixels around the tile) of tile t, two elements per thread, as fp32 * (1/255)
+    auto load_patch = [&](int t, float* pre) {
       const int z = t / tiles_per_img, r = t % tiles_per_img;
       const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
-      float* patch = s_patch + hb * kPipePatchFloats;
       const uint8_t* im = p.img + static_cast<size_t>(z) * p.img_h * p.img_w;
-      // patch(seq) was last read while producing halo(seq-2), which every producer finished before
-      // arriving on halo_full two tiles ago -> safe to overwrite after the halo_empty wait below
-      mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq >> 1) & 1u) ^ 1u);
-      for (int i = tid; i < kPipePatchFloats; i += 256) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * 256;
         const int pr = i / 20, pc = i - pr * 20;
         const int y = h0 - 2 + pr, x = w0 - 2 + pc;
         float v = 0.f;
-        if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) v = static_cast<float>(im[static_cast<size_t>(y) * p.img_w + x]) * inv255;
-        patch[i] = v;
+        if (i < kPipePatchFloats && y >= 0 && y < p.img_h && x >= 0 && x < p.img_w)
+          v = static_cast<float>(__ldg(im + static_cast<size_t>(y) * p.img_w + x)) * inv255;
+        pre[k] = v;
+      }
+    };
+    auto store_patch = [&](float* patch, const float* pre) {
+      patch[tid] = pre[0];
+      if (tid + 256 < kPipePatchFloats) patch[tid + 256] = pre[1];
+    };
+    int seq = 0;
+    {
+      float pre[2];
+      if (first < total) {
+        load_patch(first, pre);
+        store_patch(s_patch, pre);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
+    }
+    for (int t = first; t < total; t += stride, ++seq) {
+      const int hb = seq & 1;
+      const int r = t % tiles_per_img;
+      const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
+      const float* patch = s_patch + hb * kPipePatchFloats;
+      // software pipeline: the global loads of the NEXT tile's patch are in flight while this tile's
+      // halo is computed; they are published to the other patch buffer at the end of the iteration
+      float pre[2];
+      const int tn = t + stride;
+      if (tn < total) load_patch(tn, pre);
+      mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq >> 1) & 1u) ^ 1u);
       uint8_t* halo = s_halo + hb * kPipeHaloBytes;
       int px = tid >> 3;   // 32 halo pixels per sweep
       int hy = px / 18, hx = px - hy * 18;
@@ -232,6 +254,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&halo_full[hb]);
+      if (tn < total) store_patch(s_patch + (hb ^ 1) * kPipePatchFloats, pre);
+      asm volatile("bar.sync 3, 256;" ::: "memory");   // patch[hb^1] published, patch[hb] no longer read
     }
   }
   tc_fence_before();

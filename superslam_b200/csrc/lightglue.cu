@@ -20,7 +20,6 @@
 #include <string>
 
 #include "attention.cuh"
-#include "attention_v2.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -416,8 +415,8 @@ struct EpiResidual {
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float* p = xt + static_cast<size_t>(col + j) * 128;
-          const float x = valid ? *p + (v[j] + __ldg(bias + col + j)) : 0.f;
+          float* p = xt + static_cast<size_t>(c.n0 + col + j) * 128;
+          const float x = valid ? *p + (v[j] + __ldg(bias + c.n0 + col + j)) : 0.f;
           *p = x;
           v[j] = x;
         }
@@ -433,7 +432,7 @@ struct EpiResidual {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(&tm_x16, c.stage, g0, row0, c.z);
+        tma_store_3d(&tm_x16, c.stage, c.n0 + g0, row0, c.z);
         bulk_commit();
       }
     }
@@ -552,7 +551,9 @@ static int make_linear(LgWeights* W, LgLinear* L, const std::vector<float>& w, c
   uint64_t dims[3] = {static_cast<uint64_t>(k), static_cast<uint64_t>(n), 1};
   uint64_t strides[2] = {static_cast<uint64_t>(k) * 2, static_cast<uint64_t>(n) * k * 2};
   uint32_t box[3] = {64, static_cast<uint32_t>(n > 256 ? 256 : n), 1};
-  return encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box);
+  SSB_RETURN_IF(encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box));
+  uint32_t box128[3] = {64, 128, 1};   // 128-row boxes (N tiles of 128 with resident weights)
+  return encode_tmap_f16(&L->tmB128, L->w, 3, dims, strides, box128);
 }
 
 int LgWeights::load(const char* path, int dev) {
@@ -775,9 +776,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     {
-      CoreParams p = lin("lg.ffn2", 8, 0, 256);
+      CoreParams p = lin("lg.ffn2", 8, 0, 128);   // two N tiles of 128: each CTA keeps its 128 KB of weights
+      p.b_resident = 1;
       EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
-      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB128, p, e, dim3(tiles, 2, P2), stream));
     }
     return SSB_OK;
   };
@@ -790,10 +792,6 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     fp.scale_log2 = scale * 1.4426950408889634f;
     fp.ctx = ctx_;
     fp.kp = KP;
-    static const bool v2 = std::getenv("SSB_FA_V2") != nullptr;   // A/B experiment, removed once decided
-    if (v2)
-      return launch_flash_attention_v2(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
-                                       key_xor ? "lg.attn_cross" : "lg.attn_self");
     return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
                                   key_xor ? "lg.attn_cross" : "lg.attn_self");
   };
@@ -807,12 +805,14 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
+      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     {
       CoreParams p = lin("lg.out_proj", 4, 0, 256);
+      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiBias16 e{L.out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -821,12 +821,14 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
+      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     {
       CoreParams p = lin("lg.to_out", 4, 0, 256);
+      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiBias16 e{L.to_out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -836,6 +838,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   // ---- assignment ----
   {
     CoreParams p = lin("lg.final_proj", 4, 0, 256);
+      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
     EpiSplit e{w_->final_proj.bias, ts_mda_, ts_mdb_};
     SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }

@@ -27,6 +27,7 @@ struct LgLinear {
   __half* w = nullptr;   // [n][k] fp16, K-major rows (B operand)
   float* bias = nullptr; // [n]
   CUtensorMap tmB;
+  CUtensorMap tmB128;    // same matrix, 128-row boxes
 };
 
 struct LgBlockFfn {

@@ -62,6 +62,11 @@ struct CoreParams {
   // without a host round trip): tiles whose first row >= m_valid or first column >= n_valid are skipped,
   // rows >= m_valid are masked by the epilogues, K chunks beyond ceil(k_valid / 64) are not issued.
   DevCount m_valid, n_valid, k_valid;
+  // Resident B (weights): each CTA serves ONE N tile (y = blockIdx.x % grid_y), loads that tile's whole
+  // [block_n x K] weight slab into shared memory once and streams only A through the ring.  For the
+  // skinny LightGlue GEMMs (K = 256/512) re-loading B per tile made L2->SM bandwidth the bound.
+  int b_resident;
+  int resident_bytes;
   const char* label;   // host-only: kernel name for the event profiler
 };
 
@@ -116,9 +121,9 @@ __host__ __device__ inline int core_stage_bytes(int block_n) { return kATileByte
 
 constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp
 
-inline int core_smem_bytes(int block_n, int stages) {
-  return stages * core_stage_bytes(block_n) + kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-         1024 /*xchg*/;
+inline int core_smem_bytes(int block_n, int stages, int resident_bytes = 0) {
+  return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) + kCoreStagingBytes +
+         1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
 }
 
 template <class Epi>
@@ -129,13 +134,16 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
   // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = core_stage_bytes(p.block_n);
-  uint8_t* staging = smem + p.stages * stage_bytes;   // 8 x 4 KiB, 1024-aligned (stage sizes are multiples of 1 KiB)
+  const int stage_bytes = p.b_resident ? kATileBytes : core_stage_bytes(p.block_n);
+  uint8_t* s_res = smem;                               // resident weights (b_resident), else empty
+  uint8_t* ring = smem + p.resident_bytes;
+  uint8_t* staging = ring + p.stages * stage_bytes;    // 8 x 4 KiB, 1024-aligned (all sizes are multiples of 1 KiB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kCoreStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   float* xchg = reinterpret_cast<float*>(staging + kCoreStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -149,6 +157,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
@@ -163,13 +172,18 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total = p.grid_x * p.grid_y * p.grid_z;
+  // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B - a fixed y per CTA
+  const int ny = p.b_resident ? p.grid_y : 1;
+  const int y_fixed = static_cast<int>(blockIdx.x) % ny;
+  const int first = static_cast<int>(blockIdx.x) / ny;
+  const int stride = static_cast<int>(gridDim.x) / ny;
+  const int total = p.b_resident ? p.grid_x * p.grid_z : p.grid_x * p.grid_y * p.grid_z;
 
   // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
     const int x = tile % p.grid_x;
-    const int y = (tile / p.grid_x) % p.grid_y;
-    z = tile / (p.grid_x * p.grid_y);
+    const int y = p.b_resident ? y_fixed : (tile / p.grid_x) % p.grid_y;
+    z = p.b_resident ? tile / p.grid_x : tile / (p.grid_x * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
@@ -184,8 +198,16 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      if (p.b_resident) {
+        const int kct = p.kc0 + p.kc1;
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(kct * p.block_n * 128));
+        for (int c = 0; c < kct; ++c)
+          for (int part = 0; part < p.n_parts; ++part)
+            tma_load_3d(s_res + (c * p.block_n + part * p.n_part) * 128, &tmB, b_full, c * kChunkK,
+                        y_fixed * p.block_n + part * p.n_part, p.b_z_add);
+      }
       int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = first; tile < total; tile += stride) {
         int z, w0, h0, n0, m_valid, kc0;
         if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
         const int kc = kc0 + p.kc1;
@@ -199,7 +221,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
               mbar_wait(&empty_bar[s], ph ^ 1u);
               mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-              uint8_t* sa = smem + s * stage_bytes;
+              uint8_t* sa = ring + s * stage_bytes;
               uint8_t* sb = sa + kATileBytes;
               if (c < kc0) {
                 tma_load_4d(sa, &tmA0, &full_bar[s], c * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
@@ -209,7 +231,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               // B columns: source-1 chunks follow the *nominal* source-0 chunk count so that weight
               // matrices keep their layout when kc0 is clipped by k_valid.
               const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
-              for (int part = 0; part < p.n_parts; ++part) {
+              for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
                 tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
                             tap * p.b_tap_rows + n0 + part * p.n_part, bz);
               }
@@ -221,8 +243,12 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
+      if (p.b_resident) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
       int it = 0, seq = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = first; tile < total; tile += stride) {
         int z, w0, h0, n0, m_valid, kc0;
         if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
         const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
@@ -236,8 +262,13 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t sa = smem_u32(ring + s * stage_bytes);
+          // resident B: chunk index within the tap (taps == 1 for the linear layers that use it)
+          const int kcs = kc0 + p.kc1;
+          const int cidx = kk % kcs;
+          const uint32_t sb = p.b_resident
+                                  ? smem_u32(s_res) + static_cast<uint32_t>((cidx < kc0 ? cidx : p.kc0 + (cidx - kc0)) * p.block_n * 128)
+                                  : sa + kATileBytes;
           const uint64_t adesc = make_smem_desc_k_sw128(sa, 1024);
 #pragma unroll 1
           for (int part = 0; part < p.n_parts; ++part) {
@@ -259,7 +290,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = ew >> 2;         // two warps per quadrant
     int seq = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
       if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
@@ -349,8 +380,20 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   p.grid_x = static_cast<int>(grid.x);
   p.grid_y = static_cast<int>(grid.y);
   p.grid_z = static_cast<int>(grid.z);
+  if (p.b_resident) {
+    p.resident_bytes = (p.kc0 + p.kc1) * p.block_n * 128;
+    const int room = 224 * 1024 - kCoreStagingBytes - 4096 - p.resident_bytes;
+    p.stages = room / kATileBytes;
+    if (p.stages > 6) p.stages = 6;
+    if (p.taps_h * p.taps_w != 1 || p.stages < 2) {
+      set_last_error("launch_core: resident B needs taps == 1 and a weight slab <= ~150 KB");
+      return SSB_ERR_INVALID;
+    }
+  } else {
+    p.resident_bytes = 0;
+  }
   if (p.stages <= 0) p.stages = core_pick_stages(p.block_n);
-  const int smem = core_smem_bytes(p.block_n, p.stages);
+  const int smem = core_smem_bytes(p.block_n, p.stages, p.resident_bytes);
   static int configured_smem = 0;  // per template instantiation
   if (smem > configured_smem) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -358,7 +401,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   }
   const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
   if (total <= 0) return SSB_OK;
-  const int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+  int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+  if (p.b_resident) {
+    const long long xz = static_cast<long long>(grid.x) * grid.z;
+    const int per = device_sm_count() / static_cast<int>(grid.y);
+    ctas = static_cast<int>((xz < per ? xz : per) * grid.y);
+  }
   umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
