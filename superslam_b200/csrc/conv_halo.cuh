@@ -204,7 +204,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.half = 0;
     c.xchg = nullptr;
     // every MMA has completed (accum_bar), so the halo buffer is free: reuse it as TMA-store staging
-    c.stage = s_halo + (warp - 2) * 4096;
+    c.stage = s_halo + (warp - 2) * 8192;   // 2 x 4 KiB per warp
+    c.stage_cur = c.stage;
+    c.stage_bufs = 2;
+    c.stage_sel = 0;
     c.py = h0 + (c.row >> 3);
     for (int sub = 0; sub < p.subtiles; ++sub) {
       c.px = w0 + sub * 8 + (c.row & 7);

@@ -21,7 +21,7 @@ namespace ssb {
 
 constexpr int kPipeHaloBytes = 41984;                 // 18*18*128 = 41472, rounded up to 1 KiB
 constexpr int kPipeWeightBytes = 9 * 64 * 128;        // 73,728
-constexpr int kPipeStagingBytes = 4 * 4096;
+constexpr int kPipeStagingBytes = 4 * 2 * 4096;      // double-buffered 4 KiB staging per epilogue warp
 constexpr int kPipePatchFloats = 20 * 20;
 constexpr int kPipeThreads = 192;
 constexpr int kPipeThreadsFused = 192 + 256;
@@ -150,7 +150,10 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.col_end = 64;
     c.half = 0;
     c.xchg = nullptr;
-    c.stage = s_stage + (warp - 2) * 4096;
+    c.stage = s_stage + (warp - 2) * 8192;
+    c.stage_cur = c.stage;
+    c.stage_bufs = 2;
+    c.stage_sel = 0;
     for (int t = first; t < total; t += stride, ++seq) {
       const int b = seq & 1;
       const int z = t / tiles_per_img, r = t % tiles_per_img;

@@ -206,7 +206,7 @@ struct EpiQkvRope {
   int kp;
   int rope;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int row = c.px;
     const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
@@ -252,7 +252,7 @@ struct EpiQkvRope {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(tm, c.stage, 0, row0, c.z * kLgHeads + (g0 >> 6));
+        tma_store_3d(tm, c.stage_cur, 0, row0, c.z * kLgHeads + (g0 >> 6));
         bulk_commit();
       }
     }
@@ -264,7 +264,7 @@ struct EpiBias16 {
   const float* bias;
   CUtensorMap tm_out;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int row = c.px;
     const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
@@ -290,7 +290,7 @@ struct EpiBias16 {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(&tm_out, c.stage, c.n0 + g0, row0, c.z);
+        tma_store_3d(&tm_out, c.stage_cur, c.n0 + g0, row0, c.z);
         bulk_commit();
       }
     }
@@ -322,7 +322,7 @@ struct EpiLnGelu {
   const float* b;
   CUtensorMap tm_out;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int row = c.px;
     const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
@@ -383,7 +383,7 @@ struct EpiLnGelu {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(&tm_out, c.stage, g0, row0, c.z);
+        tma_store_3d(&tm_out, c.stage_cur, g0, row0, c.z);
         bulk_commit();
       }
     }
@@ -400,7 +400,7 @@ struct EpiResidual {
   CUtensorMap tm_x16;
   int kp;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int row = c.px;
     const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
@@ -432,7 +432,7 @@ struct EpiResidual {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(&tm_x16, c.stage, c.n0 + g0, row0, c.z);
+        tma_store_3d(&tm_x16, c.stage_cur, c.n0 + g0, row0, c.z);
         bulk_commit();
       }
     }
@@ -447,7 +447,7 @@ struct EpiStoreF32 {
   float scale;
   int block_n;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool has_acc) const {
+  __device__ void operator()(EpiCtx& c, bool has_acc) const {
     const int row = c.px;
     const bool valid = row < c.m_valid;
     for (int col = c.col_begin; col < c.col_end; col += 32) {
@@ -475,7 +475,7 @@ struct EpiSplit {
   const float* bias;
   CUtensorMap tm_a, tm_b;   // 3-D (768, kp, 2P)
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int row = c.px;
     const int row0 = __shfl_sync(0xffffffffu, row, 0);
     const bool valid = row < c.m_valid;
@@ -509,13 +509,13 @@ struct EpiSplit {
         stage_fence(c);
         if (c.lane == 0) {
           if (part == 0) {
-            tma_store_3d(&tm_a, c.stage, g0, row0, c.z);
-            tma_store_3d(&tm_a, c.stage, 256 + g0, row0, c.z);
-            tma_store_3d(&tm_b, c.stage, g0, row0, c.z);
-            tma_store_3d(&tm_b, c.stage, 512 + g0, row0, c.z);
+            tma_store_3d(&tm_a, c.stage_cur, g0, row0, c.z);
+            tma_store_3d(&tm_a, c.stage_cur, 256 + g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage_cur, g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage_cur, 512 + g0, row0, c.z);
           } else {
-            tma_store_3d(&tm_a, c.stage, 512 + g0, row0, c.z);
-            tma_store_3d(&tm_b, c.stage, 256 + g0, row0, c.z);
+            tma_store_3d(&tm_a, c.stage_cur, 512 + g0, row0, c.z);
+            tma_store_3d(&tm_b, c.stage_cur, 256 + g0, row0, c.z);
           }
           bulk_commit();
         }
@@ -776,10 +776,9 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     {
-      CoreParams p = lin("lg.ffn2", 8, 0, 128);   // two N tiles of 128: each CTA keeps its 128 KB of weights
-      p.b_resident = 1;
+      CoreParams p = lin("lg.ffn2", 8, 0, 256);
       EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
-      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB128, p, e, dim3(tiles, 2, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     return SSB_OK;
   };
@@ -805,14 +804,12 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
-      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     {
       CoreParams p = lin("lg.out_proj", 4, 0, 256);
-      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiBias16 e{L.out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -821,14 +818,12 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
-      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     {
       CoreParams p = lin("lg.to_out", 4, 0, 256);
-      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
       EpiBias16 e{L.to_out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
@@ -838,7 +833,6 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   // ---- assignment ----
   {
     CoreParams p = lin("lg.final_proj", 4, 0, 256);
-      p.b_resident = 1;   // 128 KB weight slab stays in shared memory
     EpiSplit e{w_->final_proj.bias, ts_mda_, ts_mdb_};
     SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }

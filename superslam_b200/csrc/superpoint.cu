@@ -96,7 +96,7 @@ struct EpiConvRelu {
   int pool;
   int row_xor;
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool has_acc) const {
+  __device__ void operator()(EpiCtx& c, bool has_acc) const {
     const int px0 = __shfl_sync(0xffffffffu, c.px, 0), py0 = __shfl_sync(0xffffffffu, c.py, 0);
     bool writer = true;
     int srow = c.lane;
@@ -112,31 +112,41 @@ struct EpiConvRelu {
         float v[32];
         tmem_ld_32x32(c.tmem_row + col, v);
         tmem_ld_wait();
-        const float* b = bias + c.n0 + col;
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
+        uint32_t h[16];   // bias + ReLU in fp32, then packed fp16 pairs
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf((has_acc ? v[j] : 0.f) + __ldg(b + j), 0.f);
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          const float x0 = fmaxf((has_acc ? v[4 * j + 0] : 0.f) + bb.x, 0.f);
+          const float x1 = fmaxf((has_acc ? v[4 * j + 1] : 0.f) + bb.y, 0.f);
+          const float x2 = fmaxf((has_acc ? v[4 * j + 2] : 0.f) + bb.z, 0.f);
+          const float x3 = fmaxf((has_acc ? v[4 * j + 3] : 0.f) + bb.w, 0.f);
+          h[2 * j] = pack_half2(x0, x1);
+          h[2 * j + 1] = pack_half2(x2, x3);
+        }
         if (pool) {
+          // fp16 rounding is monotonic, so max over the rounded values == rounding of the fp32 max:
+          // pool on packed half2 (half the shuffles, HMNMX2 instead of two FMNMX)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], row_xor));
+          for (int j = 0; j < 16; ++j) {
+            __half2 a = *reinterpret_cast<__half2*>(&h[j]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, h[j], 1);
+            a = __hmax2(a, *reinterpret_cast<__half2*>(&o1));
+            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, cur, row_xor);
+            a = __hmax2(a, *reinterpret_cast<__half2*>(&o2));
+            h[j] = *reinterpret_cast<uint32_t*>(&a);
           }
         }
         if (writer) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-            o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-            stage_put(c, srow, hc * 4 + j, o);
-          }
+          for (int j = 0; j < 4; ++j)
+            stage_put(c, srow, hc * 4 + j, make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
         }
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_4d(&tm_out, c.stage, c.n0 + g0, pool ? (px0 >> 1) : px0, pool ? (py0 >> 1) : py0, c.z);
+        tma_store_4d(&tm_out, c.stage_cur, c.n0 + g0, pool ? (px0 >> 1) : px0, pool ? (py0 >> 1) : py0, c.z);
         bulk_commit();
       }
     }
@@ -151,7 +161,7 @@ struct EpiScores {
   float* scores;      // [B][hs][ws]
   int Hc, Wc, hs, ws;
   static constexpr bool kSplit = false;  // the 65-way softmax needs the whole row in one thread
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     float v[80];
     tmem_ld_32x32(c.tmem_row, v);
     tmem_ld_32x32(c.tmem_row + 32, v + 32);
@@ -196,7 +206,7 @@ struct EpiDescNorm {
   const float* bias;
   CUtensorMap tm_out;  // 4-D (256, Wc, Hc, B), box (64, 16, 2, 1)
   static constexpr bool kSplit = true;
-  __device__ void operator()(const EpiCtx& c, bool) const {
+  __device__ void operator()(EpiCtx& c, bool) const {
     const int px0 = __shfl_sync(0xffffffffu, c.px, 0), py0 = __shfl_sync(0xffffffffu, c.py, 0);
     float ss = 0.f;
     for (int col = c.col_begin; col < c.col_end; col += 32) {
@@ -234,7 +244,7 @@ struct EpiDescNorm {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_4d(&tm_out, c.stage, g0, px0, py0, c.z);
+        tma_store_4d(&tm_out, c.stage_cur, g0, px0, py0, c.z);
         bulk_commit();
       }
     }

@@ -67,6 +67,7 @@ struct CoreParams {
   // skinny LightGlue GEMMs (K = 256/512) re-loading B per tile made L2->SM bandwidth the bound.
   int b_resident;
   int resident_bytes;
+  int stage_bufs;      // TMA-store staging depth per epilogue warp (2 unless shared memory is short)
   const char* label;   // host-only: kernel name for the event profiler
 };
 
@@ -82,19 +83,26 @@ struct EpiCtx {
                            // split the tile's columns; functors with kSplit == false get all of them)
   int half;            // 0 or 1: which of the two warps sharing this lane quadrant
   float* xchg;         // shared scratch [2][128] floats for row reductions across the two halves
-  uint8_t* stage;      // this warp's 4 KiB staging buffer (1024-byte aligned) for TMA stores
+  uint8_t* stage;      // this warp's staging area for TMA stores: stage_bufs x 4 KiB, 1024-byte aligned
+  uint8_t* stage_cur;  // buffer selected by the last stage_begin()
+  int stage_bufs;      // 1 or 2 (double-buffered: the next block is staged while the last store drains)
+  int stage_sel;
 };
 
 // ---- staged output: registers -> 128B-swizzled shared memory -> one TMA store per 32-row x 64-column
 // block.  A thread that owns a row writing 16-byte pieces straight to global memory touches 32
 // different lines per warp instruction (measured ~1 TB/s); the bulk store writes full lines.
 // All four calls are warp-collective.
-__device__ __forceinline__ void stage_begin(const EpiCtx& c) {   // previous store has drained the buffer
-  if (c.lane == 0) bulk_wait_read0();
+__device__ __forceinline__ void stage_begin(EpiCtx& c) {   // pick a buffer whose last store has been read out
+  if (c.lane == 0) {
+    if (c.stage_bufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+  }
   __syncwarp();
+  c.stage_cur = c.stage + (c.stage_bufs == 2 ? c.stage_sel * 4096 : 0);
+  c.stage_sel ^= 1;
 }
 __device__ __forceinline__ void stage_put(const EpiCtx& c, int srow, int chunk, uint4 v) {
-  *reinterpret_cast<uint4*>(c.stage + srow * 128 + ((chunk ^ (srow & 7)) << 4)) = v;
+  *reinterpret_cast<uint4*>(c.stage_cur + srow * 128 + ((chunk ^ (srow & 7)) << 4)) = v;
 }
 __device__ __forceinline__ void stage_fence(const EpiCtx&) {
   fence_proxy_async_smem();
@@ -119,11 +127,11 @@ __device__ __forceinline__ float epi_pair_sum(const EpiCtx& c, float v) {
 
 __host__ __device__ inline int core_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
 
-constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp
+constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp (x stage_bufs)
 
-inline int core_smem_bytes(int block_n, int stages, int resident_bytes = 0) {
-  return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) + kCoreStagingBytes +
-         1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
+inline int core_smem_bytes(int block_n, int stages, int resident_bytes, int stage_bufs) {
+  return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) +
+         stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
 }
 
 template <class Epi>
@@ -138,13 +146,13 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint8_t* s_res = smem;                               // resident weights (b_resident), else empty
   uint8_t* ring = smem + p.resident_bytes;
   uint8_t* staging = ring + p.stages * stage_bytes;    // 8 x 4 KiB, 1024-aligned (all sizes are multiples of 1 KiB)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kCoreStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + p.stage_bufs * kCoreStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-  float* xchg = reinterpret_cast<float*>(staging + kCoreStagingBytes + 256);
+  float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -290,6 +298,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = ew >> 2;         // two warps per quadrant
     int seq = 0;
+    EpiCtx c;
+    c.stage = staging + ew * (p.stage_bufs * 4096);
+    c.stage_cur = c.stage;
+    c.stage_bufs = p.stage_bufs;
+    c.stage_sel = 0;
     for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
       if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
@@ -298,7 +311,6 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
       mbar_wait(&tmem_full[buf], use & 1u);
       tc_fence_after();
-      EpiCtx c;
       c.row = q * 32 + lane;
       c.lane = lane;
       c.px = w0 + (c.row % p.tile_w);
@@ -308,7 +320,6 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       c.m_valid = m_valid;
       c.half = half;
       c.xchg = xchg;
-      c.stage = staging + ew * 4096;
       c.tmem_row = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
       if (Epi::kSplit) {
         const int hw = p.block_n / 2;
@@ -338,14 +349,6 @@ inline int core_tmem_cols(int cols) {
   int c = 32;
   while (c < cols) c <<= 1;
   return c;
-}
-
-inline int core_pick_stages(int block_n) {
-  const int sb = core_stage_bytes(block_n);
-  int st = (190 * 1024 - kCoreStagingBytes) / sb;   // one persistent CTA per SM owns the shared memory
-  if (st > 6) st = 6;
-  if (st < 2) st = 2;
-  return st;
 }
 
 inline int device_sm_count() {
@@ -380,7 +383,9 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   p.grid_x = static_cast<int>(grid.x);
   p.grid_y = static_cast<int>(grid.y);
   p.grid_z = static_cast<int>(grid.z);
+  p.stage_bufs = 2;
   if (p.b_resident) {
+    p.stage_bufs = 1;
     p.resident_bytes = (p.kc0 + p.kc1) * p.block_n * 128;
     const int room = 224 * 1024 - kCoreStagingBytes - 4096 - p.resident_bytes;
     p.stages = room / kATileBytes;
@@ -392,8 +397,18 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   } else {
     p.resident_bytes = 0;
   }
-  if (p.stages <= 0) p.stages = core_pick_stages(p.block_n);
-  const int smem = core_smem_bytes(p.block_n, p.stages, p.resident_bytes);
+  if (p.stages <= 0) {
+    // 222 KiB budget: ring as deep as fits next to a double-buffered staging area, at least 2 stages;
+    // very wide tiles (block_n 512) fall back to single-buffered staging
+    const int sb = core_stage_bytes(p.block_n);
+    int st = (222 * 1024 - 2 * kCoreStagingBytes - 4096) / sb;
+    if (st < 2) {
+      p.stage_bufs = 1;
+      st = (222 * 1024 - kCoreStagingBytes - 4096) / sb;
+    }
+    p.stages = st > 6 ? 6 : (st < 2 ? 2 : st);
+  }
+  const int smem = core_smem_bytes(p.block_n, p.stages, p.resident_bytes, p.stage_bufs);
   static int configured_smem = 0;  // per template instantiation
   if (smem > configured_smem) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
