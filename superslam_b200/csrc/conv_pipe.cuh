@@ -28,6 +28,23 @@ constexpr int kPipeThreadsFused = 192 + 256;
 constexpr int kPipeSmemBytes = kPipeWeightBytes + 2 * kPipeHaloBytes + kPipeStagingBytes + 2 * kPipePatchFloats * 4 +
                                (576 + 64) * 4 + 256 + 1024;
 
+// Packed fp32x2 FMA (sm_100: FFMA2): two IEEE fp32 fused multiply-adds per instruction.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 struct PipeParams {
   int tiles_w, tiles_h, batch;   // 16x16-pixel tiles per image
   int n_slices;                  // Cout / 64; CTA c serves slice c % n_slices
@@ -177,13 +194,15 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // conv1a producers: 256 threads; thread owns channel group (tid & 7) with its weights in registers.
     const int tid = threadIdx.x - 192;
     const int g = tid & 7;
-    float wr[72], br[8];
+    // weights / bias as fp32x2 pairs for FFMA2 (same per-element IEEE fma as the scalar chain)
+    unsigned long long wr[36], br[4];
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wr[tp * 8 + j] = s_w1a[tp * 64 + g * 8 + j];
+      for (int j = 0; j < 4; ++j)
+        wr[tp * 4 + j] = pack_f32x2(s_w1a[tp * 64 + g * 8 + 2 * j], s_w1a[tp * 64 + g * 8 + 2 * j + 1]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) br[j] = s_b1a[g * 8 + j];
+    for (int j = 0; j < 4; ++j) br[j] = pack_f32x2(s_b1a[g * 8 + 2 * j], s_b1a[g * 8 + 2 * j + 1]);
     const float inv255 = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32F, 1.0/255.0): value * float(1/255)
     // image patch (20 x 20 pixels around the tile) of tile t, two elements per thread, as fp32 * (1/255)
     auto load_patch = [&](int t, float* pre) {
@@ -232,20 +251,23 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int y = h0 - 1 + hy, x = w0 - 1 + hx;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);   // outside the image: conv1b's zero padding
         if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) {
-          float acc[8];
+          unsigned long long acc[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = br[j];
+          for (int j = 0; j < 4; ++j) acc[j] = br[j];
           const float* pp = patch + hy * 20 + hx;
 #pragma unroll
           for (int tp = 0; tp < 9; ++tp) {
             const float v = pp[(tp / 3) * 20 + (tp % 3)];
+            const unsigned long long vv = pack_f32x2(v, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[tp * 8 + j], acc[j]);
+            for (int j = 0; j < 4; ++j) acc[j] = ffma2(vv, wr[tp * 4 + j], acc[j]);
           }
-          o.x = pack_half2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-          o.y = pack_half2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-          o.z = pack_half2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-          o.w = pack_half2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+          const float2 a0 = unpack_f32x2(acc[0]), a1 = unpack_f32x2(acc[1]), a2 = unpack_f32x2(acc[2]),
+                       a3 = unpack_f32x2(acc[3]);
+          o.x = pack_half2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
+          o.y = pack_half2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
+          o.z = pack_half2(fmaxf(a2.x, 0.f), fmaxf(a2.y, 0.f));
+          o.w = pack_half2(fmaxf(a3.x, 0.f), fmaxf(a3.y, 0.f));
         }
         *reinterpret_cast<uint4*>(halo + px * 128 + ((g ^ (px & 7)) << 4)) = o;
         hx += 32;

@@ -260,6 +260,7 @@ struct EpiQkvRope {
 };
 
 // bias -> fp16 rows [z][kp][256] (out_proj / to_out).
+// bias -> fp16 rows [z][kp][256] (out_proj / to_out).
 struct EpiBias16 {
   const float* bias;
   CUtensorMap tm_out;

@@ -570,7 +570,7 @@ int SuperPoint::init(const char* weights_path, int max_keypoints, double thresho
   SSB_RETURN_IF(load_layer(ar, "convPb", 256, 65, 1, &lpb_));
   SSB_RETURN_IF(load_layer(ar, "convDb", 256, 256, 1, &ldb_));
   SSB_RETURN_IF(pool_.init(num_slots > 0 ? num_slots : 8, max_keypoints));
-  SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&desc_ptrs_dev_), 64 * sizeof(void*)));
+  SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&desc_ptrs_dev_), 128 * sizeof(void*)));
   return SSB_OK;
 }
 
@@ -819,7 +819,7 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
 int SuperPoint::extract(const uint8_t* const* images, int batch, int h, int w, int row_stride,
                         int channels, float* const* xy, float* const* score, int* count,
                         void** desc_dev, int* slot) {
-  SSB_CHECK(images != nullptr && batch >= 1 && batch <= 64, SSB_ERR_INVALID, "bad batch %d", batch);
+  SSB_CHECK(images != nullptr && batch >= 1 && batch <= 128, SSB_ERR_INVALID, "bad batch %d", batch);
   SSB_CHECK(channels == 1 || channels == 3, SSB_ERR_INVALID, "channels must be 1 or 3");
   SSB_CHECK(row_stride >= w * channels, SSB_ERR_INVALID, "row_stride smaller than a row");
   SSB_CUDA_CHECK(cudaSetDevice(device_));

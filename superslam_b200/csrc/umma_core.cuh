@@ -11,16 +11,16 @@
 //
 // Persistent: one CTA per SM walks the (x, y, z) tile space; the accumulator is double-buffered in
 // TMEM (2 x BLOCK_N columns) so the epilogue of tile t overlaps the TMA loads and MMAs of tile t+1.
-// Warp roles (352 threads): warp 0 = TMA producer for A, warp 10 = TMA producer for B, warp 1 = TMEM
-// allocator + MMA issuer, warps 2..9 = epilogue; warp w may only touch TMEM lanes 32*(w%4)..+31, so two
-// warps share each lane quadrant and split the accumulator columns between them.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue; warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share each lane
+// quadrant and split the accumulator columns between them.
 #pragma once
 
 #include "common.cuh"
 
 namespace ssb {
 
-constexpr int kCoreThreads = 352;
+constexpr int kCoreThreads = 320;
 constexpr int kCoreEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                  // fp16 elements per 128-byte swizzle row
@@ -50,7 +50,7 @@ struct CoreParams {
   int tile_w, tile_h, tiles_w;
   // N tiling: n0 = y * block_n; the tile is issued as n_parts MMAs of n_part columns.
   int block_n, n_part, n_parts;
-  int a_stages, b_stages, tmem_cols, tmem_bufs, buf_stride;
+  int stages, tmem_cols, tmem_bufs, buf_stride;
   int grid_x, grid_y, grid_z;   // logical tile space walked by the persistent CTAs
   // batching over z
   int a_z_mul;         // A 4th coordinate = z * a_z_mul + a_z_add
@@ -62,6 +62,11 @@ struct CoreParams {
   // without a host round trip): tiles whose first row >= m_valid or first column >= n_valid are skipped,
   // rows >= m_valid are masked by the epilogues, K chunks beyond ceil(k_valid / 64) are not issued.
   DevCount m_valid, n_valid, k_valid;
+  // Resident B (weights): each CTA serves ONE N tile (y = blockIdx.x % grid_y), loads that tile's whole
+  // [block_n x K] weight slab into shared memory once and streams only A through the ring.  For the
+  // skinny LightGlue GEMMs (K = 256/512) re-loading B per tile made L2->SM bandwidth the bound.
+  int b_resident;
+  int resident_bytes;
   int stage_bufs;      // TMA-store staging depth per epilogue warp (2 unless shared memory is short)
   const char* label;   // host-only: kernel name for the event profiler
 };
@@ -120,17 +125,15 @@ __device__ __forceinline__ float epi_pair_sum(const EpiCtx& c, float v) {
   return t;
 }
 
+__host__ __device__ inline int core_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
+
 constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp (x stage_bufs)
 
-inline int core_smem_bytes(const CoreParams& p) {
-  return p.a_stages * kATileBytes + p.b_stages * p.n_part * 128 + p.stage_bufs * kCoreStagingBytes +
-         1024 /*align slack*/ + 512 /*barriers*/ + 1024 /*xchg*/;
+inline int core_smem_bytes(int block_n, int stages, int resident_bytes, int stage_bufs) {
+  return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) +
+         stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
 }
 
-// Separate rings for A and B: A (activations, usually coming from HBM, ~2 us away) is prefetched 5-8
-// k-steps deep in 16 KiB stages, B (weights / keys, L2 resident) only 2-4 part-stages deep.  With one
-// combined ring of 48 KiB stages only 3 x 16 KiB of A were in flight per SM and the skinny LightGlue
-// GEMMs (K = 256: 4 k-steps per tile) ran at ~1.5 TB/s, bound by HBM latency.
 template <class Epi>
 __global__ void __launch_bounds__(kCoreThreads, 1)
 umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -139,18 +142,17 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
   // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int b_stage_bytes = p.n_part * 128;
-  uint8_t* ring_a = smem;
-  uint8_t* ring_b = ring_a + p.a_stages * kATileBytes;
-  uint8_t* staging = ring_b + p.b_stages * b_stage_bytes;   // 8 x stage_bufs x 4 KiB, 1024-aligned
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(staging + p.stage_bufs * kCoreStagingBytes);
-  uint64_t* empty_a = full_a + p.a_stages;
-  uint64_t* full_b = empty_a + p.a_stages;
-  uint64_t* empty_b = full_b + p.b_stages;
-  uint64_t* tmem_full = empty_b + p.b_stages;   // [2]
+  const int stage_bytes = p.b_resident ? kATileBytes : core_stage_bytes(p.block_n);
+  uint8_t* s_res = smem;                               // resident weights (b_resident), else empty
+  uint8_t* ring = smem + p.resident_bytes;
+  uint8_t* staging = ring + p.stages * stage_bytes;    // 8 x 4 KiB, 1024-aligned (all sizes are multiples of 1 KiB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + p.stage_bufs * kCoreStagingBytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 512);
+  uint64_t* b_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,14 +161,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(&full_a[s], 1);
-      mbar_init(&empty_a[s], 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < p.b_stages; ++s) {
-      mbar_init(&full_b[s], 1);
-      mbar_init(&empty_b[s], 1);
-    }
+    mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
@@ -181,14 +180,18 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total = p.grid_x * p.grid_y * p.grid_z;
+  // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B - a fixed y per CTA
+  const int ny = p.b_resident ? p.grid_y : 1;
+  const int y_fixed = static_cast<int>(blockIdx.x) % ny;
+  const int first = static_cast<int>(blockIdx.x) / ny;
+  const int stride = static_cast<int>(gridDim.x) / ny;
+  const int total = p.b_resident ? p.grid_x * p.grid_z : p.grid_x * p.grid_y * p.grid_z;
 
-  // Decode a tile index (y = N tile varies fastest so that the N tiles of one M tile run back to back
-  // and re-read A from L2); returns false for tiles entirely outside the device-side extents.
+  // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
-    const int y = tile % p.grid_y;
-    const int x = (tile / p.grid_y) % p.grid_x;
-    z = tile / (p.grid_x * p.grid_y);
+    const int x = tile % p.grid_x;
+    const int y = p.b_resident ? y_fixed : (tile / p.grid_x) % p.grid_y;
+    z = p.b_resident ? tile / p.grid_x : tile / (p.grid_x * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
@@ -201,60 +204,59 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {   // ---- A producer ----
+    if (lane == 0) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      if (p.b_resident) {
+        const int kct = p.kc0 + p.kc1;
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(kct * p.block_n * 128));
+        for (int c = 0; c < kct; ++c)
+          for (int part = 0; part < p.n_parts; ++part)
+            tma_load_3d(s_res + (c * p.block_n + part * p.n_part) * 128, &tmB, b_full, c * kChunkK,
+                        y_fixed * p.block_n + part * p.n_part, p.b_z_add);
+      }
       int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = first; tile < total; tile += stride) {
         int z, w0, h0, n0, m_valid, kc0;
         if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
         const int kc = kc0 + p.kc1;
         const int az = z * p.a_z_mul + p.a_z_add;
+        const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
         for (int th = 0; th < p.taps_h; ++th) {
           for (int tw = 0; tw < p.taps_w; ++tw) {
+            const int tap = th * p.taps_w + tw;
             for (int c = 0; c < kc; ++c, ++it) {
-              const int s = it % p.a_stages;
-              mbar_wait(&empty_a[s], (static_cast<uint32_t>(it / p.a_stages) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&full_a[s], kATileBytes);
+              const int s = it % p.stages;
+              const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+              uint8_t* sa = ring + s * stage_bytes;
+              uint8_t* sb = sa + kATileBytes;
               if (c < kc0) {
-                tma_load_4d(ring_a + s * kATileBytes, &tmA0, &full_a[s], c * kChunkK, w0 + tw - p.pad,
-                            h0 + th - p.pad, az);
+                tma_load_4d(sa, &tmA0, &full_bar[s], c * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
               } else {
-                tma_load_4d(ring_a + s * kATileBytes, &tmA1, &full_a[s], (c - kc0) * kChunkK, w0 + tw - p.pad,
-                            h0 + th - p.pad, az);
+                tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
+              }
+              // B columns: source-1 chunks follow the *nominal* source-0 chunk count so that weight
+              // matrices keep their layout when kc0 is clipped by k_valid.
+              const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
+              for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
+                tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
+                            tap * p.b_tap_rows + n0 + part * p.n_part, bz);
               }
             }
           }
         }
       }
     }
-  } else if (warp == 10) {
-    if (lane == 0) {   // ---- B producer ----
-      int ib = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        int z, w0, h0, n0, m_valid, kc0;
-        if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
-        const int kc = kc0 + p.kc1;
-        const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
-        for (int tap = 0; tap < p.taps_h * p.taps_w; ++tap) {
-          for (int c = 0; c < kc; ++c) {
-            // B columns: source-1 chunks follow the *nominal* source-0 chunk count so that weight
-            // matrices keep their layout when kc0 is clipped by k_valid.
-            const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
-            for (int part = 0; part < p.n_parts; ++part, ++ib) {
-              const int s = ib % p.b_stages;
-              mbar_wait(&empty_b[s], (static_cast<uint32_t>(ib / p.b_stages) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&full_b[s], static_cast<uint32_t>(b_stage_bytes));
-              tma_load_3d(ring_b + s * b_stage_bytes, &tmB, &full_b[s], bcol,
-                          tap * p.b_tap_rows + n0 + part * p.n_part, bz);
-            }
-          }
-        }
-      }
-    }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer ----
+    if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
-      int it = 0, ib = 0, seq = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      if (p.b_resident) {
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+      }
+      int it = 0, seq = 0;
+      for (int tile = first; tile < total; tile += stride) {
         int z, w0, h0, n0, m_valid, kc0;
         if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
         const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
@@ -264,23 +266,28 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * p.buf_stride;
         for (int kk = 0; kk < num_k; ++kk, ++it) {
-          const int sa = it % p.a_stages;
-          mbar_wait(&full_a[sa], static_cast<uint32_t>(it / p.a_stages) & 1u);
-          const uint64_t adesc = make_smem_desc_k_sw128(smem_u32(ring_a + sa * kATileBytes), 1024);
+          const int s = it % p.stages;
+          const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + s * stage_bytes);
+          // resident B: chunk index within the tap (taps == 1 for the linear layers that use it)
+          const int kcs = kc0 + p.kc1;
+          const int cidx = kk % kcs;
+          const uint32_t sb = p.b_resident
+                                  ? smem_u32(s_res) + static_cast<uint32_t>((cidx < kc0 ? cidx : p.kc0 + (cidx - kc0)) * p.block_n * 128)
+                                  : sa + kATileBytes;
+          const uint64_t adesc = make_smem_desc_k_sw128(sa, 1024);
 #pragma unroll 1
-          for (int part = 0; part < p.n_parts; ++part, ++ib) {
-            const int sb = ib % p.b_stages;
-            mbar_wait(&full_b[sb], static_cast<uint32_t>(ib / p.b_stages) & 1u);
-            tc_fence_after();
-            const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(ring_b + sb * b_stage_bytes), 1024);
+          for (int part = 0; part < p.n_parts; ++part) {
+            const uint64_t bdesc = make_smem_desc_k_sw128(sb + part * p.n_part * 128, 1024);
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k) {
               // +32 bytes per K=16 slice inside the 128B swizzle row -> +2 in the (addr>>4) field
               umma_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty_b[sb]);
           }
-          umma_commit(&empty_a[sa]);
+          umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[buf]);
         ++seq;
@@ -296,7 +303,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     c.stage_cur = c.stage;
     c.stage_bufs = p.stage_bufs;
     c.stage_sel = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
       if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
@@ -376,19 +383,32 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   p.grid_x = static_cast<int>(grid.x);
   p.grid_y = static_cast<int>(grid.y);
   p.grid_z = static_cast<int>(grid.z);
-  // shared-memory plan (222 KiB): B ring 2 part-stages when a part is 32 KiB, else 3-4; double-buffered
-  // store staging unless the tile is very wide; everything left goes to the A ring (max 8 stages)
-  const int bsb = p.n_part * 128;
-  p.b_stages = bsb >= 32768 ? (p.n_parts > 1 ? 3 : 2) : (bsb >= 16384 ? 3 : 4);
-  p.stage_bufs = p.block_n > 256 ? 1 : 2;
-  const int room = 222 * 1024 - p.b_stages * bsb - p.stage_bufs * kCoreStagingBytes - 4096;
-  p.a_stages = room / kATileBytes;
-  if (p.a_stages > 8) p.a_stages = 8;
-  if (p.a_stages < 2) {
-    set_last_error("launch_core: no room for the A ring (block_n=%d)", p.block_n);
-    return SSB_ERR_INVALID;
+  p.stage_bufs = 2;
+  if (p.b_resident) {
+    p.stage_bufs = 1;
+    p.resident_bytes = (p.kc0 + p.kc1) * p.block_n * 128;
+    const int room = 224 * 1024 - kCoreStagingBytes - 4096 - p.resident_bytes;
+    p.stages = room / kATileBytes;
+    if (p.stages > 6) p.stages = 6;
+    if (p.taps_h * p.taps_w != 1 || p.stages < 2) {
+      set_last_error("launch_core: resident B needs taps == 1 and a weight slab <= ~150 KB");
+      return SSB_ERR_INVALID;
+    }
+  } else {
+    p.resident_bytes = 0;
   }
-  const int smem = core_smem_bytes(p);
+  if (p.stages <= 0) {
+    // 222 KiB budget: ring as deep as fits next to a double-buffered staging area, at least 2 stages;
+    // very wide tiles (block_n 512) fall back to single-buffered staging
+    const int sb = core_stage_bytes(p.block_n);
+    int st = (222 * 1024 - 2 * kCoreStagingBytes - 4096) / sb;
+    if (st < 2) {
+      p.stage_bufs = 1;
+      st = (222 * 1024 - kCoreStagingBytes - 4096) / sb;
+    }
+    p.stages = st > 6 ? 6 : (st < 2 ? 2 : st);
+  }
+  const int smem = core_smem_bytes(p.block_n, p.stages, p.resident_bytes, p.stage_bufs);
   static int configured_smem = 0;  // per template instantiation
   if (smem > configured_smem) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -396,7 +416,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   }
   const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
   if (total <= 0) return SSB_OK;
-  const int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+  int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+  if (p.b_resident) {
+    const long long xz = static_cast<long long>(grid.x) * grid.z;
+    const int per = device_sm_count() / static_cast<int>(grid.y);
+    ctas = static_cast<int>((xz < per ? xz : per) * grid.y);
+  }
   umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
