@@ -111,3 +111,12 @@ def test_c2_size_1024_keypoints(lgw, lg_weights):
 
     lg = fe.LightGlue(lgw, 640, 480, max_keypoints=1024)
     _check(lg, lg_weights, *_feat(1024, 1024, 9), 640, 480, 0.985)
+
+
+def test_2048_keypoints_beyond_the_reference_engine_profile(lgw, lg_weights):
+    """BASELINE config C3 uses K = 2048; the reference's TensorRT profile stops at 1024, so the
+    oracle is the only check.  Exercises 16 key blocks per attention pass and 8 x 16 sim tiles."""
+    from superslam_b200 import frontend as fe
+
+    lg = fe.LightGlue(lgw, 1241, 376, max_keypoints=2048)
+    _check(lg, lg_weights, *_feat(2048, 1900, 11), 1241, 376, 0.98)
