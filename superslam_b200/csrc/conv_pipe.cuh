@@ -21,12 +21,18 @@ namespace ssb {
 
 constexpr int kPipeHaloBytes = 41984;                 // 18*18*128 = 41472, rounded up to 1 KiB
 constexpr int kPipeWeightBytes = 9 * 64 * 128;        // 73,728
-constexpr int kPipeStagingBytes = 4 * 2 * 4096;      // double-buffered 4 KiB staging per epilogue warp
+constexpr int kPipeStagingBytes = 4 * 2 * 4096;      // double-buffered 4 KiB staging per epilogue warp (fused variant)
+// TMA-fed variant: THREE halo buffers (a 41 KB box from HBM takes longer than one tile's MMAs, so two
+// loads must be in flight) paid for with single-buffered store staging
+constexpr int kPipeHaloBufsTma = 3;
 constexpr int kPipePatchFloats = 20 * 20;
 constexpr int kPipeThreads = 192;
 constexpr int kPipeThreadsFused = 192 + 256;
 constexpr int kPipeSmemBytes = kPipeWeightBytes + 2 * kPipeHaloBytes + kPipeStagingBytes + 2 * kPipePatchFloats * 4 +
                                (576 + 64) * 4 + 256 + 1024;
+constexpr int kPipeSmemBytesTma = kPipeWeightBytes + kPipeHaloBufsTma * kPipeHaloBytes + kPipeStagingBytes / 2 +
+                                  2 * kPipePatchFloats * 4 + (576 + 64) * 4 + 256 + 1024;
+static_assert(kPipeSmemBytesTma <= 227 * 1024 && kPipeSmemBytes <= 227 * 1024, "conv_pipe shared-memory budget");
 
 // Packed fp32x2 FMA (sm_100: FFMA2): two IEEE fp32 fused multiply-adds per instruction.
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -65,18 +71,20 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = smem;
-  uint8_t* s_halo = smem + kPipeWeightBytes;                  // [2]
-  uint8_t* s_stage = s_halo + 2 * kPipeHaloBytes;             // 4 x 4 KiB
-  float* s_patch = reinterpret_cast<float*>(s_stage + kPipeStagingBytes);   // [2][400]
+  constexpr int kHaloBufs = kFuse1a ? 2 : kPipeHaloBufsTma;
+  constexpr int kStageBufs = kFuse1a ? 2 : 1;
+  uint8_t* s_halo = smem + kPipeWeightBytes;                  // [kHaloBufs]
+  uint8_t* s_stage = s_halo + kHaloBufs * kPipeHaloBytes;     // 4 warps x kStageBufs x 4 KiB
+  float* s_patch = reinterpret_cast<float*>(s_stage + 4 * kStageBufs * 4096);   // [2][400]
   float* s_w1a = s_patch + 2 * kPipePatchFloats;              // [576]
   float* s_b1a = s_w1a + 576;                                 // [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_b1a + 64);
   uint64_t* w_full = bars;
-  uint64_t* halo_full = bars + 1;    // [2]
-  uint64_t* halo_empty = bars + 3;   // [2]
-  uint64_t* tmem_full = bars + 5;    // [2]
-  uint64_t* tmem_empty = bars + 7;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* halo_full = bars + 1;    // [3]
+  uint64_t* halo_empty = bars + 4;   // [3]
+  uint64_t* tmem_full = bars + 7;    // [2]
+  uint64_t* tmem_empty = bars + 9;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.n_slices;
@@ -89,9 +97,11 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     mbar_init(w_full, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kHaloBufs; ++b) {
       mbar_init(&halo_full[b], kFuse1a ? 8 : 1);   // one arrival per producer warp
       mbar_init(&halo_empty[b], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 4);                // one arrival per epilogue warp
     }
@@ -118,10 +128,10 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!kFuse1a) {
         int seq = 0;
         for (int t = first; t < total; t += stride, ++seq) {
-          const int hb = seq & 1;
+          const int hb = seq % kHaloBufs;
           const int z = t / tiles_per_img, r = t % tiles_per_img;
           const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
-          mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq >> 1) & 1u) ^ 1u);
+          mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq / kHaloBufs) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&halo_full[hb], 18 * 18 * 128);
           tma_load_4d(s_halo + hb * kPipeHaloBytes, &tmA, &halo_full[hb], 0, w0 - 1, h0 - 1, z);
         }
@@ -134,11 +144,12 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int seq = 0;
       for (int t = first; t < total; t += stride, ++seq) {
         const int b = seq & 1;
+        const int hb = seq % kHaloBufs;
         const uint32_t use = static_cast<uint32_t>(seq >> 1) & 1u;
         mbar_wait(&tmem_empty[b], use ^ 1u);
-        mbar_wait(&halo_full[b], use);
+        mbar_wait(&halo_full[hb], static_cast<uint32_t>(seq / kHaloBufs) & 1u);
         tc_fence_after();
-        const uint32_t hbase = smem_u32(s_halo + b * kPipeHaloBytes);
+        const uint32_t hbase = smem_u32(s_halo + hb * kPipeHaloBytes);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap % 3;
@@ -151,7 +162,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_f16(tmem_base + b * 128 + sub * 64, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&halo_empty[b]);
+        umma_commit(&halo_empty[hb]);
         umma_commit(&tmem_full[b]);
       }
     }
@@ -167,9 +178,9 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.col_end = 64;
     c.half = 0;
     c.xchg = nullptr;
-    c.stage = s_stage + (warp - 2) * 8192;
+    c.stage = s_stage + (warp - 2) * (kStageBufs * 4096);
     c.stage_cur = c.stage;
-    c.stage_bufs = 2;
+    c.stage_bufs = kStageBufs;
     c.stage_sel = 0;
     for (int t = first; t < total; t += stride, ++seq) {
       const int b = seq & 1;
@@ -294,16 +305,17 @@ int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams 
   p.tiles_w = (W + 15) / 16;
   p.tiles_h = (H + 15) / 16;
   p.batch = batch;
+  constexpr int smem_bytes = kFuse1a ? kPipeSmemBytes : kPipeSmemBytesTma;
   static bool configured = false;
   if (!configured) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kPipeSmemBytes));
+                                        smem_bytes));
     configured = true;
   }
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;
-  conv_pipe_kernel<Epi, kFuse1a><<<ctas, kFuse1a ? kPipeThreadsFused : kPipeThreads, kPipeSmemBytes, stream>>>(
+  conv_pipe_kernel<Epi, kFuse1a><<<ctas, kFuse1a ? kPipeThreadsFused : kPipeThreads, smem_bytes, stream>>>(
       tmA, tmB, p, epi);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();

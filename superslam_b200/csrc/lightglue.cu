@@ -39,33 +39,43 @@ lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __r
   const int z = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
-  if (row >= kp) return;
+  if (row >= kp) return;   // kp is a multiple of 128: uniform per block
+  // rotary table, stored frequency-major [z][32][kp] so that the 32 lanes of an epilogue warp (32
+  // consecutive rows) read one 128-byte line per frequency (EpiQkvRope); transposed through shared memory
+  __shared__ float s_cs[32][9], s_sn[32][9];
   const int n = kp_count[z];
   const size_t o = (static_cast<size_t>(z) * kp + row) * kLgDim + lane * 8;
   // fp32 master: tile-transposed [z][row/128][col][row%128] (see EpiResidual)
   float* xt = x32 + (static_cast<size_t>(z) * (kp >> 7) + (row >> 7)) * (kLgDim * 128) + (row & 127);
+  float co = 0.f, si = 0.f;
   if (row >= n || desc_ptrs[z] == nullptr) {
     *reinterpret_cast<uint4*>(x16 + o) = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = 0.f;
-    return;
-  }
-  const __half* d = static_cast<const __half*>(desc_ptrs[z]) + static_cast<size_t>(row) * kLgDim + lane * 8;
-  const uint4 raw = *reinterpret_cast<const uint4*>(d);
-  *reinterpret_cast<uint4*>(x16 + o) = raw;
-  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-  const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
-               e = __half22float2(h2[3]);
-  const float f8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, e.x, e.y};
+  } else {
+    const __half* d = static_cast<const __half*>(desc_ptrs[z]) + static_cast<size_t>(row) * kLgDim + lane * 8;
+    const uint4 raw = *reinterpret_cast<const uint4*>(d);
+    *reinterpret_cast<uint4*>(x16 + o) = raw;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
+                 e = __half22float2(h2[3]);
+    const float f8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, e.x, e.y};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = f8[j];
-  const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
-  const float nx = (xy[0] - cx) / scale;
-  const float ny = (xy[1] - cy) / scale;
-  const float proj = wr[lane * 2 + 0] * nx + wr[lane * 2 + 1] * ny;
-  const size_t t = (static_cast<size_t>(z) * kp + row) * 32 + lane;
-  cs[t] = cosf(proj);
-  sn[t] = sinf(proj);
+    for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = f8[j];
+    const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
+    const float nx = (xy[0] - cx) / scale;
+    const float ny = (xy[1] - cy) / scale;
+    const float proj = wr[lane * 2 + 0] * nx + wr[lane * 2 + 1] * ny;
+    co = cosf(proj);
+    si = sinf(proj);
+  }
+  s_cs[lane][warp] = co;
+  s_sn[lane][warp] = si;
+  __syncthreads();
+  const int f = threadIdx.x >> 3, r = threadIdx.x & 7;
+  const size_t t = (static_cast<size_t>(z) * 32 + f) * kp + blockIdx.x * 8 + r;
+  cs[t] = s_cs[f][r];
+  sn[t] = s_sn[f][r];
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -220,24 +230,34 @@ struct EpiQkvRope {
         const int col = g0 + hc * 32;
         float v[32];
         tmem_ld_32x32(c.tmem_row + col, v);
+        // the rotary factors are fetched while the TMEM load is in flight; frequency-major table: the 32
+        // lanes (consecutive rows) read one 128-byte line per frequency
+        const bool do_rope = !is_v && rope && valid;
+        float cc[16], ss[16];
+        if (do_rope) {
+          const size_t tb = (static_cast<size_t>(c.z) * 32 + ((col & 63) >> 1)) * kp + row;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            cc[i] = __ldg(cs + tb + static_cast<size_t>(i) * kp);
+            ss[i] = __ldg(sn + tb + static_cast<size_t>(i) * kp);
+          }
+        }
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(b4 + j);
+          bv[4 * j] = t.x, bv[4 * j + 1] = t.y, bv[4 * j + 2] = t.z, bv[4 * j + 3] = t.w;
+        }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + __ldg(bias + c.n0 + col + j) : 0.f;
-        if (!is_v && rope && valid) {
-          const int d0 = col & 63;
-          const float4* cr = reinterpret_cast<const float4*>(cs + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1));
-          const float4* sr = reinterpret_cast<const float4*>(sn + (static_cast<size_t>(c.z) * kp + row) * 32 + (d0 >> 1));
+        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + bv[j] : 0.f;
+        if (do_rope) {
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 co = cr[i4], si = sr[i4];
-            const float cc[4] = {co.x, co.y, co.z, co.w}, ss[4] = {si.x, si.y, si.z, si.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int i = 4 * i4 + t;
-              const float a = v[2 * i], b = v[2 * i + 1];
-              v[2 * i] = a * cc[t] - b * ss[t];
-              v[2 * i + 1] = b * cc[t] + a * ss[t];
-            }
+          for (int i = 0; i < 16; ++i) {
+            const float a = v[2 * i], b = v[2 * i + 1];
+            v[2 * i] = a * cc[i] - b * ss[i];
+            v[2 * i + 1] = b * cc[i] + a * ss[i];
           }
         }
 #pragma unroll
@@ -299,22 +319,27 @@ struct EpiBias16 {
 };
 
 // FFN first half: Linear(512->512) + LayerNorm(512, eps 1e-5) + exact GELU -> fp16 [z][kp][512].
-// Each of the two warps that share a TMEM lane quadrant owns 256 of the row's 512 columns; mean and
-// variance are all-reduced across the pair through shared memory.  The epilogue is instruction-bound
+// The 512 output columns are split over a cluster of two CTAs (umma_core cluster mode: each CTA keeps a
+// double-buffered 256-column accumulator, so the epilogue overlaps the next tile's MMAs), and within a CTA
+// over the two warps that share a TMEM lane quadrant; sum and sum of squares are all-reduced through
+// shared memory inside the CTA and through distributed shared memory across the pair.  The epilogue is instruction-bound
 // (65536 elements per tile), hence two TMEM passes instead of three, vector loads of the per-column
-// parameters and a 12-instruction erf.
-// erf(x) = sign(x) * (1 - 2^(-t * P6(t))), t = min(|x|, 4): degree-6 minimax fit of -log2(erfc(t))/t on
-// [0, 4] (max abs error 1.6e-7 in fp32, the same class as erff) in 12 instructions instead of ~22.
-__device__ __forceinline__ float fast_erf(float x) {
-  const float t = fminf(fabsf(x), 4.0f);
-  float p = -1.0015573e-04f;
-  p = fmaf(p, t, 4.6152089e-04f);
-  p = fmaf(p, t, 2.3011598e-03f);
-  p = fmaf(p, t, -2.9449446e-02f);
-  p = fmaf(p, t, 1.4896062e-01f);
-  p = fmaf(p, t, 9.1832978e-01f);
-  p = fmaf(p, t, 1.6279136e+00f);
-  return copysignf(1.0f - fast_exp2(-t * p), x);
+// parameters and a 12-instruction GELU.
+
+// Exact (erf) GELU in 12 instructions:  gelu(y) = relu(y) - 0.5|y| * E(|y|),  E(s) = erfc(s / sqrt 2) =
+// 2^(-s * P6(s)) with P6 a degree-6 minimax fit of -log2(erfc(s / sqrt 2)) / s on [0, 4 sqrt 2]
+// (max abs error 4e-7 against 0.5 y (1 + erf(y / sqrt 2)) over |y| <= 12; beyond the clamp E < 2e-8).
+__device__ __forceinline__ float gelu_erf(float y) {
+  const float t = fminf(fabsf(y), 5.6568542f);
+  float p = -8.85259948e-06f;
+  p = fmaf(p, t, 5.76901113e-05f);
+  p = fmaf(p, t, 4.06791425e-04f);
+  p = fmaf(p, t, -7.36236150e-03f);
+  p = fmaf(p, t, 5.26655323e-02f);
+  p = fmaf(p, t, 4.59164890e-01f);
+  p = fmaf(p, t, 1.15110875e+00f);
+  const float e = fast_exp2(-t * p);
+  return fmaf(-0.5f * fabsf(y), e, fmaxf(y, 0.f));
 }
 
 struct EpiLnGelu {
@@ -334,7 +359,7 @@ struct EpiLnGelu {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
-      const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+      const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 bb = __ldg(b4 + j);
@@ -346,9 +371,13 @@ struct EpiLnGelu {
         sq = fmaf(x3, x3, sq);
       }
     }
-    const float mean = epi_pair_sum(c, sum) * (1.0f / 512.0f);
-    const float var = fmaxf(epi_pair_sum(c, sq) * (1.0f / 512.0f) - mean * mean, 0.f);
+    sum = epi_pair_sum(c, sum);   // this CTA's 256 columns ...
+    sq = epi_pair_sum(c, sq);
+    epi_cluster_sum2(c, sum, sq);  // ... plus the peer CTA's 256
+    const float mean = sum * (1.0f / 512.0f);
+    const float var = fmaxf(sq * (1.0f / 512.0f) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
+    const float nmr = -mean * rstd;
     for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
       stage_begin(c);
 #pragma unroll 1
@@ -357,9 +386,9 @@ struct EpiLnGelu {
         float v[32];
         tmem_ld_32x32(c.tmem_row + col, v);
         tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-        const float4* g4 = reinterpret_cast<const float4*>(g + col);
-        const float4* be4 = reinterpret_cast<const float4*>(b + col);
+        const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
+        const float4* g4 = reinterpret_cast<const float4*>(g + c.n0 + col);
+        const float4* be4 = reinterpret_cast<const float4*>(b + c.n0 + col);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 bb = __ldg(b4 + j), gg = __ldg(g4 + j), be = __ldg(be4 + j);
@@ -367,9 +396,10 @@ struct EpiLnGelu {
                       bev[4] = {be.x, be.y, be.z, be.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            float y = fmaf((v[4 * j + t] + bbv[t] - mean) * rstd, ggv[t], bev[t]);
-            y = 0.5f * y * (1.0f + fast_erf(y * 0.70710678118654752f));
-            v[4 * j + t] = valid ? y : 0.f;
+            // LayerNorm as  ((acc + bias) * rstd + (-mean * rstd)) * gamma + beta
+            const float y = fmaf(fmaf(v[4 * j + t] + bbv[t], rstd, nmr), ggv[t], bev[t]);
+            const float ge = gelu_erf(y);
+            v[4 * j + t] = valid ? ge : 0.f;
           }
         }
 #pragma unroll
@@ -384,7 +414,7 @@ struct EpiLnGelu {
       }
       stage_fence(c);
       if (c.lane == 0) {
-        tma_store_3d(&tm_out, c.stage_cur, g0, row0, c.z);
+        tma_store_3d(&tm_out, c.stage_cur, c.n0 + g0, row0, c.z);
         bulk_commit();
       }
     }
@@ -772,9 +802,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   };
   auto ffn = [&](const LgBlockFfn& F) -> int {
     {
-      CoreParams p = lin("lg.ffn1", 4, 4, 512);
+      CoreParams p = lin("lg.ffn1", 4, 4, 256);
+      p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)
       EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, ts_h1_};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 1, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);

@@ -68,6 +68,11 @@ struct CoreParams {
   int b_resident;
   int resident_bytes;
   int stage_bufs;      // TMA-store staging depth per epilogue warp (2 unless shared memory is short)
+  // Cluster mode: the kernel is launched as clusters of grid_y CTAs; the CTA with cluster rank r serves the
+  // N tile y = r of the SAME sequence of M tiles as its peers, so an epilogue that needs whole-row
+  // statistics (LayerNorm over all N tiles) can exchange per-row partials through distributed shared
+  // memory (EpiCtx::peer_*).  Used with grid_y == 2.
+  int cluster_y;
   const char* label;   // host-only: kernel name for the event profiler
 };
 
@@ -87,6 +92,10 @@ struct EpiCtx {
   uint8_t* stage_cur;  // buffer selected by the last stage_begin()
   int stage_bufs;      // 1 or 2 (double-buffered: the next block is staged while the last store drains)
   int stage_sel;
+  // cluster mode (CoreParams::cluster_y): per-row exchange with the peer CTA
+  int seq;             // running count of tiles this CTA has processed (both CTAs of a cluster agree)
+  float* peer_slots;   // local [2 parity][128 rows][2] floats, written by the peer
+  uint64_t* peer_bar;  // local [2 parity] mbarriers, 128 arrivals each (the peer's half-0 epilogue threads)
 };
 
 // ---- staged output: registers -> 128B-swizzled shared memory -> one TMA store per 32-row x 64-column
@@ -116,6 +125,21 @@ __device__ __forceinline__ void stage_drain(const EpiCtx& c) {   // before the b
 // Barrier among the 256 epilogue threads (both halves); every epilogue thread must call it.
 __device__ __forceinline__ void epi_pair_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Cluster mode: all-reduce two per-row values (already reduced over this CTA's columns) with the peer CTA
+// that holds the other N tile of the same rows.  Every epilogue thread calls it once per tile.
+__device__ __forceinline__ void epi_cluster_sum2(const EpiCtx& c, float& a, float& b) {
+  const int par = c.seq & 1;
+  if (c.half == 0) {
+    const uint32_t peer = cluster_ctarank() ^ 1u;
+    st_cluster_f32x2(cluster_map(smem_u32(c.peer_slots + (par * 128 + c.row) * 2), peer), a, b);
+    mbar_arrive_cluster(cluster_map(smem_u32(c.peer_bar + par), peer));
+  }
+  mbar_wait_cluster(c.peer_bar + par, static_cast<uint32_t>(c.seq >> 1) & 1u);
+  const float2 r = *reinterpret_cast<const float2*>(c.peer_slots + (par * 128 + c.row) * 2);
+  a += r.x;
+  b += r.y;
+}
+
 // Row-wise all-reduce (sum) across the two column halves of a tile.
 __device__ __forceinline__ float epi_pair_sum(const EpiCtx& c, float v) {
   c.xchg[c.half * 128 + c.row] = v;
@@ -131,7 +155,8 @@ constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buf
 
 inline int core_smem_bytes(int block_n, int stages, int resident_bytes, int stage_bufs) {
   return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) +
-         stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/;
+         stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/ +
+         2048 /*peer slots*/;
 }
 
 template <class Epi>
@@ -153,6 +178,8 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* b_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 256);
+  float* peer_slots = xchg + 256;                        // [2][128][2]
+  uint64_t* peer_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,6 +196,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
+      mbar_init(&peer_bar[b], 128);
     }
     fence_mbar_init();
   }
@@ -178,20 +206,22 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster_y) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B - a fixed y per CTA
-  const int ny = p.b_resident ? p.grid_y : 1;
+  // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B / cluster - a fixed y per CTA
+  const bool fixed_y = p.b_resident || p.cluster_y;
+  const int ny = fixed_y ? p.grid_y : 1;
   const int y_fixed = static_cast<int>(blockIdx.x) % ny;
   const int first = static_cast<int>(blockIdx.x) / ny;
   const int stride = static_cast<int>(gridDim.x) / ny;
-  const int total = p.b_resident ? p.grid_x * p.grid_z : p.grid_x * p.grid_y * p.grid_z;
+  const int total = fixed_y ? p.grid_x * p.grid_z : p.grid_x * p.grid_y * p.grid_z;
 
   // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
     const int x = tile % p.grid_x;
-    const int y = p.b_resident ? y_fixed : (tile / p.grid_x) % p.grid_y;
-    z = p.b_resident ? tile / p.grid_x : tile / (p.grid_x * p.grid_y);
+    const int y = fixed_y ? y_fixed : (tile / p.grid_x) % p.grid_y;
+    z = fixed_y ? tile / p.grid_x : tile / (p.grid_x * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
@@ -320,6 +350,9 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       c.m_valid = m_valid;
       c.half = half;
       c.xchg = xchg;
+      c.seq = seq;
+      c.peer_slots = peer_slots;
+      c.peer_bar = peer_bar;
       c.tmem_row = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
       if (Epi::kSplit) {
         const int hw = p.block_n / 2;
@@ -341,6 +374,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster_y) cluster_sync_all();   // the peer may still be writing this CTA's exchange slots
   if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
@@ -422,7 +456,42 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     const int per = device_sm_count() / static_cast<int>(grid.y);
     ctas = static_cast<int>((xz < per ? xz : per) * grid.y);
   }
-  umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
+  if (p.cluster_y) {
+    if (p.b_resident || grid.y != 2) {
+      set_last_error("launch_core: cluster mode needs exactly two N tiles");
+      return SSB_ERR_INVALID;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / 2 * 2));
+    cfg.blockDim = dim3(kCoreThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent pairs: as many clusters as can be co-resident (a GPC with an odd number of free SMs
+    // cannot host a pair on its last SM), so that no cluster waits for a second wave
+    static int max_pairs = 0, max_pairs_smem = 0;
+    if (max_pairs == 0 || max_pairs_smem != smem) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = device_sm_count() / 2;
+      }
+      max_pairs = n;
+      max_pairs_smem = smem;
+    }
+    const long long xz = static_cast<long long>(grid.x) * grid.z;
+    ctas = static_cast<int>(xz < max_pairs ? xz : max_pairs) * 2;
+    cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+    SSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_core_kernel<Epi>, a0, a1, b, p, epi));
+  } else {
+    umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, p.label);

@@ -13,6 +13,18 @@ __device__ __forceinline__ float bval(int n, int c) { return float(((n * 5 + c *
 
 // mode 0: K-major A shifted by `shift` rows with base_offset `bo`; B K-major [64 n][64 k].
 // mode 1: A K-major unshifted; B MN-major stored [64 k][64 n] (n contiguous), lbo = `bo` bytes.
+// mode 2: un-swizzled K-major A [128 x 16] and B [64 x 16] (8-row x 16-byte core matrices stored densely:
+//         element (r, k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2), one K=16 MMA; `bo` selects which
+//         descriptor field carries which stride: 0 -> LBO = 128 (K direction), SBO = 256 (row groups);
+//         1 -> swapped.  (conv1a on the tensor cores: K = 9 taps + bias, padded to 16.)
+__device__ __forceinline__ uint64_t desc_k_noswizzle(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;   // layout type 0 = SWIZZLE_NONE
+}
 __global__ void probe(int mode, int shift, int bo, int* mismatches, float* sample) {
   extern __shared__ __align__(1024) uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -33,6 +45,19 @@ __global__ void probe(int mode, int shift, int bo, int* mismatches, float* sampl
     const float v = mode == 0 ? bval(r, c) : bval(c, r);
     *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(B) + off) = __float2half(v);
   }
+  if (mode == 2) {
+    __syncthreads();
+    for (int i = tid; i < 128 * 16; i += blockDim.x) {
+      const int r = i / 16, k = i % 16;
+      const int off = (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2;
+      *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(A) + off) = __float2half(aval(r, k));
+    }
+    for (int i = tid; i < 64 * 16; i += blockDim.x) {
+      const int r = i / 16, k = i % 16;
+      const int off = (r / 8) * 256 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2;
+      *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(B) + off) = __float2half(bval(r, k));
+    }
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -49,7 +74,11 @@ __global__ void probe(int mode, int shift, int bo, int* mismatches, float* sampl
   if (tid == 0) {
     const uint32_t a0 = smem_u32(A) + shift * 128;
     const uint32_t b0 = smem_u32(B);
-    for (int k = 0; k < 4; ++k) {
+    if (mode == 2) {
+      const uint32_t lbo = bo == 0 ? 128 : 256, sbo = bo == 0 ? 256 : 128;
+      umma_f16(tmem, desc_k_noswizzle(a0, lbo, sbo), desc_k_noswizzle(b0, lbo, sbo), make_idesc_f16(64), 0);
+    }
+    for (int k = 0; k < (mode == 2 ? 0 : 4); ++k) {
       uint64_t ad, bd;
       uint32_t idesc;
       if (mode == 0) {
@@ -76,7 +105,7 @@ __global__ void probe(int mode, int shift, int bo, int* mismatches, float* sampl
     const int m = warp * 32 + lane;
     for (int j = 0; j < 32; ++j) {
       float e = 0.f;
-      for (int c = 0; c < 64; ++c) e += aval(m + shift, c) * bval(col + j, c);
+      for (int c = 0; c < (mode == 2 ? 16 : 64); ++c) e += aval(m + shift, c) * bval(col + j, c);
       if (fabsf(e - v[j]) > 1e-3f) ++bad;
       if (m == 5 && col + j == 3) {
         sample[0] = v[j];
@@ -119,5 +148,7 @@ int main() {
   const int lbos[] = {16, 1024, 2048, 4096, 8192};
   for (int l : lbos)
     if (!run(1, 0, l)) return 1;
+  run(2, 0, 0);
+  run(2, 0, 1);
   return 0;
 }
