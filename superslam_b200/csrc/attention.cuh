@@ -115,48 +115,63 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tS = tmem;        // 128 columns
   const uint32_t tO = tmem + 128;  // 64 columns
 
+  // Warps 0 and 1 run their loops with all 32 lanes in warp-uniform control flow and let one elected lane
+  // issue: descriptors and coordinates then live in uniform registers and every TMA / tcgen05.mma is a
+  // single instruction (inside `if (lane == 0)` each one became an ELECT / R2UR / branch sequence of ~100
+  // cycles, which sat on the S -> softmax -> P*V critical path twelve times per key block).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 16384);
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[s], 16384);
         tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, zk);
-        if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
+      }
+      __syncwarp();
+      if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
+      if (elect_one()) {
         mbar_arrive_expect_tx(v_full, 16384);
         tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, zk);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
-      const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
-      mbar_wait(q_full, 0);
-      const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
-      const uint32_t vbase = smem_u32(sV);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
-        tc_fence_after();
-        const uint64_t kdesc = make_smem_desc_k_sw128(smem_u32(sK + s * 16384), 1024);
+    const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
+    const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
+    mbar_wait(q_full, 0);
+    const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
+    const uint32_t vbase = smem_u32(sV), pbase = smem_u32(sP), kbase = smem_u32(sK);
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+      tc_fence_after();
+      const uint64_t kdesc = make_smem_desc_k_sw128(kbase + s * 16384, 1024);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&k_empty[s]);
         umma_commit(s_full);
-        mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
-        mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
+      mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
-          const uint64_t pdesc = make_smem_desc_k_sw128(smem_u32(sP + (k >> 2) * 16384), 1024) + 2 * (k & 3);
+          const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
           const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
           umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     const int qd = warp & 3;

@@ -141,30 +141,14 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA in the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
-}
-// arrive on an mbarrier that lives in another CTA of the cluster; release at cluster scope orders the
-// preceding st.shared::cluster of this thread before the arrival
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
-  uint32_t spins = 0, ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 24)) {
-      printf("ssb: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
+// Asynchronous store of two floats into another CTA's shared memory; completion (8 bytes) is signalled on
+// an mbarrier in THAT CTA, whose phase completes once the expected byte count has landed - the data is
+// then visible to threads that observe the phase with an ordinary (CTA-scope) wait.  No cluster-scope
+// acquire is needed on the consumer side (which would invalidate its L1).
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+               "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
 }
 
 // ---- TMA ---------------------------------------------------------------------------------------

@@ -148,37 +148,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
   }
 
+  // warps 0 / 1: whole-warp uniform loops, one elected lane issues (operands stay in uniform registers)
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t halo_tx = static_cast<uint32_t>(18 * pw * 128);
+    const uint32_t halo_tx = static_cast<uint32_t>(18 * pw * 128);
+    if (elect_one()) {
       for (int s = 0; s < (kFuse1a ? 0 : p.slabs); ++s) {
         mbar_arrive_expect_tx(&halo_full[s], halo_tx);
         tma_load_4d(s_halo + s * p.slab_bytes, &tmA, &halo_full[s], s * 64, w0 - 1, h0 - 1, z);
       }
-      for (int it = 0; it < num_w; ++it) {
-        const int slab = it / 9, tap = it % 9;
-        const int st = it % p.stages;
-        const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
-        mbar_wait(&w_empty[st], ph ^ 1u);
+    }
+    __syncwarp();
+    for (int it = 0; it < num_w; ++it) {
+      const int slab = it / 9, tap = it % 9;
+      const int st = it % p.stages;
+      const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+      mbar_wait(&w_empty[st], ph ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&w_full[st], static_cast<uint32_t>(wstage));
         tma_load_3d(s_w + st * wstage, &tmB, &w_full[st], slab * 64, tap * p.cout_rows + n0, 0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.block_n));
-      const uint32_t sbo = static_cast<uint32_t>(pw * 128);
-      for (int it = 0; it < num_w; ++it) {
-        const int slab = it / 9, tap = it % 9;
-        const int kh = tap / 3, kw = tap % 3;
-        const int st = it % p.stages;
-        if (!kFuse1a && tap == 0) {
-          mbar_wait(&halo_full[slab], 0);
-        }
-        mbar_wait(&w_full[st], static_cast<uint32_t>(it / p.stages) & 1u);
-        tc_fence_after();
-        const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(s_w + st * wstage), 1024);
-        const uint32_t a_tap = smem_u32(s_halo + slab * p.slab_bytes) + static_cast<uint32_t>((kh * pw + kw) * 128);
+    const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.block_n));
+    const uint32_t sbo = static_cast<uint32_t>(pw * 128);
+    const uint32_t w_base = smem_u32(s_w), halo_base = smem_u32(s_halo);
+    for (int it = 0; it < num_w; ++it) {
+      const int slab = it / 9, tap = it % 9;
+      const int kh = tap / 3, kw = tap % 3;
+      const int st = it % p.stages;
+      if (!kFuse1a && tap == 0) {
+        mbar_wait(&halo_full[slab], 0);
+      }
+      mbar_wait(&w_full[st], static_cast<uint32_t>(it / p.stages) & 1u);
+      tc_fence_after();
+      const uint64_t bdesc = make_smem_desc_k_sw128(w_base + st * wstage, 1024);
+      const uint32_t a_tap = halo_base + slab * p.slab_bytes + static_cast<uint32_t>((kh * pw + kw) * 128);
+      if (elect_one()) {
         for (int sub = 0; sub < p.subtiles; ++sub) {
           const uint64_t adesc = make_smem_desc_k_sw128(a_tap + sub * 8 * 128, sbo);
 #pragma unroll
@@ -187,8 +193,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         umma_commit(&w_empty[st]);
       }
-      umma_commit(accum_bar);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(accum_bar);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     mbar_wait(accum_bar, 0);

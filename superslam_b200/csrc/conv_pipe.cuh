@@ -3,15 +3,19 @@
 //
 // One CTA per SM keeps the 9 x [64 x 64] fp16 weights of its 64-output-channel slice RESIDENT in shared
 // memory (73 KB, loaded once by TMA) and walks 16 x 16 pixel tiles.  Per tile:
-//   halo   (16+2) x (16+2) pixels x 64 ch, double-buffered: either one TMA box load (zero-filled padding)
-//          or - fused first layer - computed in place by eight CUDA-core warps from the u8 image
-//          (conv1a: 3x3, Cin = 1, fp32), so conv1a's activation never exists in HBM;
+//   halo   (16+2) x (16+2) pixels x 64 ch: either TMA box loads (zero-filled padding, three buffers) or -
+//          fused first layer - produced on chip from the u8 image, so conv1a's activation never exists in
+//          HBM: conv1a (3x3, Cin = 1) is itself a tensor-core product  [384 halo px x 16] x [16 x 64]  with
+//          K = 9 taps + a ones column that carries the bias; the weights are split hi + lo (two fp16) so the
+//          result is fp32-accurate.  Eight converter warps build the im2col operand (un-swizzled K-major
+//          core matrices), read the product back from TMEM, apply ReLU / the image border and write the
+//          fp16 halo in the 128B-swizzled layout the conv1b MMAs read;
 //   MMA    9 taps x 2 sub-tiles x 4 K-slices of tcgen05.mma (M = 128 = 16 rows x 8 px, N = 64); each tap
 //          reads the halo in place through a descriptor shifted by whole pixels (see conv_halo.cuh);
 //   TMEM   2 x (2 x 64) accumulator columns: the epilogue of tile t (bias, ReLU, optional 2x2 max-pool,
 //          fp16, staged TMA store) overlaps the halo production and the MMAs of tile t+1.
-// Warp roles: 0 = TMA (weights once, halo boxes), 1 = TMEM alloc + MMA issue, 2..5 = epilogue,
-// 6..13 = conv1a producers (fused variant only).
+// Warp roles: 0 = TMA (weights once, halo boxes), 1 = TMEM alloc + MMA issue, 2..9 = epilogue,
+// 10..17 = conv1a im2col builders / TMEM->halo converters (fused variant only).
 #pragma once
 
 #include "common.cuh"
@@ -21,34 +25,34 @@ namespace ssb {
 
 constexpr int kPipeHaloBytes = 41984;                 // 18*18*128 = 41472, rounded up to 1 KiB
 constexpr int kPipeWeightBytes = 9 * 64 * 128;        // 73,728
-constexpr int kPipeStagingBytes = 4 * 2 * 4096;      // double-buffered 4 KiB staging per epilogue warp (fused variant)
-// TMA-fed variant: THREE halo buffers (a 41 KB box from HBM takes longer than one tile's MMAs, so two
-// loads must be in flight) paid for with single-buffered store staging
-constexpr int kPipeHaloBufsTma = 3;
-constexpr int kPipePatchFloats = 20 * 20;
-constexpr int kPipeThreads = 192;
-constexpr int kPipeThreadsFused = 192 + 256;
-constexpr int kPipeSmemBytes = kPipeWeightBytes + 2 * kPipeHaloBytes + kPipeStagingBytes + 2 * kPipePatchFloats * 4 +
-                               (576 + 64) * 4 + 256 + 1024;
-constexpr int kPipeSmemBytesTma = kPipeWeightBytes + kPipeHaloBufsTma * kPipeHaloBytes + kPipeStagingBytes / 2 +
-                                  2 * kPipePatchFloats * 4 + (576 + 64) * 4 + 256 + 1024;
+constexpr int kPipeEpiWarps = 8;                     // two per TMEM lane quadrant: one per 128-pixel sub-tile
+constexpr int kPipeStagingBytes = kPipeEpiWarps * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp
+constexpr int kPipeHaloBufsTma = 2;
+constexpr int kPipePatchElems = 20 * 20;               // u8 patch around a tile, kept as fp16 (value / 16, exact)
+constexpr int kPipeA1Bytes = 384 * 32;                  // im2col operand of conv1a: 3 M-tiles x 128 rows x 16 fp16
+constexpr int kPipeW1Bytes = 2 * 64 * 32;               // conv1a weights [64 x 16] fp16, hi and lo parts
+constexpr float kPipeImgScale = 1.0f / 16.0f;           // A = u8 / 16 (exact), B = w * 16 / 255
+constexpr int kPipeThreads = 64 + kPipeEpiWarps * 32;
+constexpr int kPipeThreadsFused = kPipeThreads + 256;
+constexpr int kPipeSmemBytes = kPipeWeightBytes + 2 * kPipeHaloBytes + kPipeStagingBytes + 2 * kPipeA1Bytes +
+                               kPipeW1Bytes + 2048 /*patches*/ + 256 + 1024;
+constexpr int kPipeSmemBytesTma = kPipeWeightBytes + kPipeHaloBufsTma * kPipeHaloBytes + 2 * kPipeStagingBytes +
+                                  256 + 1024;
 static_assert(kPipeSmemBytesTma <= 227 * 1024 && kPipeSmemBytes <= 227 * 1024, "conv_pipe shared-memory budget");
 
-// Packed fp32x2 FMA (sm_100: FFMA2): two IEEE fp32 fused multiply-adds per instruction.
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+// Shared-memory descriptor of an UN-swizzled K-major operand made of dense 8-row x 16-byte core matrices:
+// element (r, k) lives at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2, i.e. LBO (K direction) = 128 B and
+// SBO (next 8 rows) = 256 B for a K = 16 slice (checked on hardware: tools/umma_probe.cu mode 2).
+__device__ __forceinline__ uint64_t make_smem_desc_k_plain16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
   return d;
 }
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
+__device__ __forceinline__ int plain16_offset(int r, int k) {
+  return (r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
 }
 
 struct PipeParams {
@@ -72,19 +76,23 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = smem;
   constexpr int kHaloBufs = kFuse1a ? 2 : kPipeHaloBufsTma;
-  constexpr int kStageBufs = kFuse1a ? 2 : 1;
+  constexpr int kStageBufs = kFuse1a ? 1 : 2;   // the fused variant needs the room for the conv1a operands
   uint8_t* s_halo = smem + kPipeWeightBytes;                  // [kHaloBufs]
-  uint8_t* s_stage = s_halo + kHaloBufs * kPipeHaloBytes;     // 4 warps x kStageBufs x 4 KiB
-  float* s_patch = reinterpret_cast<float*>(s_stage + 4 * kStageBufs * 4096);   // [2][400]
-  float* s_w1a = s_patch + 2 * kPipePatchFloats;              // [576]
-  float* s_b1a = s_w1a + 576;                                 // [64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b1a + 64);
+  uint8_t* s_stage = s_halo + kHaloBufs * kPipeHaloBytes;     // 8 warps x kStageBufs x 4 KiB
+  uint8_t* s_a1 = s_stage + kStageBufs * kPipeStagingBytes;   // fused: [2] im2col operands
+  uint8_t* s_w1 = s_a1 + (kFuse1a ? 2 * kPipeA1Bytes : 0);    // fused: conv1a weights hi | lo
+  __half* s_patch = reinterpret_cast<__half*>(s_w1 + (kFuse1a ? kPipeW1Bytes : 0));   // fused: [2][400]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_patch) + (kFuse1a ? 2048 : 0));
   uint64_t* w_full = bars;
   uint64_t* halo_full = bars + 1;    // [3]
   uint64_t* halo_empty = bars + 4;   // [3]
   uint64_t* tmem_full = bars + 7;    // [2]
   uint64_t* tmem_empty = bars + 9;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* a1_full = bars + 11;     // [2] fused: im2col operand built (8 warp arrivals)
+  uint64_t* c1_full = bars + 13;     // fused: conv1a product in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  constexpr uint32_t kTmemCols = kFuse1a ? 512 : 256;   // conv1b accumulators 2 x 128, conv1a product 3 x 64
+  constexpr uint32_t kC1Col = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.n_slices;
@@ -103,17 +111,30 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);                // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], kPipeEpiWarps);    // one arrival per epilogue warp
+      mbar_init(&a1_full[b], 8);
     }
+    mbar_init(c1_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   if (kFuse1a) {
-    for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w1a[i] = p.w1a[i];
-    if (threadIdx.x < 64) s_b1a[threadIdx.x] = p.b1a[threadIdx.x];
+    // conv1a B operand [n = 64][k = 16]: k < 9 tap weights * 16/255, k = 9 the bias, rest 0; hi + lo fp16
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+      const int n = i >> 4, k = i & 15;
+      const float v = k < 9 ? p.w1a[k * 64 + n] * (16.0f / 255.0f) : (k == 9 ? p.b1a[n] : 0.f);
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      *reinterpret_cast<__half*>(s_w1 + plain16_offset(n, k)) = hi;
+      *reinterpret_cast<__half*>(s_w1 + 2048 + plain16_offset(n, k)) = lo;
+    }
+    // im2col rows 324..383 of both operands stay zero for the whole kernel
+    for (int i = threadIdx.x; i < 2 * kPipeA1Bytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(s_a1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -138,36 +159,70 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(64);
-      mbar_wait(w_full, 0);
-      int seq = 0;
-      for (int t = first; t < total; t += stride, ++seq) {
-        const int b = seq & 1;
-        const int hb = seq % kHaloBufs;
-        const uint32_t use = static_cast<uint32_t>(seq >> 1) & 1u;
-        mbar_wait(&tmem_empty[b], use ^ 1u);
-        mbar_wait(&halo_full[hb], static_cast<uint32_t>(seq / kHaloBufs) & 1u);
-        tc_fence_after();
-        const uint32_t hbase = smem_u32(s_halo + hb * kPipeHaloBytes);
-#pragma unroll 1
+    // The whole warp walks the tile loop and computes descriptors in warp-uniform control flow, so they live
+    // in uniform registers and each tcgen05.mma is one instruction for the elected lane.  (Inside an
+    // `if (lane == 0)` region the operands are vector registers and every MMA becomes an
+    // ELECT / R2UR x3 / branch "waterfall" of ~100 cycles - three times the 32 cycles an N = 64 MMA takes.)
+    const uint32_t idesc = make_idesc_f16(64);
+    const uint32_t w_base = smem_u32(s_w), halo_base = smem_u32(s_halo);
+    const uint32_t a1_base = smem_u32(s_a1), w1_base = smem_u32(s_w1);
+    mbar_wait(w_full, 0);
+    // fused: conv1a of tile `seq1` = 3 M-tiles x (hi + lo) MMAs with K = 16 into TMEM columns kC1Col..
+    auto issue_conv1a = [&](int seq1) {
+      mbar_wait(&a1_full[seq1 & 1], static_cast<uint32_t>(seq1 >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t a1 = a1_base + (seq1 & 1) * kPipeA1Bytes;
+      const uint64_t bhi = make_smem_desc_k_plain16(w1_base), blo = make_smem_desc_k_plain16(w1_base + 2048);
+      if (elect_one()) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const uint64_t ad = make_smem_desc_k_plain16(a1 + m * 4096);
+          umma_f16(tmem_base + kC1Col + m * 64, ad, bhi, idesc, 0u);
+          umma_f16(tmem_base + kC1Col + m * 64, ad, blo, idesc, 1u);
+        }
+        umma_commit(c1_full);
+      }
+      __syncwarp();
+    };
+    int seq = 0;
+    if (kFuse1a && first < total) issue_conv1a(0);
+    for (int t = first; t < total; t += stride, ++seq) {
+      const int b = seq & 1;
+      const int hb = seq % kHaloBufs;
+      const uint32_t use = static_cast<uint32_t>(seq >> 1) & 1u;
+      mbar_wait(&halo_full[hb], static_cast<uint32_t>(seq / kHaloBufs) & 1u);
+      tc_fence_after();
+      // fused: the converters are done with the conv1a product of this tile (halo_full), so the next
+      // tile's conv1a goes first; its conversion then overlaps this tile's 72 conv1b MMAs
+      if (kFuse1a && t + stride < total) issue_conv1a(seq + 1);
+      mbar_wait(&tmem_empty[b], use ^ 1u);
+      tc_fence_after();
+      const uint32_t hbase = halo_base + hb * kPipeHaloBytes;
+      const uint32_t d0 = tmem_base + b * 128;
+      if (elect_one()) {
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap % 3;
-          const uint64_t bdesc = make_smem_desc_k_sw128(smem_u32(s_w + tap * 8192), 1024);
+          const uint64_t bdesc = make_smem_desc_k_sw128(w_base + tap * 8192, 1024);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const uint64_t adesc = make_smem_desc_k_sw128(hbase + ((kh * 18 + kw) + sub * 8) * 128, 18 * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + b * 128 + sub * 64, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+              umma_f16(d0 + sub * 64, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&halo_empty[hb]);
         umma_commit(&tmem_full[b]);
       }
+      __syncwarp();
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kPipeEpiWarps) {
+    // eight epilogue warps: warp w reads TMEM lanes 32*(w%4)..+31 (hardware rule) of sub-tile (w-2)/4.
+    // (With four warps - one per scheduler - the dependent chain TMEM load -> bias/ReLU -> pooling
+    // shuffles -> staging store ran at ~7 cycles per instruction and set the pace of the whole kernel.)
     const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
     int seq = 0;
     EpiCtx c;
     c.row = q * 32 + lane;
@@ -190,33 +245,22 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       c.z = z;
       c.py = h0 + (c.row >> 3);
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        c.px = w0 + sub * 8 + (c.row & 7);
-        c.tmem_row = tmem_base + b * 128 + sub * 64 + (static_cast<uint32_t>(q * 32) << 16);
-        epi(c, true);
-      }
+      c.px = w0 + sub * 8 + (c.row & 7);
+      c.tmem_row = tmem_base + b * 128 + sub * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      epi(c, true);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[b]);
     }
     stage_drain(c);
   } else if (kFuse1a) {
-    // conv1a producers: 256 threads; thread owns channel group (tid & 7) with its weights in registers.
-    const int tid = threadIdx.x - 192;
-    const int g = tid & 7;
-    // weights / bias as fp32x2 pairs for FFMA2 (same per-element IEEE fma as the scalar chain)
-    unsigned long long wr[36], br[4];
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        wr[tp * 4 + j] = pack_f32x2(s_w1a[tp * 64 + g * 8 + 2 * j], s_w1a[tp * 64 + g * 8 + 2 * j + 1]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) br[j] = pack_f32x2(s_b1a[g * 8 + 2 * j], s_b1a[g * 8 + 2 * j + 1]);
-    const float inv255 = 1.0f / 255.0f;  // cv::Mat::convertTo(CV_32F, 1.0/255.0): value * float(1/255)
-    // image patch (20 x 20 pixels around the tile) of tile t, two elements per thread, as fp32 * (1/255)
-    auto load_patch = [&](int t, float* pre) {
+    // ---- conv1a: im2col builders + TMEM->halo converters (8 warps, 256 threads) ----
+    const int tid = threadIdx.x - kPipeThreads;
+    const int cw = warp - (2 + kPipeEpiWarps);
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int colhalf = cw >> 2;       // the two warps of a quadrant split the 64 channels
+    // u8 patch (20 x 20 pixels around the tile) of tile t -> two fp16 (value / 16) per thread
+    auto load_patch = [&](int t, __half* pre) {
       const int z = t / tiles_per_img, r = t % tiles_per_img;
       const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
       const uint8_t* im = p.img + static_cast<size_t>(z) * p.img_h * p.img_w;
@@ -225,22 +269,45 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int i = tid + k * 256;
         const int pr = i / 20, pc = i - pr * 20;
         const int y = h0 - 2 + pr, x = w0 - 2 + pc;
-        float v = 0.f;
-        if (i < kPipePatchFloats && y >= 0 && y < p.img_h && x >= 0 && x < p.img_w)
-          v = static_cast<float>(__ldg(im + static_cast<size_t>(y) * p.img_w + x)) * inv255;
-        pre[k] = v;
+        float v = 0.f;   // conv1a's own zero padding
+        if (i < kPipePatchElems && y >= 0 && y < p.img_h && x >= 0 && x < p.img_w)
+          v = static_cast<float>(__ldg(im + static_cast<size_t>(y) * p.img_w + x)) * kPipeImgScale;
+        pre[k] = __float2half_rn(v);
       }
     };
-    auto store_patch = [&](float* patch, const float* pre) {
+    auto store_patch = [&](__half* patch, const __half* pre) {
       patch[tid] = pre[0];
-      if (tid + 256 < kPipePatchFloats) patch[tid + 256] = pre[1];
+      if (tid + 256 < kPipePatchElems) patch[tid + 256] = pre[1];
+    };
+    // im2col: row p = halo pixel (hy, hx); k = 3*kh + kw -> patch[hy + kh][hx + kw]; k = 9 -> 1 (bias)
+    auto build_a1 = [&](const __half* patch, uint8_t* a1) {
+#pragma unroll 1
+      for (int px = tid; px < 18 * 18; px += 256) {
+        const int hy = px / 18, hx = px - hy * 18;
+        const unsigned short* pp = reinterpret_cast<const unsigned short*>(patch) + hy * 20 + hx;
+        uint32_t e[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) e[k] = pp[(k / 3) * 20 + (k % 3)];
+        const uint4 lo = make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+        const uint4 hi = make_uint4(e[8] | (0x3C00u << 16) /* fp16 1.0: bias column */, 0u, 0u, 0u);
+        uint8_t* dst = a1 + (px >> 3) * 256 + (px & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = lo;
+        *reinterpret_cast<uint4*>(dst + 128) = hi;
+      }
     };
     int seq = 0;
-    {
-      float pre[2];
-      if (first < total) {
-        load_patch(first, pre);
-        store_patch(s_patch, pre);
+    if (first < total) {
+      __half pre[2];
+      load_patch(first, pre);
+      store_patch(s_patch, pre);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      build_a1(s_patch, s_a1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a1_full[0]);
+      if (first + stride < total) {
+        load_patch(first + stride, pre);
+        store_patch(s_patch + kPipePatchElems, pre);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
@@ -248,55 +315,59 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int hb = seq & 1;
       const int r = t % tiles_per_img;
       const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
-      const float* patch = s_patch + hb * kPipePatchFloats;
-      // software pipeline: the global loads of the NEXT tile's patch are in flight while this tile's
-      // halo is computed; they are published to the other patch buffer at the end of the iteration
-      float pre[2];
-      const int tn = t + stride;
-      if (tn < total) load_patch(tn, pre);
+      const int tn = t + stride, tnn = t + 2 * stride;
+      // software pipeline: the global loads of the patch two tiles ahead are in flight during this iteration
+      __half pre[2];
+      if (tnn < total) load_patch(tnn, pre);
+      // (1) im2col operand of the NEXT tile (its buffer was last read by conv1a of tile seq-1, whose
+      //     completion this warp observed through c1_full one iteration ago)
+      if (tn < total) {
+        build_a1(s_patch + ((seq + 1) & 1) * kPipePatchElems, s_a1 + ((seq + 1) & 1) * kPipeA1Bytes);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a1_full[(seq + 1) & 1]);
+      }
+      // (2) this tile's conv1a product -> ReLU -> fp16 halo (zero outside the image = conv1b's padding)
+      mbar_wait(c1_full, static_cast<uint32_t>(seq) & 1u);
       mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq >> 1) & 1u) ^ 1u);
+      tc_fence_after();
       uint8_t* halo = s_halo + hb * kPipeHaloBytes;
-      int px = tid >> 3;   // 32 halo pixels per sweep
-      int hy = px / 18, hx = px - hy * 18;
-      for (; px < 18 * 18; px += 32) {
-        const int y = h0 - 1 + hy, x = w0 - 1 + hx;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);   // outside the image: conv1b's zero padding
-        if (y >= 0 && y < p.img_h && x >= 0 && x < p.img_w) {
-          unsigned long long acc[4];
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        if (m * 128 + q * 32 >= 18 * 18) break;   // warp-uniform: rows beyond the halo
+        const int px = m * 128 + q * 32 + lane;
+        float v[32];
+        tmem_ld_32x32(tmem_base + kC1Col + m * 64 + colhalf * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (px < 18 * 18) {
+          const int hy = px / 18, hx = px - hy * 18;
+          const int y = h0 - 1 + hy, x = w0 - 1 + hx;
+          const bool inside = y >= 0 && y < p.img_h && x >= 0 && x < p.img_w;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = br[j];
-          const float* pp = patch + hy * 20 + hx;
-#pragma unroll
-          for (int tp = 0; tp < 9; ++tp) {
-            const float v = pp[(tp / 3) * 20 + (tp % 3)];
-            const unsigned long long vv = pack_f32x2(v, v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = ffma2(vv, wr[tp * 4 + j], acc[j]);
+          for (int j = 0; j < 4; ++j) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (inside) {
+              o.x = pack_half2(fmaxf(v[8 * j + 0], 0.f), fmaxf(v[8 * j + 1], 0.f));
+              o.y = pack_half2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f));
+              o.z = pack_half2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f));
+              o.w = pack_half2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f));
+            }
+            *reinterpret_cast<uint4*>(halo + px * 128 + (((colhalf * 4 + j) ^ (px & 7)) << 4)) = o;
           }
-          const float2 a0 = unpack_f32x2(acc[0]), a1 = unpack_f32x2(acc[1]), a2 = unpack_f32x2(acc[2]),
-                       a3 = unpack_f32x2(acc[3]);
-          o.x = pack_half2(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
-          o.y = pack_half2(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
-          o.z = pack_half2(fmaxf(a2.x, 0.f), fmaxf(a2.y, 0.f));
-          o.w = pack_half2(fmaxf(a3.x, 0.f), fmaxf(a3.y, 0.f));
-        }
-        *reinterpret_cast<uint4*>(halo + px * 128 + ((g ^ (px & 7)) << 4)) = o;
-        hx += 32;
-        while (hx >= 18) {
-          hx -= 18;
-          ++hy;
         }
       }
+      tc_fence_before();
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&halo_full[hb]);
-      if (tn < total) store_patch(s_patch + (hb ^ 1) * kPipePatchFloats, pre);
-      asm volatile("bar.sync 3, 256;" ::: "memory");   // patch[hb^1] published, patch[hb] no longer read
+      // (3) publish the prefetched patch (tile seq+2) into the buffer tile seq used (read in iteration seq-1)
+      if (tnn < total) store_patch(s_patch + hb * kPipePatchElems, pre);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 template <class Epi, bool kFuse1a>

@@ -95,7 +95,7 @@ struct EpiCtx {
   // cluster mode (CoreParams::cluster_y): per-row exchange with the peer CTA
   int seq;             // running count of tiles this CTA has processed (both CTAs of a cluster agree)
   float* peer_slots;   // local [2 parity][128 rows][2] floats, written by the peer
-  uint64_t* peer_bar;  // local [2 parity] mbarriers, 128 arrivals each (the peer's half-0 epilogue threads)
+  uint64_t* peer_bar;  // local [2 parity] mbarriers: one local arrival + 1 KiB of st.async bytes from the peer
 };
 
 // ---- staged output: registers -> 128B-swizzled shared memory -> one TMA store per 32-row x 64-column
@@ -130,11 +130,13 @@ __device__ __forceinline__ void epi_pair_sync() { asm volatile("bar.sync 1, 256;
 __device__ __forceinline__ void epi_cluster_sum2(const EpiCtx& c, float& a, float& b) {
   const int par = c.seq & 1;
   if (c.half == 0) {
+    // this tile's phase of the local barrier completes when the peer's 128 rows x 8 bytes have landed
+    if (c.row == 0) mbar_arrive_expect_tx(c.peer_bar + par, 128 * 8);
     const uint32_t peer = cluster_ctarank() ^ 1u;
-    st_cluster_f32x2(cluster_map(smem_u32(c.peer_slots + (par * 128 + c.row) * 2), peer), a, b);
-    mbar_arrive_cluster(cluster_map(smem_u32(c.peer_bar + par), peer));
+    st_async_f32x2(cluster_map(smem_u32(c.peer_slots + (par * 128 + c.row) * 2), peer), a, b,
+                   cluster_map(smem_u32(c.peer_bar + par), peer));
   }
-  mbar_wait_cluster(c.peer_bar + par, static_cast<uint32_t>(c.seq >> 1) & 1u);
+  mbar_wait(c.peer_bar + par, static_cast<uint32_t>(c.seq >> 1) & 1u);
   const float2 r = *reinterpret_cast<const float2*>(c.peer_slots + (par * 128 + c.row) * 2);
   a += r.x;
   b += r.y;
@@ -196,7 +198,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
-      mbar_init(&peer_bar[b], 128);
+      mbar_init(&peer_bar[b], 1);
     }
     fence_mbar_init();
   }
@@ -234,80 +236,89 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
-      if (p.b_resident) {
-        const int kct = p.kc0 + p.kc1;
+    // producer: whole warp in uniform control flow, one elected lane issues the TMA loads (see warp 1)
+    const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+    if (p.b_resident) {
+      const int kct = p.kc0 + p.kc1;
+      if (elect_one()) {
         mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(kct * p.block_n * 128));
         for (int c = 0; c < kct; ++c)
           for (int part = 0; part < p.n_parts; ++part)
             tma_load_3d(s_res + (c * p.block_n + part * p.n_part) * 128, &tmB, b_full, c * kChunkK,
                         y_fixed * p.block_n + part * p.n_part, p.b_z_add);
       }
-      int it = 0;
-      for (int tile = first; tile < total; tile += stride) {
-        int z, w0, h0, n0, m_valid, kc0;
-        if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
-        const int kc = kc0 + p.kc1;
-        const int az = z * p.a_z_mul + p.a_z_add;
-        const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
-        for (int th = 0; th < p.taps_h; ++th) {
-          for (int tw = 0; tw < p.taps_w; ++tw) {
-            const int tap = th * p.taps_w + tw;
-            for (int c = 0; c < kc; ++c, ++it) {
-              const int s = it % p.stages;
-              const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
-              mbar_wait(&empty_bar[s], ph ^ 1u);
+      __syncwarp();
+    }
+    int it = 0;
+    for (int tile = first; tile < total; tile += stride) {
+      int z, w0, h0, n0, m_valid, kc0;
+      if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
+      const int kc = kc0 + p.kc1;
+      const int az = z * p.a_z_mul + p.a_z_add;
+      const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
+      for (int th = 0; th < p.taps_h; ++th) {
+        for (int tw = 0; tw < p.taps_w; ++tw) {
+          const int tap = th * p.taps_w + tw;
+          for (int c = 0; c < kc; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* sa = ring + s * stage_bytes;
+            uint8_t* sb = sa + kATileBytes;
+            // B columns: source-1 chunks follow the *nominal* source-0 chunk count so that weight
+            // matrices keep their layout when kc0 is clipped by k_valid.
+            const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
+            if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-              uint8_t* sa = ring + s * stage_bytes;
-              uint8_t* sb = sa + kATileBytes;
               if (c < kc0) {
                 tma_load_4d(sa, &tmA0, &full_bar[s], c * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
               } else {
                 tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
               }
-              // B columns: source-1 chunks follow the *nominal* source-0 chunk count so that weight
-              // matrices keep their layout when kc0 is clipped by k_valid.
-              const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
               for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
                 tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
                             tap * p.b_tap_rows + n0 + part * p.n_part, bz);
               }
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
-      if (p.b_resident) {
-        mbar_wait(b_full, 0);
+    // Whole-warp, warp-uniform loop; one elected lane issues.  Keeping descriptor arithmetic out of a
+    // divergent `if (lane == 0)` region lets it live in uniform registers, so a tcgen05.mma is a single
+    // instruction instead of an ELECT / R2UR / branch sequence of ~100 cycles.
+    const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
+    const uint32_t ring_base = smem_u32(ring), res_base = smem_u32(s_res);
+    if (p.b_resident) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+    }
+    int it = 0, seq = 0;
+    for (int tile = first; tile < total; tile += stride) {
+      int z, w0, h0, n0, m_valid, kc0;
+      if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
+      const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
+      const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
+      const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
+      mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * p.buf_stride;
+      for (int kk = 0; kk < num_k; ++kk, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-      }
-      int it = 0, seq = 0;
-      for (int tile = first; tile < total; tile += stride) {
-        int z, w0, h0, n0, m_valid, kc0;
-        if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
-        const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
-        const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
-        const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
-        mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * p.buf_stride;
-        for (int kk = 0; kk < num_k; ++kk, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring + s * stage_bytes);
-          // resident B: chunk index within the tap (taps == 1 for the linear layers that use it)
-          const int kcs = kc0 + p.kc1;
-          const int cidx = kk % kcs;
-          const uint32_t sb = p.b_resident
-                                  ? smem_u32(s_res) + static_cast<uint32_t>((cidx < kc0 ? cidx : p.kc0 + (cidx - kc0)) * p.block_n * 128)
-                                  : sa + kATileBytes;
-          const uint64_t adesc = make_smem_desc_k_sw128(sa, 1024);
+        const uint32_t sa = ring_base + s * stage_bytes;
+        // resident B: chunk index within the tap (taps == 1 for the linear layers that use it)
+        const int kcs = kc0 + p.kc1;
+        const int cidx = kk % kcs;
+        const uint32_t sb = p.b_resident
+                                ? res_base + static_cast<uint32_t>((cidx < kc0 ? cidx : p.kc0 + (cidx - kc0)) * p.block_n * 128)
+                                : sa + kATileBytes;
+        const uint64_t adesc = make_smem_desc_k_sw128(sa, 1024);
+        if (elect_one()) {
 #pragma unroll 1
           for (int part = 0; part < p.n_parts; ++part) {
             const uint64_t bdesc = make_smem_desc_k_sw128(sb + part * p.n_part * 128, 1024);
@@ -319,9 +330,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full[buf]);
-        ++seq;
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
+      ++seq;
     }
   } else {
     const int ew = warp - 2;          // 0..7

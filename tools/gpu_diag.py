@@ -102,7 +102,7 @@ def main():
     os.environ["SSB_LG_STOP_AFTER"] = "1"
     lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
     dbg = olg.self_block_debug(sd, 0, k0, d0)
-    cs = lg.debug_read("cos", (2, kp, 32), np.float32)[0, :n0]
+    cs = lg.debug_read("cos", (2, 32, kp), np.float32)[0].T[:n0]   # stored frequency-major [z][32][kp]
     print(f"lg cos maxabs {np.abs(cs - dbg['cos'][:, ::2]).max()}")
     q = lg.debug_read("q", (8, kp, 64), np.float16).astype(np.float32)[:4, :n0]
     k_ = lg.debug_read("k", (8, kp, 64), np.float16).astype(np.float32)[:4, :n0]
