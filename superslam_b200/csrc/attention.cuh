@@ -146,7 +146,10 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_wait(q_full, 0);
     const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
     const uint32_t vbase = smem_u32(sV), pbase = smem_u32(sP), kbase = smem_u32(sK);
-    for (int j = 0; j < nblk; ++j) {
+    // S(j+1) is issued BEFORE P*V(j): the softmax warps get their next logits ~400 cycles earlier (they sat
+    // in the s_full wait a quarter of the time), and P*V(j) still finishes long before its result, the P
+    // buffer or V are needed again (after the max pass of block j+1).
+    auto issue_s = [&](int j) {
       const int s = j & 1;
       mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
       tc_fence_after();
@@ -158,8 +161,13 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         umma_commit(s_full);
       }
       __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);   // softmax(j) has read S(j) and written P(j)
+      tc_fence_after();
+      if (j + 1 < nblk) issue_s(j + 1);
       mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
-      mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -236,12 +244,21 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         float v[32];
         tmem_ld_32x32(tSh + c, v);
         tmem_ld_wait();
+        if (kvalid >= 64) {   // warp-uniform: no per-element masking in the common case
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
-          if (kvalid < 64 && c + i >= kvalid) e = 0.f;
-          ls[i & 3] += e;
-          v[i] = e;
+          for (int i = 0; i < 32; ++i) {
+            const float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+            ls[i & 3] += e;
+            v[i] = e;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+            if (c + i >= kvalid) e = 0.f;
+            ls[i & 3] += e;
+            v[i] = e;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {

@@ -15,7 +15,7 @@
 #include <cstring>
 #include <string>
 
-#include "conv_halo.cuh"
+#include "conv_stream.cuh"
 #include "conv_pipe.cuh"
 #include "umma_core.cuh"
 
@@ -88,8 +88,8 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __r
 // bias + ReLU (+ 2x2/2 max-pool, floor) -> fp16 NHWC, written with one TMA store per warp and 64-channel
 // group (registers -> swizzled staging -> bulk store; out-of-image pixels are clipped by the TMA unit).
 // Lane -> pixel mapping: 16x8 tiles of umma_core put two tile rows of 16 pixels in a warp
-// (row_xor = 16); conv_halo puts four rows of 8 pixels in a warp (row_xor = 8).  Either way the 2x2
-// pool is two warp shuffles.
+// (row_xor = 16); the halo kernels (conv_pipe, conv_stream) put four rows of 8 pixels in a warp
+// (row_xor = 8).  Either way the 2x2 pool is two warp shuffles.
 struct EpiConvRelu {
   const float* bias;
   CUtensorMap tm_out;  // 4-D (C, Wo, Ho, B); box = the warp's pixel block x 64 channels
@@ -529,7 +529,9 @@ int SuperPoint::load_layer(const WeightArchive& ar, const char* name, int cin, i
   uint32_t box[3] = {64, static_cast<uint32_t>(n_part), 1};
   SSB_RETURN_IF(encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box));
   uint32_t box64[3] = {64, 64, 1};   // one 64-output-channel slice of one tap (conv_pipe.cuh)
-  return encode_tmap_f16(&L->tmB64, L->w, 3, dims, strides, box64);
+  SSB_RETURN_IF(encode_tmap_f16(&L->tmB64, L->w, 3, dims, strides, box64));
+  uint32_t box128[3] = {64, static_cast<uint32_t>(pad >= 128 ? 128 : pad), 1};   // conv_stream.cuh
+  return encode_tmap_f16(&L->tmB128, L->w, 3, dims, strides, box128);
 }
 
 int SuperPoint::init(const char* weights_path, int max_keypoints, double threshold, int remove_borders,
@@ -650,6 +652,9 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_halo_tmap(&tm_p2a_, a2a_, 64, w2_, h2_, nb, 2));
   SSB_RETURN_IF(make_halo_tmap(&tm_h2b_, a2b_, 64, w4_, h4_, nb, 2));
   SSB_RETURN_IF(make_halo_tmap(&tm_h3a_, a3a_, 128, w4_, h4_, nb, 2));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h3b_, a3b_, 128, wc_, hc_, nb, 2));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h4a_, a4a_, 128, wc_, hc_, nb, 2));
+  SSB_RETURN_IF(make_halo_tmap(&tm_h4b_, a4b_, 128, wc_, hc_, nb, 2));
   // store maps: one warp's pixel block x 64 channels (halo kernels: 4 rows x 8 px, pooled 2 x 4;
   // 16x8-tile kernels: 2 rows x 16 px)
   SSB_RETURN_IF(make_act_tmap(&ts_a1b_, a1b_, 64, 64, w2_, h2_, nb, 4, 2));
@@ -657,9 +662,9 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_RETURN_IF(make_act_tmap(&ts_a2b_, a2b_, 64, 64, w4_, h4_, nb, 4, 2));
   SSB_RETURN_IF(make_act_tmap(&ts_a3a_, a3a_, 128, 128, w4_, h4_, nb, 8, 4));
   SSB_RETURN_IF(make_act_tmap(&ts_a3b_, a3b_, 128, 128, wc_, hc_, nb, 4, 2));
-  SSB_RETURN_IF(make_act_tmap(&ts_a4a_, a4a_, 128, 128, wc_, hc_, nb, 16, 2));
-  SSB_RETURN_IF(make_act_tmap(&ts_a4b_, a4b_, 128, 128, wc_, hc_, nb, 16, 2));
-  SSB_RETURN_IF(make_act_tmap(&ts_apd_, apd_, 512, 512, wc_, hc_, nb, 16, 2));
+  SSB_RETURN_IF(make_act_tmap(&ts_a4a_, a4a_, 128, 128, wc_, hc_, nb, 8, 4));
+  SSB_RETURN_IF(make_act_tmap(&ts_a4b_, a4b_, 128, 128, wc_, hc_, nb, 8, 4));
+  SSB_RETURN_IF(make_act_tmap(&ts_apd_, apd_, 512, 512, wc_, hc_, nb, 8, 4));
   SSB_RETURN_IF(make_act_tmap(&ts_grid_, grid_, 256, 256, wc_, hc_, nb, 16, 2));
   SSB_RETURN_IF(make_act_tmap(&tm_apa_, apd_, 256, 512, wc_, hc_, nb));
   SSB_RETURN_IF(make_act_tmap(&tm_ada_, apd_ + 256, 256, 512, wc_, hc_, nb));
@@ -715,28 +720,16 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   SSB_CUDA_CHECK(cudaSetDevice(device_));
   SSB_RETURN_IF(ensure_shape(batch, h, w));
   const int B = batch;
-  auto conv = [&](const char* label, const CUtensorMap& tmA, const CUtensorMap& tmS, const ConvLayer& L, int H,
-                  int W, __half* out, int Ho, int Wo, int block_n, int pool) -> int {
-    CoreParams p = conv_params(L.taps, L.cin, L.cout_pad, block_n, W);
-    p.label = label;
-    (void)out, (void)Ho, (void)Wo;
-    EpiConvRelu e{L.bias, tmS, pool, 16};
-    dim3 g(p.tiles_w * ((H + 7) / 8), L.cout / block_n, B);
-    return launch_core(tmA, tmA, L.tmB, p, e, g, stream);
-  };
-  // the five large layers (82 % of the trunk FLOPs) reuse one shared-memory halo for all nine taps
-  auto hconv = [&](const char* label, const CUtensorMap& tmH, const CUtensorMap& tmS, const ConvLayer& L, int H,
-                   int W, int subtiles, int pool) -> int {
-    HaloParams p;
+  // Cin = 128 layers: persistent halo-reuse kernel with streamed weights, 128 output channels per CTA
+  auto sconv = [&](const char* label, const CUtensorMap& tmH, const CUtensorMap& tmS, const ConvLayer& L, int H,
+                   int W, int pool) -> int {
+    StreamParams p;
     std::memset(&p, 0, sizeof(p));
-    p.slabs = L.cin / 64;
-    p.subtiles = subtiles;
-    p.block_n = L.cout;
+    p.n_slices = L.cout / 128;
     p.cout_rows = L.cout_pad;
-    p.stages = 4;
     p.label = label;
     EpiConvRelu e{L.bias, tmS, pool, 8};
-    return launch_conv_halo(tmH, L.tmB, p, e, W, H, B, 1, stream);
+    return launch_conv_stream(tmH, L.tmB128, p, e, W, H, B, stream);
   };
   // Cin = 64 layers: persistent warp-specialised kernel, weights resident, halo + TMEM double-buffered.
   // conv1a (Cin = 1) is evaluated by the halo-producer warps of conv1b: its activation never touches HBM.
@@ -760,10 +753,10 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   SSB_RETURN_IF(pconv("sp.conv2a", tm_p1b_, ts_a2a_, l2a_, h2_, w2_, 0, false));
   SSB_RETURN_IF(pconv("sp.conv2b", tm_p2a_, ts_a2b_, l2b_, h2_, w2_, 1, false));
   SSB_RETURN_IF(pconv("sp.conv3a", tm_h2b_, ts_a3a_, l3a_, h4_, w4_, 0, false));
-  SSB_RETURN_IF(hconv("sp.conv3b", tm_h3a_, ts_a3b_, l3b_, h4_, w4_, 2, 1));
-  SSB_RETURN_IF(conv("sp.conv4a", tm_a3b_, ts_a4a_, l4a_, hc_, wc_, a4a_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv("sp.conv4b", tm_a4a_, ts_a4b_, l4b_, hc_, wc_, a4b_, hc_, wc_, 128, 0));
-  SSB_RETURN_IF(conv("sp.convPaDa", tm_a4b_, ts_apd_, lpd_, hc_, wc_, apd_, hc_, wc_, 256, 0));
+  SSB_RETURN_IF(sconv("sp.conv3b", tm_h3a_, ts_a3b_, l3b_, h4_, w4_, 1));
+  SSB_RETURN_IF(sconv("sp.conv4a", tm_h3b_, ts_a4a_, l4a_, hc_, wc_, 0));
+  SSB_RETURN_IF(sconv("sp.conv4b", tm_h4a_, ts_a4b_, l4b_, hc_, wc_, 0));
+  SSB_RETURN_IF(sconv("sp.convPaDa", tm_h4b_, ts_apd_, lpd_, hc_, wc_, 0));
   {
     CoreParams p = conv_params(1, 256, lpb_.cout_pad, lpb_.cout_pad, wc_);
     p.label = "sp.convPb";

@@ -47,6 +47,7 @@ struct ConvLayer {
   float* bias = nullptr; // [cout_pad]
   CUtensorMap tmB;
   CUtensorMap tmB64;     // same matrix, 64-row boxes
+  CUtensorMap tmB128;    // same matrix, 128-row boxes (conv_stream.cuh)
 };
 
 class SuperPoint {
@@ -112,7 +113,7 @@ class SuperPoint {
   int* kp_cell_ = nullptr;               // [batch][K] cell index (row*wc + col)
   int* kp_count_ = nullptr;
   CUtensorMap tm_a1a_, tm_a1b_, tm_a2a_, tm_a2b_, tm_a3a_, tm_a3b_, tm_a4a_, tm_a4b_, tm_apa_, tm_ada_;
-  CUtensorMap tm_p1b_, tm_p2a_, tm_h2b_, tm_h3a_;  // (16+2) x (16+2) halo boxes
+  CUtensorMap tm_p1b_, tm_p2a_, tm_h2b_, tm_h3a_, tm_h3b_, tm_h4a_, tm_h4b_;  // (16+2) x (16+2) halo boxes
   CUtensorMap ts_a1b_, ts_a2a_, ts_a2b_, ts_a3a_, ts_a3b_, ts_a4a_, ts_a4b_, ts_apd_, ts_grid_;  // TMA-store maps
 
   void** desc_ptrs_dev_ = nullptr;  // [64] device table of per-image descriptor destinations
