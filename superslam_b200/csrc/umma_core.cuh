@@ -122,6 +122,22 @@ __device__ __forceinline__ void stage_drain(const EpiCtx& c) {   // before the b
   __syncwarp();
 }
 
+// Walk kChunks consecutive 32-column accumulator chunks starting at TMEM address `t0` with the loads
+// software-pipelined: the tcgen05.ld of chunk i+1 is in flight while f(i, v) works on chunk i.  (With
+// "load, wait, compute" per chunk the two epilogue warps of a scheduler spent most of their time in the
+// TMEM-load latency.)  f must consume v before it returns.
+template <int kChunks, class F>
+__device__ __forceinline__ void tmem_chunks_pipelined(uint32_t t0, F&& f) {
+  float v[2][32];
+  tmem_ld_32x32(t0, v[0]);
+#pragma unroll
+  for (int i = 0; i < kChunks; ++i) {
+    tmem_ld_wait();
+    if (i + 1 < kChunks) tmem_ld_32x32(t0 + (i + 1) * 32, v[(i + 1) & 1]);
+    f(i, v[i & 1]);
+  }
+}
+
 // Barrier among the 256 epilogue threads (both halves); every epilogue thread must call it.
 __device__ __forceinline__ void epi_pair_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
