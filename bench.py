@@ -320,7 +320,7 @@ def main():
                 # algorithmic GFLOP per launch: SuperPoint layers see 2*P images, LightGlue launches P pairs
                 gf = SP_LAYER_GF[dom] * 2 * P if dom in SP_LAYER_GF else LG_LAUNCH_GF[dom] * P
                 traffic = None
-                try:  # DRAM bytes per launch from the committed ncu captures, scaled to this run's batch
+                try:  # DRAM bytes per launch from the committed ncu capture (per image / per pair), times this run's batch
                     tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json"))).get(dom)
                     if tr:
                         traffic = int(tr["bytes"] * (2 * P if tr["per"] == "image" else P))
@@ -328,7 +328,7 @@ def main():
                     pass
                 roof = {"kernel": dom, "bound": "tensor", "achieved": gf / avg_ms, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": gf / avg_ms / peak_tf, "traffic": traffic,
-                        "traffic_source": "profiles/ncu_traffic_r01.json (ncu dram bytes at 8 pairs/step, scaled)",
+                        "traffic_source": "profiles/ncu_traffic_r01.json (ncu --set full dram bytes per image/pair at 64 pairs/step, x this run's batch)",
                         "avg_launch_ms": avg_ms,
                         "share_of_step": ms / total_prof_ms, "peak_source": peak_src,
                         "algorithmic_gflop_per_launch": gf}

@@ -1,4 +1,4 @@
-// Fused attention for LightGlue on sm_100a (flash-attention style, one CTA per 128-query tile):
+// Fused attention for LightGlue on sm_100a (flash-attention style, persistent CTAs over 128-query tiles):
 //   S = Q K^T        tcgen05.mma, fp32 accumulator in TMEM (never leaves the SM)
 //   P = exp2(S*c - m) online softmax by 256 threads (two per query row, 64 keys each), fp16 P written
 //                    straight into the 128B-swizzled shared-memory layout the next MMA reads as A
@@ -9,7 +9,7 @@
 // written to HBM.  The running max is only refreshed when it grows by more than 2^8 (the O rescale is
 // skipped otherwise), which keeps P <= 256 in fp16 and is exact after the final division by the row sum.
 //
-// Budget: 99 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's
+// Budget: 100 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's
 // exponentials (the MUFU-bound part: 16 ex2/clk/SM) overlap the other's MMAs and loads.  (A variant that
 // pipelines S/P double-buffered inside one CTA per SM measured 25 % slower: profiles/README.md.)
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
@@ -23,7 +23,7 @@ namespace ssb {
 
 constexpr int kFaThreads = 320;
 constexpr int kFaBlockKeys = 128;
-constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 2048 /*xchg*/ +
+constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 3072 /*xchg*/ +
                              128 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
@@ -33,6 +33,7 @@ struct FaParams {
   float scale_log2;    // logits scale * log2(e)
   __half* ctx;         // [img][kp][heads*64]
   int kp;
+  int q_tiles, zcount; // tile space (set by the launcher)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
@@ -47,6 +48,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
       "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -57,7 +67,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ void fa_pair_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
+// One unit of work: the 128-query tile `qt` of (image, head) `z`.
+struct FaTile {
+  int z, img, q0, nq, nk, zk, nblk;
+};
+__device__ __forceinline__ bool fa_decode(const FaParams& p, int tile, FaTile& t) {
+  t.z = tile / p.q_tiles;
+  t.q0 = (tile - t.z * p.q_tiles) * 128;
+  t.img = t.z / p.heads;
+  t.nq = p.cnt[t.img];
+  if (t.q0 >= t.nq) return false;   // no queries: nothing to compute, nothing reads these context rows
+  t.nk = p.cnt[t.img ^ p.key_xor];
+  t.zk = (t.img ^ p.key_xor) * p.heads + (t.z - t.img * p.heads);
+  t.nblk = (t.nk + kFaBlockKeys - 1) / kFaBlockKeys;
+  return true;
+}
+
 // tmQ: 4-D (64, kp, 1, Z) box (64,128,1,1).  tmK, tmV: 3-D (64, kp, Z) box (64,128,1).
+// Persistent: two CTAs per SM walk the (z, query tile) space with a stride of gridDim.x.  All mbarrier
+// phases are driven by running counters (kb = key blocks processed by this CTA, tq = tiles), so the
+// producer runs ahead across tile boundaries: Q of the next tile is loaded as soon as the last Q K^T of
+// the current one has retired, K/V blocks keep streaming through their rings, and the first S of the next
+// tile is computed underneath the last softmax of the current one.  (As one CTA per tile, ~1/3 of each
+// CTA's life went into barrier/TMEM setup and the serial Q -> K -> S -> softmax start-up latency.)
 __global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -67,9 +99,11 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sK = smem + 16384;            // 2 stages
   uint8_t* sV = smem + 16384 + 32768;    // 1 stage (V is only needed after the softmax of its block)
   uint8_t* sP = smem + 16384 + 49152;    // 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
-  float* xchg = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);  // [2][128] block max
-  float* xchg_l = xchg + 256;                                             // [2][128] row sums (epilogue)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 2048);
+  // [2 parity][2 halves][128] block maxima: softmax(b+1) may start (its S is computed underneath softmax(b))
+  // before the partner thread has read block b's exchange slot, hence two parities; [2][128] row sums follow
+  float* xchg_base = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);
+  float* xchg_l = xchg_base + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 3072);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -77,17 +111,13 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* s_full = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* s_free = bars + 9;
+  uint64_t* q_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int z = blockIdx.z;
-  const int img = z / p.heads, head = z % p.heads;
-  const int q0 = blockIdx.x * 128;
-  const int nq = p.cnt[img];
-  if (q0 >= nq) return;
-  const int nk = p.cnt[img ^ p.key_xor];
-  const int zk = (img ^ p.key_xor) * p.heads + head;
-  const int nblk = (nk + kFaBlockKeys - 1) / kFaBlockKeys;
+  const int total = p.q_tiles * p.zcount;
+  const int stride = static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -102,6 +132,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(s_full, 1);
     mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
+    mbar_init(s_free, 8);
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -120,38 +152,45 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // single instruction (inside `if (lane == 0)` each one became an ELECT / R2UR / branch sequence of ~100
   // cycles, which sat on the S -> softmax -> P*V critical path twelve times per key block).
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 16384);
-      tma_load_4d(sQ, &tmQ, q_full, 0, q0, 0, z);
-    }
-    __syncwarp();
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(&k_empty[s], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u);   // S(j-2) has consumed it
+    uint32_t kb = 0, tq = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride) {
+      FaTile t;
+      if (!fa_decode(p, tile, t) || t.nblk == 0) continue;
+      mbar_wait(q_empty, (tq & 1u) ^ 1u);    // the last Q K^T of the previous tile has read Q
       if (elect_one()) {
-        mbar_arrive_expect_tx(&k_full[s], 16384);
-        tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, zk);
+        mbar_arrive_expect_tx(q_full, 16384);
+        tma_load_4d(sQ, &tmQ, q_full, 0, t.q0, 0, t.z);
       }
       __syncwarp();
-      if (j > 0) mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);       // P*V(j-1) has consumed V
-      if (elect_one()) {
-        mbar_arrive_expect_tx(v_full, 16384);
-        tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, zk);
+      ++tq;
+      for (int j = 0; j < t.nblk; ++j, ++kb) {
+        const uint32_t s = kb & 1u;
+        mbar_wait(&k_empty[s], ((kb >> 1) & 1u) ^ 1u);   // S(kb-2) has consumed it
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[s], 16384);
+          tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, t.zk);
+        }
+        __syncwarp();
+        if (kb > 0) mbar_wait(pv_done, (kb - 1) & 1u);       // P*V(kb-1) has consumed V
+        if (elect_one()) {
+          mbar_arrive_expect_tx(v_full, 16384);
+          tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, t.zk);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
     const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
-    mbar_wait(q_full, 0);
     const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
     const uint32_t vbase = smem_u32(sV), pbase = smem_u32(sP), kbase = smem_u32(sK);
-    // S(j+1) is issued BEFORE P*V(j): the softmax warps get their next logits ~400 cycles earlier (they sat
-    // in the s_full wait a quarter of the time), and P*V(j) still finishes long before its result, the P
-    // buffer or V are needed again (after the max pass of block j+1).
-    auto issue_s = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(&k_full[s], static_cast<uint32_t>(j >> 1) & 1u);
+    // S(b+1) is issued as soon as the softmax warps have pulled S(b) out of TMEM into registers (s_free),
+    // i.e. it runs underneath the whole softmax of block b - also across a tile boundary, where it first
+    // waits for the next tile's Q; P*V(b) follows once P(b) is in shared memory.
+    // issue_s(b, last): S for global block b; `last` = final block of its tile (Q may then be replaced).
+    auto issue_s = [&](uint32_t b, bool last) {
+      const uint32_t s = b & 1u;
+      mbar_wait(&k_full[s], (b >> 1) & 1u);
       tc_fence_after();
       const uint64_t kdesc = make_smem_desc_k_sw128(kbase + s * 16384, 1024);
       if (elect_one()) {
@@ -159,27 +198,56 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&k_empty[s]);
         umma_commit(s_full);
+        if (last) umma_commit(q_empty);
       }
       __syncwarp();
     };
-    issue_s(0);
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(p_full, static_cast<uint32_t>(j) & 1u);   // softmax(j) has read S(j) and written P(j)
+    // next valid tile at or after `tile`
+    auto next_tile = [&](int tile, FaTile& t) -> int {
+      for (; tile < total; tile += stride)
+        if (fa_decode(p, tile, t) && t.nblk > 0) return tile;
+      return total;
+    };
+    uint32_t kb = 0, tq = 0;
+    FaTile cur, nxt;
+    int tile = next_tile(blockIdx.x, cur);
+    if (tile < total) {
+      mbar_wait(q_full, 0);
       tc_fence_after();
-      if (j + 1 < nblk) issue_s(j + 1);
-      mbar_wait(v_full, static_cast<uint32_t>(j) & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
-          const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
-          const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
-          umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+      issue_s(0, cur.nblk == 1);
+    }
+    while (tile < total) {
+      const int ntile = next_tile(tile + stride, nxt);
+      for (int j = 0; j < cur.nblk; ++j, ++kb) {
+        const bool more = j + 1 < cur.nblk;
+        if (more || ntile < total) {
+          mbar_wait(s_free, kb & 1u);   // every softmax warp holds S(kb) in registers
+          tc_fence_after();
+          if (!more) {                  // first block of the next tile: its Q must have landed
+            mbar_wait(q_full, (tq + 1) & 1u);
+            tc_fence_after();
+          }
+          issue_s(kb + 1, more ? (j + 2 == cur.nblk) : (nxt.nblk == 1));
         }
-        umma_commit(pv_done);
+        mbar_wait(p_full, kb & 1u);   // softmax(kb) has written P(kb)
+        tc_fence_after();
+        mbar_wait(v_full, kb & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
+            const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
+            const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
+            umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(pv_done);
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      ++tq;
+      tile = ntile;
+      cur = nxt;
     }
   } else {
     const int qd = warp & 3;
@@ -189,114 +257,137 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tSh = tS + lane_off + half * 64;
     const uint32_t tOh = tO + lane_off + half * 32;
     uint8_t* slab = sP + half * 16384 + row * 128;
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, static_cast<uint32_t>(j) & 1u);
-      tc_fence_after();
-      const int kvalid = min(64, nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
-      // pass 1: maximum of my 64 logits (raw; the positive scale is applied once)
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    uint32_t kb = 0;
+    for (int tile = blockIdx.x; tile < total; tile += stride) {
+      FaTile t;
+      if (!fa_decode(p, tile, t)) continue;
+      auto ctx_row = [&]() {
+        return reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(t.img) * p.kp + t.q0 + row) * (p.heads * 64) +
+                                        (t.z - t.img * p.heads) * 64 + half * 32);
+      };
+      if (t.nblk == 0) {   // no keys: the message is zero
+        uint4* dst = ctx_row();
 #pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tmem_ld_32x32(tSh + c, v);
+        for (int u = 0; u < 4; ++u) dst[u] = make_uint4(0u, 0u, 0u, 0u);
+        continue;
+      }
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < t.nblk; ++j, ++kb) {
+        mbar_wait(s_full, kb & 1u);
+        tc_fence_after();
+        const int kvalid = min(64, t.nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
+        // my 64 logits -> registers (one TMEM read; S is then free for the next block's Q K^T)
+        float v[64];
+        tmem_ld_32x32(tSh, v);
+        tmem_ld_32x32(tSh + 32, v + 32);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        // maximum of my 64 logits (raw; the positive scale is applied once)
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (kvalid >= 64) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+          for (int i = 0; i < 64; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+          for (int i = 0; i < 64; ++i)
+            if (i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
         }
-      }
-      xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      fa_pair_sync();
-      const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
-      float alpha = 1.f;
-      bool need = false;
-      if (j == 0) {
-        m_used = bm;
-      } else if (bm > m_used + 8.0f) {
-        alpha = fast_exp2(m_used - bm);
-        m_used = bm;
-        need = true;
-      }
-      // P and O are still being read / written by the previous P*V until pv_done fires
-      if (j > 0) {
-        mbar_wait(pv_done, static_cast<uint32_t>(j - 1) & 1u);
-        tc_fence_after();
-      }
-      if (__any_sync(0xffffffffu, need)) {
-        l *= alpha;
-        float o[32];
-        tmem_ld_32x32(tOh, o);
-        tmem_ld_wait();
+        float* xchg = xchg_base + (kb & 1u) * 256;
+        xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        fa_pair_sync();
+        const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = bm;
+        } else if (bm > m_used + 8.0f) {
+          alpha = fast_exp2(m_used - bm);
+          m_used = bm;
+          need = true;
+        }
+        // P and O are still being read / written by the previous P*V until pv_done fires
+        if (kb > 0) {
+          mbar_wait(pv_done, (kb - 1) & 1u);
+          tc_fence_after();
+        }
+        if (__any_sync(0xffffffffu, need)) {
+          l *= alpha;
+          // two 16-column pieces: the 64 logits of this block stay live in registers across the (rare) rescale
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            float o[16];
+            tmem_ld_32x16(tOh + h * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-        tmem_st_32x32(tOh, o);
-        tmem_st_wait();
-      }
-      // pass 2: probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tmem_ld_32x32(tSh + c, v);
-        tmem_ld_wait();
+            for (int i = 0; i < 16; ++i) o[i] *= alpha;
+            tmem_st_32x16(tOh + h * 16, o);
+          }
+          tmem_st_wait();
+        }
+        // probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
         if (kvalid >= 64) {   // warp-uniform: no per-element masking in the common case
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
-            ls[i & 3] += e;
-            v[i] = e;
+          for (int u = 0; u < 8; ++u) {
+            float e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              e[k] = fast_exp2(fmaf(v[8 * u + k], p.scale_log2, -m_used));
+              ls[k & 3] += e[k];
+            }
+            uint4 w;
+            w.x = pack_half2(e[0], e[1]);
+            w.y = pack_half2(e[2], e[3]);
+            w.z = pack_half2(e[4], e[5]);
+            w.w = pack_half2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(slab + ((u ^ (row & 7)) << 4)) = w;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
-            if (c + i >= kvalid) e = 0.f;
-            ls[i & 3] += e;
-            v[i] = e;
+          for (int u = 0; u < 8; ++u) {
+            float e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int i = 8 * u + k;
+              e[k] = i < kvalid ? fast_exp2(fmaf(v[i], p.scale_log2, -m_used)) : 0.f;
+              ls[k & 3] += e[k];
+            }
+            uint4 w;
+            w.x = pack_half2(e[0], e[1]);
+            w.y = pack_half2(e[2], e[3]);
+            w.z = pack_half2(e[4], e[5]);
+            w.w = pack_half2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(slab + ((u ^ (row & 7)) << 4)) = w;
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c >> 3) + u;
-          uint4 w;
-          w.x = pack_half2(v[8 * u + 0], v[8 * u + 1]);
-          w.y = pack_half2(v[8 * u + 2], v[8 * u + 3]);
-          w.z = pack_half2(v[8 * u + 4], v[8 * u + 5]);
-          w.w = pack_half2(v[8 * u + 6], v[8 * u + 7]);
-          *reinterpret_cast<uint4*>(slab + ((unit ^ (row & 7)) << 4)) = w;
-        }
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
       }
-      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
-    }
-    // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
-    xchg_l[half * 128 + row] = l;
-    fa_pair_sync();
-    const float inv = 1.0f / (xchg_l[row] + xchg_l[128 + row]);
-    mbar_wait(pv_done, static_cast<uint32_t>(nblk - 1) & 1u);
-    tc_fence_after();
-    const bool valid = (q0 + row) < nq;
-    float o[32];
-    tmem_ld_32x32(tOh, o);
-    tmem_ld_wait();
-    uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(img) * p.kp + q0 + row) * (p.heads * 64) +
-                                          head * 64 + half * 32);
+      // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
+      xchg_l[half * 128 + row] = l;
+      fa_pair_sync();
+      const float inv = 1.0f / (xchg_l[row] + xchg_l[128 + row]);
+      mbar_wait(pv_done, (kb - 1) & 1u);
+      tc_fence_after();
+      const bool valid = (t.q0 + row) < t.nq;
+      float o[32];
+      tmem_ld_32x32(tOh, o);
+      tmem_ld_wait();
+      uint4* dst = ctx_row();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      uint4 w;
-      w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
-      w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
-      w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
-      w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
-      dst[u] = w;
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
+        w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
+        w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
+        w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
+        dst[u] = w;
+      }
     }
   }
   tc_fence_before();
@@ -305,17 +396,23 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                                  const FaParams& p, int q_tiles, int z, cudaStream_t stream, const char* label) {
+                                  FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
   static bool configured = false;
   if (!configured) {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kFaSmemBytes));
-    // ask for the full shared-memory carveout so that two CTAs (2 x 99 KB) are co-resident per SM
+    // ask for the full shared-memory carveout so that two CTAs (2 x 100 KB) are co-resident per SM
     SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  flash_attention_kernel<<<dim3(q_tiles, 1, z), kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  p.q_tiles = q_tiles;
+  p.zcount = z;
+  const int total = q_tiles * z;
+  if (total <= 0) return SSB_OK;
+  const int resident = 2 * device_sm_count();
+  const int ctas = total < resident ? total : resident;
+  flash_attention_kernel<<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, label);
