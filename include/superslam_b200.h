@@ -33,6 +33,7 @@ extern "C" {
 typedef struct ssb_superpoint ssb_superpoint;
 typedef struct ssb_lightglue ssb_lightglue;
 typedef struct ssb_frontend ssb_frontend;
+typedef struct ssb_eigenplaces ssb_eigenplaces;
 
 const char* ssb_last_error(void);
 int ssb_version(void);
@@ -133,6 +134,32 @@ void ssb_profile_collect(void);
 int ssb_profile_report(char* buf, size_t bytes);
 ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe);
 ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe);
+
+/* ---- EigenPlaces: replaces class EigenPlaces (include/EigenPlaces.h:21-66) ----------------------
+ * superslam::IPlaceRecognizer (include/PlaceRecognizer.h:20-36) over a B200-native ResNet18 + GeM + FC
+ * global-descriptor network and a device-resident CosineDescriptorIndex (src/PlaceRecognizer.cc:21-52). */
+
+/* EigenPlaces(engine_file, input_width, input_height) + initialize() (include/EigenPlaces.h:26-30).
+ * `weights_path`: SSBW archive with the state-dict names of the torch.hub model
+ * (utils/convert_eigenplaces_to_onnx.py:54-60; superslam_b200/eigenplaces_weights.py).  Both sides of the
+ * network input must be multiples of 32.  `max_batch` images are processed per pass (the reference: 1). */
+int ssb_ep_create(const char* weights_path, int input_width, int input_height, int max_batch, int device_id,
+                  ssb_eigenplaces** out);
+void ssb_ep_destroy(ssb_eigenplaces* ep);
+int ssb_ep_descriptor_dim(ssb_eigenplaces* ep); /* 512 */
+/* IPlaceRecognizer::compute_global_descriptor (src/EigenPlaces.cc:145-174) for `count` same-size images:
+ * gray / BGR u8 -> RGB, cv::resize to the network input, /255, ImageNet normalisation (:123-143), network,
+ * final L2 normalisation.  descriptors: host [count][512] float32. */
+int ssb_ep_compute(ssb_eigenplaces* ep, const uint8_t* const* images, int count, int height, int width,
+                   int row_stride, int channels, float* descriptors);
+/* IPlaceRecognizer::add / ::query (include/EigenPlaces.h:36-42, src/PlaceRecognizer.cc:21-52): rows are
+ * re-normalised on insertion, insertion order is recency; a query returns at most `top_k` (and `capacity`)
+ * entries with score >= min_score among all but the last `exclude_recent` insertions, best first. */
+int ssb_ep_add(ssb_eigenplaces* ep, uint64_t keyframe_id, const float* descriptor, int dim);
+int ssb_ep_query(ssb_eigenplaces* ep, const float* descriptor, int dim, uint64_t exclude_recent, int top_k,
+                 float min_score, uint64_t* keyframe_ids, float* scores, int capacity, int* n_out);
+int ssb_ep_index_size(ssb_eigenplaces* ep); /* CosineDescriptorIndex::size() */
+int ssb_ep_debug_read(ssb_eigenplaces* ep, const char* what, void* dst, size_t bytes);
 
 #ifdef __cplusplus
 }

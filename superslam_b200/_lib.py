@@ -63,6 +63,15 @@ SYMBOLS = [
     ("ssb_fe_kernel_launches_per_call", C.c_int, [_vp, C.c_int]),
     ("ssb_fe_superpoint", _vp, [_vp]),
     ("ssb_fe_lightglue", _vp, [_vp]),
+    ("ssb_ep_create", C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_ep_destroy", None, [_vp]),
+    ("ssb_ep_descriptor_dim", C.c_int, [_vp]),
+    ("ssb_ep_compute", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    ("ssb_ep_add", C.c_int, [_vp, C.c_uint64, _fp, C.c_int]),
+    ("ssb_ep_query", C.c_int, [_vp, _fp, C.c_int, C.c_uint64, C.c_int, C.c_float, C.POINTER(C.c_uint64), _fp,
+                               C.c_int, _ip]),
+    ("ssb_ep_index_size", C.c_int, [_vp]),
+    ("ssb_ep_debug_read", C.c_int, [_vp, C.c_char_p, _vp, C.c_size_t]),
     ("ssb_kernel_launch_count", C.c_longlong, []),
     ("ssb_profile_enable", None, [C.c_int]),
     ("ssb_profile_collect", None, []),

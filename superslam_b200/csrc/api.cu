@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/superslam_b200.h"
+#include "eigenplaces.cuh"
 #include "lightglue.cuh"
 #include "superpoint.cuh"
 
@@ -16,6 +17,9 @@ struct ssb_superpoint {
 };
 struct ssb_lightglue {
   ssb::LightGlue impl;
+};
+struct ssb_eigenplaces {
+  ssb::EigenPlaces impl;
 };
 
 namespace ssb {
@@ -456,6 +460,50 @@ int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
   // conv1a + 10 tcgen05 convs + memset-free: nms, select, gather | prepare + 9 x 15 + 8 | postfilter
   return 14 + 1 + 9 * 16 + 8 + 1;
 }
+int ssb_ep_create(const char* weights_path, int input_width, int input_height, int max_batch, int device_id,
+                  ssb_eigenplaces** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  SSB_CUDA_CHECK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  SSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_id));
+  SSB_CHECK(prop.major == 10, SSB_ERR_NODEVICE, "device %d is sm_%d%d; this library needs sm_100", device_id,
+            prop.major, prop.minor);
+  std::unique_ptr<ssb_eigenplaces> h(new ssb_eigenplaces);
+  SSB_RETURN_IF(h->impl.init(weights_path, input_width, input_height, max_batch <= 0 ? 1 : max_batch, device_id));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_ep_destroy(ssb_eigenplaces* ep) { delete ep; }
+int ssb_ep_descriptor_dim(ssb_eigenplaces* ep) { return ep ? ssb::kEpDim : -1; }
+int ssb_ep_compute(ssb_eigenplaces* ep, const uint8_t* const* images, int count, int height, int width,
+                   int row_stride, int channels, float* descriptors) {
+  SSB_API_BEGIN
+  SSB_CHECK(ep != nullptr, SSB_ERR_INVALID, "ep is null");
+  return ep->impl.compute(images, count, height, width, channels, row_stride, descriptors);
+  SSB_API_END
+}
+int ssb_ep_add(ssb_eigenplaces* ep, uint64_t keyframe_id, const float* descriptor, int dim) {
+  SSB_API_BEGIN
+  SSB_CHECK(ep != nullptr, SSB_ERR_INVALID, "ep is null");
+  return ep->impl.add(keyframe_id, descriptor, dim);
+  SSB_API_END
+}
+int ssb_ep_query(ssb_eigenplaces* ep, const float* descriptor, int dim, uint64_t exclude_recent, int top_k,
+                 float min_score, uint64_t* keyframe_ids, float* scores, int capacity, int* n_out) {
+  SSB_API_BEGIN
+  SSB_CHECK(ep != nullptr, SSB_ERR_INVALID, "ep is null");
+  return ep->impl.query(descriptor, dim, exclude_recent, top_k, min_score, keyframe_ids, scores, capacity, n_out);
+  SSB_API_END
+}
+int ssb_ep_index_size(ssb_eigenplaces* ep) { return ep ? ep->impl.index_size() : -1; }
+int ssb_ep_debug_read(ssb_eigenplaces* ep, const char* what, void* dst, size_t bytes) {
+  SSB_CHECK(ep != nullptr && dst != nullptr, SSB_ERR_INVALID, "null argument");
+  return ep->impl.debug_read(what, dst, bytes);
+}
+
 ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe) { return fe ? &fe->impl.sp : nullptr; }
 ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe) { return fe ? &fe->impl.lg : nullptr; }
 

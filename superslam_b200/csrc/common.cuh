@@ -305,7 +305,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 #endif  // __CUDACC__
 
 // Host: encode TMA tensor maps (driver entry point resolved through the runtime, no libcuda link).
+// `elem_strides` (optional, rank entries): traversal stride per dimension - with stride s the box covers
+// box[i] elements of the tensor and ceil(box[i] / s) of them are loaded (strided convolutions).
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box);
+                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
+                    const uint32_t* elem_strides = nullptr);
 
 }  // namespace ssb

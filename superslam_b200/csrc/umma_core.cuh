@@ -44,6 +44,7 @@ inline DevCount dev_count(const int* ptr, int div = 1, int xr = 0, int mul = 1, 
 struct CoreParams {
   // K loop: taps_h*taps_w filter taps, each contributing kc0 (+kc1) 64-wide channel chunks.
   int taps_h, taps_w, pad;
+  int a_stride;        // convolution stride (0 or 1 = dense; 2 needs an A tensor map with element strides 2)
   int kc0, kc1;
   int b_tap_rows;      // row offset in B between consecutive taps
   // M tiling: tile x -> (tile_x, tile_y); the TMA box is tile_w x tile_h pixels (product 128).
@@ -272,6 +273,10 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int kc = kc0 + p.kc1;
       const int az = z * p.a_z_mul + p.a_z_add;
       const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
+      if (p.a_stride > 1) {   // input coordinates of the tile origin
+        w0 *= p.a_stride;
+        h0 *= p.a_stride;
+      }
       for (int th = 0; th < p.taps_h; ++th) {
         for (int tw = 0; tw < p.taps_w; ++tw) {
           const int tap = th * p.taps_w + tw;

@@ -359,3 +359,80 @@ class FramePairPipeline:
 
 def kernel_launch_count() -> int:
     return int(_lib.load().ssb_kernel_launch_count())
+
+
+class EigenPlaces:
+    """IPlaceRecognizer over ssb_ep_* (reference class EigenPlaces, include/EigenPlaces.h:21-66;
+    interface include/PlaceRecognizer.h:20-36).  compute_global_descriptor never raises on a failed
+    inference: like the reference (src/EigenPlaces.cc:146-147,157-160) it logs and returns an empty row."""
+
+    def __init__(self, weights_path: str, input_width: int, input_height: int, max_batch: int = 1,
+                 device: int = 0, min_score: float | None = None):
+        import os
+
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.input_width, self.input_height = input_width, input_height
+        # EigenPlaces::EigenPlaces reads SUPERSLAM_LOOP_MIN_SCORE (src/EigenPlaces.cc:30-34); default 0.75
+        env = os.environ.get("SUPERSLAM_LOOP_MIN_SCORE")
+        self.min_score = float(min_score) if min_score is not None else (float(env) if env else 0.75)
+        _lib.check(self._lib.ssb_ep_create(weights_path.encode(), input_width, input_height, max_batch, device,
+                                           C.byref(self._h)))
+        self.dim = self._lib.ssb_ep_descriptor_dim(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_ep_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def compute_global_descriptors(self, images) -> np.ndarray:
+        """Batch form: same-size images -> [n, 512] float32 (rows L2-normalised); empty on failure."""
+        prepared = [_as_gray_or_bgr(i) for i in images]
+        if not prepared:
+            return np.zeros((0, self.dim), np.float32)
+        h, w = prepared[0][0].shape[:2]
+        ch = prepared[0][1]
+        if any(im.shape[:2] != (h, w) or c != ch for im, c in prepared):
+            log.error("EigenPlaces: images of one call must share size and channel count")
+            return np.zeros((0, self.dim), np.float32)
+        n = len(prepared)
+        ptrs = (C.POINTER(C.c_uint8) * n)(*[im.ctypes.data_as(C.POINTER(C.c_uint8)) for im, _ in prepared])
+        out = np.zeros((n, self.dim), np.float32)
+        st = self._lib.ssb_ep_compute(self._h, ptrs, n, h, w, prepared[0][0].strides[0], ch,
+                                      out.ctypes.data_as(C.POINTER(C.c_float)))
+        if st != _lib.SSB_OK:
+            log.error("EigenPlaces: inference failed: %s", self._lib.ssb_last_error().decode())
+            return np.zeros((0, self.dim), np.float32)
+        return out
+
+    def compute_global_descriptor(self, image) -> np.ndarray:
+        """[1, 512] float32, L2-normalised; empty [0, 512] on failure."""
+        return self.compute_global_descriptors([image])
+
+    def add(self, keyframe_id: int, global_descriptor) -> None:
+        d = np.ascontiguousarray(global_descriptor, np.float32).reshape(-1)
+        _lib.check(self._lib.ssb_ep_add(self._h, int(keyframe_id), d.ctypes.data_as(C.POINTER(C.c_float)), len(d)))
+
+    def query(self, global_descriptor, exclude_recent: int, top_k: int, min_score: float | None = None):
+        """-> list of (keyframe_id, score) by descending score (LoopCandidate, PlaceRecognizer.h:11-16)."""
+        d = np.ascontiguousarray(global_descriptor, np.float32).reshape(-1)
+        cap = max(1, self.size() if top_k <= 0 else min(top_k, max(1, self.size())))
+        ids = (C.c_uint64 * cap)()
+        sc = np.zeros((cap,), np.float32)
+        n = C.c_int(0)
+        ms = self.min_score if min_score is None else float(min_score)
+        _lib.check(self._lib.ssb_ep_query(self._h, d.ctypes.data_as(C.POINTER(C.c_float)), len(d), int(exclude_recent),
+                                          int(top_k), C.c_float(ms), ids, sc.ctypes.data_as(C.POINTER(C.c_float)), cap,
+                                          C.byref(n)))
+        return [(int(ids[i]), float(sc[i])) for i in range(n.value)]
+
+    def size(self) -> int:
+        return self._lib.ssb_ep_index_size(self._h)
+
+    def debug_read(self, what: str, shape, dtype):
+        out = np.empty(shape, dtype)
+        _lib.check(self._lib.ssb_ep_debug_read(self._h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
