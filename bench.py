@@ -156,6 +156,43 @@ def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
     return float(np.median(times)), best_c, len(times)
 
 
+def bench_eigenplaces(lib, device: int, steps: int = 10, batch: int = 8):
+    """the EigenPlaces global descriptor (ResNet18 + GeM + FC on the tcgen05 conv
+    core) for `batch` 752x480 keyframes per call, host images in, host descriptors out (the public call)."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.eigenplaces_weights import make_random_weights, save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    path = f"/tmp/ssb_bench_eigenplaces_d{device}.ssbw"
+    save_state_dict(make_random_weights(11), path)
+    ep = fe.EigenPlaces(path, 512, 512, max_batch=batch, device=device)
+    imgs = [synth_pair(480, 752, 4000 + i)[0] for i in range(batch)]
+    for _ in range(3):
+        d = ep.compute_global_descriptors(imgs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d = ep.compute_global_descriptors(imgs)
+    dt = (time.perf_counter() - t0) / steps
+    lib.ssb_profile_enable(1)
+    for _ in range(3):
+        ep.compute_global_descriptors(imgs)
+        lib.ssb_profile_collect()
+    lib.ssb_profile_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    lib.ssb_profile_report(buf, len(buf))
+    k = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, ms = ln.split()
+        if name.startswith("ep."):
+            k[name] = round(float(ms) / 3, 4)
+    gf = 18.95   # 2*MAC of ResNet18 up to layer4 at 512x512 (stem 1.23, layer1 4.83, layers 2-4 4.30 each)
+    dev_ms = sum(k.values())
+    return {"images_per_s": batch / dt, "batch": batch, "workload": "C4 keyframes 752x480 gray -> 512x512 network input",
+            "ms_per_call_e2e": dt * 1e3, "device_ms_per_call": dev_ms, "kernel_ms_per_call": k,
+            "algorithmic_gflop_per_image": gf, "tflops_device": gf * batch / dev_ms if dev_ms else None,
+            "descriptor_norm": float(np.linalg.norm(d[0])) if len(d) else None}
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -343,6 +380,12 @@ def main():
             if gfl > 0 and ms > 0:
                 tensor_kernels[name] = {"avg_launch_ms": round(ms / cnt, 5), "tflops": round(gfl / (ms / cnt), 1),
                                         "frac_of_peak": round(gfl / (ms / cnt) / peak_tf, 4)}
+        eigen = None
+        if world == 1:
+            try:
+                eigen = bench_eigenplaces(lib, local)
+            except Exception as e:  # the headline line must not depend on the "next" row
+                eigen = {"error": str(e)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             sec, threads, timed = oracle_pair_seconds(5, 1, budget_s=20.0)
@@ -367,6 +410,7 @@ def main():
             "tensor_kernels": tensor_kernels,
             "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu,
+            "eigenplaces": eigen,
             "wall_s_timed_region": wall,
             "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},
         }

@@ -9,6 +9,7 @@
 //   SuperPoint(engine, max_kp, thresh, borders) + initialize()          superslam_b200::SuperPointB200
 //   LightGlue(engine, w, h) + initialize()                              superslam_b200::LightGlueB200
 //   LightGlue(shared_engine(), w, h)                                    LightGlueB200(other, w, h)
+//   EigenPlaces(engine, w, h) + initialize()  (include/EigenPlaces.h:21-66)  superslam_b200::EigenPlacesB200
 //
 // Error behaviour is the reference's: interface methods never throw; failure -> empty Features /
 // MatchResult (src/SuperPoint.cc:895-899, src/LightGlue.cc:381-390); initialize() returns bool.
@@ -21,7 +22,10 @@
 #include <utility>
 #include <vector>
 
+#include <cstdlib>
+
 #include "InferenceInterfaces.h"  // reference header: superslam::IFeatureExtractor / IFeatureMatcher
+#include "PlaceRecognizer.h"      // reference header: superslam::IPlaceRecognizer, LoopCandidate
 #include "superslam_b200.h"
 
 namespace superslam_b200 {
@@ -170,6 +174,59 @@ class LightGlueB200 : public superslam::IFeatureMatcher {
   int w_, h_, max_kp_, device_;
   ssb_lightglue* shared_ = nullptr;
   ssb_lightglue* lg_ = nullptr;
+};
+
+// superslam::IPlaceRecognizer (include/PlaceRecognizer.h:20-36) over ssb_ep_*: the global-descriptor network
+// and the cosine index both live on the GPU.  Runs on the loop worker thread like the reference's class.
+class EigenPlacesB200 : public superslam::IPlaceRecognizer {
+ public:
+  EigenPlacesB200(std::string weights_file, int input_width, int input_height, int device_id = 0)
+      : weights_(std::move(weights_file)), w_(input_width), h_(input_height), device_(device_id) {
+    if (const char* s = std::getenv("SUPERSLAM_LOOP_MIN_SCORE"))   // src/EigenPlaces.cc:30-34
+      min_score_ = static_cast<float>(std::atof(s));
+  }
+  ~EigenPlacesB200() override { ssb_ep_destroy(ep_); }
+
+  bool initialize() { return ssb_ep_create(weights_.c_str(), w_, h_, /*max_batch=*/1, device_, &ep_) == SSB_OK; }
+
+  cv::Mat compute_global_descriptor(const cv::Mat& image) override {
+    if (!ep_ || image.empty() || image.depth() != CV_8U) return cv::Mat();   // src/EigenPlaces.cc:146-147
+    const uint8_t* ptr = image.data;
+    cv::Mat desc(1, ssb_ep_descriptor_dim(ep_), CV_32F);
+    if (ssb_ep_compute(ep_, &ptr, 1, image.rows, image.cols, static_cast<int>(image.step[0]), image.channels(),
+                       desc.ptr<float>()) != SSB_OK)
+      return cv::Mat();
+    return desc;
+  }
+  void add(size_t keyframe_id, const cv::Mat& global_descriptor) override {
+    cv::Mat row = global_descriptor.reshape(1, 1);
+    if (row.type() != CV_32F) row.convertTo(row, CV_32F);
+    if (!row.isContinuous()) row = row.clone();
+    ssb_ep_add(ep_, keyframe_id, row.ptr<float>(), row.cols);
+  }
+  std::vector<superslam::LoopCandidate> query(const cv::Mat& global_descriptor, size_t excludeRecent,
+                                              int topK) override {
+    std::vector<superslam::LoopCandidate> out;
+    cv::Mat row = global_descriptor.reshape(1, 1);
+    if (row.type() != CV_32F) row.convertTo(row, CV_32F);
+    if (!row.isContinuous()) row = row.clone();
+    const int cap = topK > 0 ? topK : ssb_ep_index_size(ep_);
+    if (cap <= 0) return out;
+    std::vector<uint64_t> ids(cap);
+    std::vector<float> sc(cap);
+    int n = 0;
+    if (ssb_ep_query(ep_, row.ptr<float>(), row.cols, excludeRecent, topK, min_score_, ids.data(), sc.data(), cap,
+                     &n) != SSB_OK)
+      return out;
+    for (int i = 0; i < n; ++i) out.push_back({static_cast<size_t>(ids[i]), sc[i]});
+    return out;
+  }
+
+ private:
+  std::string weights_;
+  int w_, h_, device_;
+  float min_score_ = 0.75f;   // include/EigenPlaces.h:55
+  ssb_eigenplaces* ep_ = nullptr;
 };
 
 }  // namespace superslam_b200

@@ -493,6 +493,7 @@ int EigenPlaces::conv(const EpConv& L, const CUtensorMap& in, const CUtensorMap&
 
 int EigenPlaces::run(int batch) {
   const int H2 = in_h_ / 2, W2 = in_w_ / 2, H4 = in_h_ / 4, W4 = in_w_ / 4;
+  prof_begin(stream_);
   ep_preprocess_kernel<<<dim3((in_w_ + 255) / 256, in_h_, batch), 256, 0, stream_>>>(
       src_dev_, src_h_, src_w_, src_c_, tab_dev_, in_h_, in_w_, resize_mode_, x0_);
   SSB_CUDA_CHECK(cudaGetLastError());
