@@ -70,3 +70,70 @@ def test_kitti_size_pipeline_k2048(tmp_path, lg_weights):
                        olg.normalize_keypoints(R.keypoints, w, h), d1)
     assert (out["matches0"][0] == om0).mean() >= 0.98
     assert out["has_depth"][0].sum() > 50
+
+
+def test_c5_720p_k4096_dynamic_counts(tmp_path, lg_weights):
+    """Config C5: 1280 x 720, K = 4096, pairs with different keypoint counts in one call (dynamic N):
+    the batched pipeline must equal the per-pair interface calls exactly, and LightGlue on the sparser
+    pair must agree with the oracle."""
+    from oracle import lightglue as olg
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    h, w, K = 720, 1280, 4096
+    pairs = [synth_pair(h, w, 1234, 900), synth_pair(h, w, 1235, 3000)]
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=2)
+    out = pipe.process([im for p in pairs for im in p])
+    cnt = out["count"].tolist()
+    assert cnt[2] == K and cnt[3] == K                 # the dense pair saturates K
+    assert 256 < cnt[0] < K and 256 < cnt[1] < K       # the sparse one does not: ragged tiles inside one launch
+    sp = fe.SuperPoint(SP_WEIGHTS, K)
+    lg = fe.LightGlue(lgw, w, h, max_keypoints=K)
+    for p, (l, r) in enumerate(pairs):
+        L, R = sp.extract_stereo(l, r)
+        n0, n1 = cnt[2 * p], cnt[2 * p + 1]
+        assert (len(L.keypoints), len(R.keypoints)) == (n0, n1)
+        assert np.array_equal(out["xy"][2 * p, :n0], L.keypoints)
+        m = lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
+        assert np.array_equal(out["matches0"][p, :n0], m.matches0)
+        assert np.array_equal(out["mscores0"][p, :n0], m.mscores0)
+        assert np.all(out["matches0"][p, n0:] == -1)
+        if p == 0:
+            d0, d1 = lg.descriptors_to_host(L.descriptors), lg.descriptors_to_host(R.descriptors)
+            om0, _ = olg.match(lg_weights, olg.normalize_keypoints(L.keypoints, w, h), d0,
+                               olg.normalize_keypoints(R.keypoints, w, h), d1)
+            assert (m.matches0 == om0).mean() >= 0.98
+    assert out["has_depth"][1].sum() > 100
+
+
+def test_c4_euroc_size_with_keyframe_descriptor(tmp_path, lg_weights):
+    """Config C4: 752 x 480 stereo pairs, K = 1024, plus one EigenPlaces global descriptor per keyframe
+    computed from the left image and fed to the loop-closure index."""
+    from oracle import eigenplaces as oep
+    from superslam_b200 import frontend as fe
+    from superslam_b200.eigenplaces_weights import make_random_weights, save_state_dict as save_ep
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw, epw = str(tmp_path / "lg.ssbw"), str(tmp_path / "ep.ssbw")
+    save_state_dict(lg_weights, lgw)
+    save_ep(make_random_weights(11), epw)
+    h, w, K = 480, 752, 1024
+    pairs = [synth_pair(h, w, 300 + i) for i in range(4)]
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=4)
+    out = pipe.process([im for p in pairs for im in p])
+    assert out["count"].min() > 500 and out["has_depth"].sum(axis=1).min() > 30
+    ep = fe.EigenPlaces(epw, 512, 512, max_batch=4, min_score=0.5)
+    lefts = [p[0] for p in pairs]
+    d = ep.compute_global_descriptors(lefts)
+    ref = oep.compute_global_descriptor(oep.load_weights(epw), lefts[0], 512, 512)
+    assert float(np.sum(d[0] * ref[0])) > 0.9995
+    for i in range(4):
+        ep.add(i, d[i:i + 1])
+    # revisiting keyframe 1 (same place, sensor noise): best candidate among all but the last insertion
+    noisy = np.clip(lefts[1].astype(np.int16) + np.random.default_rng(0).integers(-3, 4, lefts[1].shape), 0, 255).astype(np.uint8)
+    res = ep.query(ep.compute_global_descriptor(noisy), 1, 3)
+    assert res and res[0][0] == 1 and res[0][1] > 0.9
