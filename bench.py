@@ -53,6 +53,28 @@ LG_LAUNCH_GF = {
 }
 
 
+_JSON_FD = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly one JSON line: everything libraries print to fd 1 (e.g. the NCCL version banner at
+    communicator creation) is sent to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def lg_weights_path(rank: int) -> str:
     from superslam_b200.lightglue_weights import make_random_weights, save_state_dict
 
@@ -210,7 +232,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -222,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -414,7 +437,7 @@ def main():
             "wall_s_timed_region": wall,
             "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -16,4 +16,8 @@ Pinning status:
     package cvg/LightGlue and no weights are available offline.  The restatement follows the
     published model (lightglue/lightglue.py) and is cross-checked against the independent
     HuggingFace port shipped in this image (transformers 5.5, models/lightglue) with shared weights.
+  * EigenPlaces (oracle/eigenplaces.py) — preprocess PINNED bit-exactly against cv2.resize, ResNet18 trunk
+    PINNED against torchvision with shared weights, CosineDescriptorIndex / TemporalConsistencyVoter PINNED
+    by the reference's tests/test_place_recognizer.cc (re-expressed); the trained network weights come from
+    an un-pinned torch.hub entry and are absent offline: network VALUES are PARITY UNPINNED.
 """
