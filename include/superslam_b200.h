@@ -117,6 +117,15 @@ int ssb_fe_process(ssb_frontend* fe, const uint8_t* const* images, int pairs, in
 int ssb_fe_enqueue_device(ssb_frontend* fe, const uint8_t* images_dev, int pairs, int height, int width);
 int ssb_fe_fetch(ssb_frontend* fe, int pairs, int* count, float* xy, float* score, int32_t* matches0,
                  float* mscores0, float* stereo_ur, uint8_t* has_depth);
+/* Streaming form of ssb_fe_process for a sequence of steps: submit enqueues the upload (on a copy stream,
+ * into one of two device image buffers), the pipeline and the read-back of one step and returns at once;
+ * collect blocks until the OLDEST submitted step has finished and copies its results out (same arrays as
+ * ssb_fe_process; `pairs` receives that step's pair count).  At most two steps may be in flight, so the
+ * upload of step i+1 overlaps the kernels of step i.  Images must stay valid until their step is collected. */
+int ssb_fe_submit(ssb_frontend* fe, const uint8_t* const* images, int pairs, int height, int width,
+                  int row_stride);
+int ssb_fe_collect(ssb_frontend* fe, int* pairs, int* count, float* xy, float* score, int32_t* matches0,
+                   float* mscores0, float* stereo_ur, uint8_t* has_depth);
 int ssb_fe_sync(ssb_frontend* fe);
 /* CUDA-event timing on the front end's own stream (torch.cuda.Event only sees torch's stream). */
 int ssb_fe_event_record(ssb_frontend* fe, int index /* 0..15 */);

@@ -56,6 +56,8 @@ SYMBOLS = [
                                  _u8p]),
     ("ssb_fe_enqueue_device", C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
     ("ssb_fe_fetch", C.c_int, [_vp, C.c_int, _ip, _fp, _fp, _i32p, _fp, _fp, _u8p]),
+    ("ssb_fe_submit", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("ssb_fe_collect", C.c_int, [_vp, _ip, _ip, _fp, _fp, _i32p, _fp, _fp, _u8p]),
     ("ssb_fe_sync", C.c_int, [_vp]),
     ("ssb_fe_event_record", C.c_int, [_vp, C.c_int]),
     ("ssb_fe_event_elapsed_ms", C.c_int, [_vp, C.c_int, C.c_int, _fp]),

@@ -317,6 +317,26 @@ class FramePairPipeline:
         _lib.check(self._lib.ssb_fe_process(self._h, ptrs, pairs, h, w, w, *self._ptrs(o)))
         return o
 
+    def submit(self, images) -> None:
+        """Streaming form of process(): enqueue one step and return; at most two steps in flight.  The
+        caller keeps `images` alive until the step is collected (they are copied asynchronously)."""
+        images = [np.ascontiguousarray(i, np.uint8) for i in images]
+        pairs = len(images) // 2
+        h, w = images[0].shape
+        ptrs = (C.POINTER(C.c_uint8) * len(images))(*[i.ctypes.data_as(C.POINTER(C.c_uint8)) for i in images])
+        _lib.check(self._lib.ssb_fe_submit(self._h, ptrs, pairs, h, w, w))
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((images, pairs))
+
+    def collect(self):
+        """Results of the oldest submitted step (same dict as process())."""
+        images, pairs = self._inflight.pop(0)
+        o = self._outputs(pairs)
+        n = C.c_int(0)
+        _lib.check(self._lib.ssb_fe_collect(self._h, C.byref(n), *self._ptrs(o)))
+        assert n.value == pairs
+        return o
+
     def upload(self, images) -> int:
         images = [np.ascontiguousarray(i, np.uint8) for i in images]
         h, w = images[0].shape

@@ -137,3 +137,39 @@ def test_c4_euroc_size_with_keyframe_descriptor(tmp_path, lg_weights):
     noisy = np.clip(lefts[1].astype(np.int16) + np.random.default_rng(0).integers(-3, 4, lefts[1].shape), 0, 255).astype(np.uint8)
     res = ep.query(ep.compute_global_descriptor(noisy), 1, 3)
     assert res and res[0][0] == 1 and res[0][1] > 0.9
+
+
+def test_streaming_submit_collect_equals_process(tmp_path, lg_weights):
+    """ssb_fe_submit / ssb_fe_collect (upload of step i+1 under the kernels of step i, two image buffers,
+    graph replay from the third use of a buffer) returns exactly what the synchronous call returns."""
+    from superslam_b200 import _lib
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    h, w, K = 240, 320, 512
+    steps = [[im for i in range(2) for im in synth_pair(h, w, 700 + 10 * s + i)] for s in range(7)]
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=2)
+    ref = [pipe.process(s) for s in steps]
+    got = []
+    pipe.submit(steps[0])
+    for s in range(1, len(steps)):
+        pipe.submit(steps[s])
+        got.append(pipe.collect())
+    with pytest.raises(Exception):
+        pipe.fetch(2)            # a step is still in flight
+    got.append(pipe.collect())
+    for r, g in zip(ref, got):
+        for k in r:
+            assert np.array_equal(r[k], g[k], equal_nan=True), k
+    # at most two steps in flight
+    pipe.submit(steps[0])
+    pipe.submit(steps[1])
+    with pytest.raises(_lib.SsbError):
+        pipe.submit(steps[2])
+    pipe.collect()
+    pipe.collect()
+    out = pipe.process(steps[3])   # the synchronous call works again once everything is collected
+    assert np.array_equal(out["matches0"], ref[3]["matches0"])
