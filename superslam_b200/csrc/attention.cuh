@@ -23,8 +23,14 @@ namespace ssb {
 
 constexpr int kFaThreads = 320;
 constexpr int kFaBlockKeys = 128;
-constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 3072 /*xchg*/ +
-                             128 /*barriers*/ + 1024 /*align*/;
+// kPT = false: P goes through shared memory (A operand via descriptor), one V stage.
+// kPT = true:  P is written to TMEM with tcgen05.st and read by the P*V MMA as a TMEM A operand (64 columns:
+//              two fp16 per 32-bit cell, lane = query row); the 32 KB that P occupied hold a second V stage.
+template <bool kPT>
+constexpr int fa_smem_bytes() {
+  return 16384 /*Q*/ + 2 * 16384 /*K*/ + (kPT ? 2 * 16384 /*V x2*/ : 16384 /*V*/ + 32768 /*P*/) + 3072 /*xchg*/ +
+         256 /*barriers*/ + 1024 /*align*/;
+}
 
 struct FaParams {
   const int* cnt;      // per-image keypoint counts
@@ -55,6 +61,24 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const float* v) {
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16_u32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand is read from tensor memory (lane = row, two fp16 per cell)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
@@ -90,6 +114,7 @@ __device__ __forceinline__ bool fa_decode(const FaParams& p, int tile, FaTile& t
 // the current one has retired, K/V blocks keep streaming through their rings, and the first S of the next
 // tile is computed underneath the last softmax of the current one.  (As one CTA per tile, ~1/3 of each
 // CTA's life went into barrier/TMEM setup and the serial Q -> K -> S -> softmax start-up latency.)
+template <bool kPT>
 __global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const FaParams p) {
@@ -97,23 +122,26 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;            // 2 stages
-  uint8_t* sV = smem + 16384 + 32768;    // 1 stage (V is only needed after the softmax of its block)
-  uint8_t* sP = smem + 16384 + 49152;    // 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
+  constexpr uint32_t kVS = kPT ? 2u : 1u;   // V stages
+  uint8_t* sV = smem + 16384 + 32768;    // kVS stages (V is only needed after the softmax of its block)
+  uint8_t* sP = smem + 16384 + 49152;    // !kPT: 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
   // [2 parity][2 halves][128] block maxima: softmax(b+1) may start (its S is computed underneath softmax(b))
   // before the partner thread has read block b's exchange slot, hence two parities; [2][128] row sums follow
-  float* xchg_base = reinterpret_cast<float*>(smem + 16384 + 49152 + 32768);
+  constexpr uint32_t kDataBytes = 16384 + 32768 + (kPT ? 32768 : 16384 + 32768);
+  float* xchg_base = reinterpret_cast<float*>(smem + kDataBytes);
   float* xchg_l = xchg_base + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 49152 + 32768 + 3072);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDataBytes + 3072);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;
+  uint64_t* v_full = bars + 12;   // [2]
+  uint64_t* v_empty = bars + 14;  // [2]
   uint64_t* s_full = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* pv_done = bars + 8;
   uint64_t* s_free = bars + 9;
   uint64_t* q_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.q_tiles * p.zcount;
@@ -128,7 +156,10 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(&k_full[1], 1);
     mbar_init(&k_empty[0], 1);
     mbar_init(&k_empty[1], 1);
-    mbar_init(v_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
@@ -146,6 +177,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem;        // 128 columns
   const uint32_t tO = tmem + 128;  // 64 columns
+  const uint32_t tP = tmem + 192;  // kPT: 64 columns = 128 fp16 probabilities per row
 
   // Warps 0 and 1 run their loops with all 32 lanes in warp-uniform control flow and let one elected lane
   // issue: descriptors and coordinates then live in uniform registers and every TMA / tcgen05.mma is a
@@ -171,10 +203,11 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tma_load_3d(sK + s * 16384, &tmK, &k_full[s], 0, j * kFaBlockKeys, t.zk);
         }
         __syncwarp();
-        if (kb > 0) mbar_wait(pv_done, (kb - 1) & 1u);       // P*V(kb-1) has consumed V
+        const uint32_t sv = kb % kVS;
+        mbar_wait(&v_empty[sv], ((kb / kVS) & 1u) ^ 1u);     // P*V(kb - kVS) has consumed it
         if (elect_one()) {
-          mbar_arrive_expect_tx(v_full, 16384);
-          tma_load_3d(sV, &tmV, v_full, 0, j * kFaBlockKeys, t.zk);
+          mbar_arrive_expect_tx(&v_full[sv], 16384);
+          tma_load_3d(sV + sv * 16384, &tmV, &v_full[sv], 0, j * kFaBlockKeys, t.zk);
         }
         __syncwarp();
       }
@@ -231,16 +264,23 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         mbar_wait(p_full, kb & 1u);   // softmax(kb) has written P(kb)
         tc_fence_after();
-        mbar_wait(v_full, kb & 1u);
+        const uint32_t sv = kb % kVS;
+        mbar_wait(&v_full[sv], (kb / kVS) & 1u);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // A: P slab k/4 (64 keys per slab), +32 B per 16 keys.  B: 16 key rows = 2048 B.
-            const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
-            const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + k * 2048, 1024, 1024);
-            umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+            // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns (kPT), or P slab k/4 (64 keys per
+            // slab) in shared memory, +32 B per 16 keys.
+            const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
+            if (kPT) {
+              umma_f16_ts(tO, tP + 8 * k, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+            } else {
+              const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
+              umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&v_empty[sv]);
           umma_commit(pv_done);
         }
         __syncwarp();
@@ -256,6 +296,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tSh = tS + lane_off + half * 64;
     const uint32_t tOh = tO + lane_off + half * 32;
+    const uint32_t tPh = tP + lane_off + half * 32;   // my 64 probabilities = 32 cells
     uint8_t* slab = sP + half * 16384 + row * 128;
     uint32_t kb = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride) {
@@ -324,11 +365,31 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             for (int i = 0; i < 16; ++i) o[i] *= alpha;
             tmem_st_32x16(tOh + h * 16, o);
           }
-          tmem_st_wait();
+          if (!kPT) tmem_st_wait();
         }
-        // probabilities -> fp16 -> swizzled A-operand layout (slab = my key half)
+        // probabilities -> fp16 -> TMEM A operand (kPT) or swizzled shared-memory A layout (slab = my key half)
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        if (kvalid >= 64) {   // warp-uniform: no per-element masking in the common case
+        if (kPT) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int i = 32 * h2 + 2 * k;
+              float e0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
+              float e1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_used));
+              if (kvalid < 64) {   // warp-uniform condition
+                e0 = i < kvalid ? e0 : 0.f;
+                e1 = i + 1 < kvalid ? e1 : 0.f;
+              }
+              ls[k & 1] += e0;
+              ls[2 + (k & 1)] += e1;
+              w[k] = pack_half2(e0, e1);
+            }
+            tmem_st_32x16_u32(tPh + 16 * h2, w);
+          }
+          tmem_st_wait();
+        } else if (kvalid >= 64) {   // warp-uniform: no per-element masking in the common case
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             float e[8];
@@ -363,7 +424,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
         }
         l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        fence_proxy_async_smem();
+        if (!kPT) fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
@@ -398,11 +459,17 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                                   FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
   static bool configured = false;
+  static bool p_in_tmem = true;   // SSB_FA_PTMEM=0 selects the shared-memory P variant (A/B measurements)
   if (!configured) {
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFaSmemBytes));
+    if (const char* e = std::getenv("SSB_FA_PTMEM")) p_in_tmem = std::atoi(e) != 0;
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        fa_smem_bytes<true>()));
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        fa_smem_bytes<false>()));
     // ask for the full shared-memory carveout so that two CTAs (2 x 100 KB) are co-resident per SM
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
@@ -412,7 +479,10 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   if (total <= 0) return SSB_OK;
   const int resident = 2 * device_sm_count();
   const int ctas = total < resident ? total : resident;
-  flash_attention_kernel<<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  if (p_in_tmem)
+    flash_attention_kernel<true><<<ctas, kFaThreads, fa_smem_bytes<true>(), stream>>>(tmQ, tmK, tmV, p);
+  else
+    flash_attention_kernel<false><<<ctas, kFaThreads, fa_smem_bytes<false>(), stream>>>(tmQ, tmK, tmV, p);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, label);

@@ -216,65 +216,97 @@ struct EpiQkvRope {
   int kp;
   int rope;
   static constexpr bool kSplit = true;
-  __device__ void operator()(EpiCtx& c, bool) const {
-    const int row = c.px;
-    const int row0 = __shfl_sync(0xffffffffu, row, 0);
-    const bool valid = row < c.m_valid;
+  // Rotary factors of this thread's row, frequencies 0..15 (first half of every head); fetched before the
+  // accumulator wait.  Frequency-major table: the 32 lanes (consecutive rows) read one 128-byte line per
+  // frequency.
+  struct Pre {
+    float cc[16], ss[16];
+  };
+  __device__ __forceinline__ bool rotates(const EpiCtx& c) const {
+    return rope && (c.n0 >> 8) != 2 && c.px < c.m_valid;
+  }
+  __device__ __forceinline__ void load_factors(const EpiCtx& c, int f0, float* cc, float* ss) const {
+    const size_t tb = (static_cast<size_t>(c.z) * 32 + f0) * kp + c.px;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      cc[i] = __ldg(cs + tb + static_cast<size_t>(i) * kp);
+      ss[i] = __ldg(sn + tb + static_cast<size_t>(i) * kp);
+    }
+  }
+  __device__ __forceinline__ void prefetch(const EpiCtx& c, Pre& t) const {
+    if (rotates(c)) load_factors(c, 0, t.cc, t.ss);
+  }
+  // one 32-column chunk: bias, rotation, fp16, 4 x 16 bytes into the staging buffer `buf` (chunk hc of the head)
+  __device__ __forceinline__ void chunk(const EpiCtx& c, float* v, int col, bool valid, bool do_rope,
+                                        const float* cc, const float* ss, uint8_t* buf, int hc) const {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(b4 + j);
+      v[4 * j] = valid ? v[4 * j] + t.x : 0.f;
+      v[4 * j + 1] = valid ? v[4 * j + 1] + t.y : 0.f;
+      v[4 * j + 2] = valid ? v[4 * j + 2] + t.z : 0.f;
+      v[4 * j + 3] = valid ? v[4 * j + 3] + t.w : 0.f;
+    }
+    if (do_rope) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        v[2 * i] = a * cc[i] - b * ss[i];
+        v[2 * i + 1] = b * cc[i] + a * ss[i];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+      o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+      o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+      const int ch = hc * 4 + j;
+      *reinterpret_cast<uint4*>(buf + c.lane * 128 + ((ch ^ (c.lane & 7)) << 4)) = o;
+    }
+  }
+  // This thread owns 128 columns = two heads (A, B).  Chunk order A.lo, B.lo, A.hi, B.hi: both heads' first
+  // halves use the prefetched factors; the second set (frequencies 16..31) is requested first thing and has two
+  // chunks of work to arrive under.  TMEM loads are software-pipelined one chunk ahead.  Both staging buffers
+  // are open at once (head A -> buffer 0, head B -> buffer 1), each leaves as one TMA store.
+  __device__ void operator()(EpiCtx& c, bool, const Pre& pre) const {
+    const int row0 = __shfl_sync(0xffffffffu, c.px, 0);
+    const bool valid = c.px < c.m_valid;
     const int which = c.n0 >> 8;
     const bool is_v = rope ? (which == 2) : (which == 1);
     const CUtensorMap* tm = is_v ? &tm_v : (which == 0 ? &tm_q : &tm_k);
-    for (int g0 = c.col_begin; g0 < c.col_end; g0 += 64) {
-      stage_begin(c);
-#pragma unroll 1
-      for (int hc = 0; hc < 2; ++hc) {
-        const int col = g0 + hc * 32;
-        float v[32];
-        tmem_ld_32x32(c.tmem_row + col, v);
-        // the rotary factors are fetched while the TMEM load is in flight; frequency-major table: the 32
-        // lanes (consecutive rows) read one 128-byte line per frequency
-        const bool do_rope = !is_v && rope && valid;
-        float cc[16], ss[16];
-        if (do_rope) {
-          const size_t tb = (static_cast<size_t>(c.z) * 32 + ((col & 63) >> 1)) * kp + row;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            cc[i] = __ldg(cs + tb + static_cast<size_t>(i) * kp);
-            ss[i] = __ldg(sn + tb + static_cast<size_t>(i) * kp);
-          }
-        }
-        const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
-        float bv[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(b4 + j);
-          bv[4 * j] = t.x, bv[4 * j + 1] = t.y, bv[4 * j + 2] = t.z, bv[4 * j + 3] = t.w;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] + bv[j] : 0.f;
-        if (do_rope) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = v[2 * i], b = v[2 * i + 1];
-            v[2 * i] = a * cc[i] - b * ss[i];
-            v[2 * i + 1] = b * cc[i] + a * ss[i];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 o;
-          o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-          stage_put(c, c.lane, hc * 4 + j, o);
-        }
-      }
-      stage_fence(c);
-      if (c.lane == 0) {
-        tma_store_3d(tm, c.stage_cur, 0, row0, c.z * kLgHeads + (g0 >> 6));
-        bulk_commit();
-      }
+    const bool do_rope = rotates(c);
+    float c2[16], s2[16];
+    if (do_rope) load_factors(c, 16, c2, s2);
+    const int cb = c.col_begin;
+    float va[32], vb[32];
+    tmem_ld_32x32(c.tmem_row + cb, va);                    // A.lo
+    if (c.lane == 0) bulk_wait_read0();                    // last tile's stores have left both buffers
+    __syncwarp();
+    uint8_t* bufA = c.stage;
+    uint8_t* bufB = c.stage + 4096;
+    tmem_ld_wait();
+    tmem_ld_32x32(c.tmem_row + cb + 64, vb);               // B.lo
+    chunk(c, va, cb, valid, do_rope, pre.cc, pre.ss, bufA, 0);
+    tmem_ld_wait();
+    tmem_ld_32x32(c.tmem_row + cb + 32, va);               // A.hi
+    chunk(c, vb, cb + 64, valid, do_rope, pre.cc, pre.ss, bufB, 0);
+    tmem_ld_wait();
+    tmem_ld_32x32(c.tmem_row + cb + 96, vb);               // B.hi
+    chunk(c, va, cb + 32, valid, do_rope, c2, s2, bufA, 1);
+    stage_fence(c);
+    if (c.lane == 0) {
+      tma_store_3d(tm, bufA, 0, row0, c.z * kLgHeads + (cb >> 6));
+      bulk_commit();
+    }
+    tmem_ld_wait();
+    chunk(c, vb, cb + 96, valid, do_rope, c2, s2, bufB, 1);
+    stage_fence(c);
+    if (c.lane == 0) {
+      tma_store_3d(tm, bufB, 0, row0, c.z * kLgHeads + (cb >> 6) + 1);
+      bulk_commit();
     }
   }
 };
@@ -604,7 +636,13 @@ int LgWeights::load(const char* path, int dev) {
   const HostTensor* wr_t = need("posenc.Wr.weight", {32, 2});
   if (!wr_t) return SSB_ERR_IO;
   SSB_RETURN_IF(upload(this, wr_t->data.data(), 64 * sizeof(float), reinterpret_cast<void**>(&wr)));
-  auto ffn = [&](int i, const char* blk, LgBlockFfn* F) -> int {
+  // The message projection is linear and feeds nothing but the FFN:  ffn.0(cat[x, Wo ctx + bo]) =
+  // W1a x + (W1b Wo) ctx + (b1 + W1b bo).  With fold_out the product W1b Wo (fp64 on the host, one fp16
+  // rounding) replaces the right half of ffn.0 and the out_proj / to_out GEMMs - a 67 MB read and a 67 MB
+  // write per block at 64 pairs - are never launched; the message itself is then never rounded to fp16.
+  fold_out = true;
+  if (const char* e = std::getenv("SSB_LG_FOLD_OUT")) fold_out = std::atoi(e) != 0;
+  auto ffn = [&](int i, const char* blk, LgBlockFfn* F, const HostTensor* wo, const HostTensor* bo) -> int {
     const HostTensor* w0 = need(key(i, blk, "ffn.0.weight"), {512, 512});
     const HostTensor* b0 = need(key(i, blk, "ffn.0.bias"), {512});
     const HostTensor* g = need(key(i, blk, "ffn.1.weight"), {512});
@@ -612,7 +650,26 @@ int LgWeights::load(const char* path, int dev) {
     const HostTensor* w3 = need(key(i, blk, "ffn.3.weight"), {256, 512});
     const HostTensor* b3 = need(key(i, blk, "ffn.3.bias"), {256});
     if (!w0 || !b0 || !g || !be || !w3 || !b3) return SSB_ERR_IO;
-    SSB_RETURN_IF(make_linear(this, &F->fc1, w0->data, b0->data, 512, 512));
+    if (fold_out) {
+      std::vector<float> w1(w0->data), b1(b0->data);
+      std::vector<double> acc(256);
+      for (int n = 0; n < 512; ++n) {
+        const float* w1b = w0->data.data() + static_cast<size_t>(n) * 512 + 256;   // row n of W1b
+        std::fill(acc.begin(), acc.end(), 0.0);
+        double bb = b0->data[n];
+        for (int j = 0; j < 256; ++j) {
+          const double a = w1b[j];
+          const float* wrow = wo->data.data() + static_cast<size_t>(j) * 256;      // row j of Wo
+          for (int kk = 0; kk < 256; ++kk) acc[kk] += a * wrow[kk];
+          bb += a * bo->data[j];
+        }
+        for (int kk = 0; kk < 256; ++kk) w1[static_cast<size_t>(n) * 512 + 256 + kk] = static_cast<float>(acc[kk]);
+        b1[n] = static_cast<float>(bb);
+      }
+      SSB_RETURN_IF(make_linear(this, &F->fc1, w1, b1, 512, 512));
+    } else {
+      SSB_RETURN_IF(make_linear(this, &F->fc1, w0->data, b0->data, 512, 512));
+    }
     SSB_RETURN_IF(make_linear(this, &F->fc2, w3->data, b3->data, 256, 512));
     SSB_RETURN_IF(upload(this, g->data.data(), 512 * sizeof(float), reinterpret_cast<void**>(&F->ln_g)));
     SSB_RETURN_IF(upload(this, be->data.data(), 512 * sizeof(float), reinterpret_cast<void**>(&F->ln_b)));
@@ -638,7 +695,7 @@ int LgWeights::load(const char* path, int dev) {
         }
     SSB_RETURN_IF(make_linear(this, &L.qkv, w, b, 768, 256));
     SSB_RETURN_IF(make_linear(this, &L.out, wo->data, bo->data, 256, 256));
-    SSB_RETURN_IF(ffn(i, "self_attn", &L.sffn));
+    SSB_RETURN_IF(ffn(i, "self_attn", &L.sffn, wo, bo));
     const HostTensor* wqk = need(key(i, "cross_attn", "to_qk.weight"), {256, 256});
     const HostTensor* bqk = need(key(i, "cross_attn", "to_qk.bias"), {256});
     const HostTensor* wv = need(key(i, "cross_attn", "to_v.weight"), {256, 256});
@@ -651,7 +708,7 @@ int LgWeights::load(const char* path, int dev) {
     bc.insert(bc.end(), bv->data.begin(), bv->data.end());
     SSB_RETURN_IF(make_linear(this, &L.qkv_c, wc, bc, 512, 256));
     SSB_RETURN_IF(make_linear(this, &L.to_out, wto->data, bto->data, 256, 256));
-    SSB_RETURN_IF(ffn(i, "cross_attn", &L.cffn));
+    SSB_RETURN_IF(ffn(i, "cross_attn", &L.cffn, wto, bto));
   }
   const std::string la = "log_assignment." + std::to_string(kLgLayers - 1) + ".";
   const HostTensor* wf = need(la + "final_proj.weight", {256, 256});
@@ -807,7 +864,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       CoreParams p = lin("lg.ffn1", 4, 4, 256);
       p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)
       EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, ts_h1_};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 2, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);
@@ -842,7 +899,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
-    {
+    if (!w_->fold_out) {
       CoreParams p = lin("lg.out_proj", 4, 0, 256);
       EpiBias16 e{L.out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.out.tmB, p, e, dim3(tiles, 1, P2), stream));
@@ -856,7 +913,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
-    {
+    if (!w_->fold_out) {
       CoreParams p = lin("lg.to_out", 4, 0, 256);
       EpiBias16 e{L.to_out.bias, ts_msg_};
       SSB_RETURN_IF(launch_core(tm_ctx_, tm_ctx_, L.to_out.tmB, p, e, dim3(tiles, 1, P2), stream));

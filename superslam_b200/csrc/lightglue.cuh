@@ -52,6 +52,7 @@ struct LgWeights {
   float* match_w = nullptr;  // [256]
   float match_b = 0.f;
   float* wr = nullptr;       // posenc.Wr.weight [32][2]
+  bool fold_out = true;      // out_proj / to_out folded into the right half of ffn.0 (LgWeights::load)
   std::vector<void*> owned;  // every device allocation, freed in the destructor
   ~LgWeights();
   int load(const char* path, int device);

@@ -16,6 +16,8 @@
 // quadrant and split the accumulator columns between them.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ssb {
@@ -138,6 +140,22 @@ __device__ __forceinline__ void tmem_chunks_pipelined(uint32_t t0, F&& f) {
     f(i, v[i & 1]);
   }
 }
+
+// Optional epilogue hook: a functor that declares a nested type `Pre` and a member
+//   void prefetch(const EpiCtx&, Pre&) const
+// gets it called BEFORE the wait for the tile's accumulator, and receives the same object as a third argument
+// of operator().  Operands that do not depend on the accumulator (rotary factors, residual rows) are then in
+// flight underneath the tile's MMAs instead of exposing a global-memory round trip per 32-column chunk.
+template <class E, class = void>
+struct EpiPrefetch {
+  static constexpr bool value = false;
+  struct type {};
+};
+template <class E>
+struct EpiPrefetch<E, std::void_t<typename E::Pre>> {
+  static constexpr bool value = true;
+  using type = typename E::Pre;
+};
 
 // Barrier among the 256 epilogue threads (both halves); every epilogue thread must call it.
 __device__ __forceinline__ void epi_pair_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -373,8 +391,6 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
       const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
-      mbar_wait(&tmem_full[buf], use & 1u);
-      tc_fence_after();
       c.row = q * 32 + lane;
       c.lane = lane;
       c.px = w0 + (c.row % p.tile_w);
@@ -388,15 +404,24 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       c.peer_slots = peer_slots;
       c.peer_bar = peer_bar;
       c.tmem_row = tmem_base + buf * p.buf_stride + (static_cast<uint32_t>(q * 32) << 16);
+      const bool mine = Epi::kSplit || half == 0;
       if (Epi::kSplit) {
         const int hw = p.block_n / 2;
         c.col_begin = half * hw;
         c.col_end = c.col_begin + hw;
-        epi(c, num_k > 0);
-      } else if (half == 0) {
+      } else {
         c.col_begin = 0;
         c.col_end = p.block_n;
-        epi(c, num_k > 0);
+      }
+      typename EpiPrefetch<Epi>::type pre;
+      if constexpr (EpiPrefetch<Epi>::value) {
+        if (mine) epi.prefetch(c, pre);
+      }
+      mbar_wait(&tmem_full[buf], use & 1u);
+      tc_fence_after();
+      if (mine) {
+        if constexpr (EpiPrefetch<Epi>::value) epi(c, num_k > 0, pre);
+        else epi(c, num_k > 0);
       }
       tc_fence_before();
       __syncwarp();
