@@ -1,20 +1,25 @@
 // Fused attention for LightGlue on sm_100a (flash-attention style, persistent CTAs over 128-query tiles):
 //   S = Q K^T        tcgen05.mma, fp32 accumulator in TMEM (never leaves the SM)
 //   P = exp2(S*c - m) online softmax by 256 threads (two per query row, 64 keys each), fp16 P written
-//                    straight into the 128B-swizzled shared-memory layout the next MMA reads as A
-//   O += P V         tcgen05.mma with V as an MN-major B operand (V rows = keys, as stored by the QKV
-//                    epilogue; no transposed copy of V exists)
+//                    back to TMEM with tcgen05.st (two fp16 per 32-bit cell, lane = query row)
+//   O += P V         tcgen05.mma with P as a TMEM A operand and V as an MN-major shared-memory B operand
+//                    (V rows = keys, as stored by the QKV epilogue; no transposed copy of V exists)
 // The N x M logits of the reference graph (softmax(q k^T / 8) v for self attention, both directions of
 // the bidirectional cross attention: oracle/lightglue.py _self_block/_cross_block) are therefore never
 // written to HBM.  The running max is only refreshed when it grows by more than 2^8 (the O rescale is
 // skipped otherwise), which keeps P <= 256 in fp16 and is exact after the final division by the row sum.
 //
-// Budget: 100 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's
+// Keeping P in tensor memory takes 64 KB per key block off the shared-memory port (32 KB of stores + 32 KB
+// of operand reads; the N = 64 P*V MMAs were shared-memory-read bound) and frees room for a second V stage.
+// Budget: 84 KB of shared memory and 256 TMEM columns (S 128, O 64, P 64) per CTA -> two CTAs per SM, so one CTA's
 // exponentials (the MUFU-bound part: 16 ex2/clk/SM) overlap the other's MMAs and loads.  (A variant that
 // pipelines S/P double-buffered inside one CTA per SM measured 25 % slower: profiles/README.md.)
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = softmax + epilogue (TMEM lane quadrant = warp % 4, key half = (warp-2) / 4).
 #pragma once
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma_core.cuh"
@@ -23,14 +28,8 @@ namespace ssb {
 
 constexpr int kFaThreads = 320;
 constexpr int kFaBlockKeys = 128;
-// kPT = false: P goes through shared memory (A operand via descriptor), one V stage.
-// kPT = true:  P is written to TMEM with tcgen05.st and read by the P*V MMA as a TMEM A operand (64 columns:
-//              two fp16 per 32-bit cell, lane = query row); the 32 KB that P occupied hold a second V stage.
-template <bool kPT>
-constexpr int fa_smem_bytes() {
-  return 16384 /*Q*/ + 2 * 16384 /*K*/ + (kPT ? 2 * 16384 /*V x2*/ : 16384 /*V*/ + 32768 /*P*/) + 3072 /*xchg*/ +
-         256 /*barriers*/ + 1024 /*align*/;
-}
+constexpr int kFaSmemBytes = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 16384 /*O staging*/ +
+                             4096 /*xchg*/ + 256 /*barriers*/ + 1024 /*align*/;
 
 struct FaParams {
   const int* cnt;      // per-image keypoint counts
@@ -40,6 +39,7 @@ struct FaParams {
   __half* ctx;         // [img][kp][heads*64]
   int kp;
   int q_tiles, zcount; // tile space (set by the launcher)
+  int stagger;         // cycles (set by the launcher)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
@@ -89,7 +89,42 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void fa_pair_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+// packed fp32x2 arithmetic (sm_100: one FMA-pipe instruction for two lanes of work)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// Barrier between the two warps (w, w + 4) that share a TMEM lane quadrant, i.e. the two halves of 32 rows.
+// (A CTA-wide barrier here made every block wait for the slowest of eight warps spread over four schedulers.)
+__device__ __forceinline__ void fa_pair_sync(int qd) {
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+}
+// Experiment hook (SSB_FA_STAGGER=<cycles>): the second CTA to arrive on an SM starts late, so that the
+// exponential phases of the two co-resident CTAs interleave instead of colliding on the MUFU.
+__device__ int g_fa_sm_slots[1024];
+// Diagnostic build of the kernel (SSB_FA_TRACE=1): warp 2 of CTA 0 time-stamps the phases of its first key
+// blocks; the launcher prints them after the first launch.  Not instantiated on the product path.
+__device__ long long g_fa_trace[64][8];
+
+#define FA_TRACE(i)                                                                              \
+  do {                                                                                           \
+    if (kTrace && blockIdx.x == 0 && warp == 2 && lane == 0 && kb < 64) g_fa_trace[kb][i] = clock64(); \
+  } while (0)
 
 // One unit of work: the 128-query tile `qt` of (image, head) `z`.
 struct FaTile {
@@ -114,23 +149,24 @@ __device__ __forceinline__ bool fa_decode(const FaParams& p, int tile, FaTile& t
 // the current one has retired, K/V blocks keep streaming through their rings, and the first S of the next
 // tile is computed underneath the last softmax of the current one.  (As one CTA per tile, ~1/3 of each
 // CTA's life went into barrier/TMEM setup and the serial Q -> K -> S -> softmax start-up latency.)
-template <bool kPT>
+template <bool kTrace>
 __global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                       const __grid_constant__ CUtensorMap tmV, const FaParams p) {
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                       const FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;            // 2 stages
-  constexpr uint32_t kVS = kPT ? 2u : 1u;   // V stages
-  uint8_t* sV = smem + 16384 + 32768;    // kVS stages (V is only needed after the softmax of its block)
-  uint8_t* sP = smem + 16384 + 49152;    // !kPT: 128 x 128 fp16 = two [128 x 64] slabs (one per key half)
+  constexpr uint32_t kVS = 2u;           // V stages
+  uint8_t* sV = smem + 16384 + 32768;    // 2 stages
   // [2 parity][2 halves][128] block maxima: softmax(b+1) may start (its S is computed underneath softmax(b))
   // before the partner thread has read block b's exchange slot, hence two parities; [2][128] row sums follow
-  constexpr uint32_t kDataBytes = 16384 + 32768 + (kPT ? 32768 : 16384 + 32768);
+  uint8_t* sO = smem + 16384 + 32768 + 32768;   // 4 quadrants x [32 rows x 128 B], swizzled, for the TMA store
+  constexpr uint32_t kDataBytes = 16384 + 32768 + 32768 + 16384;
   float* xchg_base = reinterpret_cast<float*>(smem + kDataBytes);
-  float* xchg_l = xchg_base + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDataBytes + 3072);
+  float* xchg_l = xchg_base + 512;   // [2 parity][2 halves][128] row sums of the finished tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDataBytes + 4096);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
@@ -151,6 +187,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     mbar_init(&k_full[0], 1);
     mbar_init(&k_full[1], 1);
@@ -177,13 +214,24 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem;        // 128 columns
   const uint32_t tO = tmem + 128;  // 64 columns
-  const uint32_t tP = tmem + 192;  // kPT: 64 columns = 128 fp16 probabilities per row
+  const uint32_t tP = tmem + 192;  // 64 columns = 128 fp16 probabilities per row
 
   // Warps 0 and 1 run their loops with all 32 lanes in warp-uniform control flow and let one elected lane
   // issue: descriptors and coordinates then live in uniform registers and every TMA / tcgen05.mma is a
   // single instruction (inside `if (lane == 0)` each one became an ELECT / R2UR / branch sequence of ~100
   // cycles, which sat on the S -> softmax -> P*V critical path twelve times per key block).
   if (warp == 0) {
+    if (p.stagger > 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&g_fa_sm_slots[smid & 1023u], 1) & 1;
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger) {}
+      }
+    }
     uint32_t kb = 0, tq = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride) {
       FaTile t;
@@ -216,7 +264,7 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
     const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
     const uint64_t qdesc = make_smem_desc_k_sw128(smem_u32(sQ), 1024);
-    const uint32_t vbase = smem_u32(sV), pbase = smem_u32(sP), kbase = smem_u32(sK);
+    const uint32_t vbase = smem_u32(sV), kbase = smem_u32(sK);
     // S(b+1) is issued as soon as the softmax warps have pulled S(b) out of TMEM into registers (s_free),
     // i.e. it runs underneath the whole softmax of block b - also across a tile boundary, where it first
     // waits for the next tile's Q; P*V(b) follows once P(b) is in shared memory.
@@ -270,15 +318,9 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns (kPT), or P slab k/4 (64 keys per
-            // slab) in shared memory, +32 B per 16 keys.
+            // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
             const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
-            if (kPT) {
-              umma_f16_ts(tO, tP + 8 * k, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
-            } else {
-              const uint64_t pdesc = make_smem_desc_k_sw128(pbase + (k >> 2) * 16384, 1024) + 2 * (k & 3);
-              umma_f16(tO, pdesc, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
-            }
+            umma_f16_ts(tO, tP + 8 * k, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(&v_empty[sv]);
           umma_commit(pv_done);
@@ -297,48 +339,92 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tSh = tS + lane_off + half * 64;
     const uint32_t tOh = tO + lane_off + half * 32;
     const uint32_t tPh = tP + lane_off + half * 32;   // my 64 probabilities = 32 cells
-    uint8_t* slab = sP + half * 16384 + row * 128;
+    uint8_t* slab = sO + qd * 4096;            // this quadrant's 32 rows x 128 B (both halves)
     uint32_t kb = 0;
+    // The epilogue of a tile (O / l -> fp16 context rows) is deferred into the first key block of the NEXT
+    // tile: the row sums cross between the two halves in that block's max exchange (same barrier), and O is
+    // read after that block's exponentials, when P*V of the finished tile has long retired - instead of
+    // stalling all eight warps on the last P*V, a second barrier and 128 strided 16-byte stores per warp
+    // (measured: ~4 000 of ~24 000 cycles per tile).  The rows leave through a swizzled staging slab and one
+    // TMA store per quadrant.
+    int pend = -1;   // finished tile waiting for its epilogue: img << 12 | (q0 / 128) << 4 | head, or -1
+    float l_prev = 0.f;
+    // stage O * inv for the pending tile and store it; all 64 threads of the quadrant pair call it
+    auto flush_pending = [&](float inv) {
+      const int pend_img = pend >> 12, pend_row0 = ((pend >> 4) & 0xff) << 7, pend_head = pend & 15;
+      const bool valid = (pend_row0 + row) < p.cnt[pend_img];
+      float o[32];
+      tmem_ld_32x32(tOh, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 w;
+        w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
+        w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
+        w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
+        w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
+        *reinterpret_cast<uint4*>(slab + lane * 128 + (((half * 4 + u) ^ (lane & 7)) << 4)) = w;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      fa_pair_sync(qd);
+      if (half == 0 && lane == 0) {
+        tma_store_3d(&tmO, slab, pend_head * 64, pend_row0 + qd * 32, pend_img);
+        bulk_commit();
+      }
+      pend = -1;
+    };
     for (int tile = blockIdx.x; tile < total; tile += stride) {
       FaTile t;
       if (!fa_decode(p, tile, t)) continue;
-      auto ctx_row = [&]() {
-        return reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(t.img) * p.kp + t.q0 + row) * (p.heads * 64) +
-                                        (t.z - t.img * p.heads) * 64 + half * 32);
-      };
       if (t.nblk == 0) {   // no keys: the message is zero
-        uint4* dst = ctx_row();
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<size_t>(t.img) * p.kp + t.q0 + row) * (p.heads * 64) +
+                                              (t.z - t.img * p.heads) * 64 + half * 32);
 #pragma unroll
         for (int u = 0; u < 4; ++u) dst[u] = make_uint4(0u, 0u, 0u, 0u);
         continue;
       }
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < t.nblk; ++j, ++kb) {
+        FA_TRACE(0);
         mbar_wait(s_full, kb & 1u);
         tc_fence_after();
+        FA_TRACE(1);
         const int kvalid = min(64, t.nk - j * kFaBlockKeys - half * 64);  // valid keys in my half (may be <= 0)
         // my 64 logits -> registers (one TMEM read; S is then free for the next block's Q K^T)
         float v[64];
         tmem_ld_32x32(tSh, v);
         tmem_ld_32x32(tSh + 32, v + 32);
         tmem_ld_wait();
+        FA_TRACE(2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free);
-        // maximum of my 64 logits (raw; the positive scale is applied once)
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (kvalid >= 64) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
-        } else {
+        // keys beyond the count (last block of an image only): -inf logits drop out of the maximum and give
+        // exp2(-inf) = 0 below, so the common path carries no per-element masking at all
+        if (kvalid < 64) {
 #pragma unroll
           for (int i = 0; i < 64; ++i)
-            if (i < kvalid) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+            if (i >= kvalid) v[i] = -INFINITY;
         }
+        // maximum of my 64 logits (raw; the positive scale is applied once)
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
         float* xchg = xchg_base + (kb & 1u) * 256;
+        float* xl = xchg_l + (kb & 1u) * 256;
         xchg[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        fa_pair_sync();
+        const bool flush = pend >= 0 && j == 0;   // warp-uniform
+        if (flush) {
+          xl[half * 128 + row] = l_prev;
+          if (half == 0 && lane == 0) bulk_wait_read0();   // the previous store has left the staging slab
+        }
+        FA_TRACE(3);
+        fa_pair_sync(qd);
         const float bm = fmaxf(xchg[row], xchg[128 + row]) * p.scale_log2;
+        float inv_prev = 0.f;
+        if (flush) inv_prev = 1.0f / (xl[row] + xl[128 + row]);
+        FA_TRACE(4);
         float alpha = 1.f;
         bool need = false;
         if (j == 0) {
@@ -348,108 +434,72 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           m_used = bm;
           need = true;
         }
-        // P and O are still being read / written by the previous P*V until pv_done fires
-        if (kb > 0) {
-          mbar_wait(pv_done, (kb - 1) & 1u);
-          tc_fence_after();
-        }
-        if (__any_sync(0xffffffffu, need)) {
-          l *= alpha;
-          // two 16-column pieces: the 64 logits of this block stay live in registers across the (rare) rescale
+        // probabilities: packed fp32x2 scale-and-shift and row sums (half the FMA-pipe instructions), one
+        // MUFU.EX2 per element, fp16 pairs -> TMEM A operand.  P and O are still being read / written by the
+        // previous P*V until pv_done fires: the first 32 exponentials are computed before that wait.
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int i = 32 * h2 + 2 * k;
+            float2 e = ffma2(make_float2(v[i], v[i + 1]), sc2, nm2);
+            e.x = fast_exp2(e.x);
+            e.y = fast_exp2(e.y);
+            if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
+            w[k] = pack_half2(e.x, e.y);
+          }
+          if (h2 == 0) {
+            FA_TRACE(5);
+            if (kb > 0) {
+              mbar_wait(pv_done, (kb - 1) & 1u);
+              tc_fence_after();
+            }
+            FA_TRACE(6);
+            if (__any_sync(0xffffffffu, need)) {
+              l *= alpha;
+              // two 16-column pieces (the rescale is rare: the running maximum grew by more than 2^8)
 #pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            float o[16];
-            tmem_ld_32x16(tOh + h * 16, o);
-            tmem_ld_wait();
+              for (int h = 0; h < 2; ++h) {
+                float o[16];
+                tmem_ld_32x16(tOh + h * 16, o);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] *= alpha;
-            tmem_st_32x16(tOh + h * 16, o);
-          }
-          if (!kPT) tmem_st_wait();
-        }
-        // probabilities -> fp16 -> TMEM A operand (kPT) or swizzled shared-memory A layout (slab = my key half)
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-        if (kPT) {
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            uint32_t w[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int i = 32 * h2 + 2 * k;
-              float e0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_used));
-              float e1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_used));
-              if (kvalid < 64) {   // warp-uniform condition
-                e0 = i < kvalid ? e0 : 0.f;
-                e1 = i + 1 < kvalid ? e1 : 0.f;
+                for (int i = 0; i < 16; ++i) o[i] *= alpha;
+                tmem_st_32x16(tOh + h * 16, o);
               }
-              ls[k & 1] += e0;
-              ls[2 + (k & 1)] += e1;
-              w[k] = pack_half2(e0, e1);
             }
-            tmem_st_32x16_u32(tPh + 16 * h2, w);
           }
-          tmem_st_wait();
-        } else if (kvalid >= 64) {   // warp-uniform: no per-element masking in the common case
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float e[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              e[k] = fast_exp2(fmaf(v[8 * u + k], p.scale_log2, -m_used));
-              ls[k & 3] += e[k];
-            }
-            uint4 w;
-            w.x = pack_half2(e[0], e[1]);
-            w.y = pack_half2(e[2], e[3]);
-            w.z = pack_half2(e[4], e[5]);
-            w.w = pack_half2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(slab + ((u ^ (row & 7)) << 4)) = w;
-          }
-        } else {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            float e[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int i = 8 * u + k;
-              e[k] = i < kvalid ? fast_exp2(fmaf(v[i], p.scale_log2, -m_used)) : 0.f;
-              ls[k & 3] += e[k];
-            }
-            uint4 w;
-            w.x = pack_half2(e[0], e[1]);
-            w.y = pack_half2(e[2], e[3]);
-            w.z = pack_half2(e[4], e[5]);
-            w.w = pack_half2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(slab + ((u ^ (row & 7)) << 4)) = w;
-          }
+          tmem_st_32x16_u32(tPh + 16 * h2, w);
         }
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        if (!kPT) fence_proxy_async_smem();
+        l += (ls0.x + ls0.y) + (ls1.x + ls1.y);
+        tmem_st_wait();
+        FA_TRACE(7);
+        // O of the finished tile is final (its last P*V retired before this block's pv_done wait) and stays
+        // untouched until this block's P*V, which needs all eight p_full arrivals
+        if (flush) flush_pending(inv_prev);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);   // one arrival per warp: 8 instead of 256 shared-memory atomics
       }
-      // epilogue: O / l -> fp16 context rows (heads concatenated); each half owns 32 of the 64 columns
-      xchg_l[half * 128 + row] = l;
-      fa_pair_sync();
-      const float inv = 1.0f / (xchg_l[row] + xchg_l[128 + row]);
+      // hand the finished tile to the next tile's first block (or to the tail below)
+      pend = (t.img << 12) | ((t.q0 >> 7) << 4) | (t.z - t.img * p.heads);
+      l_prev = l;
+    }
+    if (pend >= 0) {   // last tile of this CTA
+      float* xl = xchg_l + (kb & 1u) * 256;
+      xl[half * 128 + row] = l_prev;
+      if (half == 0 && lane == 0) bulk_wait_read0();
+      fa_pair_sync(qd);
+      const float inv = 1.0f / (xl[row] + xl[128 + row]);
       mbar_wait(pv_done, (kb - 1) & 1u);
       tc_fence_after();
-      const bool valid = (t.q0 + row) < t.nq;
-      float o[32];
-      tmem_ld_32x32(tOh, o);
-      tmem_ld_wait();
-      uint4* dst = ctx_row();
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        uint4 w;
-        w.x = valid ? pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv) : 0u;
-        w.y = valid ? pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv) : 0u;
-        w.z = valid ? pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv) : 0u;
-        w.w = valid ? pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv) : 0u;
-        dst[u] = w;
-      }
+      flush_pending(inv);
     }
+    if (half == 0 && lane == 0) bulk_wait_all();   // the store still reads this CTA's shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -457,32 +507,52 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 }
 
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                                  FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
+                                  const CUtensorMap& tmO, FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
   static bool configured = false;
-  static bool p_in_tmem = true;   // SSB_FA_PTMEM=0 selects the shared-memory P variant (A/B measurements)
+  static int trace = 0;
   if (!configured) {
-    if (const char* e = std::getenv("SSB_FA_PTMEM")) p_in_tmem = std::atoi(e) != 0;
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        fa_smem_bytes<true>()));
     SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        fa_smem_bytes<false>()));
-    // ask for the full shared-memory carveout so that two CTAs (2 x 100 KB) are co-resident per SM
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
+                                        kFaSmemBytes));
+    // ask for the full shared-memory carveout so that two CTAs (2 x 84 KB) are co-resident per SM
     SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
+    if (const char* e = std::getenv("SSB_FA_TRACE")) trace = std::atoi(e);
+    if (trace) {
+      SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kFaSmemBytes));
+      SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+    }
     configured = true;
   }
   p.q_tiles = q_tiles;
   p.zcount = z;
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char* e = std::getenv("SSB_FA_STAGGER");
+    stagger = e ? std::atoi(e) : 0;
+  }
+  p.stagger = stagger;
   const int total = q_tiles * z;
   if (total <= 0) return SSB_OK;
   const int resident = 2 * device_sm_count();
   const int ctas = total < resident ? total : resident;
-  if (p_in_tmem)
-    flash_attention_kernel<true><<<ctas, kFaThreads, fa_smem_bytes<true>(), stream>>>(tmQ, tmK, tmV, p);
-  else
-    flash_attention_kernel<false><<<ctas, kFaThreads, fa_smem_bytes<false>(), stream>>>(tmQ, tmK, tmV, p);
+  if (trace) {
+    flash_attention_kernel<true><<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
+    if (trace == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
+      trace = 2;
+      SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
+      static long long h[64][8];
+      SSB_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_fa_trace, sizeof(h)));
+      std::fprintf(stderr, "fa trace (%s, %d CTAs): kb | wait_s ld max bar exp1 wait_pv exp2 | gap_to_next | period\n", label, ctas);
+      for (int b = 0; b + 1 < 48; ++b)
+        std::fprintf(stderr, "%2d | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %5lld | %5lld\n", b, h[b][1] - h[b][0],
+                     h[b][2] - h[b][1], h[b][3] - h[b][2], h[b][4] - h[b][3], h[b][5] - h[b][4], h[b][6] - h[b][5],
+                     h[b][7] - h[b][6], h[b + 1][0] - h[b][7], h[b + 1][0] - h[b][0]);
+    }
+  } else {
+    flash_attention_kernel<false><<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
+  }
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, label);

@@ -794,6 +794,7 @@ int LightGlue::alloc_workspace() {
   // TMA-store maps: one warp's 32 rows x 64 columns
   SSB_RETURN_IF(tm_rows3(&ts_x16_, x16_, 256, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows3(&ts_msg_, msg_, 256, kp_, p2, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_ctx_, ctx_, 256, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows3(&ts_h1_, h1_, 512, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows3(&ts_q_, q_, 64, kp_, z, 32));
   SSB_RETURN_IF(tm_rows3(&ts_k_, k_, 64, kp_, z, 32));
@@ -882,7 +883,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     fp.scale_log2 = scale * 1.4426950408889634f;
     fp.ctx = ctx_;
     fp.kp = KP;
-    return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, fp, tiles, Z, stream,
+    return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, stream,
                                   key_xor ? "lg.attn_cross" : "lg.attn_self");
   };
 
