@@ -144,6 +144,37 @@ int ssb_profile_report(char* buf, size_t bytes);
 ssb_superpoint* ssb_fe_superpoint(ssb_frontend* fe);
 ssb_lightglue* ssb_fe_lightglue(ssb_frontend* fe);
 
+/* ---- Image front door: the data formats either side of the networks ---------------- */
+typedef struct ssb_rectifier ssb_rectifier;
+typedef struct ssb_rgbd ssb_rgbd;
+
+/* cv::remap(img, out, M1, M2, cv::INTER_LINEAR) with the CV_32FC1 maps of cv::initUndistortRectifyMap and the
+ * default constant-0 border: the EuRoC rectification the reference does on the host before track_stereo
+ * (examples/stereo/euroc.cc:118-133,176-177).  map_x / map_y: float32 [dst_height][dst_width]; results are
+ * bit-identical to OpenCV's fixed-point bilinear path.  dst_height * dst_width must be a multiple of 4. */
+int ssb_rect_create(const float* map_x, const float* map_y, int dst_height, int dst_width, int src_height,
+                    int src_width, int max_images, int device_id, ssb_rectifier** out);
+void ssb_rect_destroy(ssb_rectifier* r);
+/* host gray u8 images in (`row_stride` bytes per row), host images out (dst_width bytes per row) */
+int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, int row_stride,
+                   uint8_t* const* out);
+/* device [count][src_h][src_w] -> device [count][dst_h][dst_w]; enqueued on the rectifier's stream, then
+ * synchronised (chain it in front of ssb_fe_enqueue_device to keep rectified images off the host) */
+int ssb_rect_remap_device(ssb_rectifier* r, const uint8_t* src_dev, int count, uint8_t* dst_dev);
+
+/* RgbdFrontEnd::process after the extraction (include/RgbdFrontEnd.h:15-37, src/RgbdFrontEnd.cc:24-58):
+ * cv::undistortPoints(raw, undist, K, D, noArray(), K) when dist has a non-zero entry, depth sampled at
+ * lround(raw), stereo = (uL, uL - bf / Z, v) and has_depth = 1 iff 0 < Z < max_depth, else (uL, NaN, v). */
+int ssb_rgbd_create(int max_keypoints, int max_height, int max_width, int device_id, ssb_rgbd** out);
+void ssb_rgbd_destroy(ssb_rgbd* r);
+/* xy: host float [n][2] raw keypoints (ssb_sp_extract output).  depth: host image, depth_type 0 = CV_16U,
+ * 1 = CV_32F, `row_stride` bytes per row.  camera = {fx, fy, cx, cy}; dist: n_dist (<= 14) coefficients in
+ * OpenCV order or NULL.  out_xy float [n][2], out_stereo double [n][3], out_has_depth uint8 [n]. */
+int ssb_rgbd_process(ssb_rgbd* r, const float* xy, int n, const void* depth, int depth_type, int height,
+                     int width, int row_stride, const double* camera, const double* dist, int n_dist,
+                     double bf, double depth_factor, double max_depth, float* out_xy, double* out_stereo,
+                     uint8_t* out_has_depth);
+
 /* ---- EigenPlaces: replaces class EigenPlaces (include/EigenPlaces.h:21-66) ----------------------
  * superslam::IPlaceRecognizer (include/PlaceRecognizer.h:20-36) over a B200-native ResNet18 + GeM + FC
  * global-descriptor network and a device-resident CosineDescriptorIndex (src/PlaceRecognizer.cc:21-52). */

@@ -229,4 +229,74 @@ class EigenPlacesB200 : public superslam::IPlaceRecognizer {
   ssb_eigenplaces* ep_ = nullptr;
 };
 
+// cv::remap(img, out, M1, M2, cv::INTER_LINEAR) on the device (examples/stereo/euroc.cc:176-177): construct once per
+// camera with the CV_32F maps of cv::initUndistortRectifyMap (euroc.cc:118-133), then
+//   rect_l(imLeft, imLeftRect);   // instead of cv::remap(imLeft, imLeftRect, M1l, M2l, cv::INTER_LINEAR)
+class RemapB200 {
+ public:
+  RemapB200(const cv::Mat& map_x, const cv::Mat& map_y, cv::Size src_size, int device_id = 0) {
+    cv::Mat mx = map_x.isContinuous() ? map_x : map_x.clone(), my = map_y.isContinuous() ? map_y : map_y.clone();
+    if (mx.type() == CV_32FC1 && my.type() == CV_32FC1 && mx.size() == my.size())
+      ssb_rect_create(mx.ptr<float>(), my.ptr<float>(), mx.rows, mx.cols, src_size.height, src_size.width, 2,
+                      device_id, &r_);
+    dst_ = mx.size();
+  }
+  ~RemapB200() { ssb_rect_destroy(r_); }
+  RemapB200(const RemapB200&) = delete;
+  RemapB200& operator=(const RemapB200&) = delete;
+  bool operator()(const cv::Mat& src, cv::Mat& dst) const {
+    if (!r_ || src.type() != CV_8UC1) return false;
+    dst.create(dst_, CV_8UC1);
+    const uint8_t* in = src.data;
+    uint8_t* out = dst.data;   // freshly created: continuous
+    return ssb_rect_remap(r_, &in, 1, static_cast<int>(src.step[0]), &out) == SSB_OK;
+  }
+
+ private:
+  ssb_rectifier* r_ = nullptr;
+  cv::Size dst_;
+};
+
+// The part of RgbdFrontEnd::process after ext_->extract (src/RgbdFrontEnd.cc:27-58) as one device call;
+// a maintainer replaces that loop by
+//   post.run(raw, depth, K_.fx(), K_.fy(), K_.px(), K_.py(), dist_coeffs_, K_.fx() * K_.baseline(),
+//            depth_factor_, max_depth_, undist, stereo, has_depth);
+class RgbdPostB200 {
+ public:
+  explicit RgbdPostB200(int max_keypoints, cv::Size max_size, int device_id = 0) {
+    ssb_rgbd_create(max_keypoints, max_size.height, max_size.width, device_id, &r_);
+  }
+  ~RgbdPostB200() { ssb_rgbd_destroy(r_); }
+  RgbdPostB200(const RgbdPostB200&) = delete;
+  RgbdPostB200& operator=(const RgbdPostB200&) = delete;
+  // stereo: n x (uL, uR or NaN, v) doubles - the fields of gtsam::StereoPoint2
+  bool run(const std::vector<cv::Point2f>& raw, const cv::Mat& depth, double fx, double fy, double cx, double cy,
+           const cv::Mat& dist_coeffs, double bf, double depth_factor, double max_depth,
+           std::vector<cv::Point2f>& undist, std::vector<double>& stereo, std::vector<char>& has_depth) const {
+    const int n = static_cast<int>(raw.size());
+    undist.resize(n);
+    stereo.resize(static_cast<size_t>(n) * 3);
+    has_depth.assign(n, 0);
+    if (!r_ || n == 0) return r_ != nullptr;
+    const int type = depth.type() == CV_16U ? 0 : (depth.type() == CV_32F ? 1 : -1);
+    cv::Mat zero;
+    const cv::Mat* dm = &depth;
+    if (type < 0) {   // sampleDepth returns 0 for any other type (src/RgbdFrontEnd.cc:12-20)
+      zero = cv::Mat::zeros(depth.size(), CV_16U);
+      dm = &zero;
+    }
+    cv::Mat d64;
+    dist_coeffs.reshape(1, 1).convertTo(d64, CV_64F);
+    const double cam[4] = {fx, fy, cx, cy};
+    return ssb_rgbd_process(r_, reinterpret_cast<const float*>(raw.data()), n, dm->data, type < 0 ? 0 : type, dm->rows,
+                            dm->cols, static_cast<int>(dm->step[0]), cam, d64.empty() ? nullptr : d64.ptr<double>(),
+                            d64.empty() ? 0 : d64.cols, bf, depth_factor, max_depth,
+                            reinterpret_cast<float*>(undist.data()), stereo.data(),
+                            reinterpret_cast<uint8_t*>(has_depth.data())) == SSB_OK;
+  }
+
+ private:
+  ssb_rgbd* r_ = nullptr;
+};
+
 }  // namespace superslam_b200

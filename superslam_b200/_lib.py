@@ -28,6 +28,7 @@ _ip = C.POINTER(C.c_int)
 _fp = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)
+_dp = C.POINTER(C.c_double)
 
 SYMBOLS = [
     ("ssb_last_error", C.c_char_p, []),
@@ -74,6 +75,14 @@ SYMBOLS = [
                                C.c_int, _ip]),
     ("ssb_ep_index_size", C.c_int, [_vp]),
     ("ssb_ep_debug_read", C.c_int, [_vp, C.c_char_p, _vp, C.c_size_t]),
+    ("ssb_rect_create", C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_rect_destroy", None, [_vp]),
+    ("ssb_rect_remap", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, _u8pp]),
+    ("ssb_rect_remap_device", C.c_int, [_vp, _vp, C.c_int, _vp]),
+    ("ssb_rgbd_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("ssb_rgbd_destroy", None, [_vp]),
+    ("ssb_rgbd_process", C.c_int, [_vp, _fp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                   C.c_double, C.c_double, C.c_double, _fp, _dp, _u8p]),
     ("ssb_kernel_launch_count", C.c_longlong, []),
     ("ssb_profile_enable", None, [C.c_int]),
     ("ssb_profile_collect", None, []),

@@ -9,6 +9,7 @@
 
 #include "../../include/superslam_b200.h"
 #include "eigenplaces.cuh"
+#include "imgproc.cuh"
 #include "lightglue.cuh"
 #include "superpoint.cuh"
 
@@ -20,6 +21,12 @@ struct ssb_lightglue {
 };
 struct ssb_eigenplaces {
   ssb::EigenPlaces impl;
+};
+struct ssb_rectifier {
+  ssb::Rectifier impl;
+};
+struct ssb_rgbd {
+  ssb::RgbdPost impl;
 };
 
 namespace ssb {
@@ -595,6 +602,73 @@ int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
   (void)pairs;
   // conv1a + 10 tcgen05 convs + memset-free: nms, select, gather | prepare + 9 x 15 + 8 | postfilter
   return 14 + 1 + 9 * 16 + 8 + 1;
+}
+static int require_sm100(int device_id) {
+  SSB_CUDA_CHECK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  SSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_id));
+  SSB_CHECK(prop.major == 10, SSB_ERR_NODEVICE, "device %d is sm_%d%d; this library needs sm_100", device_id,
+            prop.major, prop.minor);
+  return SSB_OK;
+}
+int ssb_rect_create(const float* map_x, const float* map_y, int dst_height, int dst_width, int src_height,
+                    int src_width, int max_images, int device_id, ssb_rectifier** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  SSB_RETURN_IF(require_sm100(device_id));
+  std::unique_ptr<ssb_rectifier> h(new ssb_rectifier);
+  SSB_RETURN_IF(h->impl.init(map_x, map_y, dst_height, dst_width, src_height, src_width,
+                             max_images <= 0 ? 2 : max_images, device_id));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_rect_destroy(ssb_rectifier* r) { delete r; }
+int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, int row_stride,
+                   uint8_t* const* out) {
+  SSB_API_BEGIN
+  SSB_CHECK(r != nullptr, SSB_ERR_INVALID, "rectifier is null");
+  return r->impl.remap(images, count, row_stride, out);
+  SSB_API_END
+}
+int ssb_rect_remap_device(ssb_rectifier* r, const uint8_t* src_dev, int count, uint8_t* dst_dev) {
+  SSB_API_BEGIN
+  SSB_CHECK(r != nullptr, SSB_ERR_INVALID, "rectifier is null");
+  SSB_RETURN_IF(r->impl.remap_device(src_dev, count, dst_dev, r->impl.stream()));
+  SSB_CUDA_CHECK(cudaStreamSynchronize(r->impl.stream()));
+  return SSB_OK;
+  SSB_API_END
+}
+int ssb_rgbd_create(int max_keypoints, int max_height, int max_width, int device_id, ssb_rgbd** out) {
+  SSB_API_BEGIN
+  SSB_CHECK(out != nullptr, SSB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  SSB_RETURN_IF(require_sm100(device_id));
+  std::unique_ptr<ssb_rgbd> h(new ssb_rgbd);
+  SSB_RETURN_IF(h->impl.init(max_keypoints, max_height, max_width, device_id));
+  *out = h.release();
+  return SSB_OK;
+  SSB_API_END
+}
+void ssb_rgbd_destroy(ssb_rgbd* r) { delete r; }
+int ssb_rgbd_process(ssb_rgbd* r, const float* xy, int n, const void* depth, int depth_type, int height,
+                     int width, int row_stride, const double* camera, const double* dist, int n_dist,
+                     double bf, double depth_factor, double max_depth, float* out_xy, double* out_stereo,
+                     uint8_t* out_has_depth) {
+  SSB_API_BEGIN
+  SSB_CHECK(r != nullptr && camera != nullptr, SSB_ERR_INVALID, "null argument");
+  SSB_CHECK(n_dist >= 0 && n_dist <= 14 && (dist != nullptr || n_dist == 0), SSB_ERR_INVALID, "bad dist");
+  ssb::RgbdParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.fx = camera[0], p.fy = camera[1], p.cx = camera[2], p.cy = camera[3];
+  for (int i = 0; i < n_dist; ++i) {
+    p.k[i] = dist[i];
+    if (dist[i] != 0.0) p.has_dist = 1;   // cv::countNonZero(dist_coeffs_) > 0
+  }
+  p.bf = bf, p.depth_factor = depth_factor, p.max_depth = max_depth;
+  return r->impl.process(xy, n, depth, depth_type, height, width, row_stride, p, out_xy, out_stereo, out_has_depth);
+  SSB_API_END
 }
 int ssb_ep_create(const char* weights_path, int input_width, int input_height, int max_batch, int device_id,
                   ssb_eigenplaces** out) {

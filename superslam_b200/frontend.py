@@ -456,3 +456,103 @@ class EigenPlaces:
         out = np.empty(shape, dtype)
         _lib.check(self._lib.ssb_ep_debug_read(self._h, what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+
+class Rectifier:
+    """cv::remap(img, out, M1, M2, cv::INTER_LINEAR) on the device (ssb_rect_*): the stereo rectification the
+    reference's EuRoC driver applies before track_stereo (examples/stereo/euroc.cc:118-133,176-177).
+    `map_x`, `map_y` are the CV_32F maps of cv::initUndistortRectifyMap for one camera."""
+
+    def __init__(self, map_x, map_y, src_shape, max_images: int = 2, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        mx = np.ascontiguousarray(map_x, np.float32)
+        my = np.ascontiguousarray(map_y, np.float32)
+        if mx.shape != my.shape or mx.ndim != 2:
+            raise ValueError("map_x / map_y must be 2-D arrays of one shape")
+        self.dst_shape = mx.shape
+        self.src_shape = tuple(src_shape[:2])
+        _lib.check(self._lib.ssb_rect_create(mx.ctypes.data_as(C.POINTER(C.c_float)),
+                                             my.ctypes.data_as(C.POINTER(C.c_float)), mx.shape[0], mx.shape[1],
+                                             self.src_shape[0], self.src_shape[1], max_images, device,
+                                             C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_rect_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def remap(self, images):
+        """list of gray u8 images (src_shape) -> list of rectified u8 images (dst_shape)."""
+        imgs = [np.asarray(i) for i in images]
+        for im in imgs:
+            if im.dtype != np.uint8 or im.ndim != 2 or im.shape != self.src_shape or im.strides[1] != 1:
+                raise ValueError("remap expects gray u8 images of the source shape")
+        n = len(imgs)
+        outs = [np.empty(self.dst_shape, np.uint8) for _ in range(n)]
+        ip = (C.POINTER(C.c_uint8) * n)(*[im.ctypes.data_as(C.POINTER(C.c_uint8)) for im in imgs])
+        op = (C.POINTER(C.c_uint8) * n)(*[o.ctypes.data_as(C.POINTER(C.c_uint8)) for o in outs])
+        _lib.check(self._lib.ssb_rect_remap(self._h, ip, n, imgs[0].strides[0], op))
+        return outs
+
+    def remap_device(self, src_dev: int, count: int, dst_dev: int) -> None:
+        _lib.check(self._lib.ssb_rect_remap_device(self._h, C.c_void_p(src_dev), count, C.c_void_p(dst_dev)))
+
+
+class RgbdFrontEnd:
+    """include/RgbdFrontEnd.h:15-37 / src/RgbdFrontEnd.cc:24-58 over any extractor with `extract`:
+    keypoint undistortion, depth sampling and the synthetic right coordinate run on the device
+    (ssb_rgbd_process)."""
+
+    def __init__(self, ext, fx: float, fy: float, cx: float, cy: float, baseline: float, depth_factor: float,
+                 max_depth: float, dist_coeffs=None, max_keypoints: int = 4096, max_shape=(1080, 1920),
+                 device: int = 0):
+        self._lib = _lib.load()
+        self.ext = ext
+        self.camera = (C.c_double * 4)(fx, fy, cx, cy)
+        d = np.zeros((0,), np.float64) if dist_coeffs is None else np.asarray(dist_coeffs, np.float64).ravel()
+        self.dist = d
+        self.bf = float(fx) * float(baseline)   # K_.fx() * K_.baseline()
+        self.depth_factor, self.max_depth = float(depth_factor), float(max_depth)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.ssb_rgbd_create(max_keypoints, max_shape[0], max_shape[1], device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_rgbd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def postprocess(self, keypoints, depth):
+        """raw keypoints [n,2] + depth image (uint16 or float32) -> (undistorted xy, stereo [n,3], has_depth)."""
+        xy = np.ascontiguousarray(keypoints, np.float32).reshape(-1, 2)
+        n = len(xy)
+        depth = np.asarray(depth)
+        if depth.dtype == np.uint16:
+            dtype = 0
+        elif depth.dtype == np.float32:
+            dtype = 1
+        else:   # sampleDepth returns 0 for any other type: no depth anywhere
+            depth, dtype = np.zeros(depth.shape[:2], np.uint16), 0
+        if depth.strides[1] != depth.itemsize:
+            depth = np.ascontiguousarray(depth)
+        oxy = np.empty((n, 2), np.float32)
+        stereo = np.empty((n, 3), np.float64)
+        has = np.zeros((n,), np.uint8)
+        dp = self.dist.ctypes.data_as(C.POINTER(C.c_double)) if len(self.dist) else None
+        _lib.check(self._lib.ssb_rgbd_process(
+            self._h, xy.ctypes.data_as(C.POINTER(C.c_float)), n, depth.ctypes.data_as(C.c_void_p), dtype,
+            depth.shape[0], depth.shape[1], depth.strides[0], self.camera, dp, len(self.dist), self.bf,
+            self.depth_factor, self.max_depth, oxy.ctypes.data_as(C.POINTER(C.c_float)),
+            stereo.ctypes.data_as(C.POINTER(C.c_double)), has.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return oxy, stereo, has.astype(np.int8)
+
+    def process(self, gray, depth, timestamp: float = 0.0) -> StereoFrame:
+        L = self.ext.extract(gray)
+        oxy, stereo, has = self.postprocess(L.keypoints, depth)
+        return StereoFrame(timestamp, oxy, L.descriptors, stereo, has)

@@ -1,0 +1,62 @@
+"""Oracle pinning for the image front door: oracle/imgproc.py against OpenCV itself
+(cv2 of this image runs the same C++ the reference links: cv::remap, cv::undistortPoints)."""
+import numpy as np
+import pytest
+
+from oracle import imgproc as ip
+from superslam_b200.synth import synth_pair
+
+cv2 = pytest.importorskip("cv2")
+
+K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0])   # EuRoC cam0
+P = np.array([[435.2046959714599, 0, 367.4517211914062], [0, 435.2046959714599, 252.2008514404297], [0, 0, 1]])
+
+
+def euroc_maps(h=480, w=752):
+    R = cv2.Rodrigues(np.array([0.0077, -0.0049, 0.0016]))[0]
+    return cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32F)
+
+
+def test_remap_rectification_bit_exact():
+    img, _ = synth_pair(480, 752, 300, 5)
+    m1, m2 = euroc_maps()
+    assert np.array_equal(cv2.remap(img, m1, m2, cv2.INTER_LINEAR), ip.remap_linear_u8(img, m1, m2))
+
+
+def test_remap_border_and_ties_bit_exact():
+    rng = np.random.default_rng(3)
+    img, _ = synth_pair(120, 160, 60, 9)
+    h, w = img.shape
+    # coordinates well outside the image on every side (constant border 0) ...
+    mx = rng.uniform(-20, w + 20, (h, w)).astype(np.float32)
+    my = rng.uniform(-20, h + 20, (h, w)).astype(np.float32)
+    assert np.array_equal(cv2.remap(img, mx, my, cv2.INTER_LINEAR), ip.remap_linear_u8(img, mx, my))
+    # ... and exact 1/64 offsets: cvRound(v * 32) ties go to even
+    mx = (np.arange(w)[None, :] + np.zeros((h, 1)) + 1 / 64).astype(np.float32)
+    my = (np.arange(h)[:, None] + np.zeros((1, w)) + 3 / 64).astype(np.float32)
+    assert np.array_equal(cv2.remap(img, mx, my, cv2.INTER_LINEAR), ip.remap_linear_u8(img, mx, my))
+
+
+@pytest.mark.parametrize("dist", [D, np.array([-0.2, 0.05, 0.001, -0.0005, 0.01, 0.02, -0.01, 0.003])])
+def test_undistort_points_bit_exact(dist):
+    rng = np.random.default_rng(1)
+    pts = rng.uniform([0, 0], [752, 480], (1500, 2)).astype(np.float32)
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+    got = ip.undistort_points(pts, K[0, 0], K[1, 1], K[0, 2], K[1, 2], dist)
+    assert np.array_equal(ref, got)
+
+
+def test_rgbd_process_semantics():
+    # src/RgbdFrontEnd.cc:24-58: depth at the RAW pixel, uR from the UNDISTORTED uL, Z window (0, max_depth)
+    xy = np.array([[10.4, 20.6], [100.5, 50.5], [-3.0, 5.0], [30.0, 40.0]], np.float32)
+    depth = np.zeros((120, 160), np.uint16)
+    depth[21, 10] = 5000      # lround(10.4, 20.6) = (10, 21): Z = 1.0
+    depth[51, 101] = 50000    # lround(.5) goes away from zero: (101, 51); Z = 10 -> beyond max_depth 8
+    depth[40, 30] = 0         # no measurement
+    und, stereo, has = ip.rgbd_process(xy, depth, 500.0, 500.0, 80.0, 60.0, None, bf=40.0, depth_factor=5000.0,
+                                       max_depth=8.0)
+    assert np.array_equal(und, xy)                      # no distortion: keypoints unchanged
+    assert has.tolist() == [1, 0, 0, 0]
+    assert stereo[0].tolist() == [float(xy[0, 0]), float(xy[0, 0]) - 40.0, float(xy[0, 1])]
+    assert np.isnan(stereo[1:, 1]).all()
