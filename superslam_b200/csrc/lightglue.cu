@@ -28,54 +28,65 @@ namespace ssb {
 // SIMT kernels
 // =================================================================================================
 
-// One warp per keypoint row: copy the fp16 descriptor row into the fp16/fp32 residual stream (zero the
-// padding rows), normalise the pixel keypoint exactly like LightGlue::store_keypoints and evaluate
-// the learnable Fourier encoding (lane f owns frequency f).
+// One CTA per 32 keypoint rows of one image: copy the fp16 descriptor rows into the fp16/fp32 residual stream
+// (zero the padding rows), normalise the pixel keypoints exactly like LightGlue::store_keypoints and evaluate
+// the learnable Fourier encoding.  Everything leaves in full 128-byte lines: x16 row-wise as loaded, the fp32
+// master (tile-transposed [z][row/128][col][row%128], see EpiResidual) and the frequency-major rotary table
+// [z][32][kp] (see EpiQkvRope) with the 32 lanes of a warp on 32 consecutive rows; the transposition goes
+// through shared memory.  (Writing the fp32 master straight from the row-owning warp touched 256 sectors per
+// row: 0.20 ms per 64 pairs against 0.05 ms of HBM time.)
 __global__ void __launch_bounds__(256)
 lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __restrict__ kp_count,
                   void* const* __restrict__ desc_ptrs, const float* __restrict__ wr, float cx, float cy,
                   float scale, int kp, __half* __restrict__ x16, float* __restrict__ x32,
                   float* __restrict__ cs, float* __restrict__ sn) {
+  constexpr int kPitch = 258;   // halfs per staged row: 129 words, so a column read by 32 rows is conflict-free
+  __shared__ __half stash[32 * kPitch];
   const int z = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= kp) return;   // kp is a multiple of 128: uniform per block
-  // rotary table, stored frequency-major [z][32][kp] so that the 32 lanes of an epilogue warp (32
-  // consecutive rows) read one 128-byte line per frequency (EpiQkvRope); transposed through shared memory
-  __shared__ float s_cs[32][9], s_sn[32][9];
+  const int row0 = blockIdx.x * 32;   // kp is a multiple of 128
   const int n = kp_count[z];
-  const size_t o = (static_cast<size_t>(z) * kp + row) * kLgDim + lane * 8;
-  // fp32 master: tile-transposed [z][row/128][col][row%128] (see EpiResidual)
-  float* xt = x32 + (static_cast<size_t>(z) * (kp >> 7) + (row >> 7)) * (kLgDim * 128) + (row & 127);
-  float co = 0.f, si = 0.f;
-  if (row >= n || desc_ptrs[z] == nullptr) {
-    *reinterpret_cast<uint4*>(x16 + o) = make_uint4(0u, 0u, 0u, 0u);
+  const __half* desc = static_cast<const __half*>(desc_ptrs[z]);
+  // phase 1: warp w copies rows 4w .. 4w+3 (a 512-byte row = 32 lanes x 16 bytes) and stages them
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = 0.f;
-  } else {
-    const __half* d = static_cast<const __half*>(desc_ptrs[z]) + static_cast<size_t>(row) * kLgDim + lane * 8;
-    const uint4 raw = *reinterpret_cast<const uint4*>(d);
-    *reinterpret_cast<uint4*>(x16 + o) = raw;
-    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-    const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]),
-                 e = __half22float2(h2[3]);
-    const float f8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, e.x, e.y};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xt[static_cast<size_t>(lane * 8 + j) * 128] = f8[j];
-    const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
-    const float nx = (xy[0] - cx) / scale;
-    const float ny = (xy[1] - cy) / scale;
-    const float proj = wr[lane * 2 + 0] * nx + wr[lane * 2 + 1] * ny;
-    co = cosf(proj);
-    si = sinf(proj);
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 4 + i, row = row0 + r;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n && desc != nullptr)
+      raw = *reinterpret_cast<const uint4*>(desc + static_cast<size_t>(row) * kLgDim + lane * 8);
+    *reinterpret_cast<uint4*>(x16 + (static_cast<size_t>(z) * kp + row) * kLgDim + lane * 8) = raw;
+    uint32_t* st = reinterpret_cast<uint32_t*>(stash + r * kPitch + lane * 8);
+    st[0] = raw.x, st[1] = raw.y, st[2] = raw.z, st[3] = raw.w;
   }
-  s_cs[lane][warp] = co;
-  s_sn[lane][warp] = si;
+  // rotary table: lane = row, warp w owns frequencies 4w .. 4w+3
+  {
+    const int row = row0 + lane;
+    const bool valid = row < n && desc != nullptr;
+    float nx = 0.f, ny = 0.f;
+    if (valid) {
+      const float* xy = kp_xy + (static_cast<size_t>(z) * kp_stride + row) * 2;
+      nx = (xy[0] - cx) / scale;
+      ny = (xy[1] - cy) / scale;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = warp * 4 + i;
+      float co = 0.f, si = 0.f;
+      if (valid) {
+        const float proj = wr[f * 2 + 0] * nx + wr[f * 2 + 1] * ny;
+        co = cosf(proj);
+        si = sinf(proj);
+      }
+      const size_t t = (static_cast<size_t>(z) * 32 + f) * kp + row;
+      cs[t] = co;
+      sn[t] = si;
+    }
+  }
   __syncthreads();
-  const int f = threadIdx.x >> 3, r = threadIdx.x & 7;
-  const size_t t = (static_cast<size_t>(z) * 32 + f) * kp + blockIdx.x * 8 + r;
-  cs[t] = s_cs[f][r];
-  sn[t] = s_sn[f][r];
+  // phase 2: fp32 master, lane = row: 32 consecutive floats per column
+  float* xt = x32 + (static_cast<size_t>(z) * (kp >> 7) + (row0 >> 7)) * (kLgDim * 128) + (row0 & 127) + lane;
+#pragma unroll 8
+  for (int c = warp; c < kLgDim; c += 8) xt[static_cast<size_t>(c) * 128] = __half2float(stash[lane * kPitch + c]);
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -379,6 +390,36 @@ __device__ __forceinline__ __half2 gelu_erf_h2(__half2 y) {
   return __hfma2(__hmul2(a, __float2half2_rn(-0.5f)), e, __hmax2(y, __float2half2_rn(0.f)));
 }
 
+// The same on kN packed pairs at once, written stage by stage: a Horner chain is six dependent HFMA2 (4-5 cycles
+// each), and with two epilogue warps per scheduler nothing else hides that latency - ptxas kept the chains of
+// the one-pair version back to back ("wait" was the top stall of this kernel).  Eight independent chains
+// interleaved issue one instruction per cycle.
+template <int kN>
+__device__ __forceinline__ void gelu_erf_h2_batch(__half2 (&y)[kN]) {
+  __half2 t[kN], p[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i) t[i] = __hmin2(__habs2(y[i]), __float2half2_rn(5.6568542f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(__float2half2_rn(-8.85259948e-06f), t[i], __float2half2_rn(5.76901113e-05f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(4.06791425e-04f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(-7.36236150e-03f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(5.26655323e-02f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(4.59164890e-01f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(1.15110875e+00f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = __hmul2(__hneg2(t[i]), p[i]);
+#pragma unroll
+  for (int i = 0; i < kN; ++i) p[i] = h2exp2(p[i]);
+#pragma unroll
+  for (int i = 0; i < kN; ++i)
+    y[i] = __hfma2(__hmul2(__habs2(y[i]), __float2half2_rn(-0.5f)), p[i], __hmax2(y[i], __float2half2_rn(0.f)));
+}
+
 struct EpiLnGelu {
   const float* bias;
   const float* g;
@@ -391,20 +432,21 @@ struct EpiLnGelu {
     const bool valid = row < c.m_valid;
     // pass 1: sum and sum of squares together (LayerNorm inputs are O(1) with near-zero mean, so
     // E[x^2] - mean^2 in fp32 is safe), all-reduced across the two column halves
-    float sum = 0.f, sq = 0.f;
+    float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
     tmem_chunks_pipelined<4>(c.tmem_row + c.col_begin, [&](int i, float* v) {
       const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + c.col_begin + i * 32);
+      // packed fp32x2 arithmetic: three FMA-pipe instructions per PAIR of columns
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 bb = __ldg(b4 + j);
-        const float x0 = v[4 * j] + bb.x, x1 = v[4 * j + 1] + bb.y, x2 = v[4 * j + 2] + bb.z, x3 = v[4 * j + 3] + bb.w;
-        sum += (x0 + x1) + (x2 + x3);
-        sq = fmaf(x0, x0, sq);
-        sq = fmaf(x1, x1, sq);
-        sq = fmaf(x2, x2, sq);
-        sq = fmaf(x3, x3, sq);
+        const float2 x01 = fadd2(make_float2(v[4 * j], v[4 * j + 1]), make_float2(bb.x, bb.y));
+        const float2 x23 = fadd2(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(bb.z, bb.w));
+        sum2 = fadd2(sum2, fadd2(x01, x23));
+        sq2 = ffma2(x01, x01, sq2);
+        sq2 = ffma2(x23, x23, sq2);
       }
     });
+    float sum = sum2.x + sum2.y, sq = sq2.x + sq2.y;
     sum = epi_pair_sum(c, sum);   // this CTA's 256 columns ...
     sq = epi_pair_sum(c, sq);
     epi_cluster_sum2(c, sum, sq);  // ... plus the peer CTA's 256
@@ -412,6 +454,7 @@ struct EpiLnGelu {
     const float var = fmaxf(sq * (1.0f / 512.0f) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
     const float nmr = -mean * rstd;
+    const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
     tmem_chunks_pipelined<4>(c.tmem_row + c.col_begin, [&](int i, float* v) {
       const int col = c.col_begin + i * 32;
       const int hc = i & 1;
@@ -421,17 +464,23 @@ struct EpiLnGelu {
       const float4* be4 = reinterpret_cast<const float4*>(b + c.n0 + col);
       uint32_t h[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bb = __ldg(b4 + j), gg = __ldg(g4 + j), be = __ldg(be4 + j);
-        // LayerNorm (fp32) as  ((acc + bias) * rstd + (-mean * rstd)) * gamma + beta
-        const float y0 = fmaf(fmaf(v[4 * j + 0] + bb.x, rstd, nmr), gg.x, be.x);
-        const float y1 = fmaf(fmaf(v[4 * j + 1] + bb.y, rstd, nmr), gg.y, be.y);
-        const float y2 = fmaf(fmaf(v[4 * j + 2] + bb.z, rstd, nmr), gg.z, be.z);
-        const float y3 = fmaf(fmaf(v[4 * j + 3] + bb.w, rstd, nmr), gg.w, be.w);
-        const __half2 g01 = gelu_erf_h2(__floats2half2_rn(y0, y1));
-        const __half2 g23 = gelu_erf_h2(__floats2half2_rn(y2, y3));
-        h[2 * j] = valid ? *reinterpret_cast<const uint32_t*>(&g01) : 0u;
-        h[2 * j + 1] = valid ? *reinterpret_cast<const uint32_t*>(&g23) : 0u;
+      for (int g8 = 0; g8 < 2; ++g8) {   // two groups of eight pairs
+        __half2 y[8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = g8 * 4 + jj;
+          const float4 bb = __ldg(b4 + j), gg = __ldg(g4 + j), be = __ldg(be4 + j);
+          // LayerNorm (fp32, packed pairs) as  ((acc + bias) * rstd + (-mean * rstd)) * gamma + beta
+          const float2 y01 = ffma2(ffma2(fadd2(make_float2(v[4 * j], v[4 * j + 1]), make_float2(bb.x, bb.y)), rstd2, nmr2),
+                                   make_float2(gg.x, gg.y), make_float2(be.x, be.y));
+          const float2 y23 = ffma2(ffma2(fadd2(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(bb.z, bb.w)), rstd2, nmr2),
+                                   make_float2(gg.z, gg.w), make_float2(be.z, be.w));
+          y[2 * jj] = __floats2half2_rn(y01.x, y01.y);
+          y[2 * jj + 1] = __floats2half2_rn(y23.x, y23.y);
+        }
+        gelu_erf_h2_batch(y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[g8 * 8 + i] = valid ? *reinterpret_cast<const uint32_t*>(&y[i]) : 0u;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -457,50 +506,86 @@ struct EpiResidual {
   CUtensorMap tm_x16;
   int kp;
   static constexpr bool kSplit = true;
-  __device__ void operator()(EpiCtx& c, bool) const {
-    const int row = c.px;
-    const int row0 = __shfl_sync(0xffffffffu, row, 0);
-    const bool valid = row < c.m_valid;
-    float* xt = x32 + (static_cast<size_t>(c.z) * (kp >> 7) + (row >> 7)) * (kLgDim * 128) + (row & 127);
-    tmem_chunks_pipelined<4>(c.tmem_row + c.col_begin, [&](int i, float* v) {
-      const int col = c.col_begin + i * 32;
-      const int hc = i & 1;
-      if (hc == 0) stage_begin(c);
-      float* p0 = xt + static_cast<size_t>(c.n0 + col) * 128;
-      float r[32];
-      if (valid) {
+  // The residual rows do not depend on the accumulator: the first 32-column chunk is requested before the wait
+  // for the tile's MMAs and every further chunk one chunk ahead, so the HBM round trip of the fp32 master
+  // (measured: ~4 000 cycles per chunk, 18 000 per tile - twice the tile's MMA time) runs under other work.
+  struct Pre {
+    float r[32];
+  };
+  __device__ __forceinline__ float* tile_ptr(const EpiCtx& c) const {
+    return x32 + (static_cast<size_t>(c.z) * (kp >> 7) + (c.px >> 7)) * (kLgDim * 128) + (c.px & 127) +
+           static_cast<size_t>(c.n0 + c.col_begin) * 128;
+  }
+  __device__ __forceinline__ void load_chunk(const float* p0, bool valid, float* r) const {
+    if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = p0[static_cast<size_t>(j) * 128];   // all 32 loads in flight
-      }
-      const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
+      for (int j = 0; j < 32; ++j) r[j] = p0[static_cast<size_t>(j) * 128];   // 32 lanes = 32 rows: 128-byte lines
+    }
+  }
+  __device__ __forceinline__ void prefetch(const EpiCtx& c, Pre& t) const {
+    load_chunk(tile_ptr(c), c.px < c.m_valid, t.r);
+  }
+  __device__ __forceinline__ void chunk(EpiCtx& c, int i, float* v, const float* r, float* p0, bool valid,
+                                        int row0) const {
+    const int col = c.col_begin + i * 32;
+    const int hc = i & 1;
+    if (hc == 0) stage_begin(c);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + c.n0 + col);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(b4 + j);
-        v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(b4 + j);
+      v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
+    }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = valid ? r[j] + v[j] : 0.f;
-        p0[static_cast<size_t>(j) * 128] = x;
-        v[j] = x;
-      }
+    for (int j = 0; j < 32; ++j) {
+      const float x = valid ? r[j] + v[j] : 0.f;
+      p0[static_cast<size_t>(j) * 128] = x;
+      v[j] = x;
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        stage_put(c, c.lane, hc * 4 + j, o);
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+      o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+      o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+      stage_put(c, c.lane, hc * 4 + j, o);
+    }
+    if (hc == 1) {
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(&tm_x16, c.stage_cur, c.n0 + col - 32, row0, c.z);
+        bulk_commit();
       }
-      if (hc == 1) {
-        stage_fence(c);
-        if (c.lane == 0) {
-          tma_store_3d(&tm_x16, c.stage_cur, c.n0 + col - 32, row0, c.z);
-          bulk_commit();
-        }
-      }
-    });
+    }
+  }
+  __device__ void operator()(EpiCtx& c, bool, const Pre& pre) const {
+    const int row0 = __shfl_sync(0xffffffffu, c.px, 0);
+    const bool valid = c.px < c.m_valid;
+    float* xt = tile_ptr(c);
+    const uint32_t t0 = c.tmem_row + c.col_begin;
+    float va[32], ra[32], rb[32];
+    // chunk 0 (residual prefetched), chunks 1..3 requested one ahead
+    tmem_ld_32x32(t0, va);
+    load_chunk(xt + 32 * 128, valid, ra);
+    tmem_ld_wait();
+    {
+      float r0[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r0[j] = pre.r[j];
+      chunk(c, 0, va, r0, xt, valid, row0);
+    }
+    tmem_ld_32x32(t0 + 32, va);
+    load_chunk(xt + 64 * 128, valid, rb);
+    tmem_ld_wait();
+    chunk(c, 1, va, ra, xt + 32 * 128, valid, row0);
+    tmem_ld_32x32(t0 + 64, va);
+    load_chunk(xt + 96 * 128, valid, ra);
+    tmem_ld_wait();
+    chunk(c, 2, va, rb, xt + 64 * 128, valid, row0);
+    tmem_ld_32x32(t0 + 96, va);
+    tmem_ld_wait();
+    chunk(c, 3, va, ra, xt + 96 * 128, valid, row0);
   }
 };
 
@@ -839,12 +924,20 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   {
     const float scale = static_cast<float>(std::max(img_w_, img_h_)) / 2.0f;
     const float cx = img_w_ / 2.0f, cy = img_h_ / 2.0f;
-    lg_prepare_kernel<<<dim3(KP / 8, P2), 256, 0, stream>>>(kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
+    lg_prepare_kernel<<<dim3(KP / 32, P2), 256, 0, stream>>>(kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
                                                             w_->wr, cx, cy, scale, KP, x16_, x32_, cs_, sn_);
     SSB_CUDA_CHECK(cudaGetLastError());
     count_launch();
     prof_mark(stream, "lg.prepare");
   }
+  // multicast B (umma_core.cuh): pairs of row tiles share every weight chunk.  SSB_LG_MCAST selects it
+  // (A/B measurements); bit 0 = plain linears, bit 1 = ffn1 (clusters of four).  Off by default.
+  static int mcast = -1;
+  if (mcast < 0) {
+    const char* e = std::getenv("SSB_LG_MCAST");
+    mcast = e ? std::atoi(e) : 0;   // measured: no gain while the epilogues set the tile period (profiles/README.md)
+  }
+  auto bmap = [&](const LgLinear& L, bool mc) -> const CUtensorMap& { return mc ? L.tmB128 : L.tmB; };
   auto lin = [&](const char* label, int kc0, int kc1, int block_n) {
     CoreParams p;
     std::memset(&p, 0, sizeof(p));
@@ -864,13 +957,16 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     {
       CoreParams p = lin("lg.ffn1", 4, 4, 256);
       p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)
+      p.b_mcast = (mcast >> 1) & 1;
       EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, ts_h1_};
-      SSB_RETURN_IF(launch_core(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, F.fc1.tmB, p, e, dim3(tiles, 2, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, bmap(F.fc1, p.b_mcast), p, e,
+                                dim3(tiles, 2, P2), stream));
     }
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);
+      p.b_mcast = mcast & 1;
       EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
-      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, bmap(F.fc2, p.b_mcast), p, e, dim3(tiles, 1, P2), stream));
     }
     return SSB_OK;
   };
@@ -896,8 +992,9 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
+      p.b_mcast = mcast & 1;
       EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, bmap(L.qkv, p.b_mcast), p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     if (!w_->fold_out) {
@@ -910,8 +1007,9 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
+      p.b_mcast = mcast & 1;
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, bmap(L.qkv_c, p.b_mcast), p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     if (!w_->fold_out) {

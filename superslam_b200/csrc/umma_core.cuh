@@ -16,6 +16,9 @@
 // quadrant and split the accumulator columns between them.
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -76,6 +79,13 @@ struct CoreParams {
   // statistics (LayerNorm over all N tiles) can exchange per-row partials through distributed shared
   // memory (EpiCtx::peer_*).  Used with grid_y == 2.
   int cluster_y;
+  // Multicast B: clusters of two CTAs (four with cluster_y) work on two consecutive M tiles of the SAME N tile;
+  // each loads one half of every B (weight) stage and multicasts it to both, so a weight chunk crosses the
+  // L2 -> SM fabric once per pair of tiles.  (The skinny LightGlue GEMMs re-read their whole weight matrix for
+  // every 128-row tile: 2/3 of all operand bytes, and L2 -> SM bandwidth was the measured bound.)  Needs
+  // block_n == 256, a B tensor map with 128-row boxes and an even number of M tiles per row of tiles.
+  int b_mcast;
+  long long* trace;    // diagnostic (SSB_CORE_TRACE=<label>): CTA 0 time-stamps its first 32 tiles, [tile][8]
   const char* label;   // host-only: kernel name for the event profiler
 };
 
@@ -227,7 +237,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.b_mcast ? 2 : 1);   // multicast: released by both consumers of the stage
     }
     mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -243,27 +253,38 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster_y) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
+  const bool clustered = p.cluster_y || p.b_mcast;
+  if (clustered) cluster_sync_all();   // the peers' barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B / cluster - a fixed y per CTA
+  // With multicast B a group of xr = 2 CTAs (times ny) walks PAIRS of M tiles in lockstep: cluster rank =
+  // xpar * ny + y.
   const bool fixed_y = p.b_resident || p.cluster_y;
   const int ny = fixed_y ? p.grid_y : 1;
-  const int y_fixed = static_cast<int>(blockIdx.x) % ny;
-  const int first = static_cast<int>(blockIdx.x) / ny;
-  const int stride = static_cast<int>(gridDim.x) / ny;
-  const int total = fixed_y ? p.grid_x * p.grid_z : p.grid_x * p.grid_y * p.grid_z;
+  const int xr = p.b_mcast ? 2 : 1;
+  const int group = ny * xr;
+  const int in_group = static_cast<int>(blockIdx.x) % group;
+  const int y_fixed = in_group % ny;
+  const int xpar = in_group / ny;
+  const int first = static_cast<int>(blockIdx.x) / group;
+  const int stride = static_cast<int>(gridDim.x) / group;
+  const int gx = p.grid_x / xr;
+  const int total = fixed_y ? gx * p.grid_z : gx * p.grid_y * p.grid_z;
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << y_fixed) | (1u << (y_fixed + ny)));   // same N tile
 
   // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
-    const int x = tile % p.grid_x;
-    const int y = fixed_y ? y_fixed : (tile / p.grid_x) % p.grid_y;
-    z = fixed_y ? tile / p.grid_x : tile / (p.grid_x * p.grid_y);
+    const int xg = (tile % gx) * xr;   // first M tile of the group
+    const int x = xg + xpar;
+    const int y = fixed_y ? y_fixed : (tile / gx) % p.grid_y;
+    z = fixed_y ? tile / gx : tile / (gx * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
     m_valid = p.m_valid.get(z);
-    if (p.m_valid.ptr != nullptr && w0 >= m_valid) return false;
+    // the CTAs of a group skip together: the decision looks at the group's first tile
+    if (p.m_valid.ptr != nullptr && (xg % p.tiles_w) * p.tile_w >= m_valid) return false;
     if (p.n_valid.ptr != nullptr && n0 >= p.n_valid.get(z)) return false;
     kc0 = p.kc0;
     if (p.k_valid.ptr != nullptr) kc0 = min(kc0, (p.k_valid.get(z) + kChunkK - 1) / kChunkK);
@@ -314,9 +335,14 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               } else {
                 tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
               }
-              for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
-                tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
-                            tap * p.b_tap_rows + n0 + part * p.n_part, bz);
+              if (p.b_mcast) {   // my half of the weight chunk, to both CTAs that work on this N tile
+                tma_load_3d_mcast(sb + xpar * 128 * 128, &tmB, &full_bar[s], bcol,
+                                  tap * p.b_tap_rows + n0 + xpar * 128, bz, mc_mask);
+              } else {
+                for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
+                  tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
+                              tap * p.b_tap_rows + n0 + part * p.n_part, bz);
+                }
               }
             }
             __syncwarp();
@@ -341,8 +367,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
       const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && seq < 32;
+      if (tr) p.trace[seq * 8 + 0] = clock64();
       mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
       tc_fence_after();
+      if (tr) p.trace[seq * 8 + 1] = clock64();
       const uint32_t d_tmem = tmem_base + buf * p.buf_stride;
       for (int kk = 0; kk < num_k; ++kk, ++it) {
         const int s = it % p.stages;
@@ -367,12 +396,14 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               umma_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[s]);
+          if (p.b_mcast) umma_commit_mcast(&empty_bar[s], mc_mask);
+          else umma_commit(&empty_bar[s]);
         }
         __syncwarp();
       }
       if (elect_one()) umma_commit(&tmem_full[buf]);
       __syncwarp();
+      if (tr) p.trace[seq * 8 + 2] = clock64();
       ++seq;
     }
   } else {
@@ -417,8 +448,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if constexpr (EpiPrefetch<Epi>::value) {
         if (mine) epi.prefetch(c, pre);
       }
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && seq < 32;
+      if (tr) p.trace[seq * 8 + 3] = clock64();
       mbar_wait(&tmem_full[buf], use & 1u);
       tc_fence_after();
+      if (tr) p.trace[seq * 8 + 4] = clock64();
       if (mine) {
         if constexpr (EpiPrefetch<Epi>::value) epi(c, num_k > 0, pre);
         else epi(c, num_k > 0);
@@ -426,6 +460,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (tr) p.trace[seq * 8 + 5] = clock64();
       ++seq;
     }
     if (lane == 0) bulk_wait_all();   // outstanding TMA stores still read this CTA's shared memory
@@ -433,7 +468,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (p.cluster_y) cluster_sync_all();   // the peer may still be writing this CTA's exchange slots
+  if (clustered) cluster_sync_all();   // a peer may still be writing this CTA's exchange slots / operand stages
   if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
@@ -509,49 +544,83 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   }
   const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
   if (total <= 0) return SSB_OK;
+  // diagnostic: SSB_CORE_TRACE=<label> dumps CTA 0's per-tile time stamps of the first launch with that label
+  static long long* trace_dev = nullptr;
+  static int trace_state = 0;   // 0 = unknown, 1 = armed, 2 = done / off
+  bool tracing = false;
+  if (trace_state != 2) {
+    const char* want = std::getenv("SSB_CORE_TRACE");
+    if (want == nullptr) {
+      trace_state = 2;
+    } else if (p.label != nullptr && std::strcmp(want, p.label) == 0) {
+      if (trace_dev == nullptr) cudaMalloc(&trace_dev, 32 * 8 * sizeof(long long));
+      cudaMemset(trace_dev, 0, 32 * 8 * sizeof(long long));
+      p.trace = trace_dev;
+      tracing = true;
+      trace_state = 2;
+    }
+  }
   int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
   if (p.b_resident) {
     const long long xz = static_cast<long long>(grid.x) * grid.z;
     const int per = device_sm_count() / static_cast<int>(grid.y);
     ctas = static_cast<int>((xz < per ? xz : per) * grid.y);
   }
-  if (p.cluster_y) {
-    if (p.b_resident || grid.y != 2) {
+  if (p.b_mcast && (p.b_resident || p.block_n != 256 || p.n_parts != 1 || grid.x % 2 != 0 || p.tiles_w % 2 != 0)) {
+    set_last_error("launch_core: multicast B needs block_n 256 and an even number of M tiles");
+    return SSB_ERR_INVALID;
+  }
+  if (p.cluster_y || p.b_mcast) {
+    if (p.cluster_y && (p.b_resident || grid.y != 2)) {
       set_last_error("launch_core: cluster mode needs exactly two N tiles");
       return SSB_ERR_INVALID;
     }
+    const int csize = (p.cluster_y ? 2 : 1) * (p.b_mcast ? 2 : 1);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / 2 * 2));
+    cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / csize * csize));
     cfg.blockDim = dim3(kCoreThreads);
     cfg.dynamicSmemBytes = static_cast<size_t>(smem);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // persistent pairs: as many clusters as can be co-resident (a GPC with an odd number of free SMs
     // cannot host a pair on its last SM), so that no cluster waits for a second wave
-    static int max_pairs = 0, max_pairs_smem = 0;
-    if (max_pairs == 0 || max_pairs_smem != smem) {
+    static int max_clusters = 0, max_clusters_smem = 0, max_clusters_size = 0;
+    if (max_clusters == 0 || max_clusters_smem != smem || max_clusters_size != csize) {
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
-        n = device_sm_count() / 2;
+        n = device_sm_count() / csize;
       }
-      max_pairs = n;
-      max_pairs_smem = smem;
+      max_clusters = n;
+      max_clusters_smem = smem;
+      max_clusters_size = csize;
     }
-    const long long xz = static_cast<long long>(grid.x) * grid.z;
-    ctas = static_cast<int>(xz < max_pairs ? xz : max_pairs) * 2;
+    // groups of tiles walked by one cluster: (pairs of) M tiles x batch, times the N tiles unless a cluster
+    // spans them
+    const long long groups = static_cast<long long>(grid.x / (p.b_mcast ? 2 : 1)) * grid.z * (p.cluster_y ? 1 : grid.y);
+    ctas = static_cast<int>(groups < max_clusters ? groups : max_clusters) * csize;
     cfg.gridDim = dim3(static_cast<unsigned>(ctas));
     SSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_core_kernel<Epi>, a0, a1, b, p, epi));
   } else {
     umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
   }
   SSB_CUDA_CHECK(cudaGetLastError());
+  if (tracing) {
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    long long h[32][8];
+    SSB_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "core trace (%s, %d CTAs, %d stages): tile | mma: wait_empty issue | epi: wait_full epilogue | "
+                         "epi period, mma period\n", p.label, ctas, p.stages);
+    for (int t = 0; t + 1 < 32 && h[t + 1][3] != 0; ++t)
+      std::fprintf(stderr, "%2d | %6lld %6lld | %6lld %6lld | %6lld %6lld\n", t, h[t][1] - h[t][0], h[t][2] - h[t][1],
+                   h[t][4] - h[t][3], h[t][5] - h[t][4], h[t + 1][3] - h[t][3], h[t + 1][0] - h[t][0]);
+  }
   count_launch();
   prof_mark(stream, p.label);
   return SSB_OK;
