@@ -117,7 +117,9 @@ matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, 
 }
 
 // Row log-sum-exp of sim (pass 0: z = pair, rows of image 2z over columns of image 2z+1; pass 1 on
-// sim^T gives the column log-sum-exp).  blockIdx.y = pair*2 + pass.
+// sim^T gives the column log-sum-exp).  blockIdx.y = pair*2 + pass.  One warp per row, 16-byte loads with all
+// of a row's loads of one sweep in flight together (one 4-byte load per iteration left the warp waiting on
+// memory latency 32 times per row); the second sweep hits L1.
 __global__ void __launch_bounds__(256)
 lse_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp, const int* __restrict__ cnt,
                 float* __restrict__ lse) {
@@ -128,10 +130,40 @@ lse_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp, const
   if (row >= nr) return;
   const float* s = sim + pass * pass_stride + (static_cast<size_t>(pair) * kp + row) * kp;
   float m = -INFINITY;
-  for (int j = lane; j < nc; j += 32) m = fmaxf(m, s[j]);
+  for (int j0 = 0; j0 < nc; j0 += 512) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      v[u] = j < nc ? *reinterpret_cast<const float4*>(s + j) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      m = fmaxf(m, v[u].x);                      // j < nc here whenever the load happened
+      if (j + 1 < nc) m = fmaxf(m, v[u].y);
+      if (j + 2 < nc) m = fmaxf(m, v[u].z);
+      if (j + 3 < nc) m = fmaxf(m, v[u].w);
+    }
+  }
   m = warp_max(m);
   float sum = 0.f;
-  for (int j = lane; j < nc; j += 32) sum += expf(s[j] - m);
+  for (int j0 = 0; j0 < nc; j0 += 512) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      v[u] = j < nc ? *reinterpret_cast<const float4*>(s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      if (j < nc) sum += expf(v[u].x - m);
+      if (j + 1 < nc) sum += expf(v[u].y - m);
+      if (j + 2 < nc) sum += expf(v[u].z - m);
+      if (j + 3 < nc) sum += expf(v[u].w - m);
+    }
+  }
   sum = warp_sum(sum);
   if (lane == 0) lse[(static_cast<size_t>(2 * pair + pass)) * kp + row] = m + logf(sum);
 }
@@ -155,16 +187,44 @@ argmax_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp,
   const float* lse1 = lse0 + kp;
   const float* lz0 = lz + static_cast<size_t>(2 * pair) * kp;
   const float* lz1 = lz0 + kp;
+  // the row's own terms are constants of the sweep; the column terms are read 16 bytes at a time
+  const float* lse_c = pass == 0 ? lse1 : lse0;
+  const float* lz_c = pass == 0 ? lz1 : lz0;
+  const float lse_r = pass == 0 ? lse0[row] : lse1[row];
+  const float lz_r = pass == 0 ? lz0[row] : lz1[row];
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = lane; j < nc; j += 32) {
-    const float v = s[j];
-    const int i0 = pass == 0 ? row : j;  // index into image 0
-    const int i1 = pass == 0 ? j : row;  // index into image 1
-    const float val = ((v - lse0[i0]) + (v - lse1[i1])) + (lz0[i0] + lz1[i1]);
-    if (val > best) {
-      best = val;
-      bi = j;
+  for (int j0 = 0; j0 < nc; j0 += 256) {
+    float4 v[2], lc[2], zc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      if (j < nc) {
+        v[u] = *reinterpret_cast<const float4*>(s + j);
+        lc[u] = *reinterpret_cast<const float4*>(lse_c + j);
+        zc[u] = *reinterpret_cast<const float4*>(lz_c + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * 128 + lane * 4;
+      if (j < nc) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float ll[4] = {lc[u].x, lc[u].y, lc[u].z, lc[u].w};
+        const float zz[4] = {zc[u].x, zc[u].y, zc[u].z, zc[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (j + k < nc) {
+            // image-0 terms first, image-1 terms second, exactly as in the formula above
+            const float val = pass == 0 ? ((vv[k] - lse_r) + (vv[k] - ll[k])) + (lz_r + zz[k])
+                                        : ((vv[k] - ll[k]) + (vv[k] - lse_r)) + (zz[k] + lz_r);
+            if (val > best) {
+              best = val;
+              bi = j + k;
+            }
+          }
+        }
+      }
     }
   }
 #pragma unroll
@@ -589,31 +649,33 @@ struct EpiResidual {
   }
 };
 
-// fp32 logits: out[z_off + z*z_stride + row*ld + n0 + col] = acc * scale (valid rows only).
+// fp32 logits: out[z][row][n0 + col] = acc * scale, written through the staged TMA store like every other
+// epilogue (a 32-column fp32 chunk of 32 rows is the same 32 x 128-byte block as 64 fp16 columns; the tensor map
+// describes the fp32 matrix as fp16 with twice the columns).  Row-strided 16-byte stores from the row-owning
+// threads ran at ~1.5 TB/s and made this GEMM four times slower than its HBM time.  Rows beyond the keypoint
+// count inside a valid tile are written too (zeros or padding products); nothing reads them.
 struct EpiStoreF32 {
-  float* out;
-  int ld;
-  size_t z_stride;
+  CUtensorMap tm_out;   // 3-D (2 * ld, rows, Z) "fp16" view of the fp32 matrix, box (64, 32, 1)
   float scale;
-  int block_n;
   static constexpr bool kSplit = true;
   __device__ void operator()(EpiCtx& c, bool has_acc) const {
-    const int row = c.px;
-    const bool valid = row < c.m_valid;
-    for (int col = c.col_begin; col < c.col_end; col += 32) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + col, v);
-      tmem_ld_wait();
-      if (valid) {
-        float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(c.z) * z_stride +
-                                                static_cast<size_t>(row) * ld + c.n0 + col);
+    const int row0 = __shfl_sync(0xffffffffu, c.px, 0);
+    tmem_chunks_pipelined<4>(c.tmem_row + c.col_begin, [&](int i, float* v) {
+      const int col = c.col_begin + i * 32;
+      stage_begin(c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = has_acc ? make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale,
-                                         v[4 * j + 3] * scale)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) {
+        const float4 o = has_acc ? make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale,
+                                               v[4 * j + 3] * scale)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        stage_put(c, c.lane, j, *reinterpret_cast<const uint4*>(&o));
       }
-    }
+      stage_fence(c);
+      if (c.lane == 0) {
+        tma_store_3d(&tm_out, c.stage_cur, (c.n0 + col) * 2, row0, c.z);
+        bulk_commit();
+      }
+    });
   }
 };
 
@@ -884,6 +946,9 @@ int LightGlue::alloc_workspace() {
   SSB_RETURN_IF(tm_rows3(&ts_q_, q_, 64, kp_, z, 32));
   SSB_RETURN_IF(tm_rows3(&ts_k_, k_, 64, kp_, z, 32));
   SSB_RETURN_IF(tm_rows3(&ts_v_, v_, 64, kp_, z, 32));
+  // fp32 sim / sim^T [P][kp][kp] seen as fp16 [P][kp][2 kp] (EpiStoreF32)
+  SSB_RETURN_IF(tm_rows3(&ts_sim_, s_, 2 * kp_, kp_, pairs_, 32));
+  SSB_RETURN_IF(tm_rows3(&ts_simT_, s_ + static_cast<size_t>(pairs_) * KP * KP, 2 * kp_, kp_, pairs_, 32));
   SSB_RETURN_IF(tm_rows3(&ts_mda_, mda_, 768, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows3(&ts_mdb_, mdb_, 768, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows4(&tm_mda_a_, mda_, 768, kp_, p2));
@@ -1030,7 +1095,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, "lg.matchability");
-  const size_t pass_stride = static_cast<size_t>(pairs) * KP * KP;
+  const size_t pass_stride = static_cast<size_t>(pairs_) * KP * KP;   // sim^T follows the capacity-sized sim block
   {
     CoreParams p = lin("lg.sim", 12, 0, 256);  // sim[pair] = A-form(img 2p) x B-form(img 2p+1)
     p.a_z_mul = 2;
@@ -1038,7 +1103,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     p.b_z_add = 1;
     p.m_valid = dev_count(cnt, 1, 0, 2, 0);
     p.n_valid = dev_count(cnt, 1, 0, 2, 1);
-    EpiStoreF32 e{s_, KP, static_cast<size_t>(KP) * KP, 1.0f, 256};
+    EpiStoreF32 e{ts_sim_, 1.0f};
     SSB_RETURN_IF(launch_core(tm_mda_a_, tm_mda_a_, tm_mdb_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
   }
   {
@@ -1048,7 +1113,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     p.b_z_mul = 2;
     p.m_valid = dev_count(cnt, 1, 0, 2, 1);
     p.n_valid = dev_count(cnt, 1, 0, 2, 0);
-    EpiStoreF32 e{s_ + pass_stride, KP, static_cast<size_t>(KP) * KP, 1.0f, 256};
+    EpiStoreF32 e{ts_simT_, 1.0f};
     SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
   }
   lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);

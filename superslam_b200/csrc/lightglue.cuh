@@ -120,7 +120,7 @@ class LightGlue {
 
   CUtensorMap tm_x16_, tm_msg_, tm_ctx_, tm_h1_, tm_q_a_, tm_q3_, tm_k3_, tm_v3_, tm_mda_a_,
       tm_mdb_b_, tm_mdb_a_, tm_mda_b_;
-  CUtensorMap ts_x16_, ts_msg_, ts_ctx_, ts_h1_, ts_q_, ts_k_, ts_v_, ts_mda_, ts_mdb_;  // TMA-store maps
+  CUtensorMap ts_x16_, ts_msg_, ts_ctx_, ts_sim_, ts_simT_, ts_h1_, ts_q_, ts_k_, ts_v_, ts_mda_, ts_mdb_;  // TMA-store maps
 };
 
 }  // namespace ssb
