@@ -39,7 +39,6 @@ struct FaParams {
   __half* ctx;         // [img][kp][heads*64]
   int kp;
   int q_tiles, zcount; // tile space (set by the launcher)
-  int stagger;         // cycles (set by the launcher)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
@@ -114,9 +113,6 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 __device__ __forceinline__ void fa_pair_sync(int qd) {
   asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
 }
-// Experiment hook (SSB_FA_STAGGER=<cycles>): the second CTA to arrive on an SM starts late, so that the
-// exponential phases of the two co-resident CTAs interleave instead of colliding on the MUFU.
-__device__ int g_fa_sm_slots[1024];
 // Diagnostic build of the kernel (SSB_FA_TRACE=1): warp 2 of CTA 0 time-stamps the phases of its first key
 // blocks; the launcher prints them after the first launch.  Not instantiated on the product path.
 __device__ long long g_fa_trace[64][8];
@@ -221,17 +217,6 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // single instruction (inside `if (lane == 0)` each one became an ELECT / R2UR / branch sequence of ~100
   // cycles, which sat on the S -> softmax -> P*V critical path twelve times per key block).
   if (warp == 0) {
-    if (p.stagger > 0) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      int slot = 0;
-      if (lane == 0) slot = atomicAdd(&g_fa_sm_slots[smid & 1023u], 1) & 1;
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (slot) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.stagger) {}
-      }
-    }
     uint32_t kb = 0, tq = 0;
     for (int tile = blockIdx.x; tile < total; tile += stride) {
       FaTile t;
@@ -527,12 +512,6 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   }
   p.q_tiles = q_tiles;
   p.zcount = z;
-  static int stagger = -1;
-  if (stagger < 0) {
-    const char* e = std::getenv("SSB_FA_STAGGER");
-    stagger = e ? std::atoi(e) : 0;
-  }
-  p.stagger = stagger;
   const int total = q_tiles * z;
   if (total <= 0) return SSB_OK;
   const int resident = 2 * device_sm_count();
