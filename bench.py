@@ -401,7 +401,7 @@ def main():
                     pass
                 roof = {"kernel": dom, "bound": "tensor", "achieved": gf / avg_ms, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": gf / avg_ms / peak_tf, "traffic": traffic,
-                        "traffic_source": "profiles/ncu_traffic_r01.json (ncu --set full dram bytes per image/pair at 64 pairs/step, x this run's batch)",
+                        "traffic_source": "profiles/ncu_traffic_r01.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per image/pair at 64 pairs/step, x this run's batch)",
                         "avg_launch_ms": avg_ms,
                         "share_of_step": ms / total_prof_ms, "peak_source": peak_src,
                         "algorithmic_gflop_per_launch": gf}
