@@ -110,6 +110,26 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 }
 // Barrier between the two warps (w, w + 4) that share a TMEM lane quadrant, i.e. the two halves of 32 rows.
 // (A CTA-wide barrier here made every block wait for the slowest of eight warps spread over four schedulers.)
+// 2^x for a pair on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5, i.e.
+// six times below the fp16 rounding of P): n = round(x) through the 1.5 * 2^23 trick, f = x - n in [-0.5, 0.5],
+// 2^f ~ c0 + f (c1 + f (c2 + f c3)), and the exponent is added as an integer: bits(t) << 23 == n << 23 (mod 2^32).
+// One pair in kPolyEvery (template parameter of the kernel) goes this way to take load off the MUFU
+// (16 ex2/clk/SM), the bound of this kernel.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = fadd2(x, magic);
+  const float2 n = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = ffma2(make_float2(0.05517146f, 0.05517146f), f, make_float2(0.24261086f, 0.24261086f));
+  p = ffma2(p, f, make_float2(0.69326099f, 0.69326099f));
+  p = ffma2(p, f, make_float2(0.99992809f, 0.99992809f));
+  float2 r;
+  r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+  r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+  return r;
+}
 __device__ __forceinline__ void fa_pair_sync(int qd) {
   asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
 }
@@ -145,7 +165,7 @@ __device__ __forceinline__ bool fa_decode(const FaParams& p, int tile, FaTile& t
 // the current one has retired, K/V blocks keep streaming through their rings, and the first S of the next
 // tile is computed underneath the last softmax of the current one.  (As one CTA per tile, ~1/3 of each
 // CTA's life went into barrier/TMEM setup and the serial Q -> K -> S -> softmax start-up latency.)
-template <bool kTrace>
+template <bool kTrace, int kPolyEvery>
 __global__ void __launch_bounds__(kFaThreads, 2)
 flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -432,8 +452,12 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           for (int k = 0; k < 16; ++k) {
             const int i = 32 * h2 + 2 * k;
             float2 e = ffma2(make_float2(v[i], v[i + 1]), sc2, nm2);
-            e.x = fast_exp2(e.x);
-            e.y = fast_exp2(e.y);
+            if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+              e = exp2_poly2(e);     // FMA pipe instead of the MUFU
+            } else {
+              e.x = fast_exp2(e.x);
+              e.y = fast_exp2(e.y);
+            }
             if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
             w[k] = pack_half2(e.x, e.y);
           }
@@ -493,22 +517,25 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                                   const CUtensorMap& tmO, FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
-  static bool configured = false;
+  using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FaParams);
+  static Kernel kernel = nullptr;
   static int trace = 0;
-  if (!configured) {
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFaSmemBytes));
-    // ask for the full shared-memory carveout so that two CTAs (2 x 84 KB) are co-resident per SM
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
+  if (kernel == nullptr) {
     if (const char* e = std::getenv("SSB_FA_TRACE")) trace = std::atoi(e);
-    if (trace) {
-      SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kFaSmemBytes));
-      SSB_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                          cudaSharedmemCarveoutMaxShared));
-    }
-    configured = true;
+    // SSB_FA_POLY = 0 | 3 | 4 | 6 | 8: one pair of exponentials in `poly` on the FMA pipe.  Measured per 18
+    // launches at 64 pairs: 0 -> 4.84 ms, 8 -> 4.57, 6 -> 4.60, 4 -> 4.61, 3 -> 4.54.
+    int poly = 3;
+    if (const char* e = std::getenv("SSB_FA_POLY")) poly = std::atoi(e);
+    if (trace) kernel = flash_attention_kernel<true, 3>;
+    else if (poly == 0) kernel = flash_attention_kernel<false, 0>;
+    else if (poly == 4) kernel = flash_attention_kernel<false, 4>;
+    else if (poly == 6) kernel = flash_attention_kernel<false, 6>;
+    else if (poly == 8) kernel = flash_attention_kernel<false, 8>;
+    else kernel = flash_attention_kernel<false, 3>;
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+    // ask for the full shared-memory carveout so that two CTAs (2 x 101 KB) are co-resident per SM
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
   }
   p.q_tiles = q_tiles;
   p.zcount = z;
@@ -516,21 +543,17 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   if (total <= 0) return SSB_OK;
   const int resident = 2 * device_sm_count();
   const int ctas = total < resident ? total : resident;
-  if (trace) {
-    flash_attention_kernel<true><<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
-    if (trace == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
-      trace = 2;
-      SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
-      static long long h[64][8];
-      SSB_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_fa_trace, sizeof(h)));
-      std::fprintf(stderr, "fa trace (%s, %d CTAs): kb | wait_s ld max bar exp1 wait_pv exp2 | gap_to_next | period\n", label, ctas);
-      for (int b = 0; b + 1 < 48; ++b)
-        std::fprintf(stderr, "%2d | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %5lld | %5lld\n", b, h[b][1] - h[b][0],
-                     h[b][2] - h[b][1], h[b][3] - h[b][2], h[b][4] - h[b][3], h[b][5] - h[b][4], h[b][6] - h[b][5],
-                     h[b][7] - h[b][6], h[b + 1][0] - h[b][7], h[b + 1][0] - h[b][0]);
-    }
-  } else {
-    flash_attention_kernel<false><<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
+  kernel<<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
+  if (trace == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
+    trace = 2;
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    static long long h[64][8];
+    SSB_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_fa_trace, sizeof(h)));
+    std::fprintf(stderr, "fa trace (%s, %d CTAs): kb | wait_s ld max bar exp1 wait_pv exp2 | gap_to_next | period\n", label, ctas);
+    for (int b = 0; b + 1 < 48; ++b)
+      std::fprintf(stderr, "%2d | %5lld %5lld %5lld %5lld %5lld %5lld %5lld | %5lld | %5lld\n", b, h[b][1] - h[b][0],
+                   h[b][2] - h[b][1], h[b][3] - h[b][2], h[b][4] - h[b][3], h[b][5] - h[b][4], h[b][6] - h[b][5],
+                   h[b][7] - h[b][6], h[b + 1][0] - h[b][7], h[b + 1][0] - h[b][0]);
   }
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
