@@ -161,6 +161,12 @@ int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, in
 /* device [count][src_h][src_w] -> device [count][dst_h][dst_w]; enqueued on the rectifier's stream, then
  * synchronised (chain it in front of ssb_fe_enqueue_device to keep rectified images off the host) */
 int ssb_rect_remap_device(ssb_rectifier* r, const uint8_t* src_dev, int count, uint8_t* dst_dev);
+/* Put a pair of rectifiers in front of the frame-pair pipeline: every ssb_fe_process / submit / enqueue_device
+ * call then takes RAW images (the rectifiers' source size), remaps image 2p with `left` and 2p+1 with `right` on
+ * the device and runs SuperPoint x2 + LightGlue on the rectified pair - the EuRoC loop of
+ * examples/stereo/euroc.cc:176-181 without the host remap.  The rectifiers are borrowed (they must outlive the
+ * front end or be unset with NULL, NULL) and must agree on sizes. */
+int ssb_fe_set_rectifiers(ssb_frontend* fe, ssb_rectifier* left, ssb_rectifier* right);
 
 /* RgbdFrontEnd::process after the extraction (include/RgbdFrontEnd.h:15-37, src/RgbdFrontEnd.cc:24-58):
  * cv::undistortPoints(raw, undist, K, D, noArray(), K) when dist has a non-zero entry, depth sampled at

@@ -79,6 +79,7 @@ SYMBOLS = [
     ("ssb_rect_destroy", None, [_vp]),
     ("ssb_rect_remap", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, _u8pp]),
     ("ssb_rect_remap_device", C.c_int, [_vp, _vp, C.c_int, _vp]),
+    ("ssb_fe_set_rectifiers", C.c_int, [_vp, _vp, _vp]),
     ("ssb_rgbd_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     ("ssb_rgbd_destroy", None, [_vp]),
     ("ssb_rgbd_process", C.c_int, [_vp, _fp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_int,

@@ -75,6 +75,7 @@ class FrontEnd {
       if (s_host_[b]) cudaFreeHost(s_host_[b]);
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (rect_buf_) cudaFree(rect_buf_);
     if (ur_) cudaFree(ur_);
     if (hd_) cudaFree(hd_);
     if (img_dev_) cudaFree(img_dev_);
@@ -161,8 +162,43 @@ class FrontEnd {
     SSB_CUDA_CHECK(cudaGraphLaunch(e->exec, stream_));
     return SSB_OK;
   }
+  // Optional rectification in front of SuperPoint (EuRoC flow, examples/stereo/euroc.cc:176-181): image 2p goes
+  // through the left camera's maps, image 2p+1 through the right camera's, device to device.
+  int set_rectifiers(Rectifier* left, Rectifier* right) {
+    SSB_CHECK((left == nullptr) == (right == nullptr), SSB_ERR_INVALID, "set both rectifiers or neither");
+    SSB_CHECK(submitted_ == collected_, SSB_ERR_INVALID, "streamed steps are in flight: collect them first");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (auto& g : graphs_) {   // captured graphs bake the old configuration in
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g = GraphEntry{};
+    }
+    if (rect_buf_) cudaFree(rect_buf_);
+    rect_buf_ = nullptr;
+    rect_l_ = rect_r_ = nullptr;
+    if (left == nullptr) return SSB_OK;
+    SSB_CHECK(left->device() == device_ && right->device() == device_, SSB_ERR_INVALID, "rectifiers live on another device");
+    SSB_CHECK(left->dst_h() == right->dst_h() && left->dst_w() == right->dst_w() && left->src_h() == right->src_h() &&
+                  left->src_w() == right->src_w(),
+              SSB_ERR_INVALID, "left and right rectifiers must agree on source and destination sizes");
+    SSB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&rect_buf_),
+                              static_cast<size_t>(2 * pairs_) * left->dst_h() * left->dst_w()));
+    rect_l_ = left;
+    rect_r_ = right;
+    return SSB_OK;
+  }
   int enqueue_eager(const uint8_t* images_dev, int pairs, int h, int w) {
     prof_begin(stream_);
+    if (rect_l_ != nullptr) {
+      SSB_CHECK(h == rect_l_->src_h() && w == rect_l_->src_w(), SSB_ERR_INVALID,
+                "images are %dx%d but the rectifiers expect %dx%d", w, h, rect_l_->src_w(), rect_l_->src_h());
+      const size_t sp_ = static_cast<size_t>(h) * w, dp = static_cast<size_t>(rect_l_->dst_h()) * rect_l_->dst_w();
+      SSB_RETURN_IF(rect_l_->remap_device(images_dev, pairs, rect_buf_, stream_, 2 * sp_, 2 * dp));
+      SSB_RETURN_IF(rect_r_->remap_device(images_dev + sp_, pairs, rect_buf_ + dp, stream_, 2 * sp_, 2 * dp));
+      images_dev = rect_buf_;
+      h = rect_l_->dst_h();
+      w = rect_l_->dst_w();
+    }
     SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
     SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
     stereo_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
@@ -342,6 +378,9 @@ class FrontEnd {
 
   ssb_superpoint sp;
   ssb_lightglue lg;
+  Rectifier* rect_l_ = nullptr;   // not owned
+  Rectifier* rect_r_ = nullptr;
+  uint8_t* rect_buf_ = nullptr;   // [2 * pairs_][dst_h][dst_w]
   struct GraphEntry {
     const uint8_t* img = nullptr;
     int pairs = 0, h = 0, w = 0, kernels = 0;
@@ -530,6 +569,12 @@ int ssb_fe_create(const char* sp_weights, const char* lg_weights, int max_keypoi
   SSB_API_END
 }
 void ssb_fe_destroy(ssb_frontend* fe) { delete fe; }
+int ssb_fe_set_rectifiers(ssb_frontend* fe, ssb_rectifier* left, ssb_rectifier* right) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.set_rectifiers(left ? &left->impl : nullptr, right ? &right->impl : nullptr);
+  SSB_API_END
+}
 
 int ssb_fe_process(ssb_frontend* fe, const uint8_t* const* images, int pairs, int height, int width,
                    int row_stride, int* count, float* xy, float* score, int32_t* matches0, float* mscores0,

@@ -20,13 +20,14 @@ namespace ssb {
 // into the same few sectors (rectification maps are smooth) and are served by L1/L2.  The maps of a camera
 // (6 B/px) stay L2-resident across the images of a batch.
 __global__ void __launch_bounds__(256)
-remap_linear_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, const uint32_t* __restrict__ xy,
-                       const uint16_t* __restrict__ frac, int npx, uint8_t* __restrict__ dst) {
+remap_linear_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, size_t src_pitch,
+                       const uint32_t* __restrict__ xy, const uint16_t* __restrict__ frac, int npx,
+                       uint8_t* __restrict__ dst, size_t dst_pitch) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;   // group of four pixels
   const int i0 = q * 4;
   if (i0 >= npx) return;
-  const uint8_t* s = src + static_cast<size_t>(blockIdx.y) * sh * sw;
-  uint8_t* d = dst + static_cast<size_t>(blockIdx.y) * npx;
+  const uint8_t* s = src + static_cast<size_t>(blockIdx.y) * src_pitch;   // bytes between consecutive images
+  uint8_t* d = dst + static_cast<size_t>(blockIdx.y) * dst_pitch;
   uint32_t pxy[4];
   uint16_t pfr[4];
   if (i0 + 3 < npx) {
@@ -121,12 +122,16 @@ int Rectifier::init(const float* map_x, const float* map_y, int dst_h, int dst_w
   return SSB_OK;
 }
 
-int Rectifier::remap_device(const uint8_t* src_dev, int count, uint8_t* dst_dev, cudaStream_t stream) {
+int Rectifier::remap_device(const uint8_t* src_dev, int count, uint8_t* dst_dev, cudaStream_t stream,
+                            size_t src_pitch, size_t dst_pitch) {
   SSB_CHECK(src_dev && dst_dev && count >= 1, SSB_ERR_INVALID, "bad arguments");
   SSB_CUDA_CHECK(cudaSetDevice(device_));
   const int npx = dh_ * dw_;
+  if (src_pitch == 0) src_pitch = static_cast<size_t>(sh_) * sw_;
+  if (dst_pitch == 0) dst_pitch = static_cast<size_t>(npx);
+  SSB_CHECK(dst_pitch % 4 == 0, SSB_ERR_INVALID, "destination image pitch must be a multiple of 4 bytes");
   dim3 grid((npx / 4 + 255) / 256, count);
-  remap_linear_u8_kernel<<<grid, 256, 0, stream>>>(src_dev, sh_, sw_, xy_, frac_, npx, dst_dev);
+  remap_linear_u8_kernel<<<grid, 256, 0, stream>>>(src_dev, sh_, sw_, src_pitch, xy_, frac_, npx, dst_dev, dst_pitch);
   SSB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   prof_mark(stream, "fe.remap");

@@ -23,8 +23,13 @@ class Rectifier {
            int device);
   // host images in (u8 gray, row_stride bytes per row), host images out (dst_w bytes per row)
   int remap(const uint8_t* const* images, int count, int row_stride, uint8_t* const* out);
-  // device -> device: src [count][src_h][src_w], dst [count][dst_h][dst_w], enqueue only
-  int remap_device(const uint8_t* src_dev, int count, uint8_t* dst_dev, cudaStream_t stream);
+  // device -> device: src [count][src_h][src_w], dst [count][dst_h][dst_w], enqueue only.  src_pitch / dst_pitch:
+  // bytes between consecutive images (0 = contiguous), e.g. every second image of an interleaved L/R batch.
+  int remap_device(const uint8_t* src_dev, int count, uint8_t* dst_dev, cudaStream_t stream, size_t src_pitch = 0,
+                   size_t dst_pitch = 0);
+  int src_h() const { return sh_; }
+  int src_w() const { return sw_; }
+  int device() const { return device_; }
   int dst_h() const { return dh_; }
   int dst_w() const { return dw_; }
   cudaStream_t stream() const { return stream_; }

@@ -356,6 +356,12 @@ class FramePairPipeline:
     def sync(self):
         _lib.check(self._lib.ssb_fe_sync(self._h))
 
+    def set_rectifiers(self, left: "Rectifier | None", right: "Rectifier | None") -> None:
+        """Rectify on the device in front of SuperPoint: calls then take RAW images (image 2p through `left`,
+        2p+1 through `right`) - the EuRoC loop of examples/stereo/euroc.cc:176-181 without the host remap."""
+        self._rectifiers = (left, right)   # keep them alive: the library borrows the handles
+        _lib.check(self._lib.ssb_fe_set_rectifiers(self._h, left._h if left else None, right._h if right else None))
+
     def event_record(self, idx: int):
         _lib.check(self._lib.ssb_fe_event_record(self._h, idx))
 

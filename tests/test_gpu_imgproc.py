@@ -120,3 +120,33 @@ def test_rgbd_frontend_process_on_extracted_keypoints():
     assert np.array_equal(f.keypoints_left, exy) and np.array_equal(f.has_depth, eh)
     assert np.array_equal(f.stereo, est, equal_nan=True)
     assert f.has_depth.all()
+
+
+def test_pipeline_with_device_rectification_equals_host_remap(lg_weights, tmp_path):
+    """C4 flow: raw EuRoC-size pairs in, rectification + SuperPoint x2 + LightGlue + post-filter on the device;
+    identical to rectifying with the (cv2-pinned) oracle first."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+
+    h, w, K = 480, 752, 512
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    mxl, myl = _rectify_maps(h, w)
+    mxr, myr = mxl + np.float32(0.37), myl - np.float32(0.21)      # a different map for the right camera
+    rl, rr = fe.Rectifier(mxl, myl, (h, w)), fe.Rectifier(mxr, myr, (h, w))
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=2)
+    raw = []
+    for s in (5, 6):
+        raw += list(synth_pair(h, w, 400, s))
+    rect = [oip.remap_linear_u8(im, *(m)) for im, m in zip(raw, [(mxl, myl), (mxr, myr)] * 2)]
+    ref = pipe.process(rect)
+    ref = {k: v.copy() for k, v in ref.items()}
+    pipe.set_rectifiers(rl, rr)
+    for _ in range(3):                      # eager, capture, replay
+        got = pipe.process(raw)
+        for k in ("count", "xy", "matches0", "has_depth"):
+            assert np.array_equal(got[k], ref[k]), k
+    assert int(ref["count"].min()) > 5        # interpolation smooths the synthetic corners: few detections
+    pipe.set_rectifiers(None, None)
+    back = pipe.process(rect)
+    assert np.array_equal(back["matches0"], ref["matches0"])
