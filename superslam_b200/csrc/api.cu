@@ -116,7 +116,7 @@ class FrontEnd {
     const size_t P = pairs, K = K_;
     return 2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 64;
   }
-  // The whole pair pipeline (~120 kernels, no host dependency thanks to device-side counts) is
+  // The whole pair pipeline (94 kernels, no host dependency thanks to device-side counts) is
   // captured into a CUDA graph the second time a (images, pairs, h, w) combination is seen and
   // replayed afterwards; SSB_NO_GRAPH=1 or an active event profiler falls back to eager launches.
   int enqueue_device(const uint8_t* images_dev, int pairs, int h, int w) {
@@ -187,6 +187,7 @@ class FrontEnd {
     rect_r_ = right;
     return SSB_OK;
   }
+  bool has_rectifiers() const { return rect_l_ != nullptr; }
   int enqueue_eager(const uint8_t* images_dev, int pairs, int h, int w) {
     prof_begin(stream_);
     if (rect_l_ != nullptr) {
@@ -643,10 +644,11 @@ int ssb_fe_upload_images(ssb_frontend* fe, const uint8_t* const* images, int cou
   SSB_API_END
 }
 int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
-  (void)fe;
   (void)pairs;
-  // conv1a + 10 tcgen05 convs + memset-free: nms, select, gather | prepare + 9 x 15 + 8 | postfilter
-  return 14 + 1 + 9 * 16 + 8 + 1;
+  // SuperPoint: 10 convolution launches + nms, select, gather | LightGlue: prepare + 9 x (qkv, attention, ffn1,
+  // ffn2) x 2 + final_proj, matchability, sim, sim^T, lse, arg-max, mutual | post-filter | (+ 2 remaps)
+  const int lg_blocks = ssb::kLgLayers * 8 + (fe != nullptr && !fe->impl.lg.impl.weights()->fold_out ? ssb::kLgLayers * 2 : 0);
+  return 13 + 1 + lg_blocks + 7 + 1 + (fe != nullptr && fe->impl.has_rectifiers() ? 2 : 0);
 }
 static int require_sm100(int device_id) {
   SSB_CUDA_CHECK(cudaSetDevice(device_id));
