@@ -178,6 +178,42 @@ def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
     return float(np.median(times)), best_c, len(times)
 
 
+def bench_latency(device: int, rank: int, iters: int = 60, warm: int = 8):
+    """single-pair latency in the reference's natural mode - one synchronous
+    IFeatureExtractor::extract_stereo + IFeatureMatcher::match per frame (src/StereoFrontEnd.cc:14,33), host
+    images in, host keypoints / matches out - with the reference's own profile labels
+    (fe_extract_stereo, fe_lg_stereo_match), plus the same pair through the one-call pipeline (pairs = 1)."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.synth import synth_pair
+
+    sp = fe.SuperPoint(SPW, K, device=device)
+    lg = fe.LightGlue(lg_weights_path(rank), W, H, max_keypoints=K, device=device)
+    pipe1 = fe.FramePairPipeline(SPW, lg_weights_path(rank), K, W, H, max_pairs=1, device=device)
+    pairs = [synth_pair(H, W, 9000 + i) for i in range(4)]
+    t_ext, t_match, t_pipe = [], [], []
+    for it in range(warm + iters):
+        l, r = pairs[it % len(pairs)]
+        t0 = time.perf_counter()
+        L, R = sp.extract_stereo(l, r)
+        t1 = time.perf_counter()
+        lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
+        t2 = time.perf_counter()
+        pipe1.process([l, r])
+        t3 = time.perf_counter()
+        if it >= warm:
+            t_ext.append(t1 - t0), t_match.append(t2 - t1), t_pipe.append(t3 - t2)
+        del L, R
+
+    def q(v):
+        v = np.asarray(v) * 1e3
+        return {"p50_ms": round(float(np.percentile(v, 50)), 3), "p95_ms": round(float(np.percentile(v, 95)), 3)}
+
+    both = np.asarray(t_ext) + np.asarray(t_match)
+    return {"workload": "1 pair 640x480, K=1024 per call, host in / host out, synchronous", "iterations": iters,
+            "fe_extract_stereo": q(t_ext), "fe_lg_stereo_match": q(t_match), "extract_plus_match": q(both),
+            "pipeline_process_1_pair": q(t_pipe)}
+
+
 def bench_eigenplaces(lib, device: int, steps: int = 10, batch: int = 8):
     """the EigenPlaces global descriptor (ResNet18 + GeM + FC on the tcgen05 conv
     core) for `batch` 752x480 keyframes per call, host images in, host descriptors out (the public call)."""
@@ -422,6 +458,12 @@ def main():
                 eigen = bench_eigenplaces(lib, local)
             except Exception as e:  # the headline line must not depend on the "next" row
                 eigen = {"error": str(e)}
+        latency = None
+        if world == 1:
+            try:
+                latency = bench_latency(local, rank)
+            except Exception as e:
+                latency = {"error": str(e)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             sec, threads, timed = oracle_pair_seconds(5, 1, budget_s=20.0)
@@ -448,6 +490,7 @@ def main():
             "tensor_kernels": tensor_kernels,
             "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu,
+            "latency_single_pair": latency,
             "eigenplaces": eigen,
             "wall_s_timed_region": wall,
             "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},

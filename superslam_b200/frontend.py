@@ -242,6 +242,18 @@ class StereoFrame:
     descriptors_left: DeviceDescriptors = None
     stereo: np.ndarray = None     # [n,3] float64 (uL, uR, v); uR = NaN if no stereo
     has_depth: np.ndarray = None  # [n] int8
+    pose_R: np.ndarray = None     # Twc rotation [3,3] (camera-in-world); identity if None
+    pose_t: np.ndarray = None     # Twc translation [3]
+
+    def backproject(self, i: int, fx: float, fy: float, cx: float, cy: float, baseline: float) -> np.ndarray:
+        """World point of stereo feature i (src/StereoFrame.cc:5-13): Z = fx*b / (uL-uR),
+        X = (uL-cx) Z / fx, Y = (v-cy) Z / fy in the camera frame, lifted by the pose Twc."""
+        uL, uR, v = (float(x) for x in self.stereo[i])
+        Z = fx * baseline / (uL - uR)
+        p = np.array([(uL - cx) * Z / fx, (v - cy) * Z / fy, Z], np.float64)
+        R = np.eye(3) if self.pose_R is None else np.asarray(self.pose_R, np.float64)
+        t = np.zeros(3) if self.pose_t is None else np.asarray(self.pose_t, np.float64)
+        return R @ p + t
 
 
 class StereoFrontEnd:

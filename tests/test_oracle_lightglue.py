@@ -131,3 +131,21 @@ def test_free_list_semantics():
     a, b = f.acquire(), f.acquire()
     f.release(a), f.release(b)
     assert f.in_use() == 0
+
+
+def test_stereo_frame_backproject_returns_metric_world_point():
+    """Re-expression of /root/reference/tests/test_stereo_frame.cc:10-23 (StereoFrame::backproject,
+    src/StereoFrame.cc:5-13) on the Python mirror of the data carrier."""
+    from superslam_b200.frontend import StereoFrame
+
+    fx = fy = 500.0
+    cx, cy, b = 320.0, 240.0, 0.5
+    a = 0.1                                   # Rot3::Rz(0.1), t = (2, -1, 0.5): Twc
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    t = np.array([2.0, -1.0, 0.5])
+    world = np.array([3.0, 0.5, 9.0])
+    pc = R.T @ (world - t)                    # StereoCamera(camInWorld, K).project(worldPt)
+    uL = fx * pc[0] / pc[2] + cx
+    z = np.array([[uL, uL - fx * b / pc[2], fy * pc[1] / pc[2] + cy]])
+    f = StereoFrame(0.0, None, None, z, np.array([1], np.int8), R, t)
+    assert np.allclose(f.backproject(0, fx, fy, cx, cy, b), world, atol=1e-4)
