@@ -63,3 +63,15 @@ def test_weight_archive_roundtrip(tmp_path):
     sp = load_archive(SP_WEIGHTS)
     assert sp["conv1a.weight"].shape == (64, 1, 3, 3) and sp["convPb.weight"].shape == (65, 256, 1, 1)
     assert sum(v.size for v in sp.values()) == 1300865
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 on its own (no C++ types, no torch types)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", HEADER],
+                         capture_output=True, text=True)
+    assert res.returncode == 0 and res.stderr.strip() == "", res.stderr
