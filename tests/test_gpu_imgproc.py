@@ -150,3 +150,24 @@ def test_pipeline_with_device_rectification_equals_host_remap(lg_weights, tmp_pa
     pipe.set_rectifiers(None, None)
     back = pipe.process(rect)
     assert np.array_equal(back["matches0"], ref["matches0"])
+
+
+def test_device_remap_and_undistortion_against_cv2_golden():
+    """Committed outputs of cv2 itself (tests/golden/make_golden_imgproc.py): the device must reproduce them."""
+    import os
+
+    from conftest import GOLDEN
+    from superslam_b200 import frontend as fe
+
+    g = np.load(os.path.join(GOLDEN, "imgproc_cv2.npz"))
+    img = np.ascontiguousarray(g["image"])
+    for mx, my, exp in ((g["map_x"], g["map_y"], g["remap"]), (g["map_x_wide"], g["map_y_wide"], g["remap_wide"])):
+        assert np.array_equal(fe.Rectifier(mx, my, img.shape, max_images=1).remap([img])[0], exp)
+    fx, fy, cx, cy = (float(v) for v in g["camera"])
+    depth = np.zeros((img.shape[0], img.shape[1]), np.uint16)
+    for dist, exp in ((g["dist5"], g["undist5"]), (g["dist8"], g["undist8"])):
+        front = fe.RgbdFrontEnd(None, fx, fy, cx, cy, baseline=0.1, depth_factor=5000.0, max_depth=8.0,
+                                dist_coeffs=dist, max_keypoints=512, max_shape=img.shape)
+        oxy, _, has = front.postprocess(g["points"], depth)
+        assert np.array_equal(oxy, exp)
+        assert not has.any()
