@@ -11,7 +11,8 @@
 //
 // Keeping P in tensor memory takes 64 KB per key block off the shared-memory port (32 KB of stores + 32 KB
 // of operand reads; the N = 64 P*V MMAs were shared-memory-read bound) and frees room for a second V stage.
-// Budget: 84 KB of shared memory and 256 TMEM columns (S 128, O 64, P 64) per CTA -> two CTAs per SM, so one CTA's
+// Budget: 101 KB of shared memory (Q 16, K 2 x 16, V 2 x 16, O staging 16) and 256 TMEM columns (S 128, O 64,
+// P 64) per CTA -> two CTAs per SM, so one CTA's
 // exponentials (the MUFU-bound part: 16 ex2/clk/SM) overlap the other's MMAs and loads.  (A variant that
 // pipelines S/P double-buffered inside one CTA per SM measured 25 % slower: profiles/README.md.)
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
