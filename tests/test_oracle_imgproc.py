@@ -83,3 +83,44 @@ def test_oracle_against_committed_cv2_golden():
     fx, fy, cx, cy = g["camera"]
     assert np.array_equal(ip.undistort_points(g["points"], fx, fy, cx, cy, g["dist5"]), g["undist5"])
     assert np.array_equal(ip.undistort_points(g["points"], fx, fy, cx, cy, g["dist8"]), g["undist8"])
+
+
+def test_remap_properties():
+    """Size-independent properties of the fixed-point remap: identity maps reproduce the image, integer shifts move
+    it (zero-filled where the source ends), half-pixel maps average neighbours with OpenCV's rounding."""
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (37, 53)).astype(np.uint8)
+    h, w = img.shape
+    xx, yy = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    assert np.array_equal(ip.remap_linear_u8(img, xx, yy), img)
+    sh = ip.remap_linear_u8(img, xx + 5, yy - 3)            # dst(y, x) = src(y - 3, x + 5)
+    exp = np.zeros_like(img)
+    exp[3:, : w - 5] = img[: h - 3, 5:]
+    assert np.array_equal(sh, exp)
+    half = ip.remap_linear_u8(img, xx + 0.5, yy)            # (a + b) / 2 with (s + 2^14) >> 15 rounding: ties go up
+    a, b = img[:, :-1].astype(np.int64), img[:, 1:].astype(np.int64)
+    assert np.array_equal(half[:, :-1], ((a + b + 1) >> 1).astype(np.uint8))
+    assert np.array_equal(half[:, -1], ((img[:, -1].astype(np.int64) + 1) >> 1).astype(np.uint8))   # right tap is border 0
+
+
+def test_undistort_properties():
+    """Zero distortion is the identity (to float rounding of the round trip), the principal point is a fixed point,
+    and undistorting a forward-distorted point recovers it as far as five iterations go."""
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    rng = np.random.default_rng(4)
+    pts = rng.uniform([0, 0], [752, 480], (500, 2)).astype(np.float32)
+    same = ip.undistort_points(pts, fx, fy, cx, cy, np.zeros(5))
+    assert np.abs(same - pts).max() < 1e-4
+    c = ip.undistort_points(np.array([[cx, cy]], np.float32), fx, fy, cx, cy, D)
+    assert np.abs(c - np.array([[cx, cy]], np.float32)).max() < 1e-4
+    # forward Brown-Conrady model, then the inverse
+    x, y = (pts[:, 0].astype(np.float64) - cx) / fx, (pts[:, 1].astype(np.float64) - cy) / fy
+    r2 = x * x + y * y
+    kr = 1 + D[0] * r2 + D[1] * r2 * r2 + D[4] * r2 ** 3
+    xd = x * kr + 2 * D[2] * x * y + D[3] * (r2 + 2 * x * x)
+    yd = y * kr + D[2] * (r2 + 2 * y * y) + 2 * D[3] * x * y
+    dist = np.stack([xd * fx + cx, yd * fy + cy], 1).astype(np.float32)
+    back = ip.undistort_points(dist, fx, fy, cx, cy, D)
+    err = np.abs(back - pts).max(axis=1)
+    assert err[r2 < 0.25].max() < 2e-2      # five fixed-point iterations converge fast near the centre ...
+    assert err.max() < 0.5                  # ... and slowly in the corners (cv::undistortPoints' own behaviour)
