@@ -1,0 +1,36 @@
+"""The numbers bench.py quotes from profiles/ must be derivable from the committed evidence: the per-kernel DRAM
+traffic table is re-generated from the committed ncu launch list and compared."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_traffic_table_matches_the_committed_launch_list():
+    csv = os.path.join(ROOT, "profiles", "launches_r01_v14_p64.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), csv, "64", "0"],
+                         capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    exp = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+    got.pop("_comment"), exp.pop("_comment")
+    assert got == exp
+    # one step = 94 kernel launches; the dominant kernel of the roofline is the fused conv1a+conv1b
+    assert sum(v["launches"] for v in exp.values()) == 94
+    assert max(exp.items(), key=lambda kv: kv[1]["share_of_step"])[0] == "sp.conv1ab"
+    assert exp["sp.conv1ab"]["per"] == "image" and exp["lg.ffn2"]["per"] == "pair"
+
+
+def test_bench_lines_are_valid_json_with_the_contract_keys():
+    prof = os.path.join(ROOT, "profiles")
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"}
+    for name in ("bench_r01_v15_p64.json", "bench_r01_v15_n2.json"):
+        d = json.load(open(os.path.join(prof, name)))
+        assert need <= set(d), (name, need - set(d))
+        assert d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
