@@ -20,4 +20,7 @@ Pinning status:
     PINNED against torchvision with shared weights, CosineDescriptorIndex / TemporalConsistencyVoter PINNED
     by the reference's tests/test_place_recognizer.cc (re-expressed); the trained network weights come from
     an un-pinned torch.hub entry and are absent offline: network VALUES are PARITY UNPINNED.
+  * image front door (oracle/imgproc.py) - PINNED bit-for-bit against OpenCV: cv2.remap (fixed-point bilinear,
+    constant border) and cv2.undistortPoints, live (tests/test_oracle_imgproc.py) and through committed cv2
+    outputs (tests/golden/imgproc_cv2.npz, made by tests/golden/make_golden_imgproc.py).
 """
