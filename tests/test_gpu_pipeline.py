@@ -173,3 +173,33 @@ def test_streaming_submit_collect_equals_process(tmp_path, lg_weights):
     pipe.collect()
     out = pipe.process(steps[3])   # the synchronous call works again once everything is collected
     assert np.array_equal(out["matches0"], ref[3]["matches0"])
+
+
+def test_pipeline_with_a_blank_image_in_the_batch(tmp_path, lg_weights):
+    """Device-side counts: one image of a three-pair call has no keypoints at all (attention tiles without keys,
+    GEMM tiles without rows, deferred attention epilogues across skipped tiles).  That pair has no matches, the
+    other pairs are untouched."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    h, w, K = 240, 320, 512
+    pairs = [list(synth_pair(h, w, 50 + i, 100 + 20 * i)) for i in range(3)]
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=3)
+    ref = pipe.process([im for p in pairs for im in p])
+    ref = {k: v.copy() for k, v in ref.items()}
+    blank = np.full((h, w), 128, np.uint8)
+    for which in (0, 1):                       # blank left image, then blank right image, of the middle pair
+        mod = [list(p) for p in pairs]
+        mod[1][which] = blank
+        for _ in range(3):                     # eager, capture, replay
+            out = pipe.process([im for p in mod for im in p])
+        assert out["count"][2 + which] == 0 and out["count"][2 + (1 - which)] == ref["count"][2 + (1 - which)]
+        assert (out["matches0"][1] == -1).all() and not out["has_depth"][1].any()
+        for p in (0, 2):
+            n0 = ref["count"][2 * p]
+            assert np.array_equal(out["matches0"][p, :n0], ref["matches0"][p, :n0])
+            assert np.array_equal(out["mscores0"][p, :n0], ref["mscores0"][p, :n0])
+            assert np.array_equal(out["has_depth"][p], ref["has_depth"][p])
