@@ -155,6 +155,9 @@ typedef struct ssb_rgbd ssb_rgbd;
 int ssb_rect_create(const float* map_x, const float* map_y, int dst_height, int dst_width, int src_height,
                     int src_width, int max_images, int device_id, ssb_rectifier** out);
 void ssb_rect_destroy(ssb_rectifier* r);
+/* The host half of ssb_rect_create on its own (no device needed): OpenCV's conversion of `count` CV_32F map entries
+ * to fixed point - xy[i] = (uint16)ix | (uint16)iy << 16 (int16 each, saturated), frac[i] = fy * 32 + fx. */
+int ssb_rect_convert_maps(const float* map_x, const float* map_y, size_t count, uint32_t* xy, uint16_t* frac);
 /* host gray u8 images in (`row_stride` bytes per row), host images out (dst_width bytes per row) */
 int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, int row_stride,
                    uint8_t* const* out);

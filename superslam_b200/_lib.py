@@ -77,6 +77,7 @@ SYMBOLS = [
     ("ssb_ep_debug_read", C.c_int, [_vp, C.c_char_p, _vp, C.c_size_t]),
     ("ssb_rect_create", C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     ("ssb_rect_destroy", None, [_vp]),
+    ("ssb_rect_convert_maps", C.c_int, [_fp, _fp, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]),
     ("ssb_rect_remap", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, _u8pp]),
     ("ssb_rect_remap_device", C.c_int, [_vp, _vp, C.c_int, _vp]),
     ("ssb_fe_set_rectifiers", C.c_int, [_vp, _vp, _vp]),

@@ -672,6 +672,13 @@ int ssb_rect_create(const float* map_x, const float* map_y, int dst_height, int 
   SSB_API_END
 }
 void ssb_rect_destroy(ssb_rectifier* r) { delete r; }
+int ssb_rect_convert_maps(const float* map_x, const float* map_y, size_t count, uint32_t* xy, uint16_t* frac) {
+  SSB_API_BEGIN
+  SSB_CHECK(map_x && map_y && xy && frac, SSB_ERR_INVALID, "null argument");
+  ssb::convert_remap_maps(map_x, map_y, count, xy, frac);
+  return SSB_OK;
+  SSB_API_END
+}
 int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, int row_stride,
                    uint8_t* const* out) {
   SSB_API_BEGIN

@@ -91,6 +91,16 @@ static inline int cv_round_x32(float v) {
 }
 static inline int sat16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
 
+// cv::remap's float -> fixed-point map conversion (host): (int16 ix | int16 iy << 16) and fy * 32 + fx per pixel.
+void convert_remap_maps(const float* map_x, const float* map_y, size_t n, uint32_t* xy, uint16_t* frac) {
+  for (size_t i = 0; i < n; ++i) {
+    const int sx = cv_round_x32(map_x[i]), sy = cv_round_x32(map_y[i]);
+    const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);   // arithmetic shift == floor division by 32
+    xy[i] = (static_cast<uint32_t>(ix) & 0xffffu) | (static_cast<uint32_t>(iy) << 16);
+    frac[i] = static_cast<uint16_t>((sy & 31) * 32 + (sx & 31));
+  }
+}
+
 int Rectifier::init(const float* map_x, const float* map_y, int dst_h, int dst_w, int src_h, int src_w,
                     int max_images, int device) {
   SSB_CHECK(map_x && map_y, SSB_ERR_INVALID, "null map");
@@ -104,12 +114,7 @@ int Rectifier::init(const float* map_x, const float* map_y, int dst_h, int dst_w
   const size_t n = static_cast<size_t>(dst_h) * dst_w;
   std::vector<uint32_t> hxy(n);
   std::vector<uint16_t> hfr(n);
-  for (size_t i = 0; i < n; ++i) {
-    const int sx = cv_round_x32(map_x[i]), sy = cv_round_x32(map_y[i]);
-    const int ix = sat16(sx >> 5), iy = sat16(sy >> 5);   // arithmetic shift == floor division by 32
-    hxy[i] = (static_cast<uint32_t>(ix) & 0xffffu) | (static_cast<uint32_t>(iy) << 16);
-    hfr[i] = static_cast<uint16_t>((sy & 31) * 32 + (sx & 31));
-  }
+  convert_remap_maps(map_x, map_y, n, hxy.data(), hfr.data());
   SSB_CUDA_CHECK(cudaMalloc(&xy_, n * 4));
   SSB_CUDA_CHECK(cudaMalloc(&frac_, n * 2));
   SSB_CUDA_CHECK(cudaMemcpy(xy_, hxy.data(), n * 4, cudaMemcpyHostToDevice));

@@ -14,6 +14,9 @@
 
 namespace ssb {
 
+// Host half of the remap: OpenCV's conversion of CV_32F maps to 1/32-pixel fixed point (needs no device).
+void convert_remap_maps(const float* map_x, const float* map_y, size_t n, uint32_t* xy, uint16_t* frac);
+
 class Rectifier {
  public:
   ~Rectifier();

@@ -124,3 +124,28 @@ def test_undistort_properties():
     err = np.abs(back - pts).max(axis=1)
     assert err[r2 < 0.25].max() < 2e-2      # five fixed-point iterations converge fast near the centre ...
     assert err.max() < 0.5                  # ... and slowly in the corners (cv::undistortPoints' own behaviour)
+
+
+def test_library_map_conversion_matches_opencv_fixed_point():
+    """Host logic of the product, no GPU: ssb_rect_convert_maps (what ssb_rect_create uploads) equals the oracle's
+    restatement of cv::remap's map conversion - ties to even, saturation, NaN / infinity -> INT_MIN."""
+    import ctypes as C
+
+    from superslam_b200 import _lib
+
+    rng = np.random.default_rng(9)
+    mx = rng.uniform(-40000, 40000, 20000).astype(np.float32)      # beyond the int16 range: saturation
+    my = rng.uniform(-50, 600, 20000).astype(np.float32)
+    mx[:6] = [np.nan, np.inf, -np.inf, 1e12, 0.015625, 0.046875]   # 1/64 and 3/64: cvRound ties
+    my[:6] = [3.0, 4.0, 5.0, -1e12, 0.015625, 0.046875]
+    xy = np.zeros(len(mx), np.uint32)
+    fr = np.zeros(len(mx), np.uint16)
+    _lib.check(_lib.load().ssb_rect_convert_maps(mx.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 my.ctypes.data_as(C.POINTER(C.c_float)), len(mx),
+                                                 xy.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                 fr.ctypes.data_as(C.POINTER(C.c_uint16))))
+    ix, iy, frac = ip.fixed_point_maps(mx, my)
+    assert np.array_equal((xy & 0xffff).astype(np.uint16).view(np.int16), ix)
+    assert np.array_equal((xy >> 16).astype(np.uint16).view(np.int16), iy)
+    assert np.array_equal(fr, frac)
+    assert fr[4] == 0 and fr[5] == (2 * 32 + 2)                    # 0.5 -> 0 and 1.5 -> 2: round half to even
