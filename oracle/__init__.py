@@ -9,7 +9,10 @@ Pinning status:
   * SuperPoint dense network  — PINNED: checked against outputs of the reference's own torch module
     (utils/convert_superpoint_to_onnx.py, weights/superpoint_v1.pth) run in the authoring container;
     fixtures in tests/golden/ made by tests/golden/make_golden.py.
-  * keypoint select / descriptor gather / stereo post-filter / FreeList — restated line by line from
+  * FreeList / DescriptorPool handle semantics — PINNED by the reference's own code: oracle/Makefile compiles
+    /root/reference/include/DescriptorPool.h + src/DescriptorPool.cc in place into oracle/_ref/libref_pool.so
+    (tests/test_oracle_ref_pool.py).
+  * keypoint select / descriptor gather / stereo post-filter — restated line by line from
     the reference C++ (cited per function); the reference has no golden vectors for them beyond
     tests/test_stereo_frontend.cc and tests/test_descriptor_pool.cc, which are re-expressed in tests/.
   * LightGlue — PARITY UNPINNED: the arithmetic lives in the un-vendored, un-pinned third-party

@@ -1,0 +1,8 @@
+// Stand-in for the reference's spdlog-based include/Logging.h (spdlog is not in this image): the oracle/_ref build
+// compiles /root/reference/src/DescriptorPool.cc in place and only needs its two log macros to vanish.
+// TEST INFRASTRUCTURE (see oracle/__init__.py).
+#pragma once
+#define SLOG_ERROR(...) ((void)0)
+#define SLOG_WARN(...) ((void)0)
+#define SLOG_INFO(...) ((void)0)
+#define SLOG_DEBUG(...) ((void)0)
