@@ -12,7 +12,9 @@ Pinning status:
   * FreeList / DescriptorPool handle semantics — PINNED by the reference's own code: oracle/Makefile compiles
     /root/reference/include/DescriptorPool.h + src/DescriptorPool.cc in place into oracle/_ref/libref_pool.so
     (tests/test_oracle_ref_pool.py).
-  * keypoint select / descriptor gather / stereo post-filter — restated line by line from
+  * stereo post-filter / StereoFrame::backproject — PINNED by the reference's own code: src/StereoFrontEnd.cc and
+    src/StereoFrame.cc compiled in place into oracle/_ref/libref_frontend.so (tests/test_oracle_ref_frontend.py).
+  * keypoint select / descriptor gather — restated line by line from
     the reference C++ (cited per function); the reference has no golden vectors for them beyond
     tests/test_stereo_frontend.cc and tests/test_descriptor_pool.cc, which are re-expressed in tests/.
   * LightGlue — PARITY UNPINNED: the arithmetic lives in the un-vendored, un-pinned third-party
