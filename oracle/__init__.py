@@ -14,7 +14,9 @@ Pinning status:
     (tests/test_oracle_ref_pool.py).
   * stereo post-filter / StereoFrame::backproject — PINNED by the reference's own code: src/StereoFrontEnd.cc and
     src/StereoFrame.cc compiled in place into oracle/_ref/libref_frontend.so (tests/test_oracle_ref_frontend.py).
-  * keypoint select / descriptor gather — restated line by line from
+  * descriptor gather — the reference's real CUDA kernel (src/DescriptorGather.cu) is compiled in place into
+    oracle/_ref/libref_gather.so and compared with the product on the GPU (tests/test_gpu_zz_ref_gather.py).
+  * keypoint select / descriptor gather restatement — restated line by line from
     the reference C++ (cited per function); the reference has no golden vectors for them beyond
     tests/test_stereo_frontend.cc and tests/test_descriptor_pool.cc, which are re-expressed in tests/.
   * LightGlue — PARITY UNPINNED: the arithmetic lives in the un-vendored, un-pinned third-party

@@ -1,0 +1,58 @@
+"""The REFERENCE's own CUDA kernel (src/DescriptorGather.cu, compiled in place by oracle/Makefile into
+oracle/_ref/libref_gather.so) against the product's fused gather, on the product's own descriptor grid and the
+keypoint cells it selected: every fp16 descriptor row must be bit-identical (same 256-wide tree sum, same rsqrtf,
+same rounding) - SURVEY §8 row a9 pinned by the reference itself rather than by a restatement."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, SP_WEIGHTS
+
+pytestmark = pytest.mark.gpu
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref_gather.so")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_gather.so not built (build() with /root/reference mounted)")
+def test_reference_gather_kernel_equals_product_rows():
+    import torch
+
+    from oracle import superpoint as osp
+    from superslam_b200 import _lib
+    from superslam_b200 import frontend as fe
+
+    ref = C.CDLL(LIB)
+    ref.ref_launch_gather.restype = C.c_int
+    ref.ref_launch_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    imgs = np.load(os.path.join(GOLDEN, "superpoint_ref_small.npz"))["images"]
+    b, h, w = imgs.shape
+    K = 256
+    sp = fe.SuperPoint(SP_WEIGHTS, K)
+    feats = sp._extract(list(imgs))
+    hc, wc = h // 8, w // 8
+    raw = sp.debug_read("scores", (b, hc * 8, wc * 8), np.float32)
+    grid = sp.debug_read("grid", (b, hc, wc, 256), np.float16)          # the product stores it cell-major
+    checked = 0
+    for i, F in enumerate(feats):
+        k = osp.nms_select(raw[i], h, w, K, 0.005, 4)
+        assert np.array_equal(F.keypoints, k["xy"])                      # same keypoints, same order -> same cells
+        n = len(k["xy"])
+        if n == 0:
+            continue
+        chw = torch.from_numpy(np.ascontiguousarray(grid[i].transpose(2, 0, 1))).cuda()   # the reference's layout
+        ch = torch.from_numpy(np.ascontiguousarray(k["cell"][:, 0], np.int32)).cuda()
+        cw = torch.from_numpy(np.ascontiguousarray(k["cell"][:, 1], np.int32)).cuda()
+        out = torch.zeros((n, 256), dtype=torch.float16, device="cuda")
+        torch.cuda.synchronize()
+        rc = ref.ref_launch_gather(chw.data_ptr(), 256, hc, wc, ch.data_ptr(), cw.data_ptr(), n, out.data_ptr())
+        assert rc == 0, f"reference kernel failed: cudaError {rc}"
+        theirs = out.cpu().numpy()
+        ours = np.zeros((n, 256), np.float32)
+        _lib.check(_lib.load().ssb_desc_to_host_f32(0, C.c_void_p(F.descriptors.data), n, 256,
+                                                    ours.ctypes.data_as(C.POINTER(C.c_float))))
+        assert np.array_equal(ours.astype(np.float16).view(np.uint16), theirs.view(np.uint16))
+        norms = np.linalg.norm(theirs.astype(np.float32), axis=1)
+        assert np.abs(norms - 1.0).max() < 2e-3
+        checked += n
+    assert checked > 50
