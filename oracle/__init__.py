@@ -12,8 +12,9 @@ Pinning status:
   * FreeList / DescriptorPool handle semantics — PINNED by the reference's own code: oracle/Makefile compiles
     /root/reference/include/DescriptorPool.h + src/DescriptorPool.cc in place into oracle/_ref/libref_pool.so
     (tests/test_oracle_ref_pool.py).
-  * stereo post-filter / StereoFrame::backproject — PINNED by the reference's own code: src/StereoFrontEnd.cc and
-    src/StereoFrame.cc compiled in place into oracle/_ref/libref_frontend.so (tests/test_oracle_ref_frontend.py).
+  * stereo post-filter / StereoFrame::backproject / RGB-D post-process — PINNED by the reference's own code:
+    src/StereoFrontEnd.cc, src/StereoFrame.cc and src/RgbdFrontEnd.cc compiled in place into
+    oracle/_ref/libref_frontend.so (tests/test_oracle_ref_frontend.py; cv::undistortPoints served by cv2).
   * descriptor gather — the reference's real CUDA kernel (src/DescriptorGather.cu) is compiled in place into
     oracle/_ref/libref_gather.so and compared with the product on the GPU (tests/test_gpu_zz_ref_gather.py).
   * keypoint select / descriptor gather restatement — restated line by line from

@@ -14,6 +14,8 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
                         cv2.undistortPoints.
   * rgbd_process        /root/reference/src/RgbdFrontEnd.cc:24-58 after the extraction: depth sampled at the
                         RAW keypoint (lround), uR = uL - bf / Z on the UNDISTORTED uL, has_depth iff 0 < Z < max.
+                        PINNED against the reference's own RgbdFrontEnd.cc compiled in place (oracle/_ref,
+                        tests/test_oracle_ref_frontend.py).
 """
 from __future__ import annotations
 

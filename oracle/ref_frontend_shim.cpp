@@ -57,3 +57,34 @@ void ref_stereo_frame_backproject(const double* stereo3, const double* R9, const
   out3[0] = p.x(), out3[1] = p.y(), out3[2] = p.z();
 }
 }
+
+// ---- RgbdFrontEnd::process (/root/reference/src/RgbdFrontEnd.cc:23-58), the real code; cv::undistortPoints is
+// forwarded to `undistort` (the test passes cv2.undistortPoints).  depth_type 0 = CV_16U, 1 = CV_32F.
+#include <opencv4/opencv2/calib3d.hpp>
+
+#include "RgbdFrontEnd.h"
+
+extern "C" void ref_rgbd_frontend_process(const float* xy, int n, void* depth, int depth_type, int dh, int dw,
+                                          const double* cam4, double baseline, double* dist, int nd,
+                                          double depth_factor, double max_depth, cv::UndistortPointsFn undistort,
+                                          float* out_xy, double* out_stereo, char* out_has) {
+  MockExtractor ext;
+  for (int i = 0; i < n; ++i) ext.l.keypoints.emplace_back(xy[2 * i], xy[2 * i + 1], 1.0f);
+  double k9[9] = {cam4[0], 0, cam4[2], 0, cam4[1], cam4[3], 0, 0, 1};
+  const cv::Mat K(3, 3, CV_64F, k9, 3 * sizeof(double));
+  const cv::Mat D = nd > 0 ? cv::Mat(1, nd, CV_64F, dist, nd * sizeof(double)) : cv::Mat();
+  const size_t esz = depth_type == 0 ? 2 : 4;
+  const cv::Mat depth_m(dh, dw, depth_type == 0 ? CV_16U : CV_32F, depth, dw * esz);
+  cv::undistort_points_hook() = undistort;
+  superslam::RgbdFrontEnd fe(&ext, gtsam::Cal3_S2Stereo(cam4[0], cam4[1], 0, cam4[2], cam4[3], baseline), depth_factor,
+                             max_depth, K, D);
+  const superslam::StereoFrame f = fe.process(cv::Mat(), depth_m, 0.0);
+  for (int i = 0; i < n; ++i) {
+    out_xy[2 * i] = f.keypoints_left[i].pt.x;
+    out_xy[2 * i + 1] = f.keypoints_left[i].pt.y;
+    out_stereo[3 * i] = f.stereo[i].uL();
+    out_stereo[3 * i + 1] = f.stereo[i].uR();
+    out_stereo[3 * i + 2] = f.stereo[i].v();
+    out_has[i] = f.has_depth[i];
+  }
+}

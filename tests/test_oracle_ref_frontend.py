@@ -93,3 +93,60 @@ def test_backproject_reference_vs_python_mirror(ref):
     assert np.allclose(out, world, atol=1e-4)
     mirror = StereoFrame(0.0, None, None, z[None], np.array([1], np.int8), R, t).backproject(0, fx, fy, cx, cy, b)
     assert np.allclose(mirror, out, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+@pytest.mark.parametrize("with_distortion", [False, True])
+def test_restated_rgbd_process_equals_the_reference(ref, dtype, with_distortion):
+    """The real RgbdFrontEnd::process (src/RgbdFrontEnd.cc:23-58, compiled in place) with its cv::undistortPoints call
+    served by the real OpenCV (cv2) through a callback, against oracle/imgproc.py::rgbd_process: undistorted
+    keypoints, depth sampled at lround(raw), uR = uL - bf / Z, the (0, max_depth) window - bit for bit."""
+    from oracle import imgproc as oip
+
+    cv2 = pytest.importorskip("cv2")
+    CB = C.CFUNCTYPE(None, _f, C.c_int, _d, _d, C.c_int, _d, _f)
+
+    def undistort(src, n, K, D, nd, P, dst):
+        pts = np.ctypeslib.as_array(src, (n, 2)).copy()
+        k = np.ctypeslib.as_array(K, (9,)).reshape(3, 3).copy()
+        p = np.ctypeslib.as_array(P, (9,)).reshape(3, 3).copy()
+        d = np.ctypeslib.as_array(D, (max(nd, 1),))[:nd].copy()
+        out = cv2.undistortPoints(pts.reshape(-1, 1, 2), k, d, None, p).reshape(-1, 2).astype(np.float32)
+        np.ctypeslib.as_array(dst, (n, 2))[:] = out
+
+    cb = CB(undistort)
+    ref.ref_rgbd_frontend_process.argtypes = [_f, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, _d, C.c_double, _d,
+                                              C.c_int, C.c_double, C.c_double, CB, _f, _d, C.c_char_p]
+    rng = np.random.default_rng(21)
+    h, w, n = 120, 160, 400
+    fx, fy, cx, cy, baseline = 130.0, 129.0, 80.5, 59.5, 0.08
+    xy = rng.uniform([-2, -2], [w + 2, h + 2], (n, 2)).astype(np.float32)      # a few raw points fall outside the depth map
+    xy[:10] = np.floor(xy[:10]) + np.float32(0.5)                              # lround ties: away from zero
+    if dtype == np.uint16:
+        depth = rng.integers(0, 60000, (h, w)).astype(np.uint16)
+        depth[rng.random((h, w)) < 0.2] = 0
+        factor = 5000.0
+    else:
+        depth = rng.uniform(0, 12, (h, w)).astype(np.float32)
+        factor = 1.0
+    depth[3, 7] = 40000 if dtype == np.uint16 else 8.0                         # Z == max_depth exactly: rejected (strict <)
+    xy[10] = (7.2, 3.1)
+    dist = np.array([-0.28, 0.07, 0.0002, 1.8e-05, 0.0]) if with_distortion else np.zeros(5)
+    oxy = np.zeros((n, 2), np.float32)
+    st = np.zeros((n, 3), np.float64)
+    has = C.create_string_buffer(n)
+    cam = np.array([fx, fy, cx, cy])
+    dd = dist.copy()
+    ref.ref_rgbd_frontend_process(xy.ctypes.data_as(_f), n, depth.ctypes.data_as(C.c_void_p), 0 if dtype == np.uint16 else 1,
+                                  h, w, cam.ctypes.data_as(_d), baseline, dd.ctypes.data_as(_d), len(dd), factor, 8.0, cb,
+                                  oxy.ctypes.data_as(_f), st.ctypes.data_as(_d), has)
+    has_ref = np.frombuffer(has.raw[:n], np.int8)
+    exy, est, eh = oip.rgbd_process(xy, depth, fx, fy, cx, cy, dist, fx * baseline, factor, 8.0)
+    assert np.array_equal(oxy, exy)
+    assert np.array_equal(has_ref, eh)
+    assert np.array_equal(st, est, equal_nan=True)
+    assert has_ref[10] == 0 and 0 < has_ref.sum() < n
+    if with_distortion:
+        assert np.abs(oxy - xy).max() > 0.05          # the undistortion really moved the keypoints
+    else:
+        assert np.array_equal(oxy, xy)                # countNonZero(dist) == 0: undistortPoints is not called
