@@ -527,16 +527,18 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
     // launches at 64 pairs: 0 -> 4.84 ms, 8 -> 4.57, 6 -> 4.60, 4 -> 4.61, 3 -> 4.54.
     int poly = 3;
     if (const char* e = std::getenv("SSB_FA_POLY")) poly = std::atoi(e);
-    if (trace) kernel = flash_attention_kernel<true, 3>;
-    else if (poly == 0) kernel = flash_attention_kernel<false, 0>;
-    else if (poly == 4) kernel = flash_attention_kernel<false, 4>;
-    else if (poly == 6) kernel = flash_attention_kernel<false, 6>;
-    else if (poly == 8) kernel = flash_attention_kernel<false, 8>;
-    else kernel = flash_attention_kernel<false, 3>;
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+    Kernel k;
+    if (trace) k = flash_attention_kernel<true, 3>;
+    else if (poly == 0) k = flash_attention_kernel<false, 0>;
+    else if (poly == 4) k = flash_attention_kernel<false, 4>;
+    else if (poly == 6) k = flash_attention_kernel<false, 6>;
+    else if (poly == 8) k = flash_attention_kernel<false, 8>;
+    else k = flash_attention_kernel<false, 3>;
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
     // ask for the full shared-memory carveout so that two CTAs (2 x 101 KB) are co-resident per SM
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
+    kernel = k;   // published last: a second context on another thread never sees an unconfigured kernel
   }
   p.q_tiles = q_tiles;
   p.zcount = z;
