@@ -8,6 +8,8 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
                         weighted with 15-bit integer coefficients (32-fx)(32-fy)*32 ... and the sum is rounded
                         with (s + 2^14) >> 15.  PINNED bit-for-bit against cv2.remap of this image
                         (tests/test_oracle_imgproc.py).
+  * bgr_to_gray_u8      cv::cvtColor(BGR2GRAY) of the extractor's preprocess (src/SuperPoint.cc:387-388,770-771),
+                        OpenCV 4.x 15-bit coefficients; PINNED against cv2 over all 2^24 colours.
   * undistort_points    cv::undistortPoints(raw, undist, K, D, noArray(), K) as called by
                         /root/reference/src/RgbdFrontEnd.cc:27-34: five fixed-point iterations of the
                         Brown-Conrady inverse in double precision, no FMA contraction.  PINNED against
@@ -92,6 +94,13 @@ def undistort_points(xy: np.ndarray, fx: float, fy: float, cx: float, cy: float,
         ww = 1.0 / (0.0 * x + 0.0 * y + 1.0)
         out[i] = (np.float32(xx * ww), np.float32(yy * ww))
     return out
+
+
+def bgr_to_gray_u8(bgr: np.ndarray) -> np.ndarray:
+    """cv::cvtColor(img, g, cv::COLOR_BGR2GRAY) on u8 (src/SuperPoint.cc:387-388,770-771): OpenCV 4.x's 15-bit fixed
+    point (B*3735 + G*19235 + R*9798 + 2^14) >> 15.  PINNED against cv2 on all 2^24 colours."""
+    p = np.asarray(bgr, np.uint8).astype(np.int64)
+    return ((p[..., 0] * 3735 + p[..., 1] * 19235 + p[..., 2] * 9798 + (1 << 14)) >> 15).astype(np.uint8)
 
 
 def _lround(v: np.ndarray) -> np.ndarray:

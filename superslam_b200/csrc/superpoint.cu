@@ -75,12 +75,15 @@ void* SlotPool::slot_ptr(int slot) const {
 // kernels
 // =================================================================================================
 
-// cv::cvtColor(BGR2GRAY) on u8: fixed point, (B*1868 + G*9617 + R*4899 + 8192) >> 14.
+// cv::cvtColor(BGR2GRAY) on u8 as OpenCV 4.x computes it: 15-bit fixed point,
+// (B*3735 + G*19235 + R*9798 + 2^14) >> 15  (imgproc/src/color_rgb.simd.hpp: BY15, GY15, RY15, gray_shift = 15).
+// oracle/imgproc.py::bgr_to_gray_u8 is pinned against cv2 on all 2^24 colours.  (The 14-bit coefficients
+// 1868 / 9617 / 4899 of OpenCV 2.x/3.x, used here at first, differ by one grey level on 0.24 % of random pixels.)
 __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, size_t n) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint8_t* p = bgr + 3 * i;
-  gray[i] = static_cast<uint8_t>((p[0] * 1868 + p[1] * 9617 + p[2] * 4899 + 8192) >> 14);
+  gray[i] = static_cast<uint8_t>((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
 }
 
 // ---- TMEM epilogues -------------------------------------------------------------------------------

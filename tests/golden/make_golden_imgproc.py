@@ -31,7 +31,10 @@ def main():
                                            cv2.CV_32F)
     rng = np.random.default_rng(7)
     pts = rng.uniform([0, 0], [w, h], (300, 2)).astype(np.float32)
+    # a colour image whose channels differ (B = img, G = inverted, R = shifted) and OpenCV's own gray conversion
+    bgr = np.stack([img, 255 - img, np.roll(img, 7, axis=1)], -1)
     out = {
+        "bgr": bgr, "gray": cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY),
         "image": img, "map_x": m1, "map_y": m2, "remap": cv2.remap(img, m1, m2, cv2.INTER_LINEAR),
         "map_x_wide": m1b, "map_y_wide": m2b, "remap_wide": cv2.remap(img, m1b, m2b, cv2.INTER_LINEAR),
         "camera": np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]]), "dist5": D, "dist8": D8, "points": pts,

@@ -56,3 +56,16 @@ def test_reference_gather_kernel_equals_product_rows():
         assert np.abs(norms - 1.0).max() < 2e-3
         checked += n
     assert checked > 50
+
+
+def test_bgr_input_is_converted_like_opencv():
+    """IFeatureExtractor::extract on a 3-channel image (src/SuperPoint.cc:387-388: cv::cvtColor BGR2GRAY): the device
+    conversion must give exactly the features of the gray image OpenCV itself produces (committed cv2 output)."""
+    from superslam_b200 import frontend as fe
+
+    g = np.load(os.path.join(GOLDEN, "imgproc_cv2.npz"))
+    sp = fe.SuperPoint(SP_WEIGHTS, 256)
+    a = sp.extract(np.ascontiguousarray(g["bgr"]))
+    b = sp.extract(np.ascontiguousarray(g["gray"]))
+    assert len(b.keypoints) > 10
+    assert np.array_equal(a.keypoints, b.keypoints) and np.array_equal(a.responses, b.responses)

@@ -149,3 +149,24 @@ def test_library_map_conversion_matches_opencv_fixed_point():
     assert np.array_equal((xy >> 16).astype(np.uint16).view(np.int16), iy)
     assert np.array_equal(fr, frac)
     assert fr[4] == 0 and fr[5] == (2 * 32 + 2)                    # 0.5 -> 0 and 1.5 -> 2: round half to even
+
+
+@needs_cv2
+def test_bgr_to_gray_matches_opencv_on_every_colour():
+    """cv::cvtColor(BGR2GRAY) as the extractor's preprocess applies it (src/SuperPoint.cc:387-388,770-771): all 2^24
+    colours against cv2 (OpenCV 4.x uses 15-bit coefficients; the older 14-bit set differs on ~0.24 % of pixels)."""
+    b, g, r = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+    cols = np.stack([b, g, r], -1).reshape(4096, 4096, 3).astype(np.uint8)
+    assert np.array_equal(ip.bgr_to_gray_u8(cols), cv2.cvtColor(cols, cv2.COLOR_BGR2GRAY))
+    old = ((cols.astype(np.int64) @ np.array([1868, 9617, 4899]) + 8192) >> 14).astype(np.uint8)
+    assert (old != cv2.cvtColor(cols, cv2.COLOR_BGR2GRAY)).mean() > 1e-3     # the two coefficient sets do differ
+
+
+def test_bgr_to_gray_against_committed_cv2_golden():
+    import os
+
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "imgproc_cv2.npz"))
+    assert np.array_equal(ip.bgr_to_gray_u8(g["bgr"]), g["gray"])
+    assert len(np.unique(g["bgr"].reshape(-1, 3), axis=0)) > 1000      # a real colour image, not B = G = R
