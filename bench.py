@@ -37,6 +37,8 @@ sys.path.insert(0, ROOT)
 H, W, K = 480, 640, 1024
 SPW = os.path.join(ROOT, "superslam_b200", "weights", "superpoint_v1.ssbw")
 METRIC = "stereo frame-pairs/sec (SPx2+LG, 1024 kpts, 640x480)"
+WORKLOAD = ("C2: stereo pairs 640x480, K=1024, LightGlue 9 layers (seeded synthetic LightGlue weights: none ship with "
+            "the reference); SuperPoint weights = reference checkpoint")
 
 # 2*MAC counts of the dense contractions
 SP_LAYER_GF = {"sp.conv1ab": 22.65 + 0.35, "sp.conv2a": 5.66, "sp.conv2b": 5.66, "sp.conv3a": 2.83, "sp.conv3b": 5.66,
@@ -260,8 +262,9 @@ def run_reference(args, rank: int):
         "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C2: 1 stereo pair 640x480, K=1024, LightGlue 9 layers (seeded synthetic weights)",
-                   "pairs_per_step": 1},
+        "config": {"workload": WORKLOAD, "pairs_per_step": 1,
+                   "sample": "each step = one whole pair of that workload on the host cores (a bounded sample of the "
+                             "64-pair device step)"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": f"{timed} pair(s) timed after thread-count calibration and warm-up; oracle = reference's torch "
                                    "graph + restated host logic (the reference itself has no CPU path, TensorRT only)"},
@@ -474,8 +477,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "C2: stereo pairs 640x480, K=1024, LightGlue 9 layers (seeded synthetic LightGlue "
-                                   "weights: none ship with the reference); SuperPoint weights = reference checkpoint",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_step_per_gpu": P, "l2": "flushed between steps (256 MiB memset)",
                        "timing": "CUDA events per step on the pipeline stream (CUDA-graph replay), max over ranks; "
                                  "roofline/kernel shares from an eager re-run of the same steps with an event "
