@@ -1,0 +1,170 @@
+// Test double of the C-ABI (include/superslam_b200.h): the entry points the C++ adapter calls, with canned, fully
+// predictable behaviour and call recording, so that the adapter + the reference's StereoFrontEnd above it can be RUN
+// on a machine without a GPU (tests/test_dropin_adapter.py).  What is checked there is the adapter's own work:
+// cv::Mat -> (pointer, stride, channels), keypoint / DMatch construction, slot ownership through
+// shared_ptr deleters, status -> empty-result mapping.  It is linked ONLY into oracle/_ref/libdropin_fake.so;
+// nothing in the product can reach it.  TEST INFRASTRUCTURE.
+//
+// Canned rules (mirrored by the test):
+//   extract, image i:   n = min(max_keypoints, 4 * px(0,0));  px(0,0) == 255 -> SSB_ERR_CUDA for the whole call
+//                       keypoint k = (px(0,1) + 2k, px(1,0) + k % 7), score 1 / (1 + k)      [px(1,0) checks row_stride]
+//                       descriptor row k, column c (fp32 in fake "device" memory) = px(0,2) + k + c / 1024
+//                       slots from a LIFO free list (include/DescriptorPool.h:25-44); none free -> slot -1, null
+//                       pointer, SSB_ERR_EXHAUSTED, keypoints still delivered (src/SuperPoint.cc:724-727)
+//   match, query i:     i % 3 == 0 -> unmatched (-1, 0);  else train (7 i + 3) % n1, score 0.25 + 0.5 (i % 2)
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "superslam_b200.h"
+
+struct ssb_superpoint {
+  int max_kp = 0;
+  std::vector<int> free_slots, refs;
+  std::vector<std::vector<float>> slot_mem;
+};
+struct ssb_lightglue {
+  bool clone = false;
+  int width = 0, height = 0;
+};
+
+namespace {
+ssb_superpoint* g_sp = nullptr;
+int g_release_calls = 0, g_sp_destroyed = 0, g_lg_alive = 0;
+struct MatchCall {
+  int clone = -1, device_path = -1, n0 = 0, n1 = 0, slot0 = -2, slot1 = -2;
+  double xy0_sum = 0, xy1_sum = 0, d0_first = 0, d1_first = 0;
+} g_last;
+
+int slot_of(const void* p) {
+  if (!g_sp || !p) return -1;
+  for (size_t s = 0; s < g_sp->slot_mem.size(); ++s)
+    if (g_sp->slot_mem[s].data() == p) return static_cast<int>(s);
+  return -1;
+}
+int run_match(ssb_lightglue* lg, int device_path, const float* xy0, int n0, const float* xy1, int n1, int32_t* m, float* s) {
+  if (!lg || n0 < 0 || n1 < 0) return SSB_ERR_INVALID;
+  g_last.clone = lg->clone, g_last.device_path = device_path, g_last.n0 = n0, g_last.n1 = n1;
+  g_last.xy0_sum = g_last.xy1_sum = 0;
+  for (int i = 0; i < 2 * n0; ++i) g_last.xy0_sum += xy0[i];
+  for (int i = 0; i < 2 * n1; ++i) g_last.xy1_sum += xy1[i];
+  for (int i = 0; i < n0; ++i) {
+    const bool hit = n1 > 0 && i % 3 != 0;
+    m[i] = hit ? (7 * i + 3) % n1 : -1;
+    s[i] = hit ? 0.25f + 0.5f * static_cast<float>(i % 2) : 0.0f;
+  }
+  return SSB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ssb_sp_create(const char* weights_path, int max_keypoints, double, int, int num_slots, int, ssb_superpoint** out) {
+  *out = nullptr;
+  if (!weights_path || std::string(weights_path) == "missing") return SSB_ERR_IO;
+  ssb_superpoint* sp = new ssb_superpoint;
+  sp->max_kp = max_keypoints;
+  const int n = num_slots > 0 ? num_slots : 8;
+  for (int i = n - 1; i >= 0; --i) sp->free_slots.push_back(i);
+  sp->refs.assign(n, 0);
+  sp->slot_mem.assign(n, std::vector<float>(static_cast<size_t>(max_keypoints) * 256));
+  g_sp = *out = sp;
+  return SSB_OK;
+}
+void ssb_sp_destroy(ssb_superpoint* sp) {
+  if (!sp) return;
+  if (g_sp == sp) g_sp = nullptr;
+  ++g_sp_destroyed;
+  delete sp;
+}
+int ssb_sp_extract(ssb_superpoint* sp, const uint8_t* const* images, int batch, int height, int width, int row_stride,
+                   int channels, float* const* xy, float* const* score, int* count, void** desc_dev, int* slot) {
+  if (!sp || batch < 1 || height < 2 || width * channels < 3 || row_stride < width * channels) return SSB_ERR_INVALID;
+  if (images[0][0] == 255) return SSB_ERR_CUDA;
+  int rc = SSB_OK;
+  for (int i = 0; i < batch; ++i) {
+    const uint8_t* im = images[i];
+    int n = 4 * im[0];
+    if (n > sp->max_kp) n = sp->max_kp;
+    count[i] = n;
+    for (int k = 0; k < n; ++k) {
+      xy[i][2 * k] = static_cast<float>(im[1]) + 2.0f * k;
+      xy[i][2 * k + 1] = static_cast<float>(im[row_stride]) + static_cast<float>(k % 7);
+      score[i][k] = 1.0f / (1.0f + k);
+    }
+    if (sp->free_slots.empty()) {
+      slot[i] = -1, desc_dev[i] = nullptr, rc = SSB_ERR_EXHAUSTED;
+      continue;
+    }
+    const int s = sp->free_slots.back();
+    sp->free_slots.pop_back();
+    sp->refs[s] = 1;
+    float* d = sp->slot_mem[s].data();
+    for (int k = 0; k < n; ++k)
+      for (int c = 0; c < 256; ++c) d[k * 256 + c] = static_cast<float>(im[2]) + k + c / 1024.0f;
+    slot[i] = s, desc_dev[i] = d;
+  }
+  return rc;
+}
+int ssb_sp_slot_retain(ssb_superpoint* sp, int slot) {
+  if (!sp || slot < 0 || slot >= static_cast<int>(sp->refs.size()) || sp->refs[slot] <= 0) return SSB_ERR_INVALID;
+  ++sp->refs[slot];
+  return SSB_OK;
+}
+int ssb_sp_slot_release(ssb_superpoint* sp, int slot) {
+  ++g_release_calls;
+  if (!sp || slot < 0 || slot >= static_cast<int>(sp->refs.size()) || sp->refs[slot] <= 0) return SSB_ERR_INVALID;
+  if (--sp->refs[slot] == 0) sp->free_slots.push_back(slot);
+  return SSB_OK;
+}
+int ssb_sp_slots_in_use(ssb_superpoint* sp) { return sp ? static_cast<int>(sp->refs.size() - sp->free_slots.size()) : 0; }
+
+int ssb_lg_create(const char* weights_path, int image_width, int image_height, int, int, ssb_lightglue** out) {
+  *out = nullptr;
+  if (!weights_path || std::string(weights_path) == "missing") return SSB_ERR_IO;
+  *out = new ssb_lightglue{false, image_width, image_height};
+  ++g_lg_alive;
+  return SSB_OK;
+}
+int ssb_lg_clone_context(ssb_lightglue* src, int image_width, int image_height, ssb_lightglue** out) {
+  *out = nullptr;
+  if (!src) return SSB_ERR_INVALID;
+  *out = new ssb_lightglue{true, image_width, image_height};
+  ++g_lg_alive;
+  return SSB_OK;
+}
+void ssb_lg_destroy(ssb_lightglue* lg) {
+  if (!lg) return;
+  --g_lg_alive;
+  delete lg;
+}
+int ssb_lg_match_device(ssb_lightglue* lg, const float* xy0, int n0, const void* desc0_dev, const float* xy1, int n1,
+                        const void* desc1_dev, int32_t* matches0, float* mscores0) {
+  g_last.slot0 = slot_of(desc0_dev), g_last.slot1 = slot_of(desc1_dev);
+  g_last.d0_first = g_last.d1_first = 0;
+  return run_match(lg, 1, xy0, n0, xy1, n1, matches0, mscores0);
+}
+int ssb_lg_match_host(ssb_lightglue* lg, const float* xy0, int n0, const float* desc0_f32, const float* xy1, int n1,
+                      const float* desc1_f32, int32_t* matches0, float* mscores0) {
+  g_last.slot0 = g_last.slot1 = -2;
+  g_last.d0_first = n0 > 0 ? desc0_f32[0] : 0, g_last.d1_first = n1 > 0 ? desc1_f32[0] : 0;
+  return run_match(lg, 0, xy0, n0, xy1, n1, matches0, mscores0);
+}
+int ssb_desc_to_host_f32(int, const void* desc_dev_f16, int count, int dim, float* out) {
+  if (!desc_dev_f16 || count < 0 || dim != 256) return SSB_ERR_INVALID;
+  std::memcpy(out, desc_dev_f16, sizeof(float) * static_cast<size_t>(count) * dim);
+  return SSB_OK;
+}
+
+// ---- inspection hooks for the test ----------------------------------------------------------------
+int fake_slots_in_use(void) { return ssb_sp_slots_in_use(g_sp); }
+int fake_release_calls(void) { return g_release_calls; }
+int fake_sp_destroyed(void) { return g_sp_destroyed; }
+int fake_lg_alive(void) { return g_lg_alive; }
+void fake_last_match(int* info6, double* sums4) {
+  info6[0] = g_last.clone, info6[1] = g_last.device_path, info6[2] = g_last.n0, info6[3] = g_last.n1;
+  info6[4] = g_last.slot0, info6[5] = g_last.slot1;
+  sums4[0] = g_last.xy0_sum, sums4[1] = g_last.xy1_sum, sums4[2] = g_last.d0_first, sums4[3] = g_last.d1_first;
+}
+}
