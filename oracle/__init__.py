@@ -17,9 +17,16 @@ Pinning status:
     oracle/_ref/libref_frontend.so (tests/test_oracle_ref_frontend.py; cv::undistortPoints served by cv2).
   * descriptor gather — the reference's real CUDA kernel (src/DescriptorGather.cu) is compiled in place into
     oracle/_ref/libref_gather.so and compared with the product on the GPU (tests/test_gpu_zz_ref_gather.py).
-  * keypoint select / descriptor gather restatement — restated line by line from
-    the reference C++ (cited per function); the reference has no golden vectors for them beyond
-    tests/test_stereo_frontend.cc and tests/test_descriptor_pool.cc, which are re-expressed in tests/.
+  * keypoint select (border strip, float-vs-double threshold, std::sort tie order, top-K, scale factors) — PINNED by
+    the reference's own code: src/SuperPoint.cc is compiled in place (TensorRT reduced to never-called stand-ins,
+    oracle/stubs_trt/) into oracle/_ref/libref_superpoint.so and its SuperPoint::select_and_gather is run against
+    select_keypoints on the reference module's score maps, tie-heavy random maps and threshold-edge values
+    (tests/test_oracle_ref_superpoint.py); on the GPU the whole function, pool and gather kernel included, is compared
+    with the product's features (tests/test_gpu_zz_ref_gather.py).
+  * the C++ adapter above the C-ABI — EXECUTED under the reference's own caller: src/StereoFrontEnd.cc compiled in
+    place over include/superslam_b200_adapter.hpp (oracle/dropin_harness.cpp, functional cv::Mat stand-in in
+    oracle/stubs_cv/), against a C-ABI test double on the CPU (oracle/fake_capi.cpp, tests/test_dropin_adapter.py)
+    and against the real library on the GPU (tests/test_gpu_zz_dropin.py).
   * LightGlue — PARITY UNPINNED: the arithmetic lives in the un-vendored, un-pinned third-party
     package cvg/LightGlue and no weights are available offline.  The restatement follows the
     published model (lightglue/lightglue.py) and is cross-checked against the independent

@@ -108,11 +108,15 @@ def nms_select(raw: np.ndarray, input_h: int, input_w: int, max_keypoints: int, 
                remove_borders: int):
     """9x9 NMS (convert_superpoint_to_onnx.py:82-87) on a given raw heat map [H',W'] followed by
     select_keypoints: the exact index work the CUDA nms/select kernels must reproduce bit for bit."""
-    s4 = torch.from_numpy(raw)[None, None]
-    pooled = F.max_pool2d(s4, 2 * NMS_RADIUS + 1, stride=1, padding=NMS_RADIUS)
-    scores = torch.where(s4 == pooled, s4, torch.zeros_like(s4))[0, 0].numpy()
-    return select_keypoints(scores, input_h, input_w, max_keypoints, keypoint_threshold, remove_borders,
+    return select_keypoints(nms(raw), input_h, input_w, max_keypoints, keypoint_threshold, remove_borders,
                             raw.shape[0] // 8, raw.shape[1] // 8)
+
+
+def nms(raw: np.ndarray) -> np.ndarray:
+    """The in-graph 9x9 NMS alone (convert_superpoint_to_onnx.py:82-87): raw heat map [H',W'] -> score map."""
+    s4 = torch.from_numpy(np.ascontiguousarray(raw))[None, None]
+    pooled = F.max_pool2d(s4, 2 * NMS_RADIUS + 1, stride=1, padding=NMS_RADIUS)
+    return torch.where(s4 == pooled, s4, torch.zeros_like(s4))[0, 0].numpy()
 
 
 def select_keypoints(scores: np.ndarray, input_h: int, input_w: int, max_keypoints: int,

@@ -69,3 +69,41 @@ def test_bgr_input_is_converted_like_opencv():
     b = sp.extract(np.ascontiguousarray(g["gray"]))
     assert len(b.keypoints) > 10
     assert np.array_equal(a.keypoints, b.keypoints) and np.array_equal(a.responses, b.responses)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_superpoint.so")),
+                    reason="oracle/_ref/libref_superpoint.so not built (build() with /root/reference mounted)")
+@pytest.mark.parametrize("fixture,K", [("superpoint_ref_small.npz", 256), ("superpoint_ref_odd.npz", 128)])
+def test_reference_select_and_gather_equals_product_features(fixture, K):
+    """Rows a7-a9 in one piece: the reference's own SuperPoint::select_and_gather (src/SuperPoint.cc:681-750, compiled in
+    place, with its own DescriptorPool and gather kernel) fed with the product's heat map (after the graph's NMS) and
+    descriptor grid must return the product's keypoints, responses and fp16 descriptor rows bit for bit."""
+    import torch
+
+    from oracle import superpoint as osp
+    from superslam_b200 import _lib
+    from superslam_b200 import frontend as fe
+    from test_oracle_ref_superpoint import bind, ref_select
+
+    lib = bind()
+    imgs = np.load(os.path.join(GOLDEN, fixture))["images"]
+    b, h, w = imgs.shape
+    hc, wc = h // 8, w // 8
+    sp = fe.SuperPoint(SP_WEIGHTS, K)
+    feats = sp._extract(list(imgs))
+    raw = sp.debug_read("scores", (b, hc * 8, wc * 8), np.float32)
+    grid = sp.debug_read("grid", (b, hc, wc, 256), np.float16)
+    total = 0
+    for i, F in enumerate(feats):
+        chw = torch.from_numpy(np.ascontiguousarray(grid[i].transpose(2, 0, 1))).cuda()   # the reference's CHW binding
+        torch.cuda.synchronize()
+        got = ref_select(lib, osp.nms(raw[i]), h, w, K, 0.005, 4, grid_dev=C.c_void_p(chw.data_ptr()), want_desc=True)
+        assert got["ok"] == 1 and got["n"] == len(F.keypoints)
+        assert np.array_equal(got["xy"], F.keypoints) and np.array_equal(got["score"], F.responses)
+        ours = np.zeros((got["n"], 256), np.float32)
+        if got["n"]:
+            _lib.check(_lib.load().ssb_desc_to_host_f32(0, C.c_void_p(F.descriptors.data), got["n"], 256,
+                                                        ours.ctypes.data_as(C.POINTER(C.c_float))))
+        assert np.array_equal(ours.astype(np.float16).view(np.uint16), got["desc"])
+        total += got["n"]
+    assert total > 50
