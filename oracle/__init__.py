@@ -19,10 +19,14 @@ Pinning status:
     oracle/_ref/libref_gather.so and compared with the product on the GPU (tests/test_gpu_zz_ref_gather.py).
   * keypoint select (border strip, float-vs-double threshold, std::sort tie order, top-K, scale factors) — PINNED by
     the reference's own code: src/SuperPoint.cc is compiled in place (TensorRT reduced to never-called stand-ins,
-    oracle/stubs_trt/) into oracle/_ref/libref_superpoint.so and its SuperPoint::select_and_gather is run against
+    oracle/stubs_trt/) into oracle/_ref/libref_nethost.so and its SuperPoint::select_and_gather is run against
     select_keypoints on the reference module's score maps, tie-heavy random maps and threshold-edge values
     (tests/test_oracle_ref_superpoint.py); on the GPU the whole function, pool and gather kernel included, is compared
     with the product's features (tests/test_gpu_zz_ref_gather.py).
+  * LightGlue's host half (rows a10, a12: keypoint normalisation, fp32 -> fp16 descriptor binding, matches0 / mscores0
+    -> cv::DMatch) — PINNED by the reference's own code: src/LightGlue.cc compiled in place into the same library,
+    LightGlue::prepare_inputs / normalize_keypoints / postprocess_outputs run on host buffers
+    (tests/test_oracle_ref_lightglue_host.py).
   * the C++ adapter above the C-ABI — EXECUTED under the reference's own caller: src/StereoFrontEnd.cc compiled in
     place over include/superslam_b200_adapter.hpp (oracle/dropin_harness.cpp, functional cv::Mat stand-in in
     oracle/stubs_cv/), against a C-ABI test double on the CPU (oracle/fake_capi.cpp, tests/test_dropin_adapter.py)

@@ -1,10 +1,14 @@
-// C-ABI shim that RUNS the reference's own SuperPoint::select_and_gather (/root/reference/src/SuperPoint.cc:681-750,
-// SURVEY §8 rows a7-a9), compiled from the source where it lies: border / threshold scan of the score map, the
+// C-ABI shim that RUNS the host logic of the reference's two TensorRT wrapper classes, compiled from the sources where
+// they lie.  (1) SuperPoint::select_and_gather (/root/reference/src/SuperPoint.cc:681-750): border / threshold scan of the score map, the
 // std::sort on (score, (h, w)) pairs, top-K, keypoint scaling, nearest-cell indices, DescriptorPool::make and - with a
 // GPU - the reference's gather kernel on a descriptor grid.  The rest of SuperPoint.cc is TensorRT plumbing; it
 // compiles against the declaration-level stand-ins in oracle/stubs_trt/ and is never called (the stand-in members
 // below fail like a missing engine).  The function is private: this file alone is compiled with -fno-access-control.
-// Built by oracle/Makefile into oracle/_ref/libref_superpoint.so.  TEST INFRASTRUCTURE.
+// (2) LightGlue::prepare_inputs / store_keypoints / normalize_keypoints (src/LightGlue.cc:163-172, 228-283, row a10):
+// what the engine is fed - keypoints normalised as (p - size/2) / (max(w, h)/2) in float, descriptors converted to the
+// binding's type - and LightGlue::postprocess_outputs (:326-363, row a12): matches0 / mscores0 -> cv::DMatch.  The
+// tensors are plain host buffers set up by this shim the way allocate_buffers would name and type them.
+// Built by oracle/Makefile into oracle/_ref/libref_nethost.so.  TEST INFRASTRUCTURE.
 //
 // Without a GPU the pool's cudaMalloc fails, DescriptorPool::make hands back a null slot pointer and the function
 // returns false at its "pool exhausted" check - AFTER the keypoints were written, which is what the CPU test reads.
@@ -13,12 +17,16 @@
 #include <memory>
 #include <vector>
 
+#include <cstring>
+
+#include "LightGlue.h"
 #include "SuperPoint.h"
 
 // ---- "no TensorRT here" -------------------------------------------------------------------------------------------
+static nvinfer1::Dims g_tensor_shape;   // what the stand-in context reports (set per call for "matches0")
 namespace nvinfer1 {
 bool IExecutionContext::setInputShape(const char*, const Dims&) { return false; }
-Dims IExecutionContext::getTensorShape(const char*) const { return Dims(); }
+Dims IExecutionContext::getTensorShape(const char*) const { return g_tensor_shape; }
 bool IExecutionContext::setTensorAddress(const char*, void*) { return false; }
 bool IExecutionContext::enqueueV3(cudaStream_t) { return false; }
 IExecutionContext* ICudaEngine::createExecutionContext() { return nullptr; }
@@ -87,5 +95,63 @@ int ref_sp_select_and_gather(void* h, const float* scores_host, int score_h, int
   if (*ok && n > 0 && desc_out && d.data)
     cudaMemcpy(desc_out, d.data, sizeof(unsigned short) * static_cast<size_t>(n) * d.dim, cudaMemcpyDeviceToHost);
   return n;
+}
+
+// ---- LightGlue host logic -------------------------------------------------------------------------------------------
+// prepare_inputs: kpts as fp32 or fp16 (kpts_half), descriptors as fp32 or fp16 (desc_half) host "bindings".
+// out_k0 / out_k1: n*2 elements, out_d0 / out_d1: n*256 elements of the chosen width (4 or 2 bytes).
+int ref_lg_prepare_inputs(int image_width, int image_height, const float* xy0, int n0, const float* desc0,
+                          const float* xy1, int n1, const float* desc1, int kpts_half, int desc_half, void* out_k0,
+                          void* out_k1, void* out_d0, void* out_d1) {
+  LightGlue lg("none.engine", image_width, image_height);
+  std::vector<cv::KeyPoint> k0, k1;
+  for (int i = 0; i < n0; ++i) k0.emplace_back(xy0[2 * i], xy0[2 * i + 1], 1.0f);
+  for (int i = 0; i < n1; ++i) k1.emplace_back(xy1[2 * i], xy1[2 * i + 1], 1.0f);
+  cv::Mat d0(n0, 256, CV_32F, const_cast<float*>(desc0)), d1(n1, 256, CV_32F, const_cast<float*>(desc1));
+  const char* names[4] = {"kpts0", "kpts1", "desc0", "desc1"};
+  void* bufs[4] = {out_k0, out_k1, out_d0, out_d1};
+  for (int i = 0; i < 4; ++i) {
+    LightGlue::TensorInfo t;
+    t.name = names[i];
+    t.hostPtr = bufs[i];
+    t.dtype = (i < 2 ? kpts_half : desc_half) ? nvinfer1::DataType::kHALF : nvinfer1::DataType::kFLOAT;
+    lg.input_tensors_.push_back(t);
+  }
+  const bool ok = lg.prepare_inputs(k0, d0, k1, d1);
+  lg.input_tensors_.clear();   // the buffers are the caller's: keep free_buffers away from them
+  return ok ? 1 : 0;
+}
+
+// normalize_keypoints (the older float-only helper, :163-172)
+void ref_lg_normalize_keypoints(int image_width, int image_height, const float* xy, int n, float* out) {
+  LightGlue lg("none.engine", image_width, image_height);
+  std::vector<cv::KeyPoint> k;
+  for (int i = 0; i < n; ++i) k.emplace_back(xy[2 * i], xy[2 * i + 1], 1.0f);
+  lg.normalize_keypoints(k, out);
+}
+
+// postprocess_outputs on host "output bindings": matches0 int32 [1, n0]; mscores0 fp32, fp16 (scores_kind 1) or
+// absent (scores_kind 2).  Returns the number of matches (or -1 when the function returns false).
+int ref_lg_postprocess(const int* matches0, const void* mscores0, int scores_kind, int n0, int* query, int* train,
+                       float* distance) {
+  LightGlue lg("none.engine", 640, 480);
+  lg.context_.reset(new nvinfer1::IExecutionContext);
+  LightGlue::TensorInfo m, s;
+  m.name = "matches0", m.hostPtr = const_cast<int*>(matches0), m.dtype = nvinfer1::DataType::kINT32;
+  s.name = "mscores0", s.hostPtr = const_cast<void*>(mscores0);
+  s.dtype = scores_kind == 1 ? nvinfer1::DataType::kHALF : nvinfer1::DataType::kFLOAT;
+  lg.output_tensors_.push_back(m);
+  if (scores_kind != 2) lg.output_tensors_.push_back(s);
+  g_tensor_shape = nvinfer1::Dims();
+  g_tensor_shape.nbDims = 2, g_tensor_shape.d[0] = 1, g_tensor_shape.d[1] = n0;
+  MatchResult r;
+  r.matches.emplace_back(7, 7, 7.0f);   // must be cleared by the function
+  const bool ok = lg.postprocess_outputs(r);
+  lg.output_tensors_.clear();
+  if (!ok) return -1;
+  for (size_t i = 0; i < r.matches.size(); ++i) {
+    query[i] = r.matches[i].queryIdx, train[i] = r.matches[i].trainIdx, distance[i] = r.matches[i].distance;
+  }
+  return static_cast<int>(r.matches.size());
 }
 }

@@ -1,7 +1,7 @@
 // Declaration-level stand-in for the few TensorRT types /root/reference/src/SuperPoint.cc names (TensorRT is not in
 // this image), so that the file can be compiled in place for the ONE member function that does not touch TensorRT:
 // SuperPoint::select_and_gather (:681-750).  Member functions are defined in
-// oracle/ref_superpoint_shim.cpp as "no engine" failures; nothing here infers anything.  TEST INFRASTRUCTURE.
+// oracle/ref_nethost_shim.cpp as "no engine" failures; nothing here infers anything.  TEST INFRASTRUCTURE.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -71,8 +71,8 @@ def test_bgr_input_is_converted_like_opencv():
     assert np.array_equal(a.keypoints, b.keypoints) and np.array_equal(a.responses, b.responses)
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_superpoint.so")),
-                    reason="oracle/_ref/libref_superpoint.so not built (build() with /root/reference mounted)")
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_nethost.so")),
+                    reason="oracle/_ref/libref_nethost.so not built (build() with /root/reference mounted)")
 @pytest.mark.parametrize("fixture,K", [("superpoint_ref_small.npz", 256), ("superpoint_ref_odd.npz", 128)])
 def test_reference_select_and_gather_equals_product_features(fixture, K):
     """Rows a7-a9 in one piece: the reference's own SuperPoint::select_and_gather (src/SuperPoint.cc:681-750, compiled in

@@ -1,5 +1,5 @@
 """The REFERENCE's own SuperPoint::select_and_gather (/root/reference/src/SuperPoint.cc:681-750, compiled in place by
-oracle/Makefile into oracle/_ref/libref_superpoint.so; TensorRT reduced to never-called stand-ins) against the
+oracle/Makefile into oracle/_ref/libref_nethost.so; TensorRT reduced to never-called stand-ins) against the
 restatement oracle/superpoint.py::select_keypoints that the CUDA nms / select kernels are held to bit for bit:
 border strip, `float score > double threshold`, std::sort with std::greater on (score, (h, w)) - ties by row then column,
 descending -, top-K, float scale factors for a resized score map.  Without a GPU the function stops at its pool check
@@ -14,8 +14,8 @@ import pytest
 from conftest import GOLDEN, ROOT
 from oracle import superpoint as osp
 
-LIB = os.path.join(ROOT, "oracle", "_ref", "libref_superpoint.so")
-pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_superpoint.so not built")
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref_nethost.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libref_nethost.so not built")
 fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
 
 
