@@ -7,6 +7,7 @@
 //   reference (include/SuperPoint.h:37-52, include/LightGlue.h:33-57)   this header
 //   ------------------------------------------------------------------  ---------------------------
 //   SuperPoint(engine, max_kp, thresh, borders) + initialize()          superslam_b200::SuperPointB200
+//   SuperPoint::infer(image, keypoints, cv::Mat descriptors)            SuperPointB200::infer (host path of the demos)
 //   LightGlue(engine, w, h) + initialize()                              superslam_b200::LightGlueB200
 //   LightGlue(shared_engine(), w, h)                                    LightGlueB200(other, w, h)
 //   EigenPlaces(engine, w, h) + initialize()  (include/EigenPlaces.h:21-66)  superslam_b200::EigenPlacesB200
@@ -45,6 +46,21 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
   superslam::Features extract(const cv::Mat& image) override {
     std::vector<superslam::Features> f = run({&image});
     return f.empty() ? superslam::Features{} : std::move(f[0]);
+  }
+  // SuperPoint::infer (include/SuperPoint.h:45-46, src/SuperPoint.cc:427-531): the host path the reference's demo
+  // programs use (tests/test_superpoint_only.cc:71, tests/test_superpoint_cosine_matching.cc:192) - keypoints plus
+  // L2-normalised CV_32F [n, 256] descriptors on the host.  false on a failed inference, true with zero keypoints.
+  bool infer(const cv::Mat& image, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) {
+    keypoints.clear();
+    descriptors = cv::Mat();
+    std::vector<superslam::Features> f = run({&image});
+    if (f.empty()) return false;
+    keypoints = std::move(f[0].keypoints);
+    const superslam::DeviceDescriptors& d = f[0].descriptors;
+    if (keypoints.empty()) return true;
+    if (d.empty()) return false;   // pool exhausted: the reference's host path has no pool, so report the failure
+    descriptors.create(d.count, d.dim, CV_32F);
+    return ssb_desc_to_host_f32(device_, d.data, d.count, d.dim, descriptors.ptr<float>()) == SSB_OK;
   }
   std::pair<superslam::Features, superslam::Features> extract_stereo(const cv::Mat& left,
                                                                     const cv::Mat& right) override {

@@ -129,6 +129,25 @@ int dropin_verify(void* handle, int cap, int* query, int* train, float* distance
   return copy_matches(m, cap, query, train, distance);
 }
 
+// SuperPoint::infer-style host path of the adapter (the reference's demo programs): keypoints + CV_32F descriptors.
+// Returns the keypoint count, -1 when infer() reports a failure.
+int dropin_infer(void* handle, const uint8_t* image, int height, int width, int row_stride, int channels, int cap,
+                 float* xy, float* response, float* desc) {
+  Harness* h = static_cast<Harness*>(handle);
+  const cv::Mat img(height, width, CV_MAKETYPE(CV_8U, channels), const_cast<uint8_t*>(image), row_stride);
+  std::vector<cv::KeyPoint> kps;
+  cv::Mat d;
+  if (!h->sp->infer(img, kps, d)) return -1;
+  const int n = static_cast<int>(kps.size());
+  if (n > 0 && (d.rows != n || d.cols != 256 || d.type() != CV_32F)) return -2;
+  for (int i = 0; i < n && i < cap; ++i) {
+    xy[2 * i] = kps[i].pt.x, xy[2 * i + 1] = kps[i].pt.y;
+    response[i] = kps[i].response;
+    std::memcpy(desc + static_cast<size_t>(i) * 256, d.ptr<float>(i), 256 * sizeof(float));
+  }
+  return n;
+}
+
 // Keeps one more copy of the current frame alive; returns how many are held.
 int dropin_hold_frame(void* handle) {
   Harness* h = static_cast<Harness*>(handle);

@@ -111,6 +111,7 @@ class SuperPoint:
         prepared = [_as_gray_or_bgr(i) for i in images]
         h, w = prepared[0][0].shape[:2]
         ch = prepared[0][1]
+        self._last_ok = False
         for im, c in prepared:
             if im.shape[:2] != (h, w) or c != ch:
                 log.error("SuperPoint: stereo pair must share resolution (rectified)")
@@ -129,6 +130,7 @@ class SuperPoint:
         if st not in (_lib.SSB_OK, _lib.SSB_ERR_EXHAUSTED):
             log.error("SuperPoint: extract failed: %s", self._lib.ssb_last_error().decode())
             return [Features() for _ in images]
+        self._last_ok = True
         out = []
         for i in range(b):
             n = cnt[i]
@@ -147,6 +149,20 @@ class SuperPoint:
     def extract_stereo(self, left, right):
         l, r = self._extract([left, right])
         return l, r
+
+    def infer(self, image):
+        """SuperPoint::infer (include/SuperPoint.h:45-46, src/SuperPoint.cc:427-531), the host path of the reference's
+        demo programs (tests/test_superpoint_only.cc:71): (ok, keypoints [n,2], responses [n], descriptors f32 [n,256])."""
+        f = self.extract(image)
+        n = len(f.keypoints)
+        desc = np.zeros((n, DESC_DIM), np.float32)
+        if n == 0:
+            return self._last_ok, f.keypoints, f.responses, desc
+        if f.descriptors.empty():
+            return False, f.keypoints, f.responses, desc
+        st = self._lib.ssb_desc_to_host_f32(self.device, C.c_void_p(f.descriptors.data), n, DESC_DIM,
+                                            desc.ctypes.data_as(C.POINTER(C.c_float)))
+        return st == _lib.SSB_OK, f.keypoints, f.responses, desc
 
     def debug_read(self, what: str, shape, dtype):
         out = np.empty(shape, dtype)

@@ -39,6 +39,8 @@ def bind(path):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.c_int, ip, ip, fp]
     lib.dropin_release_frames.argtypes = [C.c_void_p]
+    lib.dropin_infer.restype = C.c_int
+    lib.dropin_infer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, fp]
     lib.dropin_hold_frame.restype = C.c_int
     lib.dropin_hold_frame.argtypes = [C.c_void_p]
     return lib
@@ -70,6 +72,14 @@ class Harness:
                                     stereo.ctypes.data_as(dp), has.ctypes.data_as(C.c_char_p), desc.ctypes.data_as(ip))
         return dict(n=n, xy=xy[:n], response=resp[:n], size_angle=sa[:n], stereo=stereo[:n], has_depth=has[:n],
                     desc=dict(count=int(desc[0]), dim=int(desc[1]), slot=int(desc[2]), resident=bool(desc[3])))
+
+    def infer(self, image):
+        image = np.asarray(image)
+        ch = 1 if image.ndim == 2 else image.shape[2]
+        xy, resp, desc = np.zeros((self.cap, 2), np.float32), np.zeros(self.cap, np.float32), np.zeros((self.cap, 256), np.float32)
+        n = self.lib.dropin_infer(self.h, image.ctypes.data, image.shape[0], image.shape[1], image.strides[0], ch, self.cap,
+                                  xy.ctypes.data_as(fp), resp.ctypes.data_as(fp), desc.ctypes.data_as(fp))
+        return n, xy[:max(n, 0)], resp[:max(n, 0)], desc[:max(n, 0)]
 
     def promote_keyframe(self):
         out = np.zeros((self.cap, 256), np.float32)
@@ -223,6 +233,24 @@ def test_pool_exhaustion_failed_inference_and_empty_images(fake):
     assert none_right["n"] == 40 and none_right["has_depth"].sum() == 0 and np.isnan(none_right["stereo"][:, 1]).all()
     hs.close()
     assert fake.fake_slots_in_use() == 0
+
+
+def test_host_path_infer_of_the_demo_programs(fake):
+    """SuperPoint::infer (tests/test_superpoint_only.cc:71): keypoints + CV_32F descriptors on the host, slot returned."""
+    hs = Harness(fake, "sp.ssbw", "lg.ssbw", 640, 480, max_kp=64)
+    img = image(9, 17, 3, 40, pad=5)
+    n, xy, resp, desc = hs.infer(img)
+    exy, esc, tag = fake_features(img, 64)
+    assert n == 36 and np.array_equal(xy, exy) and np.array_equal(resp, esc)
+    k, c = np.arange(36, dtype=np.float32)[:, None], np.arange(256, dtype=np.float32)[None, :]
+    assert np.array_equal(desc, (np.float32(tag) + k + c / np.float32(1024)).astype(np.float32))
+    assert fake.fake_slots_in_use() == 0                                    # the transient handle gave its slot back
+    assert hs.infer(image(0, 17, 3, 40))[0] == 0                            # no keypoints: success, empty outputs
+    assert hs.infer(image(255, 17, 3, 40))[0] == -1                         # failed inference -> false
+    hs.close()
+    broken = Harness(fake, "missing", "lg.ssbw", 640, 480)
+    assert broken.infer(img)[0] == -1
+    broken.close()
 
 
 def test_initialize_failure_leaves_a_broken_but_safe_object(fake):

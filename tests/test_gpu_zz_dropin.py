@@ -45,6 +45,13 @@ def test_reference_stereo_frontend_over_the_adapter_on_the_gpu(tmp_path, lg_weig
     assert np.array_equal(out["stereo"], frame.stereo, equal_nan=True)
     assert out["desc"]["count"] == out["n"] and out["desc"]["dim"] == 256 and out["desc"]["resident"]
 
+    n, ixy, iresp, idesc = hs.infer(padded(l))             # SuperPoint::infer, the demo programs' host path
+    assert n == out["n"] and np.array_equal(ixy, out["xy"]) and np.array_equal(iresp, out["response"])
+    assert np.array_equal(idesc, lg.descriptors_to_host(frame.descriptors_left))
+    assert np.abs(np.linalg.norm(idesc, axis=1) - 1).max() < 2e-3
+    ok, pxy, presp, pdesc = sp.infer(l)                    # the Python mirror of the same call
+    assert ok and np.array_equal(pxy, ixy) and np.array_equal(presp, iresp) and np.array_equal(pdesc, idesc)
+
     rows, kf = hs.promote_keyframe()                       # last_keyframe_ = frame; descriptors_to_host
     host0 = lg.descriptors_to_host(frame.descriptors_left)
     assert rows == out["n"] and np.array_equal(kf, host0)
