@@ -162,4 +162,83 @@ void dropin_release_frames(void* handle) {
   h->last_keyframe = superslam::StereoFrame();
   h->held.clear();
 }
+
+// ---- the other adapter classes, driven the way the reference drives the interfaces they stand behind ----------------
+
+// IPlaceRecognizer (include/PlaceRecognizer.h:20-36) as LoopCloser uses it (src/LoopCloser.cc:29-41):
+// compute_global_descriptor on the keyframe image, query against the index, add.
+void* dropin_place_create(const char* weights, int in_w, int in_h, int* ok) {
+  superslam_b200::EigenPlacesB200* ep = new superslam_b200::EigenPlacesB200(weights, in_w, in_h);
+  *ok = ep->initialize() ? 1 : 0;
+  return ep;
+}
+void dropin_place_destroy(void* h) { delete static_cast<superslam_b200::EigenPlacesB200*>(h); }
+// returns the descriptor length (0 = empty Mat)
+int dropin_place_compute(void* h, const uint8_t* image, int height, int width, int row_stride, int channels, float* out) {
+  superslam::IPlaceRecognizer* pr = static_cast<superslam_b200::EigenPlacesB200*>(h);
+  const cv::Mat img(height, width, CV_MAKETYPE(CV_8U, channels), const_cast<uint8_t*>(image), row_stride);
+  const cv::Mat d = pr->compute_global_descriptor(img);
+  if (d.empty()) return 0;
+  std::memcpy(out, d.ptr<float>(), sizeof(float) * d.total());
+  return static_cast<int>(d.total());
+}
+// descriptor handed over as a column vector of doubles when as_f64_column != 0 (add / query must reshape + convert)
+void dropin_place_add(void* h, size_t id, const float* desc, int dim, int as_f64_column) {
+  superslam::IPlaceRecognizer* pr = static_cast<superslam_b200::EigenPlacesB200*>(h);
+  cv::Mat d(1, dim, CV_32F, const_cast<float*>(desc));
+  if (as_f64_column) {
+    cv::Mat c;
+    d.reshape(1, dim).convertTo(c, CV_64F);
+    pr->add(id, c);
+  } else {
+    pr->add(id, d);
+  }
+}
+int dropin_place_query(void* h, const float* desc, int dim, size_t exclude_recent, int top_k, size_t* ids, float* scores) {
+  superslam::IPlaceRecognizer* pr = static_cast<superslam_b200::EigenPlacesB200*>(h);
+  const cv::Mat d(1, dim, CV_32F, const_cast<float*>(desc));
+  const std::vector<superslam::LoopCandidate> c = pr->query(d, exclude_recent, top_k);
+  for (size_t i = 0; i < c.size(); ++i) ids[i] = c[i].keyframe_id, scores[i] = c[i].score;
+  return static_cast<int>(c.size());
+}
+
+// RemapB200 in place of cv::remap(img, out, M1, M2, cv::INTER_LINEAR) (examples/stereo/euroc.cc:176-177)
+int dropin_remap(const float* map_x, const float* map_y, int dst_h, int dst_w, const uint8_t* src, int src_h, int src_w,
+                 int src_stride, uint8_t* dst) {
+  const cv::Mat mx(dst_h, dst_w, CV_32FC1, const_cast<float*>(map_x)), my(dst_h, dst_w, CV_32FC1, const_cast<float*>(map_y));
+  superslam_b200::RemapB200 rect(mx, my, cv::Size(src_w, src_h));
+  const cv::Mat in(src_h, src_w, CV_8UC1, const_cast<uint8_t*>(src), src_stride);
+  cv::Mat out;
+  if (!rect(in, out)) return 0;
+  if (out.rows != dst_h || out.cols != dst_w || out.type() != CV_8UC1 || !out.isContinuous()) return -1;
+  std::memcpy(dst, out.data, static_cast<size_t>(dst_h) * dst_w);
+  return 1;
+}
+
+// RgbdPostB200::run in place of the tail of RgbdFrontEnd::process (src/RgbdFrontEnd.cc:27-58).  depth_type: 0 = CV_16U,
+// 1 = CV_32F, 2 = CV_8U (an unsupported type: sampleDepth returns 0); dist as a CV_32F column when dist_f32_column != 0.
+int dropin_rgbd_post(const float* xy, int n, void* depth, int depth_type, int dh, int dw, int depth_stride,
+                     const double* cam4, const double* dist, int nd, int dist_f32_column, double bf, double depth_factor,
+                     double max_depth, float* out_xy, double* out_stereo, char* out_has) {
+  superslam_b200::RgbdPostB200 post(4096, cv::Size(dw, dh));
+  std::vector<cv::Point2f> raw(n), und;
+  for (int i = 0; i < n; ++i) raw[i] = cv::Point2f(xy[2 * i], xy[2 * i + 1]);
+  const int types[3] = {CV_16U, CV_32F, CV_8U};
+  const cv::Mat dm(dh, dw, types[depth_type], depth, depth_stride);
+  cv::Mat D;
+  if (nd > 0) {
+    D = cv::Mat(1, nd, CV_64F, const_cast<double*>(dist));
+    if (dist_f32_column) D.reshape(1, nd).convertTo(D, CV_32F);
+  }
+  std::vector<double> st;
+  std::vector<char> has;
+  if (!post.run(raw, dm, cam4[0], cam4[1], cam4[2], cam4[3], D, bf, depth_factor, max_depth, und, st, has)) return 0;
+  if (static_cast<int>(und.size()) != n || static_cast<int>(st.size()) != 3 * n || static_cast<int>(has.size()) != n) return -1;
+  for (int i = 0; i < n; ++i) {
+    out_xy[2 * i] = und[i].x, out_xy[2 * i + 1] = und[i].y;
+    for (int k = 0; k < 3; ++k) out_stereo[3 * i + k] = st[3 * i + k];
+    out_has[i] = has[i];
+  }
+  return 1;
+}
 }

@@ -12,6 +12,8 @@
 //                       slots from a LIFO free list (include/DescriptorPool.h:25-44); none free -> slot -1, null
 //                       pointer, SSB_ERR_EXHAUSTED, keypoints still delivered (src/SuperPoint.cc:724-727)
 //   match, query i:     i % 3 == 0 -> unmatched (-1, 0);  else train (7 i + 3) % n1, score 0.25 + 0.5 (i % 2)
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -156,6 +158,129 @@ int ssb_desc_to_host_f32(int, const void* desc_dev_f16, int count, int dim, floa
   std::memcpy(out, desc_dev_f16, sizeof(float) * static_cast<size_t>(count) * dim);
   return SSB_OK;
 }
+
+// ---- EigenPlaces / rectifier / RGB-D doubles ----------------------------------------------------------------------
+//   ep_compute: descriptor[c] = px(c % (width * channels)) of row 1 (checks row_stride) + 1, not normalised
+//   ep_add / ep_query: a plain cosine index (double dot products, rows normalised on insertion) with the semantics of
+//                      src/PlaceRecognizer.cc:21-52; the test compares with oracle/eigenplaces.py::CosineDescriptorIndex
+//   rect_remap: out(y, x) = in(y % src_h, x % src_w) + 1;  rgbd_process: records every scalar argument,
+//               out_xy = xy + 0.25, stereo = (x, depth(lround(y), lround(x)) / depth_factor, y), has = depth != 0
+struct ssb_eigenplaces {
+  int in_w = 0, in_h = 0;
+  std::vector<uint64_t> ids;
+  std::vector<std::vector<double>> rows;
+};
+struct ssb_rectifier {
+  int dh = 0, dw = 0, sh = 0, sw = 0;
+  float m00 = 0, m11 = 0;
+};
+struct ssb_rgbd {
+  int max_kp = 0;
+};
+namespace {
+double g_rgbd[32];
+int g_rect_stride = 0;
+std::vector<double> unit(const float* d, int dim) {
+  double n = 0;
+  for (int i = 0; i < dim; ++i) n += static_cast<double>(d[i]) * d[i];
+  n = std::sqrt(n);
+  std::vector<double> r(dim);
+  for (int i = 0; i < dim; ++i) r[i] = n > 1e-12 ? d[i] / n : d[i];
+  return r;
+}
+}  // namespace
+
+int ssb_ep_create(const char* weights_path, int input_width, int input_height, int, int, ssb_eigenplaces** out) {
+  *out = nullptr;
+  if (!weights_path || std::string(weights_path) == "missing") return SSB_ERR_IO;
+  *out = new ssb_eigenplaces;
+  (*out)->in_w = input_width, (*out)->in_h = input_height;
+  return SSB_OK;
+}
+void ssb_ep_destroy(ssb_eigenplaces* ep) { delete ep; }
+int ssb_ep_descriptor_dim(ssb_eigenplaces*) { return 512; }
+int ssb_ep_compute(ssb_eigenplaces* ep, const uint8_t* const* images, int count, int height, int width, int row_stride,
+                   int channels, float* descriptors) {
+  if (!ep || count < 1 || height < 2 || row_stride < width * channels) return SSB_ERR_INVALID;
+  if (images[0][0] == 255) return SSB_ERR_CUDA;
+  for (int i = 0; i < count; ++i)
+    for (int c = 0; c < 512; ++c) descriptors[i * 512 + c] = images[i][row_stride + c % (width * channels)] + 1.0f;
+  return SSB_OK;
+}
+int ssb_ep_add(ssb_eigenplaces* ep, uint64_t keyframe_id, const float* descriptor, int dim) {
+  if (!ep || !descriptor || dim <= 0) return SSB_ERR_INVALID;
+  ep->ids.push_back(keyframe_id);
+  ep->rows.push_back(unit(descriptor, dim));
+  return SSB_OK;
+}
+int ssb_ep_index_size(ssb_eigenplaces* ep) { return ep ? static_cast<int>(ep->ids.size()) : 0; }
+int ssb_ep_query(ssb_eigenplaces* ep, const float* descriptor, int dim, uint64_t exclude_recent, int top_k,
+                 float min_score, uint64_t* keyframe_ids, float* scores, int capacity, int* n_out) {
+  *n_out = 0;
+  if (!ep || !descriptor) return SSB_ERR_INVALID;
+  const size_t M = ep->ids.size();
+  if (M == 0 || M <= exclude_recent) return SSB_OK;
+  const std::vector<double> q = unit(descriptor, dim);
+  std::vector<std::pair<float, uint64_t>> c;
+  for (size_t i = 0; i < M - exclude_recent; ++i) {
+    double s = 0;
+    for (int k = 0; k < dim; ++k) s += ep->rows[i][k] * q[k];
+    if (static_cast<float>(s) >= min_score) c.emplace_back(static_cast<float>(s), ep->ids[i]);
+  }
+  std::stable_sort(c.begin(), c.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+  if (top_k > 0 && c.size() > static_cast<size_t>(top_k)) c.resize(top_k);
+  for (size_t i = 0; i < c.size() && static_cast<int>(i) < capacity; ++i, ++*n_out)
+    scores[i] = c[i].first, keyframe_ids[i] = c[i].second;
+  return SSB_OK;
+}
+
+int ssb_rect_create(const float* map_x, const float* map_y, int dst_height, int dst_width, int src_height, int src_width,
+                    int, int, ssb_rectifier** out) {
+  *out = nullptr;
+  if (!map_x || !map_y || (dst_height * dst_width) % 4) return SSB_ERR_INVALID;
+  *out = new ssb_rectifier{dst_height, dst_width, src_height, src_width, map_x[0], map_y[dst_width + 1]};
+  return SSB_OK;
+}
+void ssb_rect_destroy(ssb_rectifier* r) { delete r; }
+int ssb_rect_remap(ssb_rectifier* r, const uint8_t* const* images, int count, int row_stride, uint8_t* const* out) {
+  if (!r || row_stride < r->sw) return SSB_ERR_INVALID;
+  g_rect_stride = row_stride;
+  for (int i = 0; i < count; ++i)
+    for (int y = 0; y < r->dh; ++y)
+      for (int x = 0; x < r->dw; ++x)
+        out[i][y * r->dw + x] = static_cast<uint8_t>(images[i][(y % r->sh) * row_stride + x % r->sw] + 1);
+  return SSB_OK;
+}
+
+int ssb_rgbd_create(int max_keypoints, int, int, int, ssb_rgbd** out) {
+  *out = new ssb_rgbd{max_keypoints};
+  return SSB_OK;
+}
+void ssb_rgbd_destroy(ssb_rgbd* r) { delete r; }
+int ssb_rgbd_process(ssb_rgbd* r, const float* xy, int n, const void* depth, int depth_type, int height, int width,
+                     int row_stride, const double* camera, const double* dist, int n_dist, double bf, double depth_factor,
+                     double max_depth, float* out_xy, double* out_stereo, uint8_t* out_has_depth) {
+  if (!r || n > r->max_kp) return SSB_ERR_INVALID;
+  double* g = g_rgbd;
+  g[0] = n, g[1] = depth_type, g[2] = height, g[3] = width, g[4] = row_stride;
+  for (int i = 0; i < 4; ++i) g[5 + i] = camera[i];
+  g[9] = n_dist, g[10] = bf, g[11] = depth_factor, g[12] = max_depth, g[13] = dist != nullptr;
+  for (int i = 0; i < 14; ++i) g[14 + i] = (dist && i < n_dist) ? dist[i] : -1;
+  for (int i = 0; i < n; ++i) {
+    const long u = std::lround(xy[2 * i]), v = std::lround(xy[2 * i + 1]);
+    double z = 0;
+    if (u >= 0 && v >= 0 && u < width && v < height) {
+      const unsigned char* row = static_cast<const unsigned char*>(depth) + v * row_stride;
+      z = depth_type == 0 ? reinterpret_cast<const uint16_t*>(row)[u] : reinterpret_cast<const float*>(row)[u];
+    }
+    out_xy[2 * i] = xy[2 * i] + 0.25f, out_xy[2 * i + 1] = xy[2 * i + 1] + 0.25f;
+    out_stereo[3 * i] = xy[2 * i], out_stereo[3 * i + 1] = z / depth_factor, out_stereo[3 * i + 2] = xy[2 * i + 1];
+    out_has_depth[i] = z != 0;
+  }
+  return SSB_OK;
+}
+void fake_last_rgbd(double* out28) { std::memcpy(out28, g_rgbd, 28 * sizeof(double)); }
+int fake_rect_stride(void) { return g_rect_stride; }
 
 // ---- inspection hooks for the test ----------------------------------------------------------------
 int fake_slots_in_use(void) { return ssb_sp_slots_in_use(g_sp); }

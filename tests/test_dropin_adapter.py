@@ -273,3 +273,102 @@ def test_real_library_without_a_gpu_fails_loudly_and_returns_empty():
     out = hs.process(img, img)
     assert out["n"] == 0 and hs.promote_keyframe()[0] == 0 and len(hs.track()[0]) == 0
     hs.close()
+
+
+# ---- the other adapter classes (EigenPlacesB200, RemapB200, RgbdPostB200) over the C-ABI double -----------------------
+u8p = C.c_void_p
+
+
+def test_place_recognizer_adapter_marshalling_and_index_semantics(fake, monkeypatch):
+    from oracle import eigenplaces as oep
+
+    fake.dropin_place_create.restype = C.c_void_p
+    fake.dropin_place_create.argtypes = [C.c_char_p, C.c_int, C.c_int, ip]
+    fake.dropin_place_destroy.argtypes = [C.c_void_p]
+    fake.dropin_place_compute.restype = C.c_int
+    fake.dropin_place_compute.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, fp]
+    fake.dropin_place_add.argtypes = [C.c_void_p, C.c_size_t, fp, C.c_int, C.c_int]
+    fake.dropin_place_query.restype = C.c_int
+    fake.dropin_place_query.argtypes = [C.c_void_p, fp, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), fp]
+    ok = C.c_int(-1)
+    bad = fake.dropin_place_create(b"missing", 512, 512, C.byref(ok))
+    img = np.arange(6 * 50 * 3, dtype=np.uint8).reshape(6, 50, 3)
+    out = np.zeros(512, np.float32)
+    assert ok.value == 0 and fake.dropin_place_compute(bad, img.ctypes.data, 6, 50, img.strides[0], 3, out.ctypes.data_as(fp)) == 0
+    fake.dropin_place_destroy(bad)
+    monkeypatch.setenv("SUPERSLAM_LOOP_MIN_SCORE", "0.30")                  # src/EigenPlaces.cc:30-34
+    ep = fake.dropin_place_create(b"ep.ssbw", 512, 512, C.byref(ok))
+    assert ok.value == 1
+    # image -> (pointer, rows, cols, step, channels): a padded BGR view; the double echoes row 1
+    buf = np.random.default_rng(0).integers(0, 250, (6, 50 * 3 + 7), dtype=np.uint8)
+    view = buf[:, :150].reshape(6, 50, 3)
+    assert fake.dropin_place_compute(ep, view.ctypes.data, 6, 50, buf.strides[0], 3, out.ctypes.data_as(fp)) == 512
+    assert np.array_equal(out, buf[1, np.arange(512) % 150].astype(np.float32) + 1)
+    blank = np.full((6, 50), 255, np.uint8)
+    assert fake.dropin_place_compute(ep, blank.ctypes.data, 6, 50, 50, 1, out.ctypes.data_as(fp)) == 0   # failure -> empty Mat
+    # add / query against the restated CosineDescriptorIndex (src/PlaceRecognizer.cc:21-52)
+    rng = np.random.default_rng(1)
+    base = rng.normal(size=512).astype(np.float32)
+    index = oep.CosineDescriptorIndex()
+    for k in range(40):
+        d = (base + rng.normal(size=512) * (0.2 + 0.1 * k)).astype(np.float32)
+        fake.dropin_place_add(ep, 100 + k, d.ctypes.data_as(fp), 512, k % 2)            # every other one as a CV_64F column
+        index.add(100 + k, d)
+    ids, sc = (C.c_size_t * 64)(), np.zeros(64, np.float32)
+    for exclude, top_k in [(0, 5), (10, 3), (39, 0), (40, 5), (5, 0)]:
+        n = fake.dropin_place_query(ep, base.ctypes.data_as(fp), 512, exclude, top_k, ids, sc.ctypes.data_as(fp))
+        exp = index.query(base, exclude, top_k, 0.30)
+        assert n == len(exp) and [ids[i] for i in range(n)] == [e[0] for e in exp]
+        assert np.allclose(sc[:n], [e[1] for e in exp], atol=1e-6)
+    assert len(index.query(base, 5, 0, 0.30)) < 35                          # the environment threshold really filters
+    fake.dropin_place_destroy(ep)
+
+
+def test_remap_adapter_creates_the_destination_and_passes_the_stride(fake):
+    fake.dropin_remap.restype = C.c_int
+    fake.dropin_remap.argtypes = [fp, fp, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
+    fake.fake_rect_stride.restype = C.c_int
+    dh, dw, sh, sw = 10, 12, 7, 9
+    mx, my = np.zeros((dh, dw), np.float32), np.zeros((dh, dw), np.float32)
+    src = np.random.default_rng(2).integers(0, 200, (sh, sw + 5), dtype=np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    assert fake.dropin_remap(mx.ctypes.data_as(fp), my.ctypes.data_as(fp), dh, dw, src.ctypes.data, sh, sw, src.strides[0],
+                             dst.ctypes.data) == 1
+    y, x = np.mgrid[0:dh, 0:dw]
+    assert fake.fake_rect_stride() == sw + 5 and np.array_equal(dst, src[y % sh, x % sw] + 1)
+    # a map whose size the library rejects (not a multiple of four pixels): the functor reports failure
+    assert fake.dropin_remap(mx.ctypes.data_as(fp), my.ctypes.data_as(fp), 3, 3, src.ctypes.data, sh, sw, src.strides[0],
+                             dst.ctypes.data) == 0
+
+
+@pytest.mark.parametrize("depth_type,dist_f32", [(0, 0), (1, 1), (2, 0)])
+def test_rgbd_post_adapter_marshalling(fake, depth_type, dist_f32):
+    fake.dropin_rgbd_post.restype = C.c_int
+    fake.dropin_rgbd_post.argtypes = [fp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int,
+                                      C.c_double, C.c_double, C.c_double, fp, dp, C.c_char_p]
+    fake.fake_last_rgbd.argtypes = [dp]
+    rng = np.random.default_rng(3)
+    n, dh, dw = 50, 20, 30
+    xy = (rng.uniform(0, 1, (n, 2)) * [dw + 2, dh + 2] - 1).astype(np.float32)
+    dtype = [np.uint16, np.float32, np.uint8][depth_type]
+    dbuf = rng.integers(0, 4, (dh, dw + 3)).astype(dtype) * (1000 if depth_type != 2 else 1)
+    depth = dbuf[:, :dw]
+    cam = np.array([500.5, 499.25, 15.5, 9.75])
+    dist = np.array([-0.25, 0.0625, 0.001953125, -0.00048828125, 0.0078125])       # exactly representable in fp32
+    oxy, ost, ohas = np.zeros((n, 2), np.float32), np.zeros((n, 3)), np.zeros(n, np.int8)
+    assert fake.dropin_rgbd_post(xy.ctypes.data_as(fp), n, dbuf.ctypes.data, depth_type, dh, dw, dbuf.strides[0],
+                                 cam.ctypes.data_as(dp), dist.ctypes.data_as(dp), 5, dist_f32, 40.0, 5000.0, 8.0,
+                                 oxy.ctypes.data_as(fp), ost.ctypes.data_as(dp), ohas.ctypes.data_as(C.c_char_p)) == 1
+    g = np.zeros(28)
+    fake.fake_last_rgbd(g.ctypes.data_as(dp))
+    # an unsupported depth type is replaced by an all-zero CV_16U map (sampleDepth returns 0, src/RgbdFrontEnd.cc:12-20)
+    exp_type, exp_stride = (depth_type, dbuf.strides[0]) if depth_type != 2 else (0, dw * 2)
+    assert list(g[:5]) == [n, exp_type, dh, dw, exp_stride] and np.array_equal(g[5:9], cam)
+    assert list(g[9:14]) == [5, 40.0, 5000.0, 8.0, 1] and np.array_equal(g[14:19], dist) and np.all(g[19:28] == -1)
+    u, v = np.rint(xy[:, 0]).astype(int), np.rint(xy[:, 1]).astype(int)     # no .5 ties in this sample
+    inside = (u >= 0) & (v >= 0) & (u < dw) & (v < dh)
+    z = np.where(inside, depth[np.clip(v, 0, dh - 1), np.clip(u, 0, dw - 1)], 0).astype(np.float64)
+    if depth_type == 2:
+        z[:] = 0
+    assert np.array_equal(oxy, xy + np.float32(0.25)) and np.array_equal(ohas, (z != 0).astype(np.int8))
+    assert np.array_equal(ost, np.stack([xy[:, 0].astype(np.float64), z / 5000.0, xy[:, 1].astype(np.float64)], 1))
