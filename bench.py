@@ -455,6 +455,24 @@ def main():
             if gfl > 0 and ms > 0:
                 tensor_kernels[name] = {"avg_launch_ms": round(ms / cnt, 5), "tflops": round(gfl / (ms / cnt), 1),
                                         "frac_of_peak": round(gfl / (ms / cnt) / peak_tf, 4)}
+        # the HBM-bound pieces: algorithmic bytes per launch / measured launch time against the measured copy
+        # bandwidth.  Bytes per unit as stated in DESIGN.md section 3: NMS reads the fp32 heat map once (4 H' W' per image),
+        # the gather moves one 512-byte grid row in and one descriptor row out per keypoint (K * 1024 per image), the
+        # assignment sweeps read sim and sim^T once each (2 * K * K * 4 per pair).
+        hbm_kernels = {}
+        try:
+            peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+            hc8, wc8 = (H // 8) * 8, (W // 8) * 8
+            per_launch_bytes = {"sp.nms": 4 * hc8 * wc8 * 2 * P, "sp.gather": K * 1024 * 2 * P,
+                                "lg.lse": 2 * K * K * 4 * P, "lg.argmax": 2 * K * K * 4 * P}
+            for name, nbytes in per_launch_bytes.items():
+                if name in prof and prof[name][1] > 0:
+                    cnt, ms = prof[name]
+                    gbs = nbytes / (ms / cnt) / 1e6
+                    hbm_kernels[name] = {"avg_launch_ms": round(ms / cnt, 5), "algorithmic_mb_per_launch": round(nbytes / 1e6, 2),
+                                         "gb_per_s": round(gbs, 1), "frac_of_peak": round(gbs / peak_gbs, 4)}
+        except Exception as e:  # a reporting extra must never cost the headline line
+            hbm_kernels = {"error": str(e)}
         eigen = None
         if world == 1:
             try:
@@ -490,6 +508,7 @@ def main():
             "roofline": roof,
             "kernel_time_shares": shares,
             "tensor_kernels": tensor_kernels,
+            "hbm_kernels": hbm_kernels,
             "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
             "cpu_baseline": cpu,
             "latency_single_pair": latency,
