@@ -149,3 +149,48 @@ def test_stereo_frame_backproject_returns_metric_world_point():
     z = np.array([[uL, uL - fx * b / pc[2], fy * pc[1] / pc[2] + cy]])
     f = StereoFrame(0.0, None, None, z, np.array([1], np.int8), R, t)
     assert np.allclose(f.backproject(0, fx, fy, cx, cy, b), world, atol=1e-4)
+
+
+def test_converter_accepts_the_checkpoint_file_spelling(tmp_path):
+    """tools/convert_lightglue_weights.py on a checkpoint laid out like cvg's superpoint_lightglue.pth - file spelling
+    `self_attn.{i}.*` / `cross_attn.{i}.*` (the package renames them to `transformers.{i}.*` when loading), nine
+    log_assignment heads, token_confidence heads and the confidence_thresholds buffer of the early-exit machinery the
+    exporter switches off (utils/convert_lightglue_to_onnx.py:69-76) - must give the archive the in-memory names give."""
+    import re
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    from conftest import ROOT
+    from superslam_b200.lightglue_weights import make_random_weights, save_state_dict
+    from superslam_b200.weights_io import load_archive
+
+    sd = make_random_weights(3)
+    g = torch.Generator().manual_seed(0)
+    ckpt = {}
+    for k, v in sd.items():
+        m = re.match(r"^transformers\.(\d+)\.(self_attn|cross_attn)\.(.*)$", k)
+        ckpt[f"{m.group(2)}.{m.group(1)}.{m.group(3)}" if m else k] = v
+    for i in range(8):                                           # heads of the layers the export does not use
+        ckpt[f"log_assignment.{i}.matchability.weight"] = torch.randn(1, 256, generator=g)
+        ckpt[f"log_assignment.{i}.matchability.bias"] = torch.randn(1, generator=g)
+        ckpt[f"log_assignment.{i}.final_proj.weight"] = torch.randn(256, 256, generator=g)
+        ckpt[f"log_assignment.{i}.final_proj.bias"] = torch.randn(256, generator=g)
+        ckpt[f"token_confidence.{i}.token.0.weight"] = torch.randn(1, 256, generator=g)
+        ckpt[f"token_confidence.{i}.token.0.bias"] = torch.randn(1, generator=g)
+    assert not any(k.startswith("transformers.") for k in ckpt)
+    want = tmp_path / "want.ssbw"
+    save_state_dict(sd, str(want))
+    for name, obj in [("plain", ckpt), ("prefixed", {"state_dict": {"matcher." + k: v for k, v in ckpt.items()}})]:
+        src, dst = tmp_path / f"{name}.pth", tmp_path / f"{name}.ssbw"
+        torch.save(obj, src)
+        res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_lightglue_weights.py"), str(src), str(dst)],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-2000:]
+        a, b = load_archive(str(want)), load_archive(str(dst))
+        assert list(a.keys()) == list(b.keys())
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+        assert not any(k.startswith("token_confidence") for k in b)
+        assert sum(k.startswith("log_assignment.") for k in b) == 4            # only the last layer's head travels
