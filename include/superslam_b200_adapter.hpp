@@ -64,8 +64,10 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
   }
   std::pair<superslam::Features, superslam::Features> extract_stereo(const cv::Mat& left,
                                                                     const cv::Mat& right) override {
-    if (left.rows != right.rows || left.cols != right.cols || left.channels() != right.channels())
+    if (left.rows != right.rows || left.cols != right.cols)
       return {};  // "stereo pair must share resolution" (src/SuperPoint.cc:761-764)
+    if (left.channels() != right.channels())   // the reference grays each side on its own (:768-773): two single passes
+      return {extract(left), extract(right)};
     std::vector<superslam::Features> f = run({&left, &right});
     if (f.size() != 2) return {};
     return {std::move(f[0]), std::move(f[1])};
@@ -78,16 +80,23 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
     const int b = static_cast<int>(imgs.size());
     const int h = imgs[0]->rows, w = imgs[0]->cols, ch = imgs[0]->channels();
     std::vector<const uint8_t*> ptr(b);
+    std::vector<cv::Mat> packed;   // the C-ABI takes one row stride per call: images whose steps differ are packed first
+    size_t step = imgs[0]->step[0];
+    for (int i = 1; i < b; ++i)
+      if (imgs[i]->step[0] != step) packed.resize(b);
     for (int i = 0; i < b; ++i) {
-      if (imgs[i]->step[0] != imgs[0]->step[0]) return out;
-      ptr[i] = imgs[i]->data;
+      if (!packed.empty()) {
+        packed[i] = imgs[i]->clone();
+        step = packed[i].step[0];
+      }
+      ptr[i] = packed.empty() ? imgs[i]->data : packed[i].data;
     }
     std::vector<std::vector<float>> xy(b, std::vector<float>(2 * max_kp_)), sc(b, std::vector<float>(max_kp_));
     std::vector<float*> xyp(b), scp(b);
     for (int i = 0; i < b; ++i) xyp[i] = xy[i].data(), scp[i] = sc[i].data();
     std::vector<int> count(b, 0), slot(b, -1);
     std::vector<void*> desc(b, nullptr);
-    const int st = ssb_sp_extract(sp_, ptr.data(), b, h, w, static_cast<int>(imgs[0]->step[0]), ch, xyp.data(),
+    const int st = ssb_sp_extract(sp_, ptr.data(), b, h, w, static_cast<int>(step), ch, xyp.data(),
                                   scp.data(), count.data(), desc.data(), slot.data());
     if (st != SSB_OK && st != SSB_ERR_EXHAUSTED) return out;
     out.resize(b);

@@ -71,12 +71,13 @@ void dropin_destroy(void* handle) { delete static_cast<Harness*>(handle); }
 // 3).  Outputs sized `cap`: keypoints_left (x, y), response, stereo (uL, uR, v), has_depth; desc = {count, dim, slot,
 // data != nullptr}.  Returns the number of left keypoints.
 int dropin_process(void* handle, const uint8_t* left, const uint8_t* right, int height, int width, int row_stride,
-                   int channels, double timestamp, int cap, float* xy, float* response, float* size_angle,
+                   int row_stride_right, int channels, double timestamp, int cap, float* xy, float* response, float* size_angle,
                    double* stereo, char* has_depth, int* desc) {
   Harness* h = static_cast<Harness*>(handle);
-  const int type = CV_MAKETYPE(CV_8U, channels);
-  const cv::Mat l(height, width, type, const_cast<uint8_t*>(left), row_stride);
-  const cv::Mat r(height, width, type, const_cast<uint8_t*>(right), row_stride);
+  // channels: low 4 bits = left (and right); bits 4.. = right's channel count when it differs
+  const int ch_l = channels & 15, ch_r = (channels >> 4) ? (channels >> 4) : ch_l;
+  const cv::Mat l(height, width, CV_MAKETYPE(CV_8U, ch_l), const_cast<uint8_t*>(left), row_stride);
+  const cv::Mat r(height, width, CV_MAKETYPE(CV_8U, ch_r), const_cast<uint8_t*>(right), row_stride_right);
   h->frame = h->fe->process(l, r, timestamp);
   const superslam::StereoFrame& f = h->frame;
   const int n = static_cast<int>(f.keypoints_left.size());

@@ -30,7 +30,7 @@ def bind(path):
     lib.dropin_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float, ip]
     lib.dropin_destroy.argtypes = [C.c_void_p]
     lib.dropin_process.restype = C.c_int
-    lib.dropin_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+    lib.dropin_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                    C.c_int, fp, fp, fp, dp, C.c_char_p, ip]
     lib.dropin_promote_keyframe.restype = C.c_int
     lib.dropin_promote_keyframe.argtypes = [C.c_void_p, fp, C.c_int]
@@ -62,13 +62,14 @@ class Harness:
 
     def process(self, left, right, ts=0.0):
         left, right = np.asarray(left), np.asarray(right)
-        assert left.dtype == np.uint8 and left.strides == right.strides
+        assert left.dtype == np.uint8 and left.shape[:2] == right.shape[:2]
         ch = 1 if left.ndim == 2 else left.shape[2]
+        ch_r = 1 if right.ndim == 2 else right.shape[2]
         cap = self.cap
         xy, resp, sa = np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32), np.zeros((cap, 2), np.float32)
         stereo, has, desc = np.zeros((cap, 3), np.float64), np.zeros(cap, np.int8), np.zeros(4, np.int32)
         n = self.lib.dropin_process(self.h, left.ctypes.data, right.ctypes.data, left.shape[0], left.shape[1], left.strides[0],
-                                    ch, ts, cap, xy.ctypes.data_as(fp), resp.ctypes.data_as(fp), sa.ctypes.data_as(fp),
+                                    right.strides[0], ch + 16 * (ch_r if ch_r != ch else 0), ts, cap, xy.ctypes.data_as(fp), resp.ctypes.data_as(fp), sa.ctypes.data_as(fp),
                                     stereo.ctypes.data_as(dp), has.ctypes.data_as(C.c_char_p), desc.ctypes.data_as(ip))
         return dict(n=n, xy=xy[:n], response=resp[:n], size_angle=sa[:n], stereo=stereo[:n], has_depth=has[:n],
                     desc=dict(count=int(desc[0]), dim=int(desc[1]), slot=int(desc[2]), resident=bool(desc[3])))
@@ -172,6 +173,25 @@ def test_reference_stereo_frontend_over_the_adapter(fake, pad, channels):
     assert fake.fake_slots_in_use() == 0
     hs.close()
     assert fake.fake_lg_alive() == 0
+
+
+def test_left_and_right_images_with_different_row_strides(fake):
+    """cv::Mat steps may differ between the two images (an ROI on one side): the C-ABI takes one stride per call, so
+    the adapter packs them first - same features as with equal strides."""
+    hs = Harness(fake, "sp.ssbw", "lg.ssbw", 640, 480)
+    a = hs.process(image(20, 60, 10, 3, pad=0), image(20, 40, 9, 5, pad=0))
+    b = hs.process(image(20, 60, 10, 3, pad=16), image(20, 40, 9, 5, pad=40))
+    assert b["n"] == 80 and np.array_equal(a["xy"], b["xy"]) and np.array_equal(a["stereo"], b["stereo"], equal_nan=True)
+    assert np.array_equal(a["has_depth"], b["has_depth"]) and a["has_depth"].sum() > 0
+    hs.close()
+
+
+def test_bgr_left_and_gray_right(fake):
+    """The reference converts each side to gray on its own (src/SuperPoint.cc:768-773), so a colour / gray pair is legal."""
+    hs = Harness(fake, "sp.ssbw", "lg.ssbw", 640, 480)
+    out = hs.process(image(20, 60, 10, 3, channels=3), image(20, 40, 9, 5))
+    assert out["n"] == 80 and out["has_depth"].sum() > 0 and fake.fake_slots_in_use() == 1
+    hs.close()
 
 
 def test_tracking_match_keyframe_record_and_loop_verification(fake):
