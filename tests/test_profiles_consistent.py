@@ -34,3 +34,21 @@ def test_bench_lines_are_valid_json_with_the_contract_keys():
         r = d["roofline"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
         assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+
+
+def test_reference_arm_prints_one_contract_line_on_the_cpu():
+    """`bench.py --impl reference` needs no GPU: one JSON line on stdout, the product arm's metric / unit / workload,
+    the arm's own cpu_baseline and a zero-copy e2e object."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "pairs/s"
+    assert d["config"]["workload"] == bench.WORKLOAD and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
