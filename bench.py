@@ -413,6 +413,20 @@ def main():
         gathered = [torch.zeros_like(matches) for _ in range(world)]
         dist.all_gather(gathered, matches)
 
+    # ... and the result gather proper: this rank's pairs of the last step as fixed-size padded records
+    # (pair s of rank r is pair r + world * s of the round-robin stream), one all_gather over NCCL, unpacked on every rank
+    try:
+        from superslam_b200 import sharding
+
+        rec = sharding.pack_records([rank + world * s for s in range(P)], out["count"].tolist(), out["matches0"],
+                                    out["mscores0"], out["has_depth"], K, P)
+        allrec = sharding.gather_records(rec, dist, device=f"cuda:{local}") if dist is not None else rec[None]
+        got = sharding.unpack_records(allrec, K)
+        records = {"pairs_gathered": len(got), "record_bytes_per_rank": int(rec.nbytes),
+                   "matches_in_records": int(sum(int((r["matches0"][:r["n_left"]] >= 0).sum()) for r in got.values()))}
+    except Exception as e:  # never at the cost of the headline line
+        records = {"error": str(e)}
+
     if rank == 0:
         # roofline of the dominant tensor-core kernel
         peaks = {}
@@ -514,7 +528,8 @@ def main():
             "latency_single_pair": latency,
             "eigenplaces": eigen,
             "wall_s_timed_region": wall,
-            "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered]},
+            "results": {"per_rank_[matches,has_depth,keypoints]": [g.tolist() for g in gathered],
+                        "gathered_records": records},
         }
         emit(line)
     if dist is not None:
