@@ -176,3 +176,39 @@ def match(w, kpts0, desc0, kpts1, desc1, return_intermediates=False):
         inter["scores"] = scores.numpy()
         return m0.numpy(), ms0.numpy(), inter
     return m0.numpy(), ms0.numpy()
+
+
+def disagreement_report(scores: np.ndarray, m0: np.ndarray, ms0: np.ndarray, other_m0: np.ndarray,
+                        other_ms0: np.ndarray | None = None, th: float = FILTER_THRESHOLD):
+    """Classify every index where another implementation's matches0 (`other_m0`, e.g. the fp16 tensor-core path)
+    differs from the oracle's (`m0`, from `scores` = the oracle's log-assignment matrix [N, M]).
+
+    An index work path that is exact on ITS OWN scores can still disagree with the fp32 oracle where the oracle's decision
+    hangs on a near-tie.  For each disagreeing query i (r = the oracle's row arg-max) the report gives the margins of the
+    three decisions filter_matches takes (lightglue.py filter_matches; restated above):
+      row_gap   S[i, r] - S[i, j']  when the other side matched another column j', else S[i, r] - second best of row i
+      col_gap   | S[i, r] - best of column r over the other rows |        (mutual check m1[m0[i]] == i)
+      thr_gap   | exp(S[i, r]) - th |                                      (mscores0 > th)
+    and `margin` = the smallest margin that can explain the disagreement.  A disagreement is a legitimate flip when
+    its margin is within the other path's score error; a large margin is a defect.
+    Returns dict(n, disagree, rows=[dict(i, oracle, other, kind, row_gap, col_gap, thr_gap, margin)], max_margin)."""
+    S = np.asarray(scores, np.float64)
+    n, m = S.shape
+    rows = []
+    for i in np.nonzero(np.asarray(m0) != np.asarray(other_m0))[0].tolist():
+        r = int(np.argmax(S[i]))
+        top = S[i, r]
+        second = np.partition(S[i], -2)[-2] if m > 1 else -np.inf
+        col = np.delete(S[:, r], i)
+        col_gap = abs(top - col.max()) if col.size else np.inf
+        thr_gap = abs(np.exp(top) - th)
+        j = int(other_m0[i])
+        if j >= 0 and j != r:
+            kind, row_gap = "row", top - S[i, j]
+            margin = row_gap                       # the other side preferred j: only a row near-tie explains it
+        else:
+            kind, row_gap = ("validity", top - second)
+            margin = min(row_gap, col_gap, thr_gap)
+        rows.append(dict(i=i, oracle=int(m0[i]), other=j, kind=kind, row_gap=float(row_gap), col_gap=float(col_gap),
+                         thr_gap=float(thr_gap), margin=float(margin)))
+    return dict(n=n, disagree=len(rows), rows=rows, max_margin=max((r["margin"] for r in rows), default=0.0))

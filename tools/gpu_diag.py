@@ -131,6 +131,16 @@ def main():
     print(f"lg matches0 equal {np.array_equal(m.matches0, om0)} ({(m.matches0 != om0).sum()} differ of {n0}); "
           f"mscores maxabs {np.abs(m.mscores0 - oms0).max() if n0 else 0}; oracle matches {(om0 >= 0).sum()}")
     print("sim sample", sim[:2, :4], "oracle scores sample", inter["scores"][:2, :4])
+    # every disagreement with the fp32 oracle, with the margin of the oracle's decision (a legitimate fp16 flip has a
+    # margin within the score error; see oracle/lightglue.py::disagreement_report)
+    rep = olg.disagreement_report(inter["scores"], om0, oms0, m.matches0, m.mscores0)
+    both = (m.matches0 == om0) & (om0 >= 0)
+    err = float(np.abs(np.log(np.maximum(m.mscores0[both], 1e-30)) - np.log(np.maximum(oms0[both], 1e-30))).max()) if both.any() else 0.0
+    print(f"lg disagreements {rep['disagree']} of {rep['n']}; largest margin {rep['max_margin']:.4g} "
+          f"(log-score error on the agreeing matches {err:.4g})")
+    for r in rep["rows"]:
+        print(f"   i {r['i']:4d} oracle {r['oracle']:4d} gpu {r['other']:4d} {r['kind']:8s} row_gap {r['row_gap']:.4g} "
+              f"col_gap {r['col_gap']:.4g} thr_gap {r['thr_gap']:.4g}")
 
 
 if __name__ == "__main__":
