@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from conftest import ROOT, SP_WEIGHTS
@@ -75,3 +76,45 @@ def test_header_is_plain_c():
     res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", HEADER],
                          capture_output=True, text=True)
     assert res.returncode == 0 and res.stderr.strip() == "", res.stderr
+
+
+def test_committed_superpoint_archive_is_the_converted_reference_checkpoint(tmp_path):
+    """Provenance of superslam_b200/weights/superpoint_v1.ssbw: tools/convert_superpoint_weights.py on the reference's
+    own weights/superpoint_v1.pth gives the committed file, byte for byte."""
+    import subprocess
+    import sys
+
+    src = "/root/reference/weights/superpoint_v1.pth"
+    if not os.path.exists(src):
+        pytest.skip("reference checkpoint not on this machine")
+    dst = tmp_path / "sp.ssbw"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_superpoint_weights.py"), src, str(dst)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert open(dst, "rb").read() == open(SP_WEIGHTS, "rb").read()
+
+
+def test_eigenplaces_converter_keeps_names_and_drops_bn_counters(tmp_path):
+    import subprocess
+    import sys
+
+    import torch
+
+    from superslam_b200.eigenplaces_weights import make_random_weights, save_state_dict
+    from superslam_b200.weights_io import load_archive
+
+    sd = make_random_weights(5)
+    ckpt = {}
+    for k, v in sd.items():                       # as torch saves it: DataParallel prefix, BN step counters
+        ckpt["module." + k] = v
+        if k.endswith("running_var"):
+            ckpt["module." + k.replace("running_var", "num_batches_tracked")] = torch.tensor(1234)
+    want, src, dst = tmp_path / "want.ssbw", tmp_path / "ep.pth", tmp_path / "ep.ssbw"
+    save_state_dict(sd, str(want))
+    torch.save(ckpt, src)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_eigenplaces_weights.py"), str(src), str(dst)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    a, b = load_archive(str(want)), load_archive(str(dst))
+    assert list(a) == list(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    assert not any("num_batches_tracked" in k for k in b) and b["aggregation.1.p"].shape == (1,)
