@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stage-by-stage parity report of the CUDA path against the oracle (run on the GPU box):
-    python tools/gpu_diag.py [--size HxW] > gpurun_out/diag.txt
+    python tests/gpu_diag.py [--size HxW] > gpurun_out/diag.txt
 Prints one line per stage; never asserts, so one GPU call localises every defect."""
 import argparse
 import json

@@ -51,6 +51,26 @@ def test_product_package_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
 
 
+def test_only_the_allowed_places_touch_the_oracle():
+    """oracle/ is test infrastructure: outside tests/ and oracle/ itself only bench.py (its CPU legs) and
+    __graft_entry__.py (smoke) may import it; include/ and tools/ never mention it in code."""
+    users = set()
+    for dirpath, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "gpurun_out", "build", "__pycache__", "tests", "oracle", "baseline")]
+        for f in files:
+            if f.endswith((".py", ".sh")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    users.add(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert users == {"bench.py", "__graft_entry__.py"}, users
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # bench.py: every oracle import sits inside oracle_pair_seconds (the cpu_baseline / --impl reference legs)
+    body = bench[bench.index("def oracle_pair_seconds"):bench.index("def ", bench.index("def oracle_pair_seconds") + 10)]
+    assert bench.count("from oracle") == body.count("from oracle") > 0
+    for header in os.listdir(os.path.join(ROOT, "include")):
+        assert "oracle/" not in re.sub(r"//.*|/\*.*?\*/", "", open(os.path.join(ROOT, "include", header)).read(), flags=re.S)
+
+
 def test_weight_archive_roundtrip(tmp_path):
     import numpy as np
 

@@ -9,7 +9,7 @@ tag=${1:-r02}
 mkdir -p gpurun_out
 echo "== 1. pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee gpurun_out/pytest_$tag.log
 echo "== 2. smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-echo "== 3. diag"; timeout 600 python tools/gpu_diag.py --size 480x640 --k 1024 > gpurun_out/diag_c2_$tag.txt 2>&1; tail -40 gpurun_out/diag_c2_$tag.txt
+echo "== 3. diag"; timeout 600 python tests/gpu_diag.py --size 480x640 --k 1024 > gpurun_out/diag_c2_$tag.txt 2>&1; tail -40 gpurun_out/diag_c2_$tag.txt
 echo "== 4. bench"; timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python - "$tag" <<'PY'
 import json, sys
