@@ -224,7 +224,8 @@ class EigenPlacesB200 : public superslam::IPlaceRecognizer {
     return desc;
   }
   void add(size_t keyframe_id, const cv::Mat& global_descriptor) override {
-    cv::Mat row = global_descriptor.reshape(1, 1);
+    if (global_descriptor.empty()) return;   // a failed compute_global_descriptor: nothing to index
+    cv::Mat row = (global_descriptor.isContinuous() ? global_descriptor : global_descriptor.clone()).reshape(1, 1);
     if (row.type() != CV_32F) row.convertTo(row, CV_32F);
     if (!row.isContinuous()) row = row.clone();
     ssb_ep_add(ep_, keyframe_id, row.ptr<float>(), row.cols);
@@ -232,7 +233,8 @@ class EigenPlacesB200 : public superslam::IPlaceRecognizer {
   std::vector<superslam::LoopCandidate> query(const cv::Mat& global_descriptor, size_t excludeRecent,
                                               int topK) override {
     std::vector<superslam::LoopCandidate> out;
-    cv::Mat row = global_descriptor.reshape(1, 1);
+    if (global_descriptor.empty()) return out;
+    cv::Mat row = (global_descriptor.isContinuous() ? global_descriptor : global_descriptor.clone()).reshape(1, 1);
     if (row.type() != CV_32F) row.convertTo(row, CV_32F);
     if (!row.isContinuous()) row = row.clone();
     const int cap = topK > 0 ? topK : ssb_ep_index_size(ep_);
@@ -310,8 +312,11 @@ class RgbdPostB200 {
       zero = cv::Mat::zeros(depth.size(), CV_16U);
       dm = &zero;
     }
-    cv::Mat d64;
-    dist_coeffs.reshape(1, 1).convertTo(d64, CV_64F);
+    cv::Mat d64;   // (cv::Mat::reshape throws on an empty matrix: no distortion model -> no coefficients)
+    if (!dist_coeffs.empty()) {
+      const cv::Mat dc = dist_coeffs.isContinuous() ? dist_coeffs : dist_coeffs.clone();
+      dc.reshape(1, 1).convertTo(d64, CV_64F);
+    }
     const double cam[4] = {fx, fy, cx, cy};
     return ssb_rgbd_process(r_, reinterpret_cast<const float*>(raw.data()), n, dm->data, type < 0 ? 0 : type, dm->rows,
                             dm->cols, static_cast<int>(dm->step[0]), cam, d64.empty() ? nullptr : d64.ptr<double>(),

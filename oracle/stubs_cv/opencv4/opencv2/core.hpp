@@ -6,6 +6,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -103,6 +105,12 @@ class Mat {
   // same data, new channel count / row count (continuous matrices only, like cv::Mat::reshape without a copy)
   Mat reshape(int cn, int new_rows = 0) const {
     Mat m = *this;
+    // OpenCV throws here (empty matrix: "Bad new number of rows"; non-continuous: "The matrix is not continuous, thus
+    // its number of rows can not be changed"); code under test must not get that far, so the stand-in stops the process
+    if ((empty() || !isContinuous()) && new_rows != 0 && new_rows != rows) {
+      std::fprintf(stderr, "cv::Mat::reshape stand-in: OpenCV would throw (empty or non-continuous matrix)\n");
+      std::abort();
+    }
     if (empty()) return m;
     const size_t scalars = total() * static_cast<size_t>(channels());
     if (cn == 0) cn = channels();

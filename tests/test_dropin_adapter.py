@@ -361,6 +361,37 @@ def test_remap_adapter_creates_the_destination_and_passes_the_stride(fake):
                              dst.ctypes.data) == 0
 
 
+def test_rgbd_post_without_a_distortion_model_and_place_recognizer_with_empty_descriptors(fake):
+    """Empty cv::Mat arguments: cv::Mat::reshape throws on them in OpenCV (the stand-in aborts), so the adapter must
+    not reshape an empty dist_coeffs (RgbdFrontEnd allows none, src/RgbdFrontEnd.cc:30) or an empty descriptor."""
+    fake.dropin_rgbd_post.restype = C.c_int
+    fake.dropin_rgbd_post.argtypes = [fp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int,
+                                      C.c_double, C.c_double, C.c_double, fp, dp, C.c_char_p]
+    fake.fake_last_rgbd.argtypes = [dp]
+    xy = np.float32([[3, 4], [5.25, 6.5]])
+    depth = np.full((10, 12), 2000, np.uint16)
+    cam = np.array([500.0, 500.0, 6.0, 5.0])
+    oxy, ost, ohas = np.zeros((2, 2), np.float32), np.zeros((2, 3)), np.zeros(2, np.int8)
+    assert fake.dropin_rgbd_post(xy.ctypes.data_as(fp), 2, depth.ctypes.data, 0, 10, 12, 24, cam.ctypes.data_as(dp), None, 0, 0,
+                                 40.0, 5000.0, 8.0, oxy.ctypes.data_as(fp), ost.ctypes.data_as(dp),
+                                 ohas.ctypes.data_as(C.c_char_p)) == 1
+    g = np.zeros(28)
+    fake.fake_last_rgbd(g.ctypes.data_as(dp))
+    assert g[9] == 0 and g[13] == 0 and np.all(g[14:28] == -1) and ohas.tolist() == [1, 1]     # n_dist 0, dist NULL
+    fake.dropin_place_create.restype = C.c_void_p
+    fake.dropin_place_create.argtypes = [C.c_char_p, C.c_int, C.c_int, ip]
+    fake.dropin_place_add.argtypes = [C.c_void_p, C.c_size_t, fp, C.c_int, C.c_int]
+    fake.dropin_place_query.restype = C.c_int
+    fake.dropin_place_query.argtypes = [C.c_void_p, fp, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), fp]
+    ok = C.c_int()
+    ep = fake.dropin_place_create(b"ep.ssbw", 512, 512, C.byref(ok))
+    ids, sc = (C.c_size_t * 4)(), np.zeros(4, np.float32)
+    fake.dropin_place_add(ep, 7, None, 0, 0)                                # add(id, cv::Mat()) - ignored
+    assert fake.dropin_place_query(ep, None, 0, 0, 3, ids, sc.ctypes.data_as(fp)) == 0
+    fake.dropin_place_destroy.argtypes = [C.c_void_p]
+    fake.dropin_place_destroy(ep)
+
+
 @pytest.mark.parametrize("depth_type,dist_f32", [(0, 0), (1, 1), (2, 0)])
 def test_rgbd_post_adapter_marshalling(fake, depth_type, dist_f32):
     fake.dropin_rgbd_post.restype = C.c_int
