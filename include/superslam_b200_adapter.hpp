@@ -308,8 +308,8 @@ class RgbdPostB200 {
     const int type = depth.type() == CV_16U ? 0 : (depth.type() == CV_32F ? 1 : -1);
     cv::Mat zero;
     const cv::Mat* dm = &depth;
-    if (type < 0) {   // sampleDepth returns 0 for any other type (src/RgbdFrontEnd.cc:12-20)
-      zero = cv::Mat::zeros(depth.size(), CV_16U);
+    if (type < 0 || depth.empty()) {   // sampleDepth returns 0 for any other type and outside the map
+      zero = cv::Mat::zeros(depth.empty() ? cv::Size(1, 1) : depth.size(), CV_16U);   // (src/RgbdFrontEnd.cc:12-20)
       dm = &zero;
     }
     cv::Mat d64;   // (cv::Mat::reshape throws on an empty matrix: no distortion model -> no coefficients)
@@ -318,7 +318,7 @@ class RgbdPostB200 {
       dc.reshape(1, 1).convertTo(d64, CV_64F);
     }
     const double cam[4] = {fx, fy, cx, cy};
-    return ssb_rgbd_process(r_, reinterpret_cast<const float*>(raw.data()), n, dm->data, type < 0 ? 0 : type, dm->rows,
+    return ssb_rgbd_process(r_, reinterpret_cast<const float*>(raw.data()), n, dm->data, dm == &zero ? 0 : type, dm->rows,
                             dm->cols, static_cast<int>(dm->step[0]), cam, d64.empty() ? nullptr : d64.ptr<double>(),
                             d64.empty() ? 0 : d64.cols, bf, depth_factor, max_depth,
                             reinterpret_cast<float*>(undist.data()), stereo.data(),

@@ -378,6 +378,12 @@ def test_rgbd_post_without_a_distortion_model_and_place_recognizer_with_empty_de
     g = np.zeros(28)
     fake.fake_last_rgbd(g.ctypes.data_as(dp))
     assert g[9] == 0 and g[13] == 0 and np.all(g[14:28] == -1) and ohas.tolist() == [1, 1]     # n_dist 0, dist NULL
+    # no depth image at all: every sample is 0 (sampleDepth's bounds check) - a 1 x 1 zero map says the same
+    assert fake.dropin_rgbd_post(xy.ctypes.data_as(fp), 2, None, 1, 0, 0, 0, cam.ctypes.data_as(dp), None, 0, 0,
+                                 40.0, 5000.0, 8.0, oxy.ctypes.data_as(fp), ost.ctypes.data_as(dp),
+                                 ohas.ctypes.data_as(C.c_char_p)) == 1
+    fake.fake_last_rgbd(g.ctypes.data_as(dp))
+    assert list(g[1:5]) == [0, 1, 1, 2] and ohas.tolist() == [0, 0]
     fake.dropin_place_create.restype = C.c_void_p
     fake.dropin_place_create.argtypes = [C.c_char_p, C.c_int, C.c_int, ip]
     fake.dropin_place_add.argtypes = [C.c_void_p, C.c_size_t, fp, C.c_int, C.c_int]
