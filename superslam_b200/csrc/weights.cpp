@@ -68,12 +68,14 @@ int load_archive(const char* path, WeightArchive* out) {
       SSB_CHECK(rd32(p, &v), SSB_ERR_IO, "'%s': truncated dims", path);
       p += 4;
       t.dims.push_back(static_cast<int>(v));
+      SSB_CHECK(v == 0 || numel <= buf.size() / v, SSB_ERR_IO, "'%s': tensor '%s' is larger than the file", path,
+                name.c_str());   // also keeps the product from wrapping around
       numel *= v;
     }
     uint64_t off = 0, size = 0;
     SSB_CHECK(rd64(p, &off) && rd64(p + 8, &size), SSB_ERR_IO, "'%s': truncated entry", path);
     p += 16;
-    SSB_CHECK(dtype == 0 && size == numel * 4 && off + size <= buf.size(), SSB_ERR_IO,
+    SSB_CHECK(dtype == 0 && size == numel * 4 && off <= buf.size() && size <= buf.size() - off, SSB_ERR_IO,
               "'%s': tensor '%s' has bad extent", path, name.c_str());
     t.data.resize(numel);
     std::memcpy(t.data.data(), buf.data() + off, size);
