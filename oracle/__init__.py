@@ -37,7 +37,9 @@ Pinning status:
     HuggingFace port shipped in this image (transformers 5.5, models/lightglue) with shared weights.
   * EigenPlaces (oracle/eigenplaces.py) — preprocess PINNED bit-exactly against cv2.resize, ResNet18 trunk
     PINNED against torchvision with shared weights, CosineDescriptorIndex / TemporalConsistencyVoter PINNED
-    by the reference's tests/test_place_recognizer.cc (re-expressed); the trained network weights come from
+    by the reference's own code (src/PlaceRecognizer.cc compiled in place into oracle/_ref/libref_place.so,
+    tests/test_oracle_ref_place.py: control flow exact, scores to 1e-6) and by its tests/test_place_recognizer.cc
+    (re-expressed); the trained network weights come from
     an un-pinned torch.hub entry and are absent offline: network VALUES are PARITY UNPINNED.
   * image front door (oracle/imgproc.py) - PINNED bit-for-bit against OpenCV: cv2.remap (fixed-point bilinear,
     constant border) and cv2.undistortPoints, live (tests/test_oracle_imgproc.py) and through committed cv2

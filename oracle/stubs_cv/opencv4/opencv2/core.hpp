@@ -4,6 +4,7 @@
 // tests/stubs/ (OpenCV 4.x core/mat.hpp, core/types.hpp), here with bodies: cv::Mat is a ref-counted 2-D array whose
 // copies share the buffer, as in OpenCV.  TEST INFRASTRUCTURE - this image ships no OpenCV C++ headers.
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -122,6 +123,31 @@ class Mat {
     m.data = d;
     return m;
   }
+  // rows [start, end) of the same buffer
+  Mat rowRange(int start, int end) const {
+    Mat m = *this;
+    m.rows = end - start;
+    m.data = data + start * step.p[0];
+    return m;
+  }
+  // appends the rows of `m` (same type and width); like OpenCV the buffer is reallocated, older headers keep the old one
+  void push_back(const Mat& m) {
+    if (m.empty()) return;
+    if (empty()) {
+      *this = m.clone();
+      return;
+    }
+    Mat grown(rows + m.rows, cols, type());
+    for (int y = 0; y < rows; ++y) std::memcpy(grown.ptr<uchar>(y), ptr<uchar>(y), cols * elemSize());
+    for (int y = 0; y < m.rows; ++y) std::memcpy(grown.ptr<uchar>(rows + y), m.ptr<uchar>(y), cols * elemSize());
+    *this = grown;
+  }
+  Mat t() const {   // CV_32F only (what src/PlaceRecognizer.cc transposes)
+    Mat r(cols, rows, type());
+    for (int y = 0; y < rows; ++y)
+      for (int x = 0; x < cols; ++x) r.at<float>(x, y) = at<float>(y, x);
+    return r;
+  }
   Mat row(int y) const {
     Mat m = *this;
     m.rows = 1;
@@ -184,4 +210,30 @@ class Mat {
   std::shared_ptr<uchar> buf_;
 };
 
+// ---- the three arithmetic calls of src/PlaceRecognizer.cc, CV_32F only.  The arithmetic is the stand-in's (double
+// accumulation, one rounding to float), not OpenCV's SIMD kernels: results agree with OpenCV to the last few ulps,
+// which is why tests that use them compare scores with a tolerance and only the control flow exactly.
+inline double norm(const Mat& m) {
+  double s = 0;
+  for (int y = 0; y < m.rows; ++y)
+    for (int x = 0; x < m.cols; ++x) s += static_cast<double>(m.at<float>(y, x)) * m.at<float>(y, x);
+  return std::sqrt(s);
+}
+inline Mat operator/(const Mat& a, double s) {   // MatExpr a * (1 / s), evaluated by convertTo with a float scale
+  Mat r(a.rows, a.cols, a.type());
+  const float k = static_cast<float>(1.0 / s);
+  for (int y = 0; y < a.rows; ++y)
+    for (int x = 0; x < a.cols; ++x) r.at<float>(y, x) = a.at<float>(y, x) * k;
+  return r;
+}
+inline Mat operator*(const Mat& a, const Mat& b) {   // gemm
+  Mat r(a.rows, b.cols, a.type());
+  for (int y = 0; y < a.rows; ++y)
+    for (int x = 0; x < b.cols; ++x) {
+      double s = 0;
+      for (int k = 0; k < a.cols; ++k) s += static_cast<double>(a.at<float>(y, k)) * b.at<float>(k, x);
+      r.at<float>(y, x) = static_cast<float>(s);
+    }
+  return r;
+}
 }  // namespace cv
