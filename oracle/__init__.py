@@ -35,7 +35,8 @@ Pinning status:
     package cvg/LightGlue and no weights are available offline.  The restatement follows the
     published model (lightglue/lightglue.py) and is cross-checked against the independent
     HuggingFace port shipped in this image (transformers 5.5, models/lightglue) with shared weights.
-  * EigenPlaces (oracle/eigenplaces.py) — preprocess PINNED bit-exactly against cv2.resize, ResNet18 trunk
+  * EigenPlaces (oracle/eigenplaces.py) — preprocess PINNED bit-exactly against cv2.resize and against the reference's
+    own EigenPlaces::preprocess (src/EigenPlaces.cc compiled in place, cv::resize served by cv2; tests/test_oracle_ref_place.py), ResNet18 trunk
     PINNED against torchvision with shared weights, CosineDescriptorIndex / TemporalConsistencyVoter PINNED
     by the reference's own code (src/PlaceRecognizer.cc compiled in place into oracle/_ref/libref_place.so,
     tests/test_oracle_ref_place.py: control flow exact, scores to 1e-6) and by its tests/test_place_recognizer.cc

@@ -8,6 +8,7 @@
 // what the engine is fed - keypoints normalised as (p - size/2) / (max(w, h)/2) in float, descriptors converted to the
 // binding's type - and LightGlue::postprocess_outputs (:326-363, row a12): matches0 / mscores0 -> cv::DMatch.  The
 // tensors are plain host buffers set up by this shim the way allocate_buffers would name and type them.
+// (3) EigenPlaces::preprocess (src/EigenPlaces.cc:123-143) with cv::resize served by cv2 through a hook.
 // Built by oracle/Makefile into oracle/_ref/libref_nethost.so.  TEST INFRASTRUCTURE.
 //
 // Without a GPU the pool's cudaMalloc fails, DescriptorPool::make hands back a null slot pointer and the function
@@ -19,6 +20,7 @@
 
 #include <cstring>
 
+#include "EigenPlaces.h"
 #include "LightGlue.h"
 #include "SuperPoint.h"
 
@@ -40,11 +42,33 @@ IRuntime* createInferRuntime(ILogger&) { return nullptr; }
 }  // namespace nvinfer1
 namespace cv {
 static void not_on_this_path(const char* what) {
-  std::fprintf(stderr, "oracle/ref_superpoint_shim: %s is not part of the tested path\n", what);
+  std::fprintf(stderr, "oracle/ref_nethost_shim: %s is not part of the tested path\n", what);
   std::abort();
 }
-void cvtColor(const Mat&, Mat&, int) { not_on_this_path("cv::cvtColor"); }
-void resize(const Mat&, Mat&, Size) { not_on_this_path("cv::resize"); }
+// cv::resize is served by the real OpenCV: the test installs a callback into cv2.resize (INTER_LINEAR, the default)
+using ResizeFn = void (*)(const unsigned char* src, int src_h, int src_w, int channels, int src_step, unsigned char* dst,
+                          int dst_h, int dst_w);
+static ResizeFn g_resize = nullptr;
+void resize(const Mat& src, Mat& dst, Size dsize) {
+  if (!g_resize || src.depth() != CV_8U) not_on_this_path("cv::resize without a hook / on non-u8 data");
+  Mat out(dsize.height, dsize.width, src.type());
+  g_resize(src.data, src.rows, src.cols, src.channels(), static_cast<int>(src.step[0]), out.data, out.rows, out.cols);
+  dst = out;
+}
+// the two channel reorderings of EigenPlaces::preprocess are exact copies; BGR2GRAY (SuperPoint's host path) is not served
+void cvtColor(const Mat& src, Mat& dst, int code) {
+  if (src.depth() != CV_8U || (code != COLOR_GRAY2RGB && code != COLOR_BGR2RGB)) not_on_this_path("cv::cvtColor (this code)");
+  Mat out(src.rows, src.cols, CV_8UC3);
+  for (int y = 0; y < src.rows; ++y) {
+    const unsigned char* s = src.ptr<unsigned char>(y);
+    unsigned char* d = out.ptr<unsigned char>(y);
+    for (int x = 0; x < src.cols; ++x) {
+      if (code == COLOR_GRAY2RGB) d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = s[x];
+      else d[3 * x] = s[3 * x + 2], d[3 * x + 1] = s[3 * x + 1], d[3 * x + 2] = s[3 * x];
+    }
+  }
+  dst = out;
+}
 void normalize(const Mat&, Mat&, double, double, int) { not_on_this_path("cv::normalize"); }
 }  // namespace cv
 
@@ -153,5 +177,17 @@ int ref_lg_postprocess(const int* matches0, const void* mscores0, int scores_kin
     query[i] = r.matches[i].queryIdx, train[i] = r.matches[i].trainIdx, distance[i] = r.matches[i].distance;
   }
   return static_cast<int>(r.matches.size());
+}
+
+// ---- EigenPlaces host logic: EigenPlaces::preprocess (src/EigenPlaces.cc:123-143) ---------------------
+// gray / BGR u8 image -> RGB, cv::resize to (input_w, input_h) [served by cv2 through `resize`], convertTo(CV_32F,
+// 1/255), ImageNet normalisation, HWC -> CHW.  out: float [3][input_h][input_w].
+void ref_ep_preprocess(const unsigned char* image, int height, int width, int channels, int row_stride, int input_w,
+                       int input_h, cv::ResizeFn resize, float* out) {
+  cv::g_resize = resize;
+  EigenPlaces ep("none.engine", input_w, input_h);
+  const cv::Mat img(height, width, CV_MAKETYPE(CV_8U, channels), const_cast<unsigned char*>(image), row_stride);
+  ep.preprocess(img, out);
+  cv::g_resize = nullptr;
 }
 }

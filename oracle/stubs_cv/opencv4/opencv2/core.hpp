@@ -158,8 +158,14 @@ class Mat {
     const int ddepth = rtype < 0 ? depth() : (rtype & 7);
     Mat out(rows, cols, CV_MAKETYPE(ddepth, channels()));
     const int n = cols * channels();
+    // OpenCV scales in single precision when the destination is CV_32F or narrower (cvt_32f: src * (float)alpha +
+    // (float)beta, fused), in double precision for CV_64F
+    const float fa = static_cast<float>(alpha), fb = static_cast<float>(beta);
     for (int y = 0; y < rows; ++y)
-      for (int x = 0; x < n; ++x) out.store(y, x, load(y, x) * alpha + beta);
+      for (int x = 0; x < n; ++x) {
+        if (ddepth == CV_64F) out.store(y, x, load(y, x) * alpha + beta);
+        else out.store(y, x, std::fmaf(static_cast<float>(load(y, x)), fa, fb));
+      }
     m = out;
   }
   bool isContinuous() const { return rows <= 1 || step.p[0] == cols * elemSize(); }
@@ -213,6 +219,8 @@ class Mat {
 // ---- the three arithmetic calls of src/PlaceRecognizer.cc, CV_32F only.  The arithmetic is the stand-in's (double
 // accumulation, one rounding to float), not OpenCV's SIMD kernels: results agree with OpenCV to the last few ulps,
 // which is why tests that use them compare scores with a tolerance and only the control flow exactly.
+enum { NORM_L2 = 4 };
+void normalize(const Mat& src, Mat& dst, double alpha, double beta, int norm_type);   // declared only (see the shims)
 inline double norm(const Mat& m) {
   double s = 0;
   for (int y = 0; y < m.rows; ++y)

@@ -1,4 +1,4 @@
-// <opencv2/opencv.hpp> of the functional stand-in: core.hpp plus DECLARATIONS of the three imgproc / core functions
+// <opencv2/opencv.hpp> of the functional stand-in: core.hpp + imgproc.hpp (DECLARATIONS of the imgproc / core functions
 // /root/reference/src/SuperPoint.cc calls on paths that are not exercised here (image preprocessing in front of the
 // TensorRT engine, host-descriptor normalisation); oracle/ref_nethost_shim.cpp defines them to abort.
 // TEST INFRASTRUCTURE.
@@ -8,11 +8,4 @@
 #include <functional>
 
 #include "core.hpp"
-
-namespace cv {
-enum { COLOR_BGR2GRAY = 6 };
-enum { NORM_L2 = 4 };
-void cvtColor(const Mat& src, Mat& dst, int code);
-void resize(const Mat& src, Mat& dst, Size dsize);
-void normalize(const Mat& src, Mat& dst, double alpha, double beta, int norm_type);
-}  // namespace cv
+#include "imgproc.hpp"

@@ -15,7 +15,12 @@ struct Dims {
   int32_t nbDims = 0;
   int64_t d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
-using Dims4 = Dims;
+struct Dims4 : Dims {
+  Dims4(int64_t a, int64_t b, int64_t c, int64_t e) {
+    nbDims = 4;
+    d[0] = a, d[1] = b, d[2] = c, d[3] = e;
+  }
+};
 class ILogger {
  public:
   enum class Severity : int32_t { kINTERNAL_ERROR = 0, kERROR = 1, kWARNING = 2, kINFO = 3, kVERBOSE = 4 };

@@ -85,3 +85,40 @@ def test_voter_against_the_reference_code(lib, required, tol):
         kid = max(0, kid + int(rng.integers(-tol - 2, tol + 3))) if r < 0.9 else int(rng.integers(0, 10000))
         assert lib.ref_voter_vote(h, 1, kid, 0.9) == int(mine.vote((kid, 0.9)))
     lib.ref_voter_delete(h)
+
+
+# ---- EigenPlaces::preprocess (src/EigenPlaces.cc:123-143), the reference's own code, cv::resize served by cv2 --------------
+NETHOST = os.path.join(ROOT, "oracle", "_ref", "libref_nethost.so")
+RESIZE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.c_int)
+
+
+@pytest.mark.skipif(not os.path.exists(NETHOST), reason="oracle/_ref/libref_nethost.so not built")
+@pytest.mark.parametrize("shape,net", [((480, 752), (512, 512)), ((480, 640, 3), (512, 512)), ((480, 640), (640, 480)),
+                                       ((1024, 1024, 3), (512, 512)), ((99, 131, 3), (64, 96)), ((376, 1241), (224, 256))])
+def test_eigenplaces_preprocess_against_the_reference_code(shape, net):
+    """gray / BGR -> RGB, resize (incl. the exact 2x decimation and the identity size), /255, ImageNet normalisation, CHW:
+    oracle/eigenplaces.py::preprocess - what the device preprocess kernel is compared with - equals the reference's
+    function bit for bit."""
+    import cv2
+
+    lib = C.CDLL(NETHOST)
+    lib.ref_ep_preprocess.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, RESIZE_FN, fp]
+    calls = []
+
+    @RESIZE_FN
+    def resize(src, sh, sw, ch, step, dst, dh, dw):
+        a = np.ctypeslib.as_array(src, shape=(sh, step))[:, :sw * ch].reshape(sh, sw, ch)
+        out = cv2.resize(np.ascontiguousarray(a), (dw, dh))                 # INTER_LINEAR, as cv::resize defaults to
+        np.ctypeslib.as_array(dst, shape=(dh, dw * ch))[:] = out.reshape(dh, dw * ch)
+        calls.append((sh, sw, ch, dh, dw))
+
+    rng = np.random.default_rng(sum(shape))
+    ch = 1 if len(shape) == 2 else 3
+    buf = rng.integers(0, 256, (shape[0], shape[1] * ch + 13), dtype=np.uint8)     # padded rows: cv::Mat step
+    img = buf[:, :shape[1] * ch].reshape(shape)
+    in_w, in_h = net
+    got = np.zeros((3, in_h, in_w), np.float32)
+    lib.ref_ep_preprocess(img.ctypes.data, shape[0], shape[1], ch, buf.strides[0], in_w, in_h, resize, got.ctypes.data_as(fp))
+    assert calls == [(shape[0], shape[1], 3, in_h, in_w)]                   # resized once, after the colour conversion
+    exp = oep.preprocess(img, in_w, in_h)
+    assert exp.shape == got.shape and np.array_equal(exp.view(np.uint32), got.view(np.uint32))
