@@ -27,6 +27,12 @@ Pinning status:
     -> cv::DMatch) — PINNED by the reference's own code: src/LightGlue.cc compiled in place into the same library,
     LightGlue::prepare_inputs / normalize_keypoints / postprocess_outputs run on host buffers
     (tests/test_oracle_ref_lightglue_host.py).
+  * the COMPOSITION (image pair -> StereoFrame) — PINNED by the reference's own wrapper code run end to end on the CPU:
+    src/SuperPoint.cc, src/LightGlue.cc, src/DescriptorPool.cc and src/StereoFrontEnd.cc compiled in place, unchanged,
+    over a functional TensorRT stand-in whose enqueueV3 calls back into the test (the two graphs served by this oracle),
+    the CUDA runtime calls on host memory and the gather as a callback (oracle/ref_e2e_shim.cpp ->
+    oracle/_ref/libref_e2e.so).  tests/test_oracle_ref_e2e.py: keypoints, responses, fp16 descriptors, match list,
+    stereo points and depth flags of the reference run == extract + match + dmatches + stereo_postfilter, bit for bit.
   * the C++ adapter above the C-ABI — EXECUTED under the reference's own caller: src/StereoFrontEnd.cc compiled in
     place over include/superslam_b200_adapter.hpp (oracle/dropin_harness.cpp, functional cv::Mat stand-in in
     oracle/stubs_cv/), against a C-ABI test double on the CPU (oracle/fake_capi.cpp, tests/test_dropin_adapter.py)

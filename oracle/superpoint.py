@@ -50,7 +50,10 @@ def dense_forward(images_u8: np.ndarray, w, fp16_storage: bool = False):
     bias+ReLU(+pool)); accumulation, softmax, NMS and the channel norm stay fp32.
     """
     q = _q16 if fp16_storage else (lambda t: t)
-    x = preprocess(images_u8)
+    if isinstance(images_u8, np.ndarray) and images_u8.dtype == np.float32:   # an engine input [B,1,H,W], already / 255
+        x = torch.from_numpy(np.ascontiguousarray(images_u8))
+    else:
+        x = preprocess(images_u8)
     with torch.no_grad():
         for name in ENCODER:
             wt = w[name + ".weight"] if name == "conv1a" else q(w[name + ".weight"])
