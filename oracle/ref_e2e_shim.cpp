@@ -259,4 +259,34 @@ int ref_e2e_process(void* h, const unsigned char* left, const unsigned char* rig
     query[i] = m.matches[i].queryIdx, train[i] = m.matches[i].trainIdx, distance[i] = m.matches[i].distance;
   return nl;
 }
+
+// The mono / loop-closure call shapes: IFeatureExtractor::extract on two images (infer_device: batch-1 dynamic shape),
+// IFeatureMatcher::descriptors_to_host on both results (src/LightGlue.cc:460-475), then the HOST-descriptor match
+// (src/LightGlue.cc:285-324: prepare_inputs converts the CV_32F rows to the fp16 binding).  desc_host_*: cap x 256 floats.
+int ref_e2e_mono_and_host_match(void* h, const unsigned char* img0, const unsigned char* img1, int height, int width,
+                                int row_stride, int cap, int* counts, float* xy0, float* resp0, float* desc_host0, float* xy1,
+                                float* resp1, float* desc_host1, int* query, int* train, float* distance) {
+  E2E* e = static_cast<E2E*>(h);
+  superslam::IFeatureExtractor* ext = e->sp.get();
+  superslam::IFeatureMatcher* mat = e->lg.get();
+  const cv::Mat a(height, width, CV_8UC1, const_cast<unsigned char*>(img0), row_stride);
+  const cv::Mat b(height, width, CV_8UC1, const_cast<unsigned char*>(img1), row_stride);
+  const superslam::Features f0 = ext->extract(a), f1 = ext->extract(b);
+  const cv::Mat d0 = mat->descriptors_to_host(f0.descriptors), d1 = mat->descriptors_to_host(f1.descriptors);
+  const MatchResult m = mat->match(f0.keypoints, d0, f1.keypoints, d1);
+  const int n0 = static_cast<int>(f0.keypoints.size()), n1 = static_cast<int>(f1.keypoints.size());
+  counts[0] = n0, counts[1] = n1, counts[2] = static_cast<int>(m.matches.size());
+  if (n0 > cap || n1 > cap || d0.rows != n0 || d1.rows != n1 || (n0 && (d0.cols != 256 || d0.type() != CV_32F))) return -1;
+  for (int i = 0; i < n0; ++i) {
+    xy0[2 * i] = f0.keypoints[i].pt.x, xy0[2 * i + 1] = f0.keypoints[i].pt.y, resp0[i] = f0.keypoints[i].response;
+    std::memcpy(desc_host0 + 256 * i, d0.ptr<float>(i), 256 * sizeof(float));
+  }
+  for (int i = 0; i < n1; ++i) {
+    xy1[2 * i] = f1.keypoints[i].pt.x, xy1[2 * i + 1] = f1.keypoints[i].pt.y, resp1[i] = f1.keypoints[i].response;
+    std::memcpy(desc_host1 + 256 * i, d1.ptr<float>(i), 256 * sizeof(float));
+  }
+  for (size_t i = 0; i < m.matches.size(); ++i)
+    query[i] = m.matches[i].queryIdx, train[i] = m.matches[i].trainIdx, distance[i] = m.matches[i].distance;
+  return n0;
+}
 }

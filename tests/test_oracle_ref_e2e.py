@@ -138,6 +138,46 @@ def test_reference_wrappers_end_to_end_equal_the_oracle_composition(ref, sp_weig
     assert ref["lib"].ref_e2e_live_allocations() == 0                       # every buffer and pool slot was returned
 
 
+def test_mono_extract_descriptors_to_host_and_host_descriptor_match(ref, sp_weights, lg_weights):
+    """The other call shapes of the interfaces, through the reference's own code: IFeatureExtractor::extract (batch-1
+    dynamic shape, preprocess_image), IFeatureMatcher::descriptors_to_host, and the host-descriptor match of loop closure
+    (CV_32F rows -> fp16 binding in prepare_inputs)."""
+    from superslam_b200.synth import synth_pair
+
+    lib = ref["lib"]
+    lib.ref_e2e_mono_and_host_match.restype = C.c_int
+    lib.ref_e2e_mono_and_host_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, fp,
+                                                fp, fp, fp, fp, ip, ip, fp]
+    a, b = synth_pair(120, 160, 9, 50)
+    b = np.ascontiguousarray(np.roll(a, 3, axis=0))                         # the "same place" seen again, shifted
+    K, h, w = 200, 120, 160
+    st = C.c_int(-1)
+    hnd = lib.ref_e2e_create(str(ref["dir"] / "sp.engine").encode(), str(ref["dir"] / "lg.engine").encode(), K, 0.005, 4, w, h,
+                             1.0, C.byref(st))
+    assert st.value == 3
+    counts = np.zeros(3, np.int32)
+    xy, resp, dh = [np.zeros((K, 2), np.float32) for _ in range(2)], [np.zeros(K, np.float32) for _ in range(2)], \
+        [np.zeros((K, 256), np.float32) for _ in range(2)]
+    q, t, dist = np.zeros(K, np.int32), np.zeros(K, np.int32), np.zeros(K, np.float32)
+    ref["calls"]["sp"].clear(), ref["calls"]["lg"].clear()
+    n = lib.ref_e2e_mono_and_host_match(hnd, a.ctypes.data, b.ctypes.data, h, w, a.strides[0], K, counts.ctypes.data_as(ip),
+                                        xy[0].ctypes.data_as(fp), resp[0].ctypes.data_as(fp), dh[0].ctypes.data_as(fp),
+                                        xy[1].ctypes.data_as(fp), resp[1].ctypes.data_as(fp), dh[1].ctypes.data_as(fp),
+                                        q.ctypes.data_as(ip), t.ctypes.data_as(ip), dist.ctypes.data_as(fp))
+    lib.ref_e2e_destroy(hnd)
+    n0, n1, nm = (int(v) for v in counts)
+    assert n == n0 > 10 and ref["calls"]["sp"] == [(1, h, w), (1, h, w)]    # two batch-1 passes
+    f = [osp.extract(img[None], sp_weights, K)[0] for img in (a, b)]
+    for i, cnt in enumerate((n0, n1)):
+        assert cnt == len(f[i]["xy"]) and np.array_equal(xy[i][:cnt], f[i]["xy"]) and np.array_equal(resp[i][:cnt], f[i]["score"])
+        assert np.array_equal(dh[i][:cnt], f[i]["desc"].astype(np.float32))                # fp16 slot widened to CV_32F
+    m0, ms0 = olg.match(lg_weights, olg.normalize_keypoints(f[0]["xy"], w, h), f[0]["desc"],
+                        olg.normalize_keypoints(f[1]["xy"], w, h), f[1]["desc"])
+    eq, et, ed = ofe.dmatches(m0, ms0)
+    assert nm == len(eq) > 5 and np.array_equal(q[:nm], eq) and np.array_equal(t[:nm], et) and np.array_equal(dist[:nm], ed)
+    assert lib.ref_e2e_live_allocations() == 0
+
+
 def test_a_foreign_engine_file_fails_initialize_like_a_tensorrt_mismatch(ref):
     lib = ref["lib"]
     st = C.c_int(-1)
