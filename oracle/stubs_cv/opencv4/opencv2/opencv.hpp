@@ -1,7 +1,6 @@
-// <opencv2/opencv.hpp> of the functional stand-in: core.hpp + imgproc.hpp (DECLARATIONS of the imgproc / core functions
-// /root/reference/src/SuperPoint.cc calls on paths that are not exercised here (image preprocessing in front of the
-// TensorRT engine, host-descriptor normalisation); oracle/ref_nethost_shim.cpp defines them to abort.
-// TEST INFRASTRUCTURE.
+// <opencv2/opencv.hpp> of the functional stand-in: core.hpp + imgproc.hpp + the std headers the real one drags in.
+// cv::cvtColor / cv::resize / cv::normalize are only DECLARED (imgproc.hpp, core.hpp); each shim that links the reference's
+// wrapper classes defines them - to serve the calls its test exercises, to abort on the others.  TEST INFRASTRUCTURE.
 #pragma once
 #include <algorithm>   // the real opencv2/core pulls these in; src/SuperPoint.cc relies on that for std::sort
 #include <cmath>

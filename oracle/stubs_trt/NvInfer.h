@@ -1,7 +1,8 @@
-// Declaration-level stand-in for the few TensorRT types /root/reference/src/SuperPoint.cc names (TensorRT is not in
-// this image), so that the file can be compiled in place for the ONE member function that does not touch TensorRT:
-// SuperPoint::select_and_gather (:681-750).  Member functions are defined in
-// oracle/ref_nethost_shim.cpp as "no engine" failures; nothing here infers anything.  TEST INFRASTRUCTURE.
+// Declaration-level stand-in for the few TensorRT types /root/reference/src/SuperPoint.cc, LightGlue.cc and EigenPlaces.cc
+// name (TensorRT is not in this image), so that those files can be compiled in place.  The member functions are DEFINED by
+// the shim that links them: oracle/ref_nethost_shim.cpp as "no engine" failures (only host-side member functions of the
+// wrapper classes are called there), oracle/ref_e2e_shim.cpp functionally (two fixed engines whose enqueueV3 calls back
+// into the test, which serves the graphs with the CPU oracle).  Nothing here infers anything.  TEST INFRASTRUCTURE.
 #pragma once
 #include <cuda_runtime.h>
 
