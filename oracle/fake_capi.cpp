@@ -31,6 +31,16 @@ struct ssb_lightglue {
   int width = 0, height = 0;
 };
 
+// Served mode (fake_set_servers): extract / match are answered by callbacks - the test plugs the CPU oracle in - and the
+// slot memory holds real fp16 rows [n][256], so that the adapter classes can be compared with the reference's own
+// SuperPoint / LightGlue classes running over the same networks (tests/test_oracle_ref_e2e.py).
+using ExtractServer = int (*)(const uint8_t* image, int height, int width, int row_stride, int max_keypoints, float* xy,
+                              float* score, unsigned short* desc_f16);   // returns the keypoint count
+using MatchServer = void (*)(const float* xy0, int n0, const unsigned short* d0, const float* xy1, int n1,
+                             const unsigned short* d1, int image_width, int image_height, int32_t* matches0, float* mscores0);
+static ExtractServer g_extract_server = nullptr;
+static MatchServer g_match_server = nullptr;
+
 namespace {
 ssb_superpoint* g_sp = nullptr;
 int g_release_calls = 0, g_sp_destroyed = 0, g_lg_alive = 0;
@@ -83,10 +93,25 @@ void ssb_sp_destroy(ssb_superpoint* sp) {
 int ssb_sp_extract(ssb_superpoint* sp, const uint8_t* const* images, int batch, int height, int width, int row_stride,
                    int channels, float* const* xy, float* const* score, int* count, void** desc_dev, int* slot) {
   if (!sp || batch < 1 || height < 2 || width * channels < 3 || row_stride < width * channels) return SSB_ERR_INVALID;
-  if (images[0][0] == 255) return SSB_ERR_CUDA;
+  if (!g_extract_server && images[0][0] == 255) return SSB_ERR_CUDA;
   int rc = SSB_OK;
   for (int i = 0; i < batch; ++i) {
     const uint8_t* im = images[i];
+    if (g_extract_server) {   // served mode: gray images only; rows land in the slot as fp16
+      if (channels != 1) return SSB_ERR_INVALID;
+      std::vector<unsigned short> rows(static_cast<size_t>(sp->max_kp) * 256);
+      count[i] = g_extract_server(im, height, width, row_stride, sp->max_kp, xy[i], score[i], rows.data());
+      if (sp->free_slots.empty()) {
+        slot[i] = -1, desc_dev[i] = nullptr, rc = SSB_ERR_EXHAUSTED;
+        continue;
+      }
+      const int s = sp->free_slots.back();
+      sp->free_slots.pop_back();
+      sp->refs[s] = 1;
+      std::memcpy(sp->slot_mem[s].data(), rows.data(), sizeof(unsigned short) * 256 * count[i]);
+      slot[i] = s, desc_dev[i] = sp->slot_mem[s].data();
+      continue;
+    }
     int n = 4 * im[0];
     if (n > sp->max_kp) n = sp->max_kp;
     count[i] = n;
@@ -143,6 +168,12 @@ void ssb_lg_destroy(ssb_lightglue* lg) {
 }
 int ssb_lg_match_device(ssb_lightglue* lg, const float* xy0, int n0, const void* desc0_dev, const float* xy1, int n1,
                         const void* desc1_dev, int32_t* matches0, float* mscores0) {
+  if (g_match_server) {
+    if (!lg || !desc0_dev || !desc1_dev) return SSB_ERR_INVALID;
+    g_match_server(xy0, n0, static_cast<const unsigned short*>(desc0_dev), xy1, n1,
+                   static_cast<const unsigned short*>(desc1_dev), lg->width, lg->height, matches0, mscores0);
+    return SSB_OK;
+  }
   g_last.slot0 = slot_of(desc0_dev), g_last.slot1 = slot_of(desc1_dev);
   g_last.d0_first = g_last.d1_first = 0;
   return run_match(lg, 1, xy0, n0, xy1, n1, matches0, mscores0);
@@ -153,8 +184,34 @@ int ssb_lg_match_host(ssb_lightglue* lg, const float* xy0, int n0, const float* 
   g_last.d0_first = n0 > 0 ? desc0_f32[0] : 0, g_last.d1_first = n1 > 0 ? desc1_f32[0] : 0;
   return run_match(lg, 0, xy0, n0, xy1, n1, matches0, mscores0);
 }
+static float half_bits_to_float(unsigned short h) {
+  const uint32_t sign = (h & 0x8000u) << 16, exp = (h >> 10) & 31u, man = h & 1023u;
+  uint32_t bits;
+  if (exp == 0) {
+    if (man == 0) {
+      bits = sign;
+    } else {   // subnormal: renormalise
+      int e = -1;
+      uint32_t m = man;
+      do { ++e; m <<= 1; } while (!(m & 1024u));
+      bits = sign | ((112 - e) << 23) | ((m & 1023u) << 13);
+    }
+  } else if (exp == 31) {
+    bits = sign | 0x7F800000u | (man << 13);
+  } else {
+    bits = sign | ((exp + 112) << 23) | (man << 13);
+  }
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
 int ssb_desc_to_host_f32(int, const void* desc_dev_f16, int count, int dim, float* out) {
   if (!desc_dev_f16 || count < 0 || dim != 256) return SSB_ERR_INVALID;
+  if (g_extract_server) {   // served mode: the slot holds fp16 rows
+    const unsigned short* h = static_cast<const unsigned short*>(desc_dev_f16);
+    for (long i = 0; i < static_cast<long>(count) * dim; ++i) out[i] = half_bits_to_float(h[i]);
+    return SSB_OK;
+  }
   std::memcpy(out, desc_dev_f16, sizeof(float) * static_cast<size_t>(count) * dim);
   return SSB_OK;
 }
@@ -281,6 +338,8 @@ int ssb_rgbd_process(ssb_rgbd* r, const float* xy, int n, const void* depth, int
 }
 void fake_last_rgbd(double* out28) { std::memcpy(out28, g_rgbd, 28 * sizeof(double)); }
 int fake_rect_stride(void) { return g_rect_stride; }
+
+void fake_set_servers(ExtractServer e, MatchServer m) { g_extract_server = e, g_match_server = m; }
 
 // ---- inspection hooks for the test ----------------------------------------------------------------
 int fake_slots_in_use(void) { return ssb_sp_slots_in_use(g_sp); }

@@ -185,3 +185,61 @@ def test_a_foreign_engine_file_fails_initialize_like_a_tensorrt_mismatch(ref):
                            160, 120, 1.0, C.byref(st))
     assert st.value == 0
     lib.ref_e2e_destroy(h)
+
+
+def test_adapter_classes_equal_the_reference_classes_over_the_same_networks(ref, sp_weights, lg_weights):
+    """Differential check of the drop-in boundary: StereoFrontEnd::process over the REFERENCE's SuperPoint / LightGlue classes
+    (fake TensorRT, networks = oracle) against StereoFrontEnd::process over the ADAPTER's SuperPointB200 / LightGlueB200
+    (C-ABI double in served mode, the same oracle behind ssb_sp_extract / ssb_lg_match_device): the frames must be identical -
+    keypoints, responses, stereo points, depth flags, the descriptor handle's shape and the rows it points to."""
+    from superslam_b200.synth import synth_pair
+    from test_dropin_adapter import FAKE, Harness, bind
+
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_ref/libdropin_fake.so not built")
+    left, right = synth_pair(120, 160, 33, 60)
+    h, w, K = 120, 160, 160
+    want = run(ref, left, right, K)
+
+    fake = bind(FAKE)
+    EX = C.CFUNCTYPE(C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp, u16p)
+    MT = C.CFUNCTYPE(None, fp, C.c_int, u16p, fp, C.c_int, u16p, C.c_int, C.c_int, ip, fp)
+    pair = osp.extract(np.stack([left, right]), sp_weights, K)              # one batch-2 pass, like extract_stereo
+    by_image = {left.tobytes(): pair[0], right.tobytes(): pair[1]}
+
+    @EX
+    def extract(image, hh, ww, stride, max_kp, xy, score, desc):
+        img = np.ctypeslib.as_array(image, shape=(hh, stride))[:, :ww]
+        f = by_image[np.ascontiguousarray(img).tobytes()]
+        n = len(f["xy"])
+        assert n <= max_kp
+        arr(xy, (n, 2), np.float32)[:] = f["xy"]
+        arr(score, (n,), np.float32)[:] = f["score"]
+        arr(desc, (n, 256), np.uint16)[:] = f["desc"].view(np.uint16)
+        return n
+
+    @MT
+    def match(k0, n0, d0, k1, n1, d1, iw, ih, m0, ms0):
+        a = olg.match(lg_weights, olg.normalize_keypoints(arr(k0, (n0, 2), np.float32).copy(), iw, ih),
+                      arr(d0, (n0, 256), np.uint16).view(np.float16).copy(),
+                      olg.normalize_keypoints(arr(k1, (n1, 2), np.float32).copy(), iw, ih),
+                      arr(d1, (n1, 256), np.uint16).view(np.float16).copy())
+        arr(m0, (n0,), np.int32)[:] = a[0]
+        arr(ms0, (n0,), np.float32)[:] = a[1]
+
+    fake.fake_set_servers.argtypes = [EX, MT]
+    fake.fake_set_servers(extract, match)
+    try:
+        hs = Harness(fake, "sp.ssbw", "lg.ssbw", w, h, max_kp=K)
+        got = hs.process(left, right, 0.0)
+        rows, host = hs.promote_keyframe()
+        hs.release_frames()
+        hs.close()
+    finally:
+        fake.fake_set_servers(C.cast(None, EX), C.cast(None, MT))
+    n = len(want["xy"][0])
+    assert got["n"] == n > 20 and np.array_equal(got["xy"], want["xy"][0]) and np.array_equal(got["response"], want["score"][0])
+    assert np.array_equal(got["has_depth"], want["has_depth"]) and got["has_depth"].sum() > 3
+    assert np.array_equal(got["stereo"], want["stereo"], equal_nan=True)
+    assert got["desc"] == dict(count=n, dim=256, slot=0, resident=True)     # L took the first slot in both object graphs
+    assert rows == n and np.array_equal(host, want["desc"][0].astype(np.float32))
