@@ -93,11 +93,11 @@ nvinfer1::Dims dims_of(std::initializer_list<int64_t> v) {
   return d;
 }
 using DT = nvinfer1::DataType;
-const std::vector<Binding> kSuperPoint = {{"image", DT::kFLOAT, true, dims_of({-1, 1, -1, -1})},
+const std::vector<Binding> kSuperPoint = {{"input", DT::kFLOAT, true, dims_of({-1, 1, -1, -1})},
                                           {"scores", DT::kFLOAT, false, dims_of({-1, -1, -1})},
                                           {"descriptors", DT::kHALF, false, dims_of({-1, 256, -1, -1})}};
-const std::vector<Binding> kLightGlue = {{"kpts0", DT::kFLOAT, true, dims_of({1, -1, 2})},   {"kpts1", DT::kFLOAT, true, dims_of({1, -1, 2})},
-                                         {"desc0", DT::kHALF, true, dims_of({1, -1, 256})},  {"desc1", DT::kHALF, true, dims_of({1, -1, 256})},
+const std::vector<Binding> kLightGlue = {{"kpts0", DT::kFLOAT, true, dims_of({1, -1, 2})},   {"desc0", DT::kHALF, true, dims_of({1, -1, 256})},
+                                         {"kpts1", DT::kFLOAT, true, dims_of({1, -1, 2})},   {"desc1", DT::kHALF, true, dims_of({1, -1, 256})},
                                          {"matches0", DT::kINT32, false, dims_of({1, -1})},  {"mscores0", DT::kFLOAT, false, dims_of({1, -1})}};
 struct EngineState {
   const std::vector<Binding>* io;
@@ -156,7 +156,7 @@ Dims IExecutionContext::getTensorShape(const char* n) const {
     return it == c.shape.end() ? b->dims : it->second;
   }
   if (c.io == &kSuperPoint) {
-    auto it = c.shape.find("image");
+    auto it = c.shape.find("input");
     if (it == c.shape.end()) return b->dims;
     const int64_t B = it->second.d[0], hc = it->second.d[2] / 8, wc = it->second.d[3] / 8;
     return std::strcmp(n, "scores") == 0 ? dims_of({B, hc * 8, wc * 8}) : dims_of({B, 256, hc, wc});
@@ -175,8 +175,8 @@ bool IExecutionContext::enqueueV3(cudaStream_t) {
   for (const Binding& b : *c.io)
     if (!c.addr.count(b.name) || (b.input && !c.shape.count(b.name))) return false;
   if (c.io == &kSuperPoint) {
-    const Dims& d = c.shape.at("image");
-    g_sp_infer(static_cast<const float*>(c.addr.at("image")), static_cast<int>(d.d[0]), static_cast<int>(d.d[2]),
+    const Dims& d = c.shape.at("input");
+    g_sp_infer(static_cast<const float*>(c.addr.at("input")), static_cast<int>(d.d[0]), static_cast<int>(d.d[2]),
                static_cast<int>(d.d[3]), static_cast<float*>(c.addr.at("scores")),
                static_cast<unsigned short*>(c.addr.at("descriptors")));
   } else {
