@@ -37,6 +37,12 @@ sys.path.insert(0, ROOT)
 H, W, K = 480, 640, 1024
 SPW = os.path.join(ROOT, "superslam_b200", "weights", "superpoint_v1.ssbw")
 METRIC = "stereo frame-pairs/sec (SPx2+LG, 1024 kpts, 640x480)"
+CPU_ARM = {
+    "reference": "StereoFrontEnd::process over the reference's own SuperPoint / LightGlue C++ classes (compiled in place, "
+                 "oracle/_ref/libref_e2e.so); their two TensorRT engines have no CPU form and are served by the fp32 torch "
+                 "graphs of the oracle",
+    "port": "oracle = the reference's torch graph + restated host logic (the reference itself has no CPU path, TensorRT only)",
+}
 WORKLOAD = ("C2: stereo pairs 640x480, K=1024, LightGlue 9 layers (seeded synthetic LightGlue weights: none ship with "
             "the reference); SuperPoint weights = reference checkpoint")
 
@@ -128,7 +134,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
+def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0, reference_classes: bool = False):
     """One stereo pair through the CPU oracle (fp32 torch restatement of the reference graph +
     restated host logic).  The intra-op thread count is calibrated first (8, 16, ... up to every host
     thread; the fastest wins: on a 128-thread box the oracle's many small ops run several times slower with
@@ -146,7 +152,7 @@ def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
     wlg = make_random_weights(7)
     l, r = synth_pair(H, W, 1234)
 
-    def one_pair():
+    def one_pair_port():
         t = time.perf_counter()
         res = osp.extract(np.stack([l, r]), wsp, K)
         m0, ms0 = olg.match(wlg, olg.normalize_keypoints(res[0]["xy"], W, H), res[0]["desc"],
@@ -154,6 +160,15 @@ def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
         q, tr, _ = ofe.dmatches(m0, ms0)
         ofe.stereo_postfilter(res[0]["xy"], res[1]["xy"], q, tr)
         return time.perf_counter() - t
+
+    one_pair, kind = one_pair_port, "port"
+    if reference_classes:   # --impl reference: the reference's own wrapper classes when they were compiled in place
+        try:                # (oracle/_ref/libref_e2e.so, see oracle/Makefile); the GPU arm's cpu_baseline keeps the plain port
+            one_pair_ref = _reference_classes_pair(osp, olg, wsp, wlg, l, r)
+            if one_pair_ref is not None:
+                one_pair, kind = one_pair_ref, "reference"
+        except Exception as e:  # the baseline must not depend on it
+            sys.stderr.write(f"bench: reference classes unavailable ({e}); timing the oracle port\n")
 
     try:
         ncpu = len(os.sched_getaffinity(0))
@@ -177,7 +192,78 @@ def oracle_pair_seconds(n_iters: int, warmup: int, budget_s: float = 25.0):
     while len(times) < max(1, n_iters) and (not times or spent < budget_s):
         times.append(one_pair())
         spent += times[-1]
-    return float(np.median(times)), best_c, len(times)
+    return float(np.median(times)), best_c, len(times), kind
+
+
+_E2E_KEEP = []   # ctypes callbacks and buffers of _reference_classes_pair must outlive the call
+
+
+def _reference_classes_pair(osp, olg, wsp, wlg, l, r):
+    """StereoFrontEnd::process over the reference's own SuperPoint / LightGlue classes (src/*.cc compiled in place into
+    oracle/_ref/libref_e2e.so), their two TensorRT engines - which have no CPU form - served by the fp32 torch graphs of the
+    oracle, CUDA runtime calls on host memory.  Returns a callable that times one pair, or None when the library is absent."""
+    import ctypes as C
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_e2e.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    fp, ip, u16p = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint16)
+    SP = C.CFUNCTYPE(None, fp, C.c_int, C.c_int, C.c_int, fp, u16p)
+    LG = C.CFUNCTYPE(None, fp, C.c_int, u16p, fp, C.c_int, u16p, ip, fp)
+    GA = C.CFUNCTYPE(None, u16p, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, u16p)
+
+    def arr(ptr, shape, dtype):
+        return np.ctypeslib.as_array(ptr, shape=(int(np.prod(shape)),)).view(dtype).reshape(shape)
+
+    @SP
+    def sp_infer(image, b, h, w, scores, desc):
+        s, grid, _ = osp.dense_forward(arr(image, (b, 1, h, w), np.float32).copy(), wsp, fp16_storage=False)
+        arr(scores, s.shape, np.float32)[:] = s
+        arr(desc, grid.shape, np.uint16)[:] = grid.astype(np.float16).view(np.uint16)
+
+    @LG
+    def lg_infer(k0, n0, d0, k1, n1, d1, m0, ms0):
+        a = olg.match(wlg, arr(k0, (n0, 2), np.float32).copy(), arr(d0, (n0, 256), np.uint16).view(np.float16).copy(),
+                      arr(k1, (n1, 2), np.float32).copy(), arr(d1, (n1, 256), np.uint16).view(np.float16).copy())
+        arr(m0, (n0,), np.int32)[:] = a[0]
+        arr(ms0, (n0,), np.float32)[:] = a[1]
+
+    @GA
+    def gather(grid, c, gh, gw, cell_h, cell_w, n, out):
+        cell = np.stack([arr(cell_h, (n,), np.int32), arr(cell_w, (n,), np.int32)], 1)
+        arr(out, (n, c), np.uint16)[:] = osp.gather_normalize(arr(grid, (c, gh, gw), np.uint16).view(np.float16).copy(),
+                                                              cell).view(np.uint16)
+
+    lib.ref_e2e_set_hooks(sp_infer, lg_infer, gather)
+    lib.ref_e2e_create.restype = C.c_void_p
+    lib.ref_e2e_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float, ip]
+    lib.ref_e2e_process_only.restype = C.c_int
+    lib.ref_e2e_process_only.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, ip]
+    engines = []
+    for tag in (b"superpoint", b"lightglue"):
+        p = f"/tmp/ssb_bench_{tag.decode()}_{os.getpid()}.engine"
+        with open(p, "wb") as f:
+            f.write(tag + b" stand-in engine")
+        engines.append(p.encode())
+    st = C.c_int(-1)
+    h = lib.ref_e2e_create(engines[0], engines[1], K, 0.005, 4, W, H, 1.0, C.byref(st))
+    if st.value != 3:
+        return None
+    left, right = np.ascontiguousarray(l), np.ascontiguousarray(r)
+    _E2E_KEEP.extend([lib, sp_infer, lg_infer, gather, left, right])
+
+    def one_pair():
+        nd = C.c_int(0)
+        t = time.perf_counter()
+        n = lib.ref_e2e_process_only(h, left.ctypes.data, right.ctypes.data, H, W, left.strides[0], C.byref(nd))
+        dt = time.perf_counter() - t
+        if n <= 0:
+            raise RuntimeError("the reference classes returned no keypoints")
+        return dt
+
+    one_pair()   # proves the path before it is chosen
+    return one_pair
 
 
 def bench_latency(device: int, rank: int, iters: int = 60, warm: int = 8):
@@ -256,7 +342,8 @@ def bench_eigenplaces(lib, device: int, steps: int = 10, batch: int = 8):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    sec, threads, timed = oracle_pair_seconds(max(1, args.steps), min(1, args.warmup), budget_s=90.0)
+    sec, threads, timed, kind = oracle_pair_seconds(max(1, args.steps), min(1, args.warmup), budget_s=90.0,
+                                                    reference_classes=True)
     v = 1.0 / sec
     line = {
         "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -265,9 +352,8 @@ def run_reference(args, rank: int):
         "config": {"workload": WORKLOAD, "pairs_per_step": 1,
                    "sample": "each step = one whole pair of that workload on the host cores (a bounded sample of the "
                              "64-pair device step)"},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": f"{timed} pair(s) timed after thread-count calibration and warm-up; oracle = reference's torch "
-                                   "graph + restated host logic (the reference itself has no CPU path, TensorRT only)"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                         "sample": f"{timed} pair(s) timed after thread-count calibration and warm-up; " + CPU_ARM[kind]},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -501,10 +587,9 @@ def main():
                 latency = {"error": str(e)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            sec, threads, timed = oracle_pair_seconds(5, 1, budget_s=20.0)
-            cpu = {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": "port",
-                   "sample": f"{timed} pair(s) of the same C2 workload through oracle/ (fp32 torch restatement), "
-                             "after warm-up and thread-count calibration"}
+            sec, threads, timed, kind = oracle_pair_seconds(5, 1, budget_s=20.0)
+            cpu = {"value": 1.0 / sec, "unit": "pairs/s", "cores": threads, "kind": kind,
+                   "sample": f"{timed} pair(s) of the same C2 workload after warm-up and thread-count calibration; " + CPU_ARM[kind]}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": max_ms / args.steps, "higher_is_better": True,

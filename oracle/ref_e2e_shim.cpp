@@ -260,6 +260,20 @@ int ref_e2e_process(void* h, const unsigned char* left, const unsigned char* rig
   return nl;
 }
 
+// StereoFrontEnd::process alone (the timed call of bench.py's CPU legs); returns the number of left keypoints and, through
+// n_depth, how many of them received a stereo depth.
+int ref_e2e_process_only(void* h, const unsigned char* left, const unsigned char* right, int height, int width, int row_stride,
+                         int* n_depth) {
+  E2E* e = static_cast<E2E*>(h);
+  const cv::Mat l(height, width, CV_8UC1, const_cast<unsigned char*>(left), row_stride);
+  const cv::Mat r(height, width, CV_8UC1, const_cast<unsigned char*>(right), row_stride);
+  const superslam::StereoFrame f = e->fe->process(l, r, 0.0);
+  int nd = 0;
+  for (char c : f.has_depth) nd += c != 0;
+  if (n_depth) *n_depth = nd;
+  return static_cast<int>(f.keypoints_left.size());
+}
+
 // The mono / loop-closure call shapes: IFeatureExtractor::extract on two images (infer_device: batch-1 dynamic shape),
 // IFeatureMatcher::descriptors_to_host on both results (src/LightGlue.cc:460-475), then the HOST-descriptor match
 // (src/LightGlue.cc:285-324: prepare_inputs converts the CV_32F rows to the fp16 binding).  desc_host_*: cap x 256 floats.
