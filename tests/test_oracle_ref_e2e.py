@@ -39,12 +39,18 @@ def ref(sp_weights, lg_weights, tmp_path_factory):
     lib.ref_e2e_process.restype = C.c_int
     lib.ref_e2e_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, ip, fp, fp, u16p, fp,
                                     fp, u16p, C.POINTER(C.c_double), C.c_char_p, ip, ip, fp]
-    calls = {"sp": [], "lg": [], "gather": 0}
+    calls = {"sp": [], "lg": [], "gather": 0, "module": None}
 
     @SP_FN
     def sp_infer(image, b, h, w, scores, desc):
         x = arr(image, (b, 1, h, w), np.float32).copy()
-        s, grid, _ = osp.dense_forward(x, sp_weights, fp16_storage=False)   # the graph of convert_superpoint_to_onnx.py
+        if calls["module"] is not None:   # the reference's own torch module as the engine (the graph the ONNX is traced from)
+            import torch
+
+            with torch.no_grad():
+                s, grid = (t.numpy() for t in calls["module"](torch.from_numpy(x)))
+        else:
+            s, grid, _ = osp.dense_forward(x, sp_weights, fp16_storage=False)   # the restated graph
         arr(scores, s.shape, np.float32)[:] = s
         arr(desc, grid.shape, np.uint16)[:] = grid.astype(np.float16).view(np.uint16)   # the engine's fp16 binding
         calls["sp"].append((b, h, w))
@@ -136,6 +142,39 @@ def test_reference_wrappers_end_to_end_equal_the_oracle_composition(ref, sp_weig
     if case != "few_keypoints":
         assert len(q) > 5
     assert ref["lib"].ref_e2e_live_allocations() == 0                       # every buffer and pool slot was returned
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/convert_superpoint_to_onnx.py"),
+                    reason="the reference's torch module is not on this machine")
+def test_reference_wrappers_over_the_reference_torch_module(ref, sp_weights, lg_weights):
+    """No restated piece on the SuperPoint side: the reference's C++ wrapper code around the reference's OWN torch graph
+    (utils/convert_superpoint_to_onnx.py: SuperPoint + DenseSuperPoint(nms_radius 4), weights/superpoint_v1.pth - what the
+    TensorRT engine is built from) - i.e. the reference itself, run here in fp32.  The oracle reproduces its frame bit for bit."""
+    import sys
+
+    import torch
+
+    from superslam_b200.synth import synth_pair
+
+    sys.path.insert(0, "/root/reference/utils")
+    import convert_superpoint_to_onnx as refmod
+
+    net = refmod.SuperPoint()
+    net.load_state_dict(torch.load("/root/reference/weights/superpoint_v1.pth", map_location="cpu", weights_only=True))
+    ref["calls"]["module"] = refmod.DenseSuperPoint(net.eval(), 4).eval()
+    try:
+        left, right = synth_pair(240, 320, 1234, 120)
+        K = 512
+        got = run(ref, left, right, K)
+    finally:
+        ref["calls"]["module"] = None
+    f, q, t, d, stereo, has = oracle_frame(left, right, sp_weights, lg_weights, K)
+    for i in range(2):
+        assert len(got["xy"][i]) == len(f[i]["xy"]) > 100
+        assert np.array_equal(got["xy"][i], f[i]["xy"]) and np.array_equal(got["score"][i], f[i]["score"])
+        assert np.array_equal(got["desc"][i].view(np.uint16), f[i]["desc"].view(np.uint16))
+    assert np.array_equal(got["query"], q) and np.array_equal(got["train"], t) and np.array_equal(got["distance"], d)
+    assert np.array_equal(got["has_depth"], has) and np.array_equal(got["stereo"], stereo, equal_nan=True) and has.sum() > 10
 
 
 def test_mono_extract_descriptors_to_host_and_host_descriptor_match(ref, sp_weights, lg_weights):
