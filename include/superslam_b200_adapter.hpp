@@ -37,10 +37,13 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
                  int device_id = 0)
       : weights_(std::move(weights_file)), max_kp_(max_keypoints), thresh_(keypoint_threshold),
         borders_(remove_borders), device_(device_id) {}
-  ~SuperPointB200() override { ssb_sp_destroy(sp_); }
+  ~SuperPointB200() override = default;   // the extractor dies with its last live descriptor handle (see sp_)
 
   bool initialize() {
-    return ssb_sp_create(weights_.c_str(), max_kp_, thresh_, borders_, /*num_slots=*/8, device_, &sp_) == SSB_OK;
+    ssb_superpoint* sp = nullptr;
+    if (ssb_sp_create(weights_.c_str(), max_kp_, thresh_, borders_, /*num_slots=*/8, device_, &sp) != SSB_OK) return false;
+    sp_ = std::shared_ptr<ssb_superpoint>(sp, [](ssb_superpoint* p) { ssb_sp_destroy(p); });
+    return true;
   }
 
   superslam::Features extract(const cv::Mat& image) override {
@@ -96,7 +99,7 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
     for (int i = 0; i < b; ++i) xyp[i] = xy[i].data(), scp[i] = sc[i].data();
     std::vector<int> count(b, 0), slot(b, -1);
     std::vector<void*> desc(b, nullptr);
-    const int st = ssb_sp_extract(sp_, ptr.data(), b, h, w, static_cast<int>(step), ch, xyp.data(),
+    const int st = ssb_sp_extract(sp_.get(), ptr.data(), b, h, w, static_cast<int>(step), ch, xyp.data(),
                                   scp.data(), count.data(), desc.data(), slot.data());
     if (st != SSB_OK && st != SSB_ERR_EXHAUSTED) return out;
     out.resize(b);
@@ -110,9 +113,12 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
       f.descriptors.slot = slot[i];
       if (slot[i] >= 0) {  // DescriptorPool::make (include/DescriptorPool.h:62-76)
         f.descriptors.data = desc[i];
-        ssb_superpoint* sp = sp_;
+        // The deleter owns a share of the extractor: "a handle may outlive the pool" (include/DescriptorPool.h:71-75,
+        // where the reference captures the shared FreeList, not `this`).  The slot memory and the free list live
+        // inside ssb_superpoint, so it is destroyed only after the last Features handle has let go.
+        std::shared_ptr<ssb_superpoint> sp = sp_;
         const int s = slot[i];
-        f.descriptors.slot_ref = std::shared_ptr<void>(desc[i], [sp, s](void*) { ssb_sp_slot_release(sp, s); });
+        f.descriptors.slot_ref = std::shared_ptr<void>(desc[i], [sp, s](void*) { ssb_sp_slot_release(sp.get(), s); });
       }
     }
     return out;
@@ -122,7 +128,7 @@ class SuperPointB200 : public superslam::IFeatureExtractor {
   int max_kp_;
   double thresh_;
   int borders_, device_;
-  ssb_superpoint* sp_ = nullptr;
+  std::shared_ptr<ssb_superpoint> sp_;   // shared with every live descriptor handle
 };
 
 class LightGlueB200 : public superslam::IFeatureMatcher {

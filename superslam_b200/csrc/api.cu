@@ -122,6 +122,17 @@ class FrontEnd {
   int enqueue_device(const uint8_t* images_dev, int pairs, int h, int w) {
     SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
     SSB_CUDA_CHECK(cudaSetDevice(device_));
+    // A captured graph holds SuperPoint's activation pointers and tensor maps: size the workspace first and drop
+    // every graph if that moved it (a larger batch or another image size since the capture).
+    {
+      const int eh = rect_l_ ? rect_l_->dst_h() : h, ew = rect_l_ ? rect_l_->dst_w() : w;
+      SSB_RETURN_IF(sp.impl.prepare(2 * pairs, eh, ew));
+      if (sp.impl.shape_generation() != sp_gen_) {
+        SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        drop_graphs();
+        sp_gen_ = sp.impl.shape_generation();
+      }
+    }
     static const bool no_graph = std::getenv("SSB_NO_GRAPH") != nullptr;
     if (no_graph || prof_enabled()) return enqueue_eager(images_dev, pairs, h, w);
     // graph cache keyed by (image buffer, pairs, h, w): the resident-input bench, process() and the two
@@ -169,10 +180,7 @@ class FrontEnd {
     SSB_CHECK(submitted_ == collected_, SSB_ERR_INVALID, "streamed steps are in flight: collect them first");
     SSB_CUDA_CHECK(cudaSetDevice(device_));
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (auto& g : graphs_) {   // captured graphs bake the old configuration in
-      if (g.exec) cudaGraphExecDestroy(g.exec);
-      g = GraphEntry{};
-    }
+    drop_graphs();   // captured graphs bake the old configuration in
     if (rect_buf_) cudaFree(rect_buf_);
     rect_buf_ = nullptr;
     rect_l_ = rect_r_ = nullptr;
@@ -188,6 +196,12 @@ class FrontEnd {
     return SSB_OK;
   }
   bool has_rectifiers() const { return rect_l_ != nullptr; }
+  void drop_graphs() {
+    for (auto& g : graphs_) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g = GraphEntry{};
+    }
+  }
   int enqueue_eager(const uint8_t* images_dev, int pairs, int h, int w) {
     prof_begin(stream_);
     if (rect_l_ != nullptr) {
@@ -391,6 +405,7 @@ class FrontEnd {
   static constexpr int kGraphSlots = 4;
   GraphEntry graphs_[kGraphSlots];
   unsigned graph_next_ = 0;
+  unsigned long long sp_gen_ = 0;   // SuperPoint::shape_generation() the cached graphs were captured against
   cudaStream_t stream_ = nullptr;
   // streaming state (submit / collect)
   cudaStream_t copy_stream_ = nullptr;

@@ -19,6 +19,7 @@
 // warps 2..9 = softmax + epilogue (TMEM lane quadrant = warp % 4, key half = (warp-2) / 4).
 #pragma once
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -519,27 +520,27 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                                   const CUtensorMap& tmO, FaParams p, int q_tiles, int z, cudaStream_t stream, const char* label) {
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FaParams);
-  static Kernel kernel = nullptr;
-  static int trace = 0;
-  if (kernel == nullptr) {
-    if (const char* e = std::getenv("SSB_FA_TRACE")) trace = std::atoi(e);
-    // SSB_FA_POLY = 0 | 3 | 4 | 6 | 8: one pair of exponentials in `poly` on the FMA pipe.  Measured per 18
-    // launches at 64 pairs: 0 -> 4.84 ms, 8 -> 4.57, 6 -> 4.60, 4 -> 4.61, 3 -> 4.54.
-    int poly = 3;
-    if (const char* e = std::getenv("SSB_FA_POLY")) poly = std::atoi(e);
-    Kernel k;
-    if (trace) k = flash_attention_kernel<true, 3>;
-    else if (poly == 0) k = flash_attention_kernel<false, 0>;
-    else if (poly == 4) k = flash_attention_kernel<false, 4>;
-    else if (poly == 6) k = flash_attention_kernel<false, 6>;
-    else if (poly == 8) k = flash_attention_kernel<false, 8>;
-    else k = flash_attention_kernel<false, 3>;
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+  // Variant selection is process-wide (environment), the shared-memory opt-in is per device (common.cuh).
+  // SSB_FA_POLY = 0 | 3 | 4 | 6 | 8: one pair of exponentials in `poly` on the FMA pipe.  Measured per 18
+  // launches at 64 pairs: 0 -> 4.84 ms, 8 -> 4.57, 6 -> 4.60, 4 -> 4.61, 3 -> 4.54.
+  static const int trace_env = [] { const char* e = std::getenv("SSB_FA_TRACE"); return e ? std::atoi(e) : 0; }();
+  static const int poly = [] { const char* e = std::getenv("SSB_FA_POLY"); return e ? std::atoi(e) : 3; }();
+  static std::atomic<int> trace{trace_env};
+  Kernel kernel;
+  if (trace_env) kernel = flash_attention_kernel<true, 3>;
+  else if (poly == 0) kernel = flash_attention_kernel<false, 0>;
+  else if (poly == 4) kernel = flash_attention_kernel<false, 4>;
+  else if (poly == 6) kernel = flash_attention_kernel<false, 6>;
+  else if (poly == 8) kernel = flash_attention_kernel<false, 8>;
+  else kernel = flash_attention_kernel<false, 3>;
+  auto configure = [&]() -> int {
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
     // ask for the full shared-memory carveout so that two CTAs (2 x 101 KB) are co-resident per SM
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         cudaSharedmemCarveoutMaxShared));
-    kernel = k;   // published last: a second context on another thread never sees an unconfigured kernel
-  }
+    return SSB_OK;
+  };
+  SSB_DEVICE_CONFIG(kernel, 1, configure());
   p.q_tiles = q_tiles;
   p.zcount = z;
   const int total = q_tiles * z;
@@ -547,8 +548,7 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   const int resident = 2 * device_sm_count();
   const int ctas = total < resident ? total : resident;
   kernel<<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
-  if (trace == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
-    trace = 2;
+  if (trace.exchange(trace_env ? 2 : 0) == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
     static long long h[64][8];
     SSB_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_fa_trace, sizeof(h)));

@@ -41,6 +41,15 @@ void prof_mark(cudaStream_t stream, const char* label);
 void prof_collect();
 int prof_report(char* buf, size_t bytes);
 const char* last_error();
+// Per-device launch configuration.  cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in, the carveout),
+// the SM count and cluster occupancy belong to ONE device, while every handle of this library names its own
+// device_id and contexts may live on several host threads: a process-wide `static bool configured` would leave the
+// second GPU's kernels without the opt-in.  device_config_begin() takes the registry lock and returns the int slot
+// of (current device, key), zero on first use; the caller configures the device if the slot is below what it
+// needs, stores the new value and calls device_config_end().  device_sm_count() is cached per device the same way.
+int* device_config_begin(const void* key);
+void device_config_end();
+int device_sm_count();
 
 #define SSB_CUDA_CHECK(expr)                                                                  \
   do {                                                                                        \
@@ -58,6 +67,19 @@ const char* last_error();
       ssb::set_last_error(__VA_ARGS__);                                                       \
       return (code);                                                                          \
     }                                                                                         \
+  } while (0)
+
+// Run `stmt` (an int-status expression) once per device and `want` level for `key`.
+#define SSB_DEVICE_CONFIG(key, want, stmt)                                                    \
+  do {                                                                                        \
+    int* _slot = ssb::device_config_begin(reinterpret_cast<const void*>(key));                \
+    int _st = SSB_OK;                                                                         \
+    if (*_slot < (want)) {                                                                    \
+      _st = (stmt);                                                                           \
+      if (_st == SSB_OK) *_slot = (want);                                                     \
+    }                                                                                         \
+    ssb::device_config_end();                                                                 \
+    if (_st != SSB_OK) return _st;                                                            \
   } while (0)
 
 #define SSB_RETURN_IF(expr)                                                                   \

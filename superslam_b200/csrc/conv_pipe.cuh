@@ -377,12 +377,12 @@ int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams 
   p.tiles_h = (H + 15) / 16;
   p.batch = batch;
   constexpr int smem_bytes = kFuse1a ? kPipeSmemBytes : kPipeSmemBytesTma;
-  static bool configured = false;
-  if (!configured) {
+  auto configure = [&]() -> int {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem_bytes));
-    configured = true;
-  }
+    return SSB_OK;
+  };
+  SSB_DEVICE_CONFIG((&conv_pipe_kernel<Epi, kFuse1a>), 1, configure());
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;

@@ -209,12 +209,12 @@ int launch_conv_stream(const CUtensorMap& tmA, const CUtensorMap& tmB, StreamPar
   p.tiles_w = (W + 15) / 16;
   p.tiles_h = (H + 15) / 16;
   p.batch = batch;
-  static bool configured = false;
-  if (!configured) {
+  auto configure = [&]() -> int {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_stream_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kStreamSmemBytes));
-    configured = true;
-  }
+    return SSB_OK;
+  };
+  SSB_DEVICE_CONFIG((&conv_stream_kernel<Epi>), 1, configure());
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   if (total <= 0) return SSB_OK;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;

@@ -261,8 +261,9 @@ __global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* 
     mscores0[o] = 0.f;
     return;
   }
+  // a row of NaN scores (NaN keypoints / descriptors from the caller) leaves the arg-max sentinel: unmatched
   const int j = arg0[o];
-  const bool mutual = arg1[static_cast<size_t>(pair) * kp + j] == i;
+  const bool mutual = j >= 0 && j < n1 && arg1[static_cast<size_t>(pair) * kp + j] == i;
   const float ms = mutual ? expf(max0[o]) : 0.f;
   matches0[o] = (mutual && ms > threshold) ? j : -1;
   mscores0[o] = ms;
@@ -995,14 +996,6 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     count_launch();
     prof_mark(stream, "lg.prepare");
   }
-  // multicast B (umma_core.cuh): pairs of row tiles share every weight chunk.  SSB_LG_MCAST selects it
-  // (A/B measurements); bit 0 = plain linears, bit 1 = ffn1 (clusters of four).  Off by default.
-  static int mcast = -1;
-  if (mcast < 0) {
-    const char* e = std::getenv("SSB_LG_MCAST");
-    mcast = e ? std::atoi(e) : 0;   // measured: no gain while the epilogues set the tile period (profiles/README.md)
-  }
-  auto bmap = [&](const LgLinear& L, bool mc) -> const CUtensorMap& { return mc ? L.tmB128 : L.tmB; };
   auto lin = [&](const char* label, int kc0, int kc1, int block_n) {
     CoreParams p;
     std::memset(&p, 0, sizeof(p));
@@ -1022,16 +1015,14 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     {
       CoreParams p = lin("lg.ffn1", 4, 4, 256);
       p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)
-      p.b_mcast = (mcast >> 1) & 1;
       EpiLnGelu e{F.fc1.bias, F.ln_g, F.ln_b, ts_h1_};
-      SSB_RETURN_IF(launch_core(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, bmap(F.fc1, p.b_mcast), p, e,
+      SSB_RETURN_IF(launch_core(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, F.fc1.tmB, p, e,
                                 dim3(tiles, 2, P2), stream));
     }
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);
-      p.b_mcast = mcast & 1;
       EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
-      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, bmap(F.fc2, p.b_mcast), p, e, dim3(tiles, 1, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     return SSB_OK;
   };
@@ -1057,9 +1048,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- self block ----
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
-      p.b_mcast = mcast & 1;
       EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, bmap(L.qkv, p.b_mcast), p, e, dim3(tiles, 3, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     if (!w_->fold_out) {
@@ -1072,9 +1062,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     // ---- cross block ----
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
-      p.b_mcast = mcast & 1;
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, bmap(L.qkv_c, p.b_mcast), p, e, dim3(tiles, 2, P2), stream));
+      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     if (!w_->fold_out) {

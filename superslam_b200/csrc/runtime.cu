@@ -27,6 +27,38 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
+struct DeviceConfig {
+  std::mutex mu;
+  std::map<std::pair<int, const void*>, int> slots;
+  int sms[64] = {};
+};
+DeviceConfig& device_config() {
+  static DeviceConfig c;
+  return c;
+}
+}  // namespace
+int* device_config_begin(const void* key) {
+  DeviceConfig& c = device_config();
+  c.mu.lock();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &c.slots[std::make_pair(dev, key)];
+}
+void device_config_end() { device_config().mu.unlock(); }
+int device_sm_count() {
+  DeviceConfig& c = device_config();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(c.mu);
+  int& sms = c.sms[dev & 63];
+  if (sms == 0) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+namespace {
 struct Prof {
   bool on = false;
   std::vector<cudaEvent_t> ev;

@@ -646,6 +646,7 @@ int SuperPoint::ensure_shape(int batch, int h, int w) {
   SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
   const int nb = std::max(batch, (h == h_ && w == w_) ? cap_batch_ : 0);
   free_shape();
+  ++shape_gen_;
   h_ = h, w_ = w;
   h2_ = h / 2, w2_ = w / 2, h4_ = h2_ / 2, w4_ = w2_ / 2, hc_ = h4_ / 2, wc_ = w4_ / 2;
   hs_ = hc_ * 8, ws_ = wc_ * 8;
@@ -820,12 +821,12 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     const float sx = static_cast<float>(w) / ws_;  // SuperPoint.cc:708-709
     const float sy = static_cast<float>(h) / hs_;
     const size_t smem = static_cast<size_t>(sort_cap) * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    auto configure = [&]() -> int {
       SSB_CUDA_CHECK(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           8192 * 8));
-      attr_set = true;
-    }
+      return SSB_OK;
+    };
+    SSB_DEVICE_CONFIG(&select_topk_kernel, 1, configure());
     select_topk_kernel<<<B, 1024, smem, stream>>>(cand_, cand_cap_, cand_count_, max_kpts_, sort_cap, ws_,
                                                   hc_, wc_, sx, sy, kp_xy_, kp_score_, kp_cell_, kp_count_);
     SSB_CUDA_CHECK(cudaGetLastError());

@@ -68,6 +68,12 @@ class SuperPoint {
 
   int debug_read(const char* what, void* dst, size_t bytes);
 
+  // Size the workspace for (batch, h, w) now.  shape_generation() changes whenever that frees and reallocates the
+  // activation buffers (and re-encodes their tensor maps): anything that has baked the old pointers in - a captured
+  // CUDA graph - must be dropped when it moves.
+  int prepare(int batch, int h, int w) { return ensure_shape(batch, h, w); }
+  unsigned long long shape_generation() const { return shape_gen_; }
+
   int max_keypoints() const { return max_kpts_; }
   SlotPool& pool() { return pool_; }
   cudaStream_t stream() const { return stream_; }
@@ -100,6 +106,7 @@ class SuperPoint {
 
   // shape-dependent state
   int cap_batch_ = 0, h_ = 0, w_ = 0;
+  unsigned long long shape_gen_ = 0;
   int h2_ = 0, w2_ = 0, h4_ = 0, w4_ = 0, hc_ = 0, wc_ = 0, hs_ = 0, ws_ = 0;
   uint8_t* img_ = nullptr;  // owned copy target for extract() [batch][h][w]
   __half *a1a_ = nullptr, *a1b_ = nullptr, *a2a_ = nullptr, *a2b_ = nullptr, *a3a_ = nullptr,

@@ -68,23 +68,12 @@ struct CoreParams {
   // without a host round trip): tiles whose first row >= m_valid or first column >= n_valid are skipped,
   // rows >= m_valid are masked by the epilogues, K chunks beyond ceil(k_valid / 64) are not issued.
   DevCount m_valid, n_valid, k_valid;
-  // Resident B (weights): each CTA serves ONE N tile (y = blockIdx.x % grid_y), loads that tile's whole
-  // [block_n x K] weight slab into shared memory once and streams only A through the ring.  For the
-  // skinny LightGlue GEMMs (K = 256/512) re-loading B per tile made L2->SM bandwidth the bound.
-  int b_resident;
-  int resident_bytes;
   int stage_bufs;      // TMA-store staging depth per epilogue warp (2 unless shared memory is short)
   // Cluster mode: the kernel is launched as clusters of grid_y CTAs; the CTA with cluster rank r serves the
   // N tile y = r of the SAME sequence of M tiles as its peers, so an epilogue that needs whole-row
   // statistics (LayerNorm over all N tiles) can exchange per-row partials through distributed shared
   // memory (EpiCtx::peer_*).  Used with grid_y == 2.
   int cluster_y;
-  // Multicast B: clusters of two CTAs (four with cluster_y) work on two consecutive M tiles of the SAME N tile;
-  // each loads one half of every B (weight) stage and multicasts it to both, so a weight chunk crosses the
-  // L2 -> SM fabric once per pair of tiles.  (The skinny LightGlue GEMMs re-read their whole weight matrix for
-  // every 128-row tile: 2/3 of all operand bytes, and L2 -> SM bandwidth was the measured bound.)  Needs
-  // block_n == 256, a B tensor map with 128-row boxes and an even number of M tiles per row of tiles.
-  int b_mcast;
   long long* trace;    // diagnostic (SSB_CORE_TRACE=<label>): CTA 0 time-stamps its first 32 tiles, [tile][8]
   const char* label;   // host-only: kernel name for the event profiler
 };
@@ -200,9 +189,8 @@ __host__ __device__ inline int core_stage_bytes(int block_n) { return kATileByte
 
 constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp (x stage_bufs)
 
-inline int core_smem_bytes(int block_n, int stages, int resident_bytes, int stage_bufs) {
-  return resident_bytes + stages * (resident_bytes ? kATileBytes : core_stage_bytes(block_n)) +
-         stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/ +
+inline int core_smem_bytes(int block_n, int stages, int stage_bufs) {
+  return stages * core_stage_bytes(block_n) + stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/ +
          2048 /*peer slots*/;
 }
 
@@ -214,16 +202,14 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
   // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.b_resident ? kATileBytes : core_stage_bytes(p.block_n);
-  uint8_t* s_res = smem;                               // resident weights (b_resident), else empty
-  uint8_t* ring = smem + p.resident_bytes;
+  const int stage_bytes = core_stage_bytes(p.block_n);
+  uint8_t* ring = smem;
   uint8_t* staging = ring + p.stages * stage_bytes;    // 8 x 4 KiB, 1024-aligned (all sizes are multiples of 1 KiB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + p.stage_bufs * kCoreStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* b_full = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 3);
   float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 256);
   float* peer_slots = xchg + 256;                        // [2][128][2]
   uint64_t* peer_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [2]
@@ -237,9 +223,8 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], p.b_mcast ? 2 : 1);   // multicast: released by both consumers of the stage
+      mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
@@ -253,38 +238,29 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  const bool clustered = p.cluster_y || p.b_mcast;
+  const bool clustered = p.cluster_y != 0;
   if (clustered) cluster_sync_all();   // the peers' barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // tile walk: all (x, y, z) tiles strided over the CTAs, or - resident B / cluster - a fixed y per CTA
-  // With multicast B a group of xr = 2 CTAs (times ny) walks PAIRS of M tiles in lockstep: cluster rank =
-  // xpar * ny + y.
-  const bool fixed_y = p.b_resident || p.cluster_y;
+  // tile walk: all (x, y, z) tiles strided over the CTAs, or - cluster mode - a fixed y per CTA (= its cluster rank)
+  const bool fixed_y = p.cluster_y != 0;
   const int ny = fixed_y ? p.grid_y : 1;
-  const int xr = p.b_mcast ? 2 : 1;
-  const int group = ny * xr;
-  const int in_group = static_cast<int>(blockIdx.x) % group;
-  const int y_fixed = in_group % ny;
-  const int xpar = in_group / ny;
-  const int first = static_cast<int>(blockIdx.x) / group;
-  const int stride = static_cast<int>(gridDim.x) / group;
-  const int gx = p.grid_x / xr;
+  const int y_fixed = static_cast<int>(blockIdx.x) % ny;
+  const int first = static_cast<int>(blockIdx.x) / ny;
+  const int stride = static_cast<int>(gridDim.x) / ny;
+  const int gx = p.grid_x;
   const int total = fixed_y ? gx * p.grid_z : gx * p.grid_y * p.grid_z;
-  const uint16_t mc_mask = static_cast<uint16_t>((1u << y_fixed) | (1u << (y_fixed + ny)));   // same N tile
 
   // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
-    const int xg = (tile % gx) * xr;   // first M tile of the group
-    const int x = xg + xpar;
+    const int x = tile % gx;
     const int y = fixed_y ? y_fixed : (tile / gx) % p.grid_y;
     z = fixed_y ? tile / gx : tile / (gx * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
     m_valid = p.m_valid.get(z);
-    // the CTAs of a group skip together: the decision looks at the group's first tile
-    if (p.m_valid.ptr != nullptr && (xg % p.tiles_w) * p.tile_w >= m_valid) return false;
+    if (p.m_valid.ptr != nullptr && w0 >= m_valid) return false;
     if (p.n_valid.ptr != nullptr && n0 >= p.n_valid.get(z)) return false;
     kc0 = p.kc0;
     if (p.k_valid.ptr != nullptr) kc0 = min(kc0, (p.k_valid.get(z) + kChunkK - 1) / kChunkK);
@@ -294,17 +270,6 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // producer: whole warp in uniform control flow, one elected lane issues the TMA loads (see warp 1)
     const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
-    if (p.b_resident) {
-      const int kct = p.kc0 + p.kc1;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(kct * p.block_n * 128));
-        for (int c = 0; c < kct; ++c)
-          for (int part = 0; part < p.n_parts; ++part)
-            tma_load_3d(s_res + (c * p.block_n + part * p.n_part) * 128, &tmB, b_full, c * kChunkK,
-                        y_fixed * p.block_n + part * p.n_part, p.b_z_add);
-      }
-      __syncwarp();
-    }
     int it = 0;
     for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
@@ -335,14 +300,9 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               } else {
                 tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
               }
-              if (p.b_mcast) {   // my half of the weight chunk, to both CTAs that work on this N tile
-                tma_load_3d_mcast(sb + xpar * 128 * 128, &tmB, &full_bar[s], bcol,
-                                  tap * p.b_tap_rows + n0 + xpar * 128, bz, mc_mask);
-              } else {
-                for (int part = 0; part < (p.b_resident ? 0 : p.n_parts); ++part) {
-                  tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
-                              tap * p.b_tap_rows + n0 + part * p.n_part, bz);
-                }
+              for (int part = 0; part < p.n_parts; ++part) {
+                tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
+                            tap * p.b_tap_rows + n0 + part * p.n_part, bz);
               }
             }
             __syncwarp();
@@ -355,11 +315,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // divergent `if (lane == 0)` region lets it live in uniform registers, so a tcgen05.mma is a single
     // instruction instead of an ELECT / R2UR / branch sequence of ~100 cycles.
     const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
-    const uint32_t ring_base = smem_u32(ring), res_base = smem_u32(s_res);
-    if (p.b_resident) {
-      mbar_wait(b_full, 0);
-      tc_fence_after();
-    }
+    const uint32_t ring_base = smem_u32(ring);
     int it = 0, seq = 0;
     for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
@@ -379,12 +335,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = ring_base + s * stage_bytes;
-        // resident B: chunk index within the tap (taps == 1 for the linear layers that use it)
-        const int kcs = kc0 + p.kc1;
-        const int cidx = kk % kcs;
-        const uint32_t sb = p.b_resident
-                                ? res_base + static_cast<uint32_t>((cidx < kc0 ? cidx : p.kc0 + (cidx - kc0)) * p.block_n * 128)
-                                : sa + kATileBytes;
+        const uint32_t sb = sa + kATileBytes;
         const uint64_t adesc = make_smem_desc_k_sw128(sa, 1024);
         if (elect_one()) {
 #pragma unroll 1
@@ -396,8 +347,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               umma_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
             }
           }
-          if (p.b_mcast) umma_commit_mcast(&empty_bar[s], mc_mask);
-          else umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[s]);
         }
         __syncwarp();
       }
@@ -479,17 +429,6 @@ inline int core_tmem_cols(int cols) {
   return c;
 }
 
-inline int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
-
 // `grid` is the logical tile space (x = M tiles, y = N tiles, z = batch); the launch itself uses one
 // persistent CTA per SM.
 template <class Epi>
@@ -512,19 +451,6 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   p.grid_y = static_cast<int>(grid.y);
   p.grid_z = static_cast<int>(grid.z);
   p.stage_bufs = 2;
-  if (p.b_resident) {
-    p.stage_bufs = 1;
-    p.resident_bytes = (p.kc0 + p.kc1) * p.block_n * 128;
-    const int room = 224 * 1024 - kCoreStagingBytes - 4096 - p.resident_bytes;
-    p.stages = room / kATileBytes;
-    if (p.stages > 6) p.stages = 6;
-    if (p.taps_h * p.taps_w != 1 || p.stages < 2) {
-      set_last_error("launch_core: resident B needs taps == 1 and a weight slab <= ~150 KB");
-      return SSB_ERR_INVALID;
-    }
-  } else {
-    p.resident_bytes = 0;
-  }
   if (p.stages <= 0) {
     // 222 KiB budget: ring as deep as fits next to a double-buffered staging area, at least 2 stages;
     // very wide tiles (block_n 512) fall back to single-buffered staging
@@ -536,12 +462,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     }
     p.stages = st > 6 ? 6 : (st < 2 ? 2 : st);
   }
-  const int smem = core_smem_bytes(p.block_n, p.stages, p.resident_bytes, p.stage_bufs);
-  static int configured_smem = 0;  // per template instantiation
-  if (smem > configured_smem) {
+  const int smem = core_smem_bytes(p.block_n, p.stages, p.stage_bufs);
+  auto configure = [&]() -> int {   // per device and template instantiation (common.cuh)
     SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured_smem = smem;
-  }
+    return SSB_OK;
+  };
+  SSB_DEVICE_CONFIG((&umma_core_kernel<Epi>), smem, configure());
   const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
   if (total <= 0) return SSB_OK;
   // diagnostic: SSB_CORE_TRACE=<label> dumps CTA 0's per-tile time stamps of the first launch with that label
@@ -561,21 +487,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     }
   }
   int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-  if (p.b_resident) {
-    const long long xz = static_cast<long long>(grid.x) * grid.z;
-    const int per = device_sm_count() / static_cast<int>(grid.y);
-    ctas = static_cast<int>((xz < per ? xz : per) * grid.y);
-  }
-  if (p.b_mcast && (p.b_resident || p.block_n != 256 || p.n_parts != 1 || grid.x % 2 != 0 || p.tiles_w % 2 != 0)) {
-    set_last_error("launch_core: multicast B needs block_n 256 and an even number of M tiles");
-    return SSB_ERR_INVALID;
-  }
-  if (p.cluster_y || p.b_mcast) {
-    if (p.cluster_y && (p.b_resident || grid.y != 2)) {
+  if (p.cluster_y) {
+    if (grid.y != 2) {
       set_last_error("launch_core: cluster mode needs exactly two N tiles");
       return SSB_ERR_INVALID;
     }
-    const int csize = (p.cluster_y ? 2 : 1) * (p.b_mcast ? 2 : 1);
+    const int csize = 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(device_sm_count() / csize * csize));
     cfg.blockDim = dim3(kCoreThreads);
@@ -590,20 +507,25 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     cfg.numAttrs = 1;
     // persistent pairs: as many clusters as can be co-resident (a GPC with an odd number of free SMs
     // cannot host a pair on its last SM), so that no cluster waits for a second wave
-    static int max_clusters = 0, max_clusters_smem = 0, max_clusters_size = 0;
-    if (max_clusters == 0 || max_clusters_smem != smem || max_clusters_size != csize) {
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi>, &cfg) != cudaSuccess || n <= 0) {
-        cudaGetLastError();
-        n = device_sm_count() / csize;
+    // (cached per device and shared-memory size: the registry slot holds smem << 12 | clusters)
+    static char occupancy_key;   // one per template instantiation
+    int max_clusters = 0;
+    const int sms = device_sm_count();
+    {
+      int* slot = device_config_begin(&occupancy_key);
+      if ((*slot >> 12) != smem) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi>, &cfg) != cudaSuccess || n <= 0) {
+          cudaGetLastError();
+          n = sms / csize;
+        }
+        *slot = (smem << 12) | n;
       }
-      max_clusters = n;
-      max_clusters_smem = smem;
-      max_clusters_size = csize;
+      max_clusters = *slot & 0xfff;
+      device_config_end();
     }
-    // groups of tiles walked by one cluster: (pairs of) M tiles x batch, times the N tiles unless a cluster
-    // spans them
-    const long long groups = static_cast<long long>(grid.x / (p.b_mcast ? 2 : 1)) * grid.z * (p.cluster_y ? 1 : grid.y);
+    // groups of tiles walked by one cluster: M tiles x batch (a cluster spans the N tiles)
+    const long long groups = static_cast<long long>(grid.x) * grid.z;
     ctas = static_cast<int>(groups < max_clusters ? groups : max_clusters) * csize;
     cfg.gridDim = dim3(static_cast<unsigned>(ctas));
     SSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_core_kernel<Epi>, a0, a1, b, p, epi));

@@ -203,3 +203,45 @@ def test_pipeline_with_a_blank_image_in_the_batch(tmp_path, lg_weights):
             assert np.array_equal(out["matches0"][p, :n0], ref["matches0"][p, :n0])
             assert np.array_equal(out["mscores0"][p, :n0], ref["mscores0"][p, :n0])
             assert np.array_equal(out["has_depth"][p], ref["has_depth"][p])
+
+
+def test_cached_graphs_survive_workspace_reallocation(tmp_path, lg_weights):
+    """One pipeline, sizes and pair counts revisited after a change.  Captured CUDA graphs hold SuperPoint's activation
+    pointers and tensor maps; a larger batch or another image size reallocates them (SuperPoint::ensure_shape), so every
+    cached graph must be dropped then - a stale replay would run on freed memory.  Each visit must reproduce the first
+    result for that input exactly (calls 2 and 3 of a key are the capture and the first replay)."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    K = 256
+    big = [im for i in range(4) for im in synth_pair(240, 320, 7 + i, 60)]
+    small = [im for i in range(2) for im in synth_pair(120, 160, 70 + i, 40)]
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, 320, 240, max_pairs=4)
+    keys = ("count", "xy", "score", "matches0", "mscores0", "has_depth")
+
+    def snap(o):
+        return {k: o[k].copy() for k in keys}
+
+    def same(a, b):
+        return all(np.array_equal(a[k], b[k]) for k in keys)
+
+    first = {}
+    # host path (shared upload buffer): 1 pair x3 (eager, capture, replay) -> other size -> more pairs -> revisit
+    plan = [("b1", big[:2])] * 3 + [("s1", small[:2])] * 3 + [("b1", big[:2])] * 3 + [("b4", big)] * 3 + \
+           [("b1", big[:2])] * 3 + [("s2", small)] * 3 + [("b4", big)] * 2 + [("s1", small[:2])] * 2
+    for name, imgs in plan:
+        got = snap(pipe.process(imgs))
+        if name in first:
+            assert same(got, first[name]), f"result for {name} changed after a workspace reallocation"
+        else:
+            first[name] = got
+    # caller-owned device buffers: pairs = 1 twice, pairs = 4 once, pairs = 1 again (the advisor's sequence)
+    d1 = pipe.upload(big[:2])
+    d4 = pipe.upload(big)
+    for dev, pairs, name in [(d1, 1, "b1"), (d1, 1, "b1"), (d4, 4, "b4"), (d1, 1, "b1"), (d1, 1, "b1"), (d4, 4, "b4")]:
+        pipe.enqueue_device(dev, pairs, 240, 320)
+        assert same(snap(pipe.fetch(pairs)), first[name])
+    assert int(first["b4"]["count"].min()) > 20

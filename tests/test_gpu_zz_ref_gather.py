@@ -73,8 +73,8 @@ def test_bgr_input_is_converted_like_opencv():
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_nethost.so")),
                     reason="oracle/_ref/libref_nethost.so not built (build() with /root/reference mounted)")
-@pytest.mark.parametrize("fixture,K", [("superpoint_ref_small.npz", 256), ("superpoint_ref_odd.npz", 128)])
-def test_reference_select_and_gather_equals_product_features(fixture, K):
+@pytest.mark.parametrize("fixture,K,least", [("superpoint_ref_small.npz", 256, 50), ("superpoint_ref_odd.npz", 128, 20)])
+def test_reference_select_and_gather_equals_product_features(fixture, K, least):
     """Rows a7-a9 in one piece: the reference's own SuperPoint::select_and_gather (src/SuperPoint.cc:681-750, compiled in
     place, with its own DescriptorPool and gather kernel) fed with the product's heat map (after the graph's NMS) and
     descriptor grid must return the product's keypoints, responses and fp16 descriptor rows bit for bit."""
@@ -106,4 +106,4 @@ def test_reference_select_and_gather_equals_product_features(fixture, K):
                                                         ours.ctypes.data_as(C.POINTER(C.c_float))))
         assert np.array_equal(ours.astype(np.float16).view(np.uint16), got["desc"])
         total += got["n"]
-    assert total > 50
+    assert total > least   # sanity only (the 99x131 fixture holds 42 keypoints in all): the equalities above are the test
