@@ -127,6 +127,50 @@ int ssb_fe_submit(ssb_frontend* fe, const uint8_t* const* images, int pairs, int
 int ssb_fe_collect(ssb_frontend* fe, int* pairs, int* count, float* xy, float* score, int32_t* matches0,
                    float* mscores0, float* stereo_ur, uint8_t* has_depth);
 int ssb_fe_sync(ssb_frontend* fe);
+/* Extract-only mode (BASELINE config C1, tests/test_superpoint_only.cc of the reference: SuperPoint alone): the
+ * 2*pairs images of a call are independent mono frames; count / xy / score are delivered, the match and stereo
+ * outputs are undefined.  Switch only while no streamed step is in flight. */
+int ssb_fe_set_extract_only(ssb_frontend* fe, int on);
+
+/* ---- Tracking chain: the SECOND LightGlue call the live pipeline makes per frame -------------------
+ * VoEstimator::track matches the last keyframe's left features against the current left features
+ * (src/VoEstimator.cc:240-246: matcher_->match(last_keyframe_.keypoints_left, last_keyframe_.descriptors_left,
+ * frame.keypoints_left, frame.descriptors_left)) and later makes the frame the new keyframe (:327).  With tracking
+ * enabled every pair slot p of a call is a stream that retains its keyframe (keypoints, fp16 descriptor rows, depth
+ * flags) on the device, and each call runs SuperPoint x2 + LightGlue (stereo) + post-filter + LightGlue (keyframe <->
+ * left) + the depth test of :250-256 in the same captured graph: no descriptor ever visits the host between the two
+ * matches.  A stream without a keyframe (before its first promotion) yields no tracking matches, like the reference's
+ * first frame (:206-236). */
+int ssb_fe_enable_tracking(ssb_frontend* fe, int enable);
+int ssb_fe_reset_tracking(ssb_frontend* fe); /* forget every keyframe */
+/* "last_keyframe_ = frame" for the streams with promote[p] != 0 (NULL: all `pairs` streams): the left image of pair
+ * p of the step delivered last becomes stream p's keyframe, device to device.  The decision is the host's
+ * (should_insert_keyframe, src/VoEstimator.cc:291-297); call it after collecting that step, before the next one. */
+int ssb_fe_promote_keyframes(ssb_frontend* fe, const uint8_t* promote, int pairs);
+/* Tracking outputs of the step delivered last by ssb_fe_process / ssb_fe_fetch / ssb_fe_collect (no further device
+ * work): keyframe_count [pairs] = features of the keyframe (0: none yet); track_matches0 [pairs][K]: index into the
+ * current LEFT keypoints per keyframe feature (queryIdx = keyframe, trainIdx = frame) or -1; track_mscores0;
+ * track_usable [pairs][K] = 1 where the match exists and both ends have stereo depth (:253-256).  Any may be NULL. */
+int ssb_fe_tracking_results(ssb_frontend* fe, int pairs, int* keyframe_count, int32_t* track_matches0,
+                            float* track_mscores0, uint8_t* track_usable);
+
+/* ---- Multi-device driver: the front end on every GPU of a box, one process -------------------------
+ * The object graph of src/SuperSLAM.cc:82-86,107 once per device: one host thread + one ssb_frontend per entry of
+ * `device_ids` (NULL: devices 0 .. n_devices-1), weights replicated.  Pair p of a call runs on device p mod n
+ * (ssb_mg_device_of_pair) in steps of at most `max_pairs_per_device` pairs through ssb_fe_submit / ssb_fe_collect;
+ * there is no data-path collective - every worker writes its pairs' rows into the caller's arrays, which are laid out
+ * and indexed exactly like ssb_fe_process's (any may be NULL).  `pairs` is unbounded.  Blocking; not re-entrant. */
+typedef struct ssb_multigpu ssb_multigpu;
+int ssb_mg_create(const char* sp_weights, const char* lg_weights, int max_keypoints, double keypoint_threshold,
+                  int remove_borders, int lg_image_width, int lg_image_height, float min_disparity,
+                  int max_pairs_per_device, const int* device_ids, int n_devices, ssb_multigpu** out);
+void ssb_mg_destroy(ssb_multigpu* mg);
+int ssb_mg_device_count(ssb_multigpu* mg);
+int ssb_mg_device_of_pair(ssb_multigpu* mg, int pair);
+const char* ssb_mg_last_error(ssb_multigpu* mg); /* of the last failed ssb_mg_process */
+int ssb_mg_process(ssb_multigpu* mg, const uint8_t* const* images, int pairs, int height, int width, int row_stride,
+                   int* count, float* xy, float* score, int32_t* matches0, float* mscores0, float* stereo_ur,
+                   uint8_t* has_depth);
 /* CUDA-event timing on the front end's own stream (torch.cuda.Event only sees torch's stream). */
 int ssb_fe_event_record(ssb_frontend* fe, int index /* 0..15 */);
 int ssb_fe_event_elapsed_ms(ssb_frontend* fe, int start_index, int stop_index, float* ms);

@@ -60,6 +60,18 @@ SYMBOLS = [
     ("ssb_fe_submit", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("ssb_fe_collect", C.c_int, [_vp, _ip, _ip, _fp, _fp, _i32p, _fp, _fp, _u8p]),
     ("ssb_fe_sync", C.c_int, [_vp]),
+    ("ssb_fe_set_extract_only", C.c_int, [_vp, C.c_int]),
+    ("ssb_fe_enable_tracking", C.c_int, [_vp, C.c_int]),
+    ("ssb_fe_reset_tracking", C.c_int, [_vp]),
+    ("ssb_fe_promote_keyframes", C.c_int, [_vp, _u8p, C.c_int]),
+    ("ssb_fe_tracking_results", C.c_int, [_vp, C.c_int, _ip, _i32p, _fp, _u8p]),
+    ("ssb_mg_create", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float,
+                                C.c_int, _ip, C.c_int, C.POINTER(_vp)]),
+    ("ssb_mg_destroy", None, [_vp]),
+    ("ssb_mg_device_count", C.c_int, [_vp]),
+    ("ssb_mg_device_of_pair", C.c_int, [_vp, C.c_int]),
+    ("ssb_mg_last_error", C.c_char_p, [_vp]),
+    ("ssb_mg_process", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp, _i32p, _fp, _fp, _u8p]),
     ("ssb_fe_event_record", C.c_int, [_vp, C.c_int]),
     ("ssb_fe_event_elapsed_ms", C.c_int, [_vp, C.c_int, C.c_int, _fp]),
     ("ssb_fe_upload_images", C.c_int, [_vp, _u8pp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),

@@ -58,6 +58,61 @@ __global__ void stereo_postfilter_kernel(const float* __restrict__ kp_xy, int K,
   has_depth[o] = hd;
 }
 
+// ---- tracking chain (src/VoEstimator.cc:240-246): last keyframe <-> current left image -------------
+// LightGlue::run takes its pairs as images (2p, 2p+1) of one keypoint array: even rows = the retained keyframe of
+// stream p, odd rows = the left image SuperPoint has just extracted for stream p.
+__global__ void tracking_assemble_kernel(const float* __restrict__ kf_xy, const int* __restrict__ kf_count,
+                                         const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int K,
+                                         float* __restrict__ trk_xy, int* __restrict__ trk_count) {
+  const int z = blockIdx.y, p = z >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool frame = (z & 1) != 0;
+  const float2* src = reinterpret_cast<const float2*>(frame ? kp_xy + static_cast<size_t>(2 * p) * K * 2
+                                                            : kf_xy + static_cast<size_t>(p) * K * 2);
+  if (i < K) reinterpret_cast<float2*>(trk_xy)[static_cast<size_t>(z) * K + i] = src[i];
+  if (i == 0) trk_count[z] = frame ? kp_count[2 * p] : kf_count[p];
+}
+// The part of VoEstimator::track's match loop that needs no pose (src/VoEstimator.cc:250-260): a tracking match
+// (keyframe feature i -> frame feature j) is usable iff both ends carry stereo depth.
+__global__ void tracking_postfilter_kernel(const int32_t* __restrict__ matches0, int kp, const int* __restrict__ trk_count,
+                                           const uint8_t* __restrict__ kf_hd, const uint8_t* __restrict__ hd, int K,
+                                           uint8_t* __restrict__ ok) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  uint8_t r = 0;
+  if (i < trk_count[2 * p]) {
+    const int j = matches0[static_cast<size_t>(p) * kp + i];
+    if (j >= 0 && j < trk_count[2 * p + 1]) r = kf_hd[static_cast<size_t>(p) * K + i] & hd[static_cast<size_t>(p) * K + j];
+  }
+  ok[static_cast<size_t>(p) * K + i] = r;
+}
+// "last_keyframe_ = frame" (src/VoEstimator.cc:327) for the streams whose mask byte is set: keypoints, count, depth
+// flags and the fp16 descriptor rows of the current left image move into the stream's keyframe slot, device to device.
+// grid (K / 8, pairs), block 256: one warp per descriptor row (512 bytes = 32 lanes x 16 bytes).
+__global__ void __launch_bounds__(256)
+promote_keyframe_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ kp_xy,
+                        const int* __restrict__ kp_count, const uint8_t* __restrict__ hd,
+                        void* const* __restrict__ slot_ptrs, int K, float* __restrict__ kf_xy,
+                        int* __restrict__ kf_count, uint8_t* __restrict__ kf_hd, __half* __restrict__ kf_desc,
+                        size_t kf_desc_stride) {
+  const int p = blockIdx.y;
+  if (mask[p] == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= K) return;
+  const int n = kp_count[2 * p];
+  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __half*>(slot_ptrs[2 * p]) + static_cast<size_t>(row) * 256);
+  uint4* dst = reinterpret_cast<uint4*>(kf_desc + p * kf_desc_stride + static_cast<size_t>(row) * 256);
+  dst[lane] = row < n ? src[lane] : make_uint4(0u, 0u, 0u, 0u);
+  if (lane == 0) {
+    const size_t o = static_cast<size_t>(p) * K + row;
+    reinterpret_cast<float2*>(kf_xy)[o] = reinterpret_cast<const float2*>(kp_xy)[static_cast<size_t>(2 * p) * K + row];
+    kf_hd[o] = row < n ? hd[o] : 0;
+    if (row == 0) kf_count[p] = n;
+  }
+}
+
 class FrontEnd {
  public:
   ~FrontEnd() {
@@ -75,6 +130,9 @@ class FrontEnd {
       if (s_host_[b]) cudaFreeHost(s_host_[b]);
     }
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    void* trk[] = {kf_xy_, kf_count_, kf_hd_, kf_desc_, trk_xy_, trk_count_, trk_desc_ptrs_, trk_ok_, promote_mask_};
+    for (void* p : trk)
+      if (p) cudaFree(p);
     if (rect_buf_) cudaFree(rect_buf_);
     if (ur_) cudaFree(ur_);
     if (hd_) cudaFree(hd_);
@@ -96,7 +154,7 @@ class FrontEnd {
     SSB_RETURN_IF(lg.impl.init(w, lw, lh, K, max_pairs));
     stream_ = sp.impl.stream();
     // fixed descriptor slots: image i of a call always lands in slot i
-    std::vector<void*> ptrs;
+    std::vector<void*>& ptrs = slot_host_;
     for (int i = 0; i < 2 * max_pairs; ++i) {
       const int s = sp.impl.pool().acquire();
       SSB_CHECK(s >= 0, SSB_ERR_EXHAUSTED, "front end could not reserve descriptor slots");
@@ -111,11 +169,112 @@ class FrontEnd {
     for (auto& e : events_) SSB_CUDA_CHECK(cudaEventCreate(&e));
     return SSB_OK;
   }
-  // pinned result block: count | xy | score | matches | mscores | ur | has_depth
+  // pinned result block: count | xy | score | matches | mscores | ur | has_depth | (tracking, same call: keyframe
+  // count | tracking matches | scores | usable flags)
   size_t result_bytes(int pairs) const {
     const size_t P = pairs, K = K_;
-    return 2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 64;
+    return 2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 64 +
+           P * 4 + P * K * 4 + P * K * 4 + P * K + 64;
   }
+  size_t tracking_offset(int pairs) const {   // of the tracking part inside a result block (16-byte aligned)
+    const size_t P = pairs, K = K_;
+    return (2 * P * 4 + 2 * P * K * 8 + 2 * P * K * 4 + P * K * 4 + P * K * 4 + P * K * 4 + P * K + 15) / 16 * 16;
+  }
+
+  // ---- tracking chain: SP x2 + LG (stereo) + LG (last keyframe <-> left) in one captured graph ------------------
+  // Every pair slot p of a call is a stream with its own retained keyframe (count 0 until the first promotion: the
+  // reference makes no tracking match for the first frame either, src/VoEstimator.cc:206-236).
+  int enable_tracking(bool on) {
+    SSB_CHECK(submitted_ == collected_, SSB_ERR_INVALID, "streamed steps are in flight: collect them first");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    drop_graphs();
+    if (!on) {
+      tracking_ = false;
+      return SSB_OK;
+    }
+    if (kf_xy_ == nullptr) {
+      const size_t P = pairs_, K = K_;
+      SSB_RETURN_IF(lg_trk.impl.init(lg.impl.weights(), lg.impl.image_width(), lg.impl.image_height(), K_, pairs_));
+      kf_desc_stride_ = static_cast<size_t>((K_ + 127) / 128 * 128) * 256;   // whole 128-row TMA boxes per stream
+      auto alloc = [&](void** p, size_t bytes) -> int {
+        SSB_CUDA_CHECK(cudaMalloc(p, bytes));
+        SSB_CUDA_CHECK(cudaMemset(*p, 0, bytes));
+        return SSB_OK;
+      };
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kf_xy_), P * K * 8));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kf_count_), P * 4));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kf_hd_), P * K));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&kf_desc_), P * kf_desc_stride_ * 2 + 65536));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&trk_xy_), 2 * P * K * 8));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&trk_count_), 2 * P * 4));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&trk_desc_ptrs_), 2 * P * sizeof(void*)));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&trk_ok_), P * K));
+      SSB_RETURN_IF(alloc(reinterpret_cast<void**>(&promote_mask_), P));
+      std::vector<void*> ptrs(2 * P);
+      for (size_t p = 0; p < P; ++p) {
+        ptrs[2 * p] = kf_desc_ + p * kf_desc_stride_;
+        ptrs[2 * p + 1] = slot_host_[2 * p];   // the left image of pair p always lands in this slot
+      }
+      SSB_CUDA_CHECK(cudaMemcpy(trk_desc_ptrs_, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
+    }
+    tracking_ = true;
+    return SSB_OK;
+  }
+  int reset_tracking() {   // forget every keyframe
+    SSB_CHECK(kf_count_ != nullptr, SSB_ERR_INVALID, "tracking was never enabled");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    SSB_CUDA_CHECK(cudaMemsetAsync(kf_count_, 0, static_cast<size_t>(pairs_) * 4, stream_));
+    return SSB_OK;
+  }
+  // mask[p] != 0: the left image of pair p of the LAST call becomes stream p's keyframe (nullptr: every stream).
+  int promote_keyframes(const uint8_t* mask, int pairs) {
+    SSB_CHECK(tracking_, SSB_ERR_INVALID, "tracking is not enabled");
+    SSB_CHECK(pairs >= 1 && pairs <= pairs_, SSB_ERR_INVALID, "pairs %d exceeds capacity %d", pairs, pairs_);
+    SSB_CHECK(submitted_ == collected_, SSB_ERR_INVALID,
+              "a streamed step is in flight: its features would be promoted instead of the last collected ones");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    uint8_t m[64];
+    for (int p = 0; p < pairs; ++p) m[p] = mask == nullptr ? 1 : (mask[p] != 0);
+    SSB_CUDA_CHECK(cudaMemcpyAsync(promote_mask_, m, pairs, cudaMemcpyHostToDevice, stream_));   // m: see the sync below
+    promote_keyframe_kernel<<<dim3((K_ + 7) / 8, pairs), 256, 0, stream_>>>(
+        promote_mask_, sp.impl.kp_xy(), sp.impl.kp_count(), hd_, slot_ptrs_, K_, kf_xy_, kf_count_, kf_hd_, kf_desc_,
+        kf_desc_stride_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    return SSB_OK;
+  }
+  // Tracking outputs of the step whose results were delivered last (ssb_fe_process / fetch / collect).
+  int tracking_results(int pairs, int* kf_count, int32_t* matches0, float* mscores0, uint8_t* ok) const {
+    SSB_CHECK(tracking_ && last_block_ != nullptr && last_block_tracking_, SSB_ERR_INVALID,
+              "no tracking results: enable tracking, then process / fetch / collect a step");
+    SSB_CHECK(pairs == last_block_pairs_, SSB_ERR_INVALID, "the last delivered step had %d pairs, not %d",
+              last_block_pairs_, pairs);
+    const size_t P = pairs, K = K_;
+    const uint8_t* t = last_block_ + tracking_offset(pairs);
+    const int* h_kc = reinterpret_cast<const int*>(t);
+    const int32_t* h_m = reinterpret_cast<const int32_t*>(t + (P * 4 + 15) / 16 * 16);
+    const float* h_ms = reinterpret_cast<const float*>(h_m + P * K);
+    const uint8_t* h_ok = reinterpret_cast<const uint8_t*>(h_ms + P * K);
+    if (kf_count) std::memcpy(kf_count, h_kc, P * 4);
+    if (matches0) std::memcpy(matches0, h_m, P * K * 4);
+    if (mscores0) std::memcpy(mscores0, h_ms, P * K * 4);
+    if (ok) std::memcpy(ok, h_ok, P * K);
+    return SSB_OK;
+  }
+  bool tracking() const { return tracking_; }
+  // extract-only mode: SuperPoint on 2 * pairs independent frames, no matching (the match / stereo outputs of a
+  // call are then undefined)
+  int set_extract_only(bool on) {
+    SSB_CHECK(submitted_ == collected_, SSB_ERR_INVALID, "streamed steps are in flight: collect them first");
+    SSB_CUDA_CHECK(cudaSetDevice(device_));
+    SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    drop_graphs();
+    extract_only_ = on;
+    return SSB_OK;
+  }
+  bool extract_only() const { return extract_only_; }
   // The whole pair pipeline (94 kernels, no host dependency thanks to device-side counts) is
   // captured into a CUDA graph the second time a (images, pairs, h, w) combination is seen and
   // replayed afterwards; SSB_NO_GRAPH=1 or an active event profiler falls back to eager launches.
@@ -215,12 +374,26 @@ class FrontEnd {
       w = rect_l_->dst_w();
     }
     SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
+    if (extract_only_) return SSB_OK;   // mono frames (BASELINE config C1): the 2 * pairs images are independent
     SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
     stereo_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
         sp.impl.kp_xy(), K_, sp.impl.kp_count(), lg.impl.matches_dev(), lg.impl.kp(), min_disp_, ur_, hd_);
     SSB_CUDA_CHECK(cudaGetLastError());
     count_launch();
     prof_mark(stream_, "fe.postfilter");
+    if (tracking_) {
+      tracking_assemble_kernel<<<dim3((K_ + 255) / 256, 2 * pairs), 256, 0, stream_>>>(
+          kf_xy_, kf_count_, sp.impl.kp_xy(), sp.impl.kp_count(), K_, trk_xy_, trk_count_);
+      SSB_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      prof_mark(stream_, "fe.track_assemble");
+      SSB_RETURN_IF(lg_trk.impl.run(pairs, trk_xy_, K_, trk_count_, trk_desc_ptrs_, stream_));
+      tracking_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
+          lg_trk.impl.matches_dev(), lg_trk.impl.kp(), trk_count_, kf_hd_, hd_, K_, trk_ok_);
+      SSB_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      prof_mark(stream_, "fe.track_postfilter");
+    }
     return SSB_OK;
   }
   // Result block layout in pinned memory: count | xy | score | matches | mscores | ur | has_depth
@@ -240,6 +413,17 @@ class FrontEnd {
     SSB_CUDA_CHECK(cudaMemcpy2DAsync(h_ms, K * 4, lg.impl.mscores_dev(), KP * 4, K * 4, P, cudaMemcpyDeviceToHost, stream_));
     SSB_CUDA_CHECK(cudaMemcpyAsync(h_ur, ur_, P * K * 4, cudaMemcpyDeviceToHost, stream_));
     SSB_CUDA_CHECK(cudaMemcpyAsync(h_hd, hd_, P * K, cudaMemcpyDeviceToHost, stream_));
+    if (tracking_) {
+      const size_t KT = lg_trk.impl.kp();
+      uint8_t* t = h + tracking_offset(pairs);
+      int32_t* t_m = reinterpret_cast<int32_t*>(t + (P * 4 + 15) / 16 * 16);
+      float* t_ms = reinterpret_cast<float*>(t_m + P * K);
+      uint8_t* t_ok = reinterpret_cast<uint8_t*>(t_ms + P * K);
+      SSB_CUDA_CHECK(cudaMemcpy2DAsync(t, 4, trk_count_, 8, 4, P, cudaMemcpyDeviceToHost, stream_));   // even entries
+      SSB_CUDA_CHECK(cudaMemcpy2DAsync(t_m, K * 4, lg_trk.impl.matches_dev(), KT * 4, K * 4, P, cudaMemcpyDeviceToHost, stream_));
+      SSB_CUDA_CHECK(cudaMemcpy2DAsync(t_ms, K * 4, lg_trk.impl.mscores_dev(), KT * 4, K * 4, P, cudaMemcpyDeviceToHost, stream_));
+      SSB_CUDA_CHECK(cudaMemcpyAsync(t_ok, trk_ok_, P * K, cudaMemcpyDeviceToHost, stream_));
+    }
     return SSB_OK;
   }
   void copy_out(const uint8_t* h, int pairs, int* count, float* xy, float* score, int32_t* matches0,
@@ -268,6 +452,7 @@ class FrontEnd {
     SSB_RETURN_IF(enqueue_results(host_, pairs));
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
     copy_out(host_, pairs, count, xy, score, matches0, mscores0, ur, hd);
+    last_block_ = host_, last_block_pairs_ = pairs, last_block_tracking_ = tracking_;
     return SSB_OK;
   }
 
@@ -341,6 +526,7 @@ class FrontEnd {
     const int b = static_cast<int>(collected_ & 1);
     SSB_CUDA_CHECK(cudaEventSynchronize(ev_done_[b]));
     copy_out(s_host_[b], s_pairs_[b], count, xy, score, matches0, mscores0, ur, hd);
+    last_block_ = s_host_[b], last_block_pairs_ = s_pairs_[b], last_block_tracking_ = tracking_;
     if (pairs_out) *pairs_out = s_pairs_[b];
     ++collected_;
     return SSB_OK;
@@ -393,6 +579,23 @@ class FrontEnd {
 
   ssb_superpoint sp;
   ssb_lightglue lg;
+  ssb_lightglue lg_trk;            // second context (shared weights) for the keyframe <-> frame match
+  bool tracking_ = false;
+  bool extract_only_ = false;
+  float* kf_xy_ = nullptr;         // [pairs_][K][2] keyframe keypoints per stream
+  int* kf_count_ = nullptr;        // [pairs_]
+  uint8_t* kf_hd_ = nullptr;       // [pairs_][K] stereo-depth flags of the keyframe's features
+  __half* kf_desc_ = nullptr;      // [pairs_][kf_desc_stride_] fp16 descriptor rows
+  size_t kf_desc_stride_ = 0;
+  float* trk_xy_ = nullptr;        // [2 pairs_][K][2]: (keyframe, frame) per stream, LightGlue::run's layout
+  int* trk_count_ = nullptr;       // [2 pairs_]
+  void** trk_desc_ptrs_ = nullptr; // [2 pairs_]
+  uint8_t* trk_ok_ = nullptr;      // [pairs_][K]
+  uint8_t* promote_mask_ = nullptr;
+  std::vector<void*> slot_host_;   // host copy of slot_ptrs_
+  const uint8_t* last_block_ = nullptr;   // pinned result block delivered last
+  int last_block_pairs_ = 0;
+  bool last_block_tracking_ = false;
   Rectifier* rect_l_ = nullptr;   // not owned
   Rectifier* rect_r_ = nullptr;
   uint8_t* rect_buf_ = nullptr;   // [2 * pairs_][dst_h][dst_w]
@@ -630,6 +833,37 @@ int ssb_fe_collect(ssb_frontend* fe, int* pairs, int* count, float* xy, float* s
   return fe->impl.collect(pairs, count, xy, score, matches0, mscores0, stereo_ur, has_depth);
   SSB_API_END
 }
+int ssb_fe_set_extract_only(ssb_frontend* fe, int on) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.set_extract_only(on != 0);
+  SSB_API_END
+}
+int ssb_fe_enable_tracking(ssb_frontend* fe, int enable) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.enable_tracking(enable != 0);
+  SSB_API_END
+}
+int ssb_fe_reset_tracking(ssb_frontend* fe) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.reset_tracking();
+  SSB_API_END
+}
+int ssb_fe_promote_keyframes(ssb_frontend* fe, const uint8_t* promote, int pairs) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.promote_keyframes(promote, pairs);
+  SSB_API_END
+}
+int ssb_fe_tracking_results(ssb_frontend* fe, int pairs, int* keyframe_count, int32_t* track_matches0,
+                            float* track_mscores0, uint8_t* track_usable) {
+  SSB_API_BEGIN
+  SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
+  return fe->impl.tracking_results(pairs, keyframe_count, track_matches0, track_mscores0, track_usable);
+  SSB_API_END
+}
 int ssb_fe_sync(ssb_frontend* fe) {
   SSB_CHECK(fe != nullptr, SSB_ERR_INVALID, "fe is null");
   SSB_CUDA_CHECK(cudaSetDevice(fe->impl.device_));
@@ -663,7 +897,10 @@ int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
   // SuperPoint: 10 convolution launches + nms, select, gather | LightGlue: prepare + 9 x (qkv, attention, ffn1,
   // ffn2) x 2 + final_proj, matchability, sim, sim^T, lse, arg-max, mutual | post-filter | (+ 2 remaps)
   const int lg_blocks = ssb::kLgLayers * 8 + (fe != nullptr && !fe->impl.lg.impl.weights()->fold_out ? ssb::kLgLayers * 2 : 0);
-  return 13 + 1 + lg_blocks + 7 + 1 + (fe != nullptr && fe->impl.has_rectifiers() ? 2 : 0);
+  const int lg_all = 1 + lg_blocks + 7;
+  if (fe != nullptr && fe->impl.extract_only()) return 13 + (fe->impl.has_rectifiers() ? 2 : 0);
+  return 13 + lg_all + 1 + (fe != nullptr && fe->impl.has_rectifiers() ? 2 : 0) +
+         (fe != nullptr && fe->impl.tracking() ? lg_all + 2 : 0);
 }
 static int require_sm100(int device_id) {
   SSB_CUDA_CHECK(cudaSetDevice(device_id));

@@ -390,6 +390,44 @@ class FramePairPipeline:
         self._rectifiers = (left, right)   # keep them alive: the library borrows the handles
         _lib.check(self._lib.ssb_fe_set_rectifiers(self._h, left._h if left else None, right._h if right else None))
 
+    def set_extract_only(self, on: bool) -> None:
+        """SuperPoint only (BASELINE config C1): the 2*pairs images of a call are independent mono frames."""
+        _lib.check(self._lib.ssb_fe_set_extract_only(self._h, int(bool(on))))
+
+    # ---- tracking chain (SURVEY 8f-2, src/VoEstimator.cc:240-246,327) ----
+    def enable_tracking(self, on: bool = True) -> None:
+        """Every pair slot becomes a stream with a device-resident keyframe; each call also matches that keyframe
+        against the current left image (the second LightGlue call of the live pipeline) in the same graph."""
+        _lib.check(self._lib.ssb_fe_enable_tracking(self._h, int(bool(on))))
+
+    def reset_tracking(self) -> None:
+        _lib.check(self._lib.ssb_fe_reset_tracking(self._h))
+
+    def promote_keyframes(self, pairs: int, mask=None) -> None:
+        """`last_keyframe_ = frame` for the streams whose mask entry is set (None: all), on the device."""
+        if mask is None:
+            _lib.check(self._lib.ssb_fe_promote_keyframes(self._h, None, pairs))
+        else:
+            m = np.ascontiguousarray(mask, np.uint8)
+            assert m.shape == (pairs,)
+            _lib.check(self._lib.ssb_fe_promote_keyframes(self._h, m.ctypes.data_as(C.POINTER(C.c_uint8)), pairs))
+
+    def tracking_results(self, pairs: int):
+        """Tracking outputs of the step delivered last: keyframe_count [pairs], track_matches0 / track_mscores0 /
+        track_usable [pairs, K] (queryIdx = keyframe feature, trainIdx = current left feature)."""
+        K = self.K
+        o = dict(keyframe_count=np.zeros((pairs,), np.int32), track_matches0=np.zeros((pairs, K), np.int32),
+                 track_mscores0=np.zeros((pairs, K), np.float32), track_usable=np.zeros((pairs, K), np.uint8))
+        _lib.check(self._lib.ssb_fe_tracking_results(
+            self._h, pairs, o["keyframe_count"].ctypes.data_as(C.POINTER(C.c_int)),
+            o["track_matches0"].ctypes.data_as(C.POINTER(C.c_int32)),
+            o["track_mscores0"].ctypes.data_as(C.POINTER(C.c_float)),
+            o["track_usable"].ctypes.data_as(C.POINTER(C.c_uint8))))
+        return o
+
+    def kernel_launches_per_call(self, pairs: int) -> int:
+        return int(self._lib.ssb_fe_kernel_launches_per_call(self._h, pairs))
+
     def event_record(self, idx: int):
         _lib.check(self._lib.ssb_fe_event_record(self._h, idx))
 
@@ -409,6 +447,49 @@ class FramePairPipeline:
         h = self._lib.ssb_fe_superpoint(self._h)
         _lib.check(self._lib.ssb_sp_debug_read(C.c_void_p(h), what.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+
+class MultiGpuFrontEnd:
+    """ssb_mg_*: the frame-pair front end on several GPUs of one process (one host thread + one front end per device,
+    pair p on device p mod G, no data-path collective).  Same outputs as FramePairPipeline.process, any number of pairs."""
+
+    def __init__(self, sp_weights: str, lg_weights: str, max_keypoints: int, lg_image_width: int, lg_image_height: int,
+                 devices, max_pairs_per_device: int = 8, keypoint_threshold: float = 0.005, remove_borders: int = 4,
+                 min_disparity: float = 1.0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.K = max_keypoints
+        ids = (C.c_int * len(devices))(*devices)
+        _lib.check(self._lib.ssb_mg_create(sp_weights.encode(), lg_weights.encode(), max_keypoints,
+                                           float(keypoint_threshold), remove_borders, lg_image_width, lg_image_height,
+                                           float(min_disparity), max_pairs_per_device, ids, len(devices),
+                                           C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ssb_mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def device_of_pair(self, pair: int) -> int:
+        return int(self._lib.ssb_mg_device_of_pair(self._h, pair))
+
+    def process(self, images):
+        images = [np.ascontiguousarray(i, np.uint8) for i in images]
+        pairs = len(images) // 2
+        h, w = images[0].shape
+        ptrs = (C.POINTER(C.c_uint8) * len(images))(*[i.ctypes.data_as(C.POINTER(C.c_uint8)) for i in images])
+        K = self.K
+        o = dict(count=np.zeros((2 * pairs,), np.int32), xy=np.zeros((2 * pairs, K, 2), np.float32),
+                 score=np.zeros((2 * pairs, K), np.float32), matches0=np.zeros((pairs, K), np.int32),
+                 mscores0=np.zeros((pairs, K), np.float32), stereo_ur=np.zeros((pairs, K), np.float32),
+                 has_depth=np.zeros((pairs, K), np.uint8))
+        st = self._lib.ssb_mg_process(self._h, ptrs, pairs, h, w, w, *FramePairPipeline._ptrs(o))
+        if st != _lib.SSB_OK:
+            raise _lib.SsbError(st, (self._lib.ssb_mg_last_error(self._h) or b"").decode())
+        return o
 
 
 def kernel_launch_count() -> int:

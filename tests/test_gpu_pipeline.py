@@ -245,3 +245,68 @@ def test_cached_graphs_survive_workspace_reallocation(tmp_path, lg_weights):
         pipe.enqueue_device(dev, pairs, 240, 320)
         assert same(snap(pipe.fetch(pairs)), first[name])
     assert int(first["b4"]["count"].min()) > 20
+
+
+def test_tracking_chain_equals_two_interface_calls(tmp_path, lg_weights):
+    """the live pipeline makes TWO LightGlue calls per frame - the stereo match and the tracking match of
+    the last keyframe's left features against the current left features (src/VoEstimator.cc:240-246) - and promotes the
+    frame to keyframe on the host's decision (:327).  With tracking enabled the pair pipeline keeps each stream's
+    keyframe on the device and chains both matches in one graph; it must give exactly what the interface calls give:
+    matcher.match(kf.keypoints, kf.descriptors, L.keypoints, L.descriptors), plus the depth test of :253-256."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import save_state_dict
+    from superslam_b200.synth import synth_pair
+
+    lgw = str(tmp_path / "lg.ssbw")
+    save_state_dict(lg_weights, lgw)
+    h, w, K, S = 240, 320, 512, 2
+    sp = fe.SuperPoint(SP_WEIGHTS, K, num_slots=16)
+    lg = fe.LightGlue(lgw, w, h, max_keypoints=K)
+    front = fe.StereoFrontEnd(sp, lg)
+    pipe = fe.FramePairPipeline(SP_WEIGHTS, lgw, K, w, h, max_pairs=S)
+    pipe.enable_tracking(True)
+    # two streams; frame t of stream s = the stream's scene shifted by 3 t pixels (camera motion)
+    base = [synth_pair(h, w, 300 + s, 120) for s in range(S)]
+    frames = [[tuple(np.roll(im, -3 * t, axis=1) for im in base[s]) for s in range(S)] for t in range(4)]
+    kf = [None] * S        # interface-call side: (Features of the keyframe's left image, has_depth)
+    promote_plan = [np.array([1, 1], np.uint8), np.array([1, 0], np.uint8), np.array([0, 0], np.uint8), None]
+    for t in range(4):
+        flat = [im for s in range(S) for im in frames[t][s]]
+        out = pipe.process(flat)
+        trk = pipe.tracking_results(S)
+        cur = []
+        for s in range(S):
+            L, R = sp.extract_stereo(*frames[t][s])
+            m = lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
+            frame = front.process(*frames[t][s])
+            n0 = len(L.keypoints)
+            assert np.array_equal(out["matches0"][s, :n0], m.matches0)
+            cur.append((L, frame.has_depth.astype(np.uint8)))
+            if kf[s] is None:
+                assert trk["keyframe_count"][s] == 0 and np.all(trk["track_matches0"][s] == -1)
+                assert not trk["track_usable"][s].any()
+                continue
+            KF, kf_hd = kf[s]
+            nk = len(KF.keypoints)
+            assert trk["keyframe_count"][s] == nk
+            tm = lg.match(KF.keypoints, KF.descriptors, L.keypoints, L.descriptors)
+            assert np.array_equal(trk["track_matches0"][s, :nk], tm.matches0)
+            assert np.array_equal(trk["track_mscores0"][s, :nk], tm.mscores0)
+            usable = np.zeros(K, np.uint8)
+            ok = tm.matches0 >= 0
+            usable[:nk][ok] = kf_hd[:nk][ok] & cur[s][1][tm.matches0[ok]]
+            assert np.array_equal(trk["track_usable"][s], usable)
+            if t == 1:
+                assert ok.sum() > 20   # the scene moved by 3 px: most keyframe features are found again
+        mask = promote_plan[t]
+        if mask is not None:
+            pipe.promote_keyframes(S, mask)
+            for s in range(S):
+                if mask[s]:
+                    kf[s] = cur[s]
+    # tracking off again: the stereo results do not change, tracking results are refused
+    pipe.enable_tracking(False)
+    again = pipe.process([im for s in range(S) for im in frames[3][s]])
+    assert np.array_equal(again["matches0"], out["matches0"])
+    with pytest.raises(Exception):
+        pipe.tracking_results(S)
