@@ -481,6 +481,10 @@ __device__ __forceinline__ void gelu_erf_h2_batch(__half2 (&y)[kN]) {
     y[i] = __hfma2(__hmul2(__habs2(y[i]), __float2half2_rn(-0.5f)), p[i], __hmax2(y[i], __float2half2_rn(0.f)));
 }
 
+}  // namespace ssb
+#include "ffn_fused.cuh"   // uses gelu_erf_h2_batch above
+namespace ssb {
+
 struct EpiLnGelu {
   const float* bias;
   const float* g;
@@ -1011,7 +1015,17 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     p.m_valid = dev_count(cnt);
     return p;
   };
+  // One kernel per FFN (ffn_fused.cuh): the 512-wide hidden activation stays in tensor memory.  SSB_LG_FUSED_FFN=0
+  // selects the two-kernel version (ffn1 on a CTA pair + ffn2) for A/B measurements.
+  static const bool fused_ffn = [] { const char* e = std::getenv("SSB_LG_FUSED_FFN"); return e == nullptr || std::atoi(e) != 0; }();
   auto ffn = [&](const LgBlockFfn& F) -> int {
+    if (fused_ffn) {
+      FfnParams fp;
+      fp.b1 = F.fc1.bias, fp.ln_g = F.ln_g, fp.ln_b = F.ln_b, fp.b2 = F.fc2.bias;
+      fp.x32 = x32_, fp.cnt = cnt, fp.kp = KP, fp.tiles_per_img = tiles, fp.images = P2;
+      fp.label = "lg.ffn";
+      return launch_ffn_fused(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, F.fc1.tmB, F.fc2.tmB, ts_x16_, fp, stream);
+    }
     {
       CoreParams p = lin("lg.ffn1", 4, 4, 256);
       p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)

@@ -34,6 +34,19 @@ def pack_records(pair_indices, counts, matches0, mscores0, has_depth, K: int, sl
     return rec
 
 
+def pack_records_block(first_pair: int, stride: int, counts, matches0, mscores0, has_depth, K: int) -> np.ndarray:
+    """pack_records for a whole step at once (no per-pair Python loop): slot s holds pair `first_pair + stride * s`
+    (rank r of a world of G owns pairs r, r + G, ...: first_pair = r + G * pairs_done, stride = G)."""
+    P = len(matches0)
+    rec = np.empty((P, record_len(K)), np.int32)
+    rec[:, 0] = first_pair + stride * np.arange(P, dtype=np.int32)
+    rec[:, 1:3] = np.asarray(counts, np.int32).reshape(P, 2)
+    rec[:, 3:3 + K] = matches0
+    rec[:, 3 + K:3 + 2 * K] = np.ascontiguousarray(mscores0, np.float32).view(np.int32)
+    rec[:, 3 + 2 * K:] = has_depth
+    return rec
+
+
 def unpack_records(all_records: np.ndarray, K: int):
     """{pair_index: dict(n_left, n_right, matches0, mscores0, has_depth)} from gathered records."""
     out = {}

@@ -68,3 +68,15 @@ def test_two_rank_gather_gloo():
     for p in procs:
         p.join(60)
     assert all(ok for _, ok, _ in res) and all(total == N_PAIRS for _, _, total in res)
+
+
+def test_block_packing_equals_per_pair_packing():
+    rng = np.random.default_rng(3)
+    P = 6
+    counts = rng.integers(0, K + 1, 2 * P).astype(np.int32)
+    m = rng.integers(-1, K, (P, K)).astype(np.int32)
+    s = rng.random((P, K)).astype(np.float32)
+    hd = rng.integers(0, 2, (P, K)).astype(np.uint8)
+    a = sharding.pack_records([3 + 4 * i for i in range(P)], counts.tolist(), m, s, hd, K, P)
+    b = sharding.pack_records_block(3, 4, counts, m, s, hd, K)
+    assert np.array_equal(a, b)

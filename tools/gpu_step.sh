@@ -1,0 +1,45 @@
+# usage (under gpurun):  bash tools/gpu_step.sh <tag> [what...]     what = tests diag bench ab configs ncu  (default: tests diag bench)
+# One development step on the GPU box: every part is bounded by its own timeout and none blocks the next.
+tag=${1:-step}; shift
+what=${@:-tests diag bench}
+mkdir -p gpurun_out
+for w in $what; do
+case $w in
+tests) echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 | tee gpurun_out/pytest_$tag.log ;;
+tests_all) echo "== pytest -m gpu (no -x)"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 | tee gpurun_out/pytest_$tag.log ;;
+lgtests) echo "== pytest lightglue + pipeline"; timeout 600 python -m pytest tests/test_gpu_lightglue.py tests/test_gpu_pipeline.py -q -x 2>&1 | tail -25 | tee gpurun_out/pytest_$tag.log ;;
+smoke) echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
+diag) echo "== diag"; timeout 600 python tests/gpu_diag.py --size 480x640 --k 1024 > gpurun_out/diag_c2_$tag.txt 2>&1; grep -E "lg x32 final|lg matches0|disagreements|e2e\[|margin" gpurun_out/diag_c2_$tag.txt ;;
+bench) echo "== bench"; timeout 600 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; tail -3 gpurun_out/bench_$tag.err
+python - "$tag" <<'PY'
+import json, sys
+d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}.json"))
+print("value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), d["clocks"], d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "pipeline frac", round(d["pipeline_roofline"]["frac"], 3))
+print(d["kernel_ms_per_step"]); print("spread", d["value_spread_per_step"], "e2e repeats", d["e2e"]["repeats"])
+print("live", d.get("live_pipeline")); print("latency", d.get("latency_single_pair")); print("records", d["results"]["gathered_records"])
+PY
+;;
+ab) echo "== A/B: two-kernel FFN"; SSB_LG_FUSED_FFN=0 timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_unfused.json 2> gpurun_out/bench_${tag}_unfused.err
+python - "$tag" <<'PY'
+import json, sys
+d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}_unfused.json"))
+print("unfused value", round(d["value"], 1), d["clocks"]); print(d["kernel_ms_per_step"])
+PY
+;;
+configs) for c in C1 C3 C4 C5; do echo "== bench --config $c"; timeout 600 python bench.py --config $c --steps 5 --no-cpu-baseline > gpurun_out/bench_${tag}_$c.json 2> gpurun_out/bench_${tag}_$c.err; tail -2 gpurun_out/bench_${tag}_$c.err
+python - "$tag" "$c" <<'PY'
+import json, sys
+try:
+    d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}_{sys.argv[2]}.json"))
+    print(sys.argv[2], "value", round(d["value"], 1), d["unit"], "e2e", round(d["e2e"]["value"], 1), "pipeline frac", round(d["pipeline_roofline"]["frac"], 3), "attn share of LG flops", d["pipeline_roofline"]["attention_frac_of_lightglue_flops"], d["config"]["keypoints_per_image"], "sweep", d.get("micro_batch_sweep"))
+    print({k: v for k, v in list(d["kernel_ms_per_step"].items())[:10]})
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+done ;;
+ncu) echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_$tag.csv python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 1 > gpurun_out/ncu_$tag.log 2>&1
+python tools/ncu_traffic.py gpurun_out/launches_$tag.csv 64 > gpurun_out/ncu_traffic_$tag.json 2>> gpurun_out/ncu_$tag.log && echo "traffic table written" ;;
+esac
+done
