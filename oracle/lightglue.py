@@ -126,7 +126,7 @@ def _cross_block(w, i, x0, x1):
     return x0, x1
 
 
-def log_assignment(w, i, x0, x1):
+def log_assignment(w, i, x0, x1, return_sim=False):
     """MatchAssignment + sigmoid_log_double_softmax, inner [N,M] block only (the dustbin row/column
     never enters filter_matches)."""
     p = f"log_assignment.{i}."
@@ -138,6 +138,8 @@ def log_assignment(w, i, x0, x1):
     cert = F.logsigmoid(z0) + F.logsigmoid(z1).t()
     s0 = F.log_softmax(sim, 1)
     s1 = F.log_softmax(sim.t().contiguous(), 1).t()
+    if return_sim:
+        return s0 + s1 + cert, sim
     return s0 + s1 + cert
 
 
@@ -170,10 +172,11 @@ def match(w, kpts0, desc0, kpts1, desc1, return_intermediates=False):
             x0, x1 = _cross_block(w, i, x0, x1)
             if return_intermediates:
                 inter[f"cross{i}"] = (x0.numpy().copy(), x1.numpy().copy())
-        scores = log_assignment(w, N_LAYERS - 1, x0, x1)
+        scores, sim = log_assignment(w, N_LAYERS - 1, x0, x1, return_sim=True)
         m0, ms0 = filter_matches(scores)
     if return_intermediates:
         inter["scores"] = scores.numpy()
+        inter["sim"] = sim.numpy()
         return m0.numpy(), ms0.numpy(), inter
     return m0.numpy(), ms0.numpy()
 
@@ -191,7 +194,10 @@ def disagreement_report(scores: np.ndarray, m0: np.ndarray, ms0: np.ndarray, oth
       thr_gap   | exp(S[i, r]) - th |                                      (mscores0 > th)
     and `margin` = the smallest margin that can explain the disagreement.  A disagreement is a legitimate flip when
     its margin is within the other path's score error; a large margin is a defect.
-    Returns dict(n, disagree, rows=[dict(i, oracle, other, kind, row_gap, col_gap, thr_gap, margin)], max_margin)."""
+    `thr_gap_log` = | S[i, r] - log(th) | and `margin_log` is the same minimum with the threshold term in log-score
+    units, so that it can be compared with an error measured on the log-assignment scores (explained_by_score_error).
+    Returns dict(n, disagree, rows=[dict(i, oracle, other, kind, row_gap, col_gap, thr_gap, margin, thr_gap_log,
+    margin_log)], max_margin, max_margin_log)."""
     S = np.asarray(scores, np.float64)
     n, m = S.shape
     rows = []
@@ -202,13 +208,35 @@ def disagreement_report(scores: np.ndarray, m0: np.ndarray, ms0: np.ndarray, oth
         col = np.delete(S[:, r], i)
         col_gap = abs(top - col.max()) if col.size else np.inf
         thr_gap = abs(np.exp(top) - th)
+        thr_gap_log = abs(top - np.log(th))
         j = int(other_m0[i])
         if j >= 0 and j != r:
             kind, row_gap = "row", top - S[i, j]
-            margin = row_gap                       # the other side preferred j: only a row near-tie explains it
+            margin = margin_log = row_gap          # the other side preferred j: only a row near-tie explains it
         else:
             kind, row_gap = ("validity", top - second)
             margin = min(row_gap, col_gap, thr_gap)
+            margin_log = min(row_gap, col_gap, thr_gap_log)
         rows.append(dict(i=i, oracle=int(m0[i]), other=j, kind=kind, row_gap=float(row_gap), col_gap=float(col_gap),
-                         thr_gap=float(thr_gap), margin=float(margin)))
-    return dict(n=n, disagree=len(rows), rows=rows, max_margin=max((r["margin"] for r in rows), default=0.0))
+                         thr_gap=float(thr_gap), margin=float(margin), thr_gap_log=float(thr_gap_log),
+                         margin_log=float(margin_log)))
+    return dict(n=n, disagree=len(rows), rows=rows, max_margin=max((r["margin"] for r in rows), default=0.0),
+                max_margin_log=max((r["margin_log"] for r in rows), default=0.0))
+
+
+def competitive_score_error(scores: np.ndarray, other_scores: np.ndarray, window: float = 3.0) -> float:
+    """Largest |other - oracle| over the entries of the log-assignment matrix that can take part in a decision of
+    filter_matches: those within `window` log units of their row's or their column's maximum (an entry far below both
+    maxima decides nothing, and its absolute error grows with its distance from them)."""
+    S = np.asarray(scores, np.float64)
+    O = np.asarray(other_scores, np.float64)
+    if S.size == 0:
+        return 0.0
+    near = (S >= S.max(1, keepdims=True) - window) | (S >= S.max(0, keepdims=True) - window)
+    return float(np.abs(O - S)[near].max())
+
+
+def explained_by_score_error(report: dict, score_error: float) -> list:
+    """The rows of a disagreement_report that a score error of `score_error` (log units, both competitors of a decision
+    may move by it) does NOT explain: empty for an implementation whose only differences are near-tie flips."""
+    return [r for r in report["rows"] if not r["margin_log"] <= 2.0 * score_error]

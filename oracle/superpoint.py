@@ -147,6 +147,61 @@ def select_keypoints(scores: np.ndarray, input_h: int, input_w: int, max_keypoin
     return dict(xy=xy.reshape(-1, 2), score=sc, hw=np.stack([hs, ws], 1).reshape(-1, 2), cell=cell.reshape(-1, 2))
 
 
+def keypoint_disagreements(raw_ref: np.ndarray, raw_other: np.ndarray, hw_ref: np.ndarray, hw_other: np.ndarray,
+                           max_keypoints: int, keypoint_threshold: float = 0.005, remove_borders: int = 4):
+    """Index parity of another implementation's keypoint SET (`hw_other`, (row, col) on the score map, selected from
+    its own heat map `raw_other`) against the oracle's (`hw_ref` from `raw_ref`, the reference graph's softmax heat
+    map before NMS), decision by decision.  A pixel is a keypoint iff (SuperPoint.cc:696-719 after the graph's NMS,
+    convert_superpoint_to_onnx.py:82-87)  score > threshold,  score >= every other pixel of its 9x9 window,  it is
+    inside the border, and it ranks among the max_keypoints best.  For every pixel in the symmetric difference:
+      selected by the oracle only:   margin = the smallest slack of those decisions in the oracle's map
+      selected by the other only:    margin = the largest violation of them in the oracle's map
+    and `bound` = 2 x the largest |raw_other - raw_ref| over the pixel's 9x9 window and the two candidates that sit
+    at the top-K cut (the pixel's own score and its competitor's can each move by that much).  A disagreement with
+    margin <= bound is a near-tie the other implementation's score error legitimately flips; anything else is a
+    defect.  Returns dict(n_ref, n_other, differ, rows=[dict(hw, oracle_selected, score, margin, bound, why)],
+    unexplained=[rows with margin > bound])."""
+    R = NMS_RADIUS
+    H, W = raw_ref.shape
+    thr = float(keypoint_threshold)
+    ref = set(map(tuple, np.asarray(hw_ref).reshape(-1, 2).tolist()))
+    oth = set(map(tuple, np.asarray(hw_other).reshape(-1, 2).tolist()))
+    cand = select_keypoints(nms(raw_ref), H, W, 1 << 30, keypoint_threshold, remove_borders, H // 8, W // 8)
+    K = max_keypoints
+    err = np.abs(np.asarray(raw_other, np.float64) - np.asarray(raw_ref, np.float64))
+    s_last = s_next = None          # lowest selected / best excluded score of the oracle, when the top-K cut is active
+    e_cut = 0.0
+    if len(cand["score"]) > K:
+        s_last, s_next = float(cand["score"][K - 1]), float(cand["score"][K])
+        e_cut = float(max(err[tuple(cand["hw"][K - 1])], err[tuple(cand["hw"][K])]))
+    pad = np.pad(np.asarray(raw_ref, np.float64), R, constant_values=-np.inf)
+    pad_err = np.pad(err, R)
+    rows = []
+    for (h, w) in sorted(ref ^ oth):
+        win = pad[h:h + 2 * R + 1, w:w + 2 * R + 1].copy()
+        s = float(win[R, R])
+        win[R, R] = -np.inf
+        nb = float(win.max())
+        e = float(pad_err[h:h + 2 * R + 1, w:w + 2 * R + 1].max())
+        inside = remove_borders <= h < H - remove_borders and remove_borders <= w < W - remove_borders
+        if (h, w) in ref:
+            terms = {"threshold": s - thr, "nms": s - nb}
+            if s_next is not None:
+                terms["top-k"] = s - s_next
+            why = min(terms, key=terms.get)
+            margin = max(terms[why], 0.0)
+        else:
+            terms = {"threshold": thr - s, "nms": nb - s}
+            if s_last is not None:
+                terms["top-k"] = s_last - s
+            why = max(terms, key=terms.get)
+            margin = max(terms[why], 0.0) if inside else np.inf
+        bound = 2.0 * max(e, e_cut if "top-k" in terms else 0.0)
+        rows.append(dict(hw=(h, w), oracle_selected=(h, w) in ref, score=s, margin=float(margin), bound=bound, why=why))
+    return dict(n_ref=len(ref), n_other=len(oth), differ=len(rows), rows=rows,
+                unexplained=[r for r in rows if not r["margin"] <= r["bound"]])
+
+
 def gather_normalize(grid_f16: np.ndarray, cell: np.ndarray) -> np.ndarray:
     """gather_normalize_kernel (DescriptorGather.cu:14-56).  grid_f16 [256,Hc,Wc] fp16, cell [n,2]
     (row, col).  fp32 sum of squares in the kernel's 256-wide tree order (strides 128..1),

@@ -187,6 +187,11 @@ class LightGlue:
                                                device, C.byref(self._h)))
             self.max_keypoints = max_keypoints
 
+    @property
+    def kp(self) -> int:
+        """Rows per image in the workspace (max_keypoints rounded up to 256): the leading dimension of debug buffers."""
+        return (self.max_keypoints + 255) // 256 * 256
+
     def shared_context(self, image_width=None, image_height=None) -> "LightGlue":
         """LightGlue(shared_engine(), w, h): same weights, own stream/workspace (src/SuperSLAM.cc:129-133)."""
         return LightGlue(None, image_width or self.image_width, image_height or self.image_height,
@@ -435,6 +440,11 @@ class FramePairPipeline:
         ms = C.c_float()
         _lib.check(self._lib.ssb_fe_event_elapsed_ms(self._h, a, b, C.byref(ms)))
         return ms.value
+
+    @property
+    def kp(self) -> int:
+        """Rows per image in the LightGlue workspace (K rounded up to 256): leading dimension of its debug buffers."""
+        return (self.K + 255) // 256 * 256
 
     def lightglue_debug_read(self, what, shape, dtype):
         out = np.empty(shape, dtype)

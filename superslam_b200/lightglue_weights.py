@@ -78,6 +78,30 @@ def make_random_weights(seed: int = 7, sharpen: float = 2.0, matchability_bias: 
     return OrderedDict((k, v.contiguous()) for k, v in sd.items())
 
 
+def make_trained_like_weights(seed: int = 7, update_gain: float = 0.5, proj_gain: float = 2.2,
+                              matchability_bias: float = 3.0):
+    """Seeded synthetic weights whose assignment logits have the scale of a trained matcher instead of the ~50 of
+    make_random_weights (whose sharpened final projection multiplies every upstream rounding error by that scale):
+    the second FFN linear of every block is scaled by `update_gain` (residual updates about half the size of a default
+    init, so the descriptors still dominate the residual stream) and the final projection is `proj_gain` x a random
+    orthogonal matrix with zero bias, i.e. sim = proj_gain^2 / 16 * <x0, x1>: on the descriptor-like features of the
+    tests the matched logits stand ~10 above the rest, the log-assignment scores of the competitive entries are O(1).
+    Used where the north-star tolerances are asserted (mscores0 within 1e-3); a real checkpoint
+    (tools/convert_lightglue_weights.py) replaces both synthetic sets."""
+    sd = make_random_weights(seed, sharpen=1.0, matchability_bias=matchability_bias)
+    g = torch.Generator().manual_seed(seed + 1)
+    for i in range(N_LAYERS):
+        for blk in ("self_attn", "cross_attn"):
+            q = f"transformers.{i}.{blk}.ffn.3."
+            sd[q + "weight"] = (sd[q + "weight"] * update_gain).contiguous()
+            sd[q + "bias"] = (sd[q + "bias"] * update_gain).contiguous()
+    qmat, _ = torch.linalg.qr(torch.randn(DIM, DIM, generator=g))
+    last = f"log_assignment.{N_LAYERS - 1}."
+    sd[last + "final_proj.weight"] = (qmat * proj_gain).contiguous()
+    sd[last + "final_proj.bias"] = torch.zeros(DIM)
+    return sd
+
+
 def save_state_dict(sd, path: str) -> None:
     """Write a (normalised) LightGlue state dict as an SSBW archive; token_confidence.* (unused with
     early exit disabled) and non-final log_assignment layers are dropped."""

@@ -1,7 +1,8 @@
 """GPU parity tests for the LightGlue path through the C-ABI, against oracle/lightglue.py (fp32) on
 seeded synthetic weights (reference weights are unavailable offline: parity with the reference engine
-is unpinned, see oracle/__init__.py).  Bar: matches0 identical, mscores0 within 1e-3 (north_star);
-the fp16 tensor-core path is allowed a small measured flip rate on near-ties, asserted below."""
+is unpinned, see oracle/__init__.py).  Bar (tests/parity.py): the log-assignment scores within 1e-3 of the logit scale,
+EVERY differing matches0 entry a near-tie of the oracle below twice the score error measured in the same run,
+mscores0 within the bound that error implies - and within the north star's 1e-3 on unit-scale logits."""
 import numpy as np
 import pytest
 
@@ -32,30 +33,25 @@ def _feat(n0, n1, seed):
     return xy0, d0.astype(np.float16).astype(np.float32), xy1, d1.astype(np.float16).astype(np.float32)
 
 
-def _check(lg, lg_weights, xy0, d0, xy1, d1, w, h, min_agree):
-    from oracle import lightglue as olg
+def _check(lg, lg_weights, xy0, d0, xy1, d1, w, h, mscore_tol=None):
+    import parity
 
     m = lg.match(xy0, d0, xy1, d1)
-    om0, oms0 = olg.match(lg_weights, olg.normalize_keypoints(xy0, w, h), d0, olg.normalize_keypoints(xy1, w, h), d1)
-    assert m.matches0.shape == om0.shape
-    agree = (m.matches0 == om0)
-    assert agree.mean() >= min_agree, f"only {agree.mean():.4f} of matches0 agree"
-    both = agree & (om0 >= 0)
-    if both.any():
-        # fp16 operands / fp32 accumulation through 18 blocks leave ~8e-4 relative error on the residual
-        # stream; on assignment logits of magnitude ~50 (synthetic weights) that is a few 1e-3 on exp(score)
-        assert np.abs(m.mscores0[both] - oms0[both]).max() < 5e-3
+    rep = parity.check_matches(lg.debug_read, lg.kp, lg_weights, m.matches0, m.mscores0, xy0, d0, xy1, d1, w, h,
+                               mscore_tol=mscore_tol)
+    print(f"matches0: {rep['differ']} of {rep['n']} differ (all near-ties, largest margin {rep['max_margin_log']:.3g}); score "
+          f"error {rep['score_err']:.3g} at logit scale {rep['logit_scale']:.3g}; mscores0 error {rep['mscore_err']:.3g}")
     # MatchResult ordering / distance (src/LightGlue.cc:352-361)
     assert np.all(np.diff(m.query) > 0) and np.array_equal(m.train, m.matches0[m.query])
     assert np.allclose(m.distance, 1 - m.mscores0[m.query])
-    return m, om0
+    return m, rep["om0"]
 
 
 def test_host_path_matches_oracle(lgw, lg_weights):
     from superslam_b200 import frontend as fe
 
     lg = fe.LightGlue(lgw, 640, 480, max_keypoints=512)
-    m, om0 = _check(lg, lg_weights, *_feat(300, 300, 0), 640, 480, 0.99)
+    m, om0 = _check(lg, lg_weights, *_feat(300, 300, 0), 640, 480)
     assert (om0 >= 0).sum() > 50
 
 
@@ -63,10 +59,10 @@ def test_ragged_counts_single_keypoint_and_empty(lgw, lg_weights):
     from superslam_b200 import frontend as fe
 
     lg = fe.LightGlue(lgw, 640, 480, max_keypoints=512)
-    _check(lg, lg_weights, *_feat(37, 5, 3), 640, 480, 0.97)
-    _check(lg, lg_weights, *_feat(129, 257, 4), 640, 480, 0.98)
+    _check(lg, lg_weights, *_feat(37, 5, 3), 640, 480)
+    _check(lg, lg_weights, *_feat(129, 257, 4), 640, 480)
     xy0, d0, xy1, d1 = _feat(1, 64, 5)
-    _check(lg, lg_weights, xy0, d0, xy1, d1, 640, 480, 1.0)
+    _check(lg, lg_weights, xy0, d0, xy1, d1, 640, 480)
     empty = lg.match(np.zeros((0, 2), np.float32), np.zeros((0, 256), np.float32), xy1, d1)
     assert len(empty.query) == 0            # n0 == 0 -> empty result, not an error
     empty = lg.match(xy0, d0, np.zeros((0, 2), np.float32), np.zeros((0, 256), np.float32))
@@ -93,10 +89,10 @@ def test_device_path_stereo_frontend_and_shared_context(lgw, lg_weights):
     assert np.array_equal(frame.keypoints_left, L.keypoints)
     d0, d1 = lg.descriptors_to_host(L.descriptors), lg.descriptors_to_host(R.descriptors)
     assert d0.shape == (len(L.keypoints), 256) and np.abs(np.linalg.norm(d0, axis=1) - 1).max() < 2e-3
+    import parity
+
     m = lg.match(L.keypoints, L.descriptors, R.keypoints, R.descriptors)
-    om0, oms0 = olg.match(lg_weights, olg.normalize_keypoints(L.keypoints, w, h), d0,
-                          olg.normalize_keypoints(R.keypoints, w, h), d1)
-    assert (m.matches0 == om0).mean() >= 0.98
+    parity.check_matches(lg.debug_read, lg.kp, lg_weights, m.matches0, m.mscores0, L.keypoints, d0, R.keypoints, d1, w, h)
     q, t, _ = ofe.dmatches(m.matches0, m.mscores0)
     st, hd = ofe.stereo_postfilter(L.keypoints, R.keypoints, q, t)
     assert np.array_equal(hd, frame.has_depth) and np.array_equal(np.isnan(st[:, 1]), np.isnan(frame.stereo[:, 1]))
@@ -110,7 +106,7 @@ def test_c2_size_1024_keypoints(lgw, lg_weights):
     from superslam_b200 import frontend as fe
 
     lg = fe.LightGlue(lgw, 640, 480, max_keypoints=1024)
-    _check(lg, lg_weights, *_feat(1024, 1024, 9), 640, 480, 0.985)
+    _check(lg, lg_weights, *_feat(1024, 1024, 9), 640, 480)
 
 
 def test_2048_keypoints_beyond_the_reference_engine_profile(lgw, lg_weights):
@@ -119,4 +115,35 @@ def test_2048_keypoints_beyond_the_reference_engine_profile(lgw, lg_weights):
     from superslam_b200 import frontend as fe
 
     lg = fe.LightGlue(lgw, 1241, 376, max_keypoints=2048)
-    _check(lg, lg_weights, *_feat(2048, 1900, 11), 1241, 376, 0.98)
+    _check(lg, lg_weights, *_feat(2048, 1900, 11), 1241, 376)
+
+
+def test_unit_scale_logits_meet_the_north_star_tolerances(tmp_path):
+    """north_star: "within 1e-3 on descriptors and exactly on match indices".  make_random_weights drives the assignment
+    logits to ~50, where one fp16 ulp upstream is already > 1e-3 on exp(score); with logits of the scale a trained matcher
+    produces (make_trained_like_weights) mscores0 must be within 1e-3 of the oracle outright and matches0 may differ at
+    near-ties only - at C2 size and on a ragged pair."""
+    from superslam_b200 import frontend as fe
+    from superslam_b200.lightglue_weights import make_trained_like_weights, save_state_dict
+
+    sd = make_trained_like_weights(7)
+    p = str(tmp_path / "lg_unit.ssbw")
+    save_state_dict(sd, p)
+    lg = fe.LightGlue(p, 640, 480, max_keypoints=1024)
+    m, om0 = _check(lg, sd, *_feat(1024, 1024, 21), 640, 480, mscore_tol=1e-3)
+    assert (om0 >= 0).sum() > 300
+    _check(lg, sd, *_feat(300, 517, 22), 640, 480, mscore_tol=1e-3)
+
+
+def test_nan_inputs_give_no_matches_and_no_fault(lgw):
+    """a row of NaN scores leaves the arg-max sentinel; the mutual check must not index with it."""
+    from superslam_b200 import frontend as fe
+
+    lg = fe.LightGlue(lgw, 640, 480, max_keypoints=512)
+    xy0, d0, xy1, d1 = _feat(64, 64, 31)
+    bad = d0.copy()
+    bad[:] = np.nan
+    m = lg.match(xy0, bad, xy1, d1)
+    assert len(m.query) == 0
+    ok = lg.match(xy0, d0, xy1, d1)          # the context is still usable
+    assert (ok.matches0 >= 0).sum() > 10

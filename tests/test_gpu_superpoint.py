@@ -2,7 +2,10 @@
   1. layer-by-layer against the oracle's fp16-storage model (same precision plan as the kernels),
   2. bit-exact index work: NMS + threshold + borders + sort + top-K + cells + gather on the GPU's own
      heat map / descriptor grid, against the restated reference logic,
-  3. end to end against the fp32 reference graph (golden fixtures made by the reference module).
+  3. end to end against the fp32 reference graph (golden fixtures made by the reference module): descriptors within the
+     north star's 1e-3, and the keypoint SET identical up to near-ties - every differing keypoint must be a decision
+     (threshold, 9x9 NMS, top-K cut) whose margin in the reference heat map is below twice the heat-map error measured
+     around it in the same run (tests/parity.py).
 Tolerances are written next to each assert."""
 import ctypes as C
 import os
@@ -68,34 +71,41 @@ def test_layers_scores_grid_and_exact_selection(fe, sp_weights, fixture, K):
         exp = osp.gather_normalize(np.ascontiguousarray(grid16[i].transpose(2, 0, 1)), k["cell"])
         assert np.array_equal(_desc_host(F).astype(np.float16), exp)   # bit-exact, tree-sum order included
     # (3) end to end against the fp32 reference graph
+    import parity
+
     ref = osp.extract(imgs, sp_weights, K)
     for i, F in enumerate(feats):
-        a, bb = set(map(tuple, ref[i]["xy"].tolist())), set(map(tuple, F.keypoints.tolist()))
-        assert len(a & bb) >= 0.97 * len(a)
+        rep = parity.check_keypoints(raw[i], ref[i]["raw_map"], F.keypoints, ref[i]["xy"], h, w, K)
+        print(f"image {i}: {rep['differ']} keypoints differ of {rep['n_ref']} (all near-ties), heat map error {rep['heatmap_err']:.3g}")
         ia = {tuple(x): j for j, x in enumerate(ref[i]["xy"].tolist())}
         d = _desc_host(F)
         common = [(j, ia[tuple(x)]) for j, x in enumerate(F.keypoints.tolist()) if tuple(x) in ia]
         gj, rj = zip(*common)
-        # north_star tolerance: 1e-3 on descriptors (measured ~5e-4 for the fp16-storage plan); 2e-3 bound
-        assert np.abs(d[list(gj)] - ref[i]["desc"][list(rj)].astype(np.float32)).max() < 2e-3
+        # north_star tolerance: 1e-3 on descriptors (measured ~5e-4 for the fp16-storage plan)
+        assert np.abs(d[list(gj)] - ref[i]["desc"][list(rj)].astype(np.float32)).max() < parity.DESC_TOL
 
 
 def test_c2_workload_against_reference_goldens(fe, sp_weights):
     """640x480 pair, K=1024 (BASELINE config C2): compare with candidates computed from the reference
-    module's own score map (tests/golden/superpoint_ref_c2.npz)."""
+    module's own score map (tests/golden/superpoint_ref_c2.npz).  The oracle's heat map (bit-identical to the reference
+    module's: tests/test_oracle_superpoint.py) supplies the margins of the keypoints that differ."""
+    import parity
+    from oracle import superpoint as osp
     from superslam_b200.synth import synth_pair
 
     g = np.load(os.path.join(GOLDEN, "superpoint_ref_c2.npz"))
     l, r = synth_pair(480, 640, 1234)
     sp = fe.SuperPoint(SP_WEIGHTS, 1024)
     L, R = sp.extract_stereo(l, r)
+    raw_gpu = sp.debug_read("scores", (2, 480, 640), np.float32)
+    _, _, raw_ref = osp.dense_forward(np.stack([l, r]), sp_weights)
     for i, F in enumerate((L, R)):
         hw, sc = g[f"hw{i}"], g[f"score{i}"]
         order = np.lexsort((-hw[:, 1], -hw[:, 0], -sc.astype(np.float64)))[:1024]
         ref_xy = hw[order][:, ::-1].astype(np.float32)
         assert len(F.keypoints) == 1024
-        a, b = set(map(tuple, ref_xy.tolist())), set(map(tuple, F.keypoints.tolist()))
-        assert len(a & b) >= 0.98 * 1024          # fp16-storage flips near ties / the 1024th score
+        rep = parity.check_keypoints(raw_gpu[i], raw_ref[i], F.keypoints, ref_xy, 480, 640, 1024)
+        print(f"C2 image {i}: {rep['differ']} keypoints differ of 1024 (all near-ties), heat map error {rep['heatmap_err']:.3g}")
         assert np.all(np.diff(F.responses) <= 0)  # sorted by score
         d = _desc_host(F)
         assert np.abs(np.linalg.norm(d, axis=1) - 1).max() < 2e-3
@@ -104,10 +114,12 @@ def test_c2_workload_against_reference_goldens(fe, sp_weights):
         rows /= np.linalg.norm(rows, axis=1, keepdims=True)
         common = [(j, ia[tuple(x)]) for j, x in enumerate(F.keypoints.tolist()) if tuple(x) in ia]
         gj, rj = zip(*common)
-        assert np.abs(d[list(gj)] - rows[list(rj)]).max() < 2e-3
+        assert np.abs(d[list(gj)] - rows[list(rj)]).max() < parity.DESC_TOL     # north star: 1e-3
 
 
-def test_kitti_odd_width_scale_and_k2048(fe):
+def test_kitti_odd_width_scale_and_k2048(fe, sp_weights):
+    import parity
+    from oracle import superpoint as osp
     from superslam_b200.synth import synth_image
 
     g = np.load(os.path.join(GOLDEN, "superpoint_ref_kitti.npz"))
@@ -119,8 +131,10 @@ def test_kitti_odd_width_scale_and_k2048(fe):
     sx = np.float32(1241) / np.float32(1240)
     ref_xy = np.stack([hw[order][:, 1].astype(np.float32) * sx, hw[order][:, 0].astype(np.float32)], 1)
     assert len(F.keypoints) == 2048
-    a, b = set(map(tuple, ref_xy.tolist())), set(map(tuple, F.keypoints.tolist()))
-    assert len(a & b) >= 0.98 * 2048
+    raw_gpu = sp.debug_read("scores", (1, 376, 1240), np.float32)[0]
+    _, _, raw_ref = osp.dense_forward(img[None], sp_weights)
+    rep = parity.check_keypoints(raw_gpu, raw_ref[0], F.keypoints, ref_xy, 376, 1241, 2048)
+    print(f"KITTI size: {rep['differ']} keypoints differ of 2048 (all near-ties), heat map error {rep['heatmap_err']:.3g}")
 
 
 def test_edge_cases_blank_image_bgr_and_pool_exhaustion(fe):

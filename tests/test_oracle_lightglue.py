@@ -235,3 +235,33 @@ def test_disagreement_report_separates_near_ties_from_defects(lg_weights):
     bad[i] = -1
     rep = olg.disagreement_report(inter["scores"], m0, ms0, bad)
     assert rep["rows"][0]["kind"] == "validity" and rep["rows"][0]["margin"] > 0.05
+
+
+def test_score_error_explains_only_near_tie_disagreements():
+    """explained_by_score_error / competitive_score_error (the rule tests/test_gpu_lightglue.py asserts): matches computed from a
+    slightly perturbed log-assignment matrix may differ from the oracle's only where the oracle's decision margin is within
+    twice the measured score error."""
+    import torch
+
+    from oracle import lightglue as olg
+
+    rng = np.random.default_rng(4)
+    n = 200
+    S = rng.normal(-12, 3, (n, n))
+    idx = rng.permutation(n)
+    S[np.arange(n), idx] = rng.uniform(-2.5, -2.1, n)          # one partner per row, scores straddling log(0.1) = -2.30
+    S = S.astype(np.float32)
+    noise = rng.normal(0, 0.02, S.shape).astype(np.float32)
+    m0, ms0 = (t.numpy() for t in olg.filter_matches(torch.from_numpy(S)))
+    g0, gs0 = (t.numpy() for t in olg.filter_matches(torch.from_numpy(S + noise)))
+    err = olg.competitive_score_error(S, S + noise)
+    assert 0.02 < err <= np.abs(noise).max()
+    rep = olg.disagreement_report(S, m0, ms0, g0, gs0)
+    assert rep["disagree"] > 0 and not olg.explained_by_score_error(rep, err)
+    # a defect: one confident match replaced by another column
+    bad = g0.copy()
+    i = int(np.argmax(ms0))
+    bad[i] = (m0[i] + 1) % n
+    rep = olg.disagreement_report(S, m0, ms0, bad, gs0)
+    left = olg.explained_by_score_error(rep, err)
+    assert [r["i"] for r in left] == [i] and left[0]["kind"] == "row"
