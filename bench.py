@@ -604,28 +604,27 @@ def main():
         return allrec
 
     def e2e_region(steps):
-        pipe.submit(images)
+        """Exactly `steps` steps submitted AND collected inside the timed region (pipeline fill and drain included):
+        the upload of step i+1 is in flight while step i computes and step i-1's results are gathered."""
         t0 = time.perf_counter()
+        pipe.submit(images)
+        res_ = None
         for i in range(steps):
-            pipe.submit(images)
-            res_ = pipe.collect()     # results of the previous step; one step stays in flight across the loop
+            if i + 1 < steps:
+                pipe.submit(images)
+            res_ = pipe.collect()
             if extra is not None:
                 extra()
             gather(res_, i)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        return dt, pipe.collect()
+        return time.perf_counter() - t0, res_
 
     for _ in range(2):
         pipe.process(images)
-    pipe.submit(images)
-    for _ in range(6):           # both image buffers seen three times: eager, capture, replay
-        pipe.submit(images)
-        gather(pipe.collect(), 0)
-    pipe.collect()
+    e2e_region(7)                # both image buffers seen three times: eager, capture, replay
     barrier()
     e2e_s, res = e2e_region(args.steps)
-    last_records = gather(res, args.steps)
+    last_records = gather(res, args.steps - 1)
     e2e_repeats = [e2e_s]
     for _ in range(2):
         barrier()
@@ -661,7 +660,7 @@ def main():
     if last_records is not None:
         try:
             got = sharding.unpack_records(last_records, K)
-            mine = [rank + world * (args.steps * P + s_) for s_ in range(P)]
+            mine = [rank + world * ((args.steps - 1) * P + s_) for s_ in range(P)]
             ok = all(np.array_equal(got[g]["matches0"], res["matches0"][s_]) for s_, g in enumerate(mine))
             records.update({"pairs_in_last_gather": len(got), "own_pairs_intact": bool(ok),
                             "pair_index": "slot s of rank r at step i = pair r + world * (i * P + s), the same rule "

@@ -897,7 +897,7 @@ int ssb_fe_kernel_launches_per_call(ssb_frontend* fe, int pairs) {
   // SuperPoint: 10 convolution launches + nms, select, gather | LightGlue: prepare + 9 x (qkv, attention, ffn1,
   // ffn2) x 2 + final_proj, matchability, sim, sim^T, lse, arg-max, mutual | post-filter | (+ 2 remaps)
   const int lg_blocks = ssb::kLgLayers * 8 + (fe != nullptr && !fe->impl.lg.impl.weights()->fold_out ? ssb::kLgLayers * 2 : 0);
-  const int lg_all = 1 + lg_blocks + 7;
+  const int lg_all = 1 + lg_blocks + 8;   // prepare | blocks | final_proj, matchability, sim, 2 sweeps + 2 merges, mutual
   if (fe != nullptr && fe->impl.extract_only()) return 13 + (fe->impl.has_rectifiers() ? 2 : 0);
   return 13 + lg_all + 1 + (fe != nullptr && fe->impl.has_rectifiers() ? 2 : 0) +
          (fe != nullptr && fe->impl.tracking() ? lg_all + 2 : 0);

@@ -246,6 +246,203 @@ argmax_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp,
   }
 }
 
+// ---- assignment statistics from ONE copy of sim ---------------------------------------------------
+// The double log-softmax needs the row AND the column log-sum-exp of sim, the filter the row AND the column arg-max of
+// the scores.  Instead of a second GEMM that writes sim^T (so that both become coalesced row passes: 2 x 4 MB written
+// and 4 x 4 MB read per pair at K = 1024), each of the two sweeps below reads sim once in 64 x 128 tiles and produces
+// row partials (over the tile's 128 columns, by warp shuffles) and column partials (over its 64 rows: 8 rows per warp
+// in registers, then across the 8 warps through shared memory); tiny merge kernels fold the partials.
+// grid (kp / 128, kp / 64, pairs), block 256: warp w owns rows 8w .. 8w+7, lane l columns 4l .. 4l+3 of the tile.
+constexpr int kAsgRows = 64, kAsgCols = 128;
+__device__ __forceinline__ float asg_exp(float x) { return fast_exp2(x * 1.4426950408889634f); }   // x <= 0 or -inf
+
+__global__ void __launch_bounds__(256)
+assign_stats_kernel(const float* __restrict__ sim, int kp, const int* __restrict__ cnt, float2* __restrict__ rowpart,
+                    float2* __restrict__ colpart) {
+  __shared__ float2 cpart[8][kAsgCols];
+  const int cb = blockIdx.x, rb = blockIdx.y, pair = blockIdx.z;
+  const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
+  const int row0 = rb * kAsgRows, col0 = cb * kAsgCols;
+  if (row0 >= n0 || col0 >= n1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = col0 + lane * 4;
+  const float* s = sim + (static_cast<size_t>(pair) * kp + row0 + warp * 8) * kp + c;
+  float v[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (row < n0 && c < n1) t = *reinterpret_cast<const float4*>(s + static_cast<size_t>(r) * kp);
+    v[r][0] = t.x;
+    v[r][1] = c + 1 < n1 ? t.y : -INFINITY;
+    v[r][2] = c + 2 < n1 ? t.z : -INFINITY;
+    v[r][3] = c + 3 < n1 ? t.w : -INFINITY;
+  }
+  // rows: (max, sum of exp(v - max)) over the tile's columns
+  float2* rp = rowpart + (static_cast<size_t>(pair) * (kp / kAsgCols) + cb) * kp;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    const float m = warp_max(fmaxf(fmaxf(v[r][0], v[r][1]), fmaxf(v[r][2], v[r][3])));
+    float e = 0.f;
+    if (m > -INFINITY) e = (asg_exp(v[r][0] - m) + asg_exp(v[r][1] - m)) + (asg_exp(v[r][2] - m) + asg_exp(v[r][3] - m));
+    e = warp_sum(e);
+    if (lane == 0 && row < n0) rp[row] = make_float2(m, e);
+  }
+  // columns: this warp's 8 rows in registers ...
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float m = v[0][k];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) m = fmaxf(m, v[r][k]);
+    float e = 0.f;
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) e += asg_exp(v[r][k] - m);
+    }
+    cpart[warp][lane * 4 + k] = make_float2(m, e);
+  }
+  __syncthreads();
+  // ... then across the 8 warps
+  if (threadIdx.x < kAsgCols) {
+    const int col = col0 + threadIdx.x;
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, cpart[w][threadIdx.x].x);
+    float e = 0.f;
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) e += cpart[w][threadIdx.x].y * asg_exp(cpart[w][threadIdx.x].x - m);
+    }
+    if (col < n1) colpart[(static_cast<size_t>(pair) * (kp / kAsgRows) + rb) * kp + col] = make_float2(m, e);
+  }
+}
+
+// lse[2 pair + side][i] = log-sum-exp over the partials of row i (side 0) / column i (side 1).  grid (kp / 256, 2, pairs)
+__global__ void __launch_bounds__(256)
+assign_merge_lse_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int kp,
+                        const int* __restrict__ cnt, float* __restrict__ lse) {
+  const int side = blockIdx.y, pair = blockIdx.z;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int n = cnt[2 * pair + side], other = cnt[2 * pair + (side ^ 1)];
+  if (i >= n) return;
+  const int span = side == 0 ? kAsgCols : kAsgRows;
+  const int blocks = (other + span - 1) / span;
+  const float2* part = (side == 0 ? rowpart : colpart) + static_cast<size_t>(pair) * (kp / span) * kp + i;
+  float m = -INFINITY;
+  for (int b = 0; b < blocks; ++b) m = fmaxf(m, part[static_cast<size_t>(b) * kp].x);
+  float e = 0.f;
+  if (m > -INFINITY) {
+    for (int b = 0; b < blocks; ++b) {
+      const float2 t = part[static_cast<size_t>(b) * kp];
+      e += t.y * asg_exp(t.x - m);
+    }
+  }
+  lse[static_cast<size_t>(2 * pair + side) * kp + i] = m + logf(e);
+}
+
+// Second sweep: score(i,j) = ((sim - lse_row0[i]) + (sim - lse_col1[j])) + (lz0[i] + lz1[j]) and its per-tile row /
+// column arg-max partials (value, index; ties -> lowest index, like the oracle's max()).  Same tiling.
+struct AsgBest {
+  float v;
+  int i;
+};
+__device__ __forceinline__ void asg_better(float& bv, int& bi, float v, int i) {
+  if (v > bv || (v == bv && i < bi)) {
+    bv = v;
+    bi = i;
+  }
+}
+__global__ void __launch_bounds__(256)
+assign_argmax_kernel(const float* __restrict__ sim, int kp, const int* __restrict__ cnt, const float* __restrict__ lse,
+                     const float* __restrict__ lz, AsgBest* __restrict__ rowbest, AsgBest* __restrict__ colbest) {
+  __shared__ AsgBest cpart[8][kAsgCols];
+  const int cb = blockIdx.x, rb = blockIdx.y, pair = blockIdx.z;
+  const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
+  const int row0 = rb * kAsgRows, col0 = cb * kAsgCols;
+  if (row0 >= n0 || col0 >= n1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = col0 + lane * 4;
+  const float* s = sim + (static_cast<size_t>(pair) * kp + row0 + warp * 8) * kp + c;
+  const float* lse0 = lse + static_cast<size_t>(2 * pair) * kp;
+  const float* lse1 = lse0 + kp;
+  const float* lz0 = lz + static_cast<size_t>(2 * pair) * kp;
+  const float* lz1 = lz0 + kp;
+  float lc[4] = {0.f, 0.f, 0.f, 0.f}, zc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < n1) {   // kp is a multiple of 4 and the buffers are kp long: the 16-byte loads stay inside them
+    const float4 a = *reinterpret_cast<const float4*>(lse1 + c), b = *reinterpret_cast<const float4*>(lz1 + c);
+    lc[0] = a.x, lc[1] = a.y, lc[2] = a.z, lc[3] = a.w;
+    zc[0] = b.x, zc[1] = b.y, zc[2] = b.z, zc[3] = b.w;
+  }
+  float cbv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int cbi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  AsgBest* rbp = rowbest + (static_cast<size_t>(pair) * (kp / kAsgCols) + cb) * kp;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int row = row0 + warp * 8 + r;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (row < n0 && c < n1) {
+      const float4 t = *reinterpret_cast<const float4*>(s + static_cast<size_t>(r) * kp);
+      const float vv[4] = {t.x, t.y, t.z, t.w};
+      const float lr = lse0[row], zr = lz0[row];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c + k < n1) {
+          const float val = ((vv[k] - lr) + (vv[k] - lc[k])) + (zr + zc[k]);   // image-0 terms first, as the oracle
+          asg_better(bv, bi, val, c + k);
+          asg_better(cbv[k], cbi[k], val, row);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      asg_better(bv, bi, ov, oi);
+    }
+    if (lane == 0 && row < n0) rbp[row] = AsgBest{bv, bi};
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cpart[warp][lane * 4 + k] = AsgBest{cbv[k], cbi[k]};
+  __syncthreads();
+  if (threadIdx.x < kAsgCols) {
+    const int col = col0 + threadIdx.x;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) asg_better(bv, bi, cpart[w][threadIdx.x].v, cpart[w][threadIdx.x].i);
+    if (col < n1) colbest[(static_cast<size_t>(pair) * (kp / kAsgRows) + rb) * kp + col] = AsgBest{bv, bi};
+  }
+}
+
+// max0 / arg0 (rows of image 0) and arg1 (columns = image 1) from the partials.  grid (kp / 256, 2, pairs)
+__global__ void __launch_bounds__(256)
+assign_merge_best_kernel(const AsgBest* __restrict__ rowbest, const AsgBest* __restrict__ colbest, int kp,
+                         const int* __restrict__ cnt, float* __restrict__ max0, int* __restrict__ arg0,
+                         int* __restrict__ arg1) {
+  const int side = blockIdx.y, pair = blockIdx.z;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int n = cnt[2 * pair + side], other = cnt[2 * pair + (side ^ 1)];
+  if (i >= n) return;
+  const int span = side == 0 ? kAsgCols : kAsgRows;
+  const int blocks = (other + span - 1) / span;
+  const AsgBest* part = (side == 0 ? rowbest : colbest) + static_cast<size_t>(pair) * (kp / span) * kp + i;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int b = 0; b < blocks; ++b) {
+    const AsgBest t = part[static_cast<size_t>(b) * kp];
+    asg_better(bv, bi, t.v, t.i);
+  }
+  const size_t o = static_cast<size_t>(pair) * kp + i;
+  if (side == 0) {
+    max0[o] = bv;
+    arg0[o] = bi;
+  } else {
+    arg1[o] = bi;
+  }
+}
+
 // filter_matches: mutual nearest neighbours, score = exp(max) if mutual else 0, valid iff > 0.1.
 __global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* __restrict__ arg0,
                                      const int* __restrict__ arg1, const int* __restrict__ cnt, int kp,
@@ -879,7 +1076,7 @@ int LgWeights::load(const char* path, int dev) {
 // =================================================================================================
 LightGlue::~LightGlue() {
   cudaSetDevice(device_);
-  void* bufs[] = {kp_xy_, kp_count_, desc_ptrs_, desc_stage_, cs_, sn_, x32_, x16_, q_, k_, v_, s_,
+  void* bufs[] = {kp_xy_, kp_count_, desc_ptrs_, desc_stage_, cs_, sn_, x32_, x16_, q_, k_, v_, s_, asg_part_,
                   ctx_, msg_, h1_, mda_, mdb_, lz_, lse_, max0_, arg0_, arg1_, matches_, mscores_};
   for (void* p : bufs)
     if (p) cudaFree(p);
@@ -920,7 +1117,10 @@ int LightGlue::alloc_workspace() {
   A(q_, Z * KP * kLgHeadDim * 2);
   A(k_, Z * KP * kLgHeadDim * 2);
   A(v_, Z * KP * kLgHeadDim * 2);
-  A(s_, P2 * KP * KP * 4);  // sim and sim^T per pair
+  A(s_, P2 * KP * KP * 4);  // sim per pair (the second half: sim^T of the first assignment version, SSB_LG_ASSIGN_V1)
+  // per-tile partials of the assignment sweeps: row (kp/128 column blocks) + column (kp/64 row blocks) entries of
+  // 8 bytes, once for the log-sum-exp and once for the arg-max
+  A(asg_part_, 2 * static_cast<size_t>(pairs_) * (KP / kAsgCols + KP / kAsgRows) * KP * 8);
   A(ctx_, P2 * KP * kLgDim * 2);
   A(msg_, P2 * KP * kLgDim * 2);
   A(h1_, P2 * KP * 512 * 2);
@@ -1015,9 +1215,11 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     p.m_valid = dev_count(cnt);
     return p;
   };
-  // One kernel per FFN (ffn_fused.cuh): the 512-wide hidden activation stays in tensor memory.  SSB_LG_FUSED_FFN=0
-  // selects the two-kernel version (ffn1 on a CTA pair + ffn2) for A/B measurements.
-  static const bool fused_ffn = [] { const char* e = std::getenv("SSB_LG_FUSED_FFN"); return e == nullptr || std::atoi(e) != 0; }();
+  // SSB_LG_FUSED_FFN=1: one kernel per FFN (ffn_fused.cuh), the 512-wide hidden activation stays in tensor memory.
+  // Correct (same tests), but measured SLOWER than the two kernels below (4.18 vs 3.66 ms per 18 FFNs at 64 pairs):
+  // acc1 fills all 512 TMEM columns, so nothing can be double-buffered and LayerNorm+GELU (E1) and the HBM-bound
+  // residual update (E2) - each longer than the tile's MMAs - run exposed instead of under the next tile's MMAs.
+  static const bool fused_ffn = [] { const char* e = std::getenv("SSB_LG_FUSED_FFN"); return e != nullptr && std::atoi(e) != 0; }();
   auto ffn = [&](const LgBlockFfn& F) -> int {
     if (fused_ffn) {
       FfnParams fp;
@@ -1109,25 +1311,52 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     EpiStoreF32 e{ts_sim_, 1.0f};
     SSB_RETURN_IF(launch_core(tm_mda_a_, tm_mda_a_, tm_mdb_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
   }
-  {
-    CoreParams p = lin("lg.simT", 12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
-    p.a_z_mul = 2;
-    p.a_z_add = 1;
-    p.b_z_mul = 2;
-    p.m_valid = dev_count(cnt, 1, 0, 2, 1);
-    p.n_valid = dev_count(cnt, 1, 0, 2, 0);
-    EpiStoreF32 e{ts_simT_, 1.0f};
-    SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
+  // row / column statistics and arg-max from the one copy of sim (assign_*_kernel above).  SSB_LG_ASSIGN_V1=1 selects
+  // the first version (second GEMM for sim^T + two row passes over both) for A/B measurements.
+  static const bool assign_v1 = [] { const char* e = std::getenv("SSB_LG_ASSIGN_V1"); return e != nullptr && std::atoi(e) != 0; }();
+  if (assign_v1) {
+    {
+      CoreParams p = lin("lg.simT", 12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
+      p.a_z_mul = 2;
+      p.a_z_add = 1;
+      p.b_z_mul = 2;
+      p.m_valid = dev_count(cnt, 1, 0, 2, 1);
+      p.n_valid = dev_count(cnt, 1, 0, 2, 0);
+      EpiStoreF32 e{ts_simT_, 1.0f};
+      SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
+    }
+    lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.lse");
+    argmax_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_, lz_, max0_,
+                                                                   arg0_, arg1_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.argmax");
+  } else {
+    float2* rowpart = reinterpret_cast<float2*>(asg_part_);
+    float2* colpart = rowpart + static_cast<size_t>(pairs_) * (KP / kAsgCols) * KP;
+    AsgBest* rowbest = reinterpret_cast<AsgBest*>(colpart + static_cast<size_t>(pairs_) * (KP / kAsgRows) * KP);
+    AsgBest* colbest = rowbest + static_cast<size_t>(pairs_) * (KP / kAsgCols) * KP;
+    const dim3 tiles2(KP / kAsgCols, KP / kAsgRows, pairs), lines(KP / 256, 2, pairs);
+    assign_stats_kernel<<<tiles2, 256, 0, stream>>>(s_, KP, cnt, rowpart, colpart);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.lse");
+    assign_merge_lse_kernel<<<lines, 256, 0, stream>>>(rowpart, colpart, KP, cnt, lse_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.lse_merge");
+    assign_argmax_kernel<<<tiles2, 256, 0, stream>>>(s_, KP, cnt, lse_, lz_, rowbest, colbest);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.argmax");
+    assign_merge_best_kernel<<<lines, 256, 0, stream>>>(rowbest, colbest, KP, cnt, max0_, arg0_, arg1_);
+    SSB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    prof_mark(stream, "lg.argmax_merge");
   }
-  lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);
-  SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-  prof_mark(stream, "lg.lse");
-  argmax_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_, lz_, max0_,
-                                                                 arg0_, arg1_);
-  SSB_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-  prof_mark(stream, "lg.argmax");
   mutual_filter_kernel<<<dim3((KP + 255) / 256, pairs), 256, 0, stream>>>(max0_, arg0_, arg1_, cnt, KP, 0.1f,
                                                                          matches_, mscores_);
   SSB_CUDA_CHECK(cudaGetLastError());

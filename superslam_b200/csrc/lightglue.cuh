@@ -105,7 +105,8 @@ class LightGlue {
   __half* x16_ = nullptr;       // [2P][kp][256] fp16 copy (GEMM operand)
   __half *q_ = nullptr, *k_ = nullptr;  // [2P*4][kp][64]
   __half* v_ = nullptr;         // [2P*4][kp][64]
-  float* s_ = nullptr;          // [2P][kp][kp] assignment similarity sim / sim^T (fp32)
+  float* s_ = nullptr;          // [2P][kp][kp] assignment similarity sim (/ sim^T, first version only) (fp32)
+  uint8_t* asg_part_ = nullptr; // per-tile partials of the two assignment sweeps (lightglue.cu assign_*_kernel)
   __half *ctx_ = nullptr, *msg_ = nullptr;  // [2P][kp][256]
   __half* h1_ = nullptr;        // [2P][kp][512]
   __half *mda_ = nullptr, *mdb_ = nullptr;  // [2P][kp][768] split-precision final projections

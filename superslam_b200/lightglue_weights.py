@@ -79,7 +79,7 @@ def make_random_weights(seed: int = 7, sharpen: float = 2.0, matchability_bias: 
 
 
 def make_trained_like_weights(seed: int = 7, update_gain: float = 0.5, proj_gain: float = 2.2,
-                              matchability_bias: float = 3.0):
+                              matchability_bias: float = 3.0, centre: bool = True):
     """Seeded synthetic weights whose assignment logits have the scale of a trained matcher instead of the ~50 of
     make_random_weights (whose sharpened final projection multiplies every upstream rounding error by that scale):
     the second FFN linear of every block is scaled by `update_gain` (residual updates about half the size of a default
@@ -99,7 +99,64 @@ def make_trained_like_weights(seed: int = 7, update_gain: float = 0.5, proj_gain
     last = f"log_assignment.{N_LAYERS - 1}."
     sd[last + "final_proj.weight"] = (qmat * proj_gain).contiguous()
     sd[last + "final_proj.bias"] = torch.zeros(DIM)
+    if centre:
+        # A random transformer adds the same bias-driven vector to every token, so <x0, x1> carries a large constant
+        # (similarity logits ~50 of which ~10 discriminate).  A trained projection does not spend its dynamic range on
+        # a constant: cancel the mean residual of a seeded calibration set in the projection's bias.
+        mu = _calibration_mean(sd, seed)
+        sd[last + "final_proj.bias"] = (-(sd[last + "final_proj.weight"] @ mu)).contiguous()
     return sd
+
+
+def _calibration_mean(sd, seed: int) -> "torch.Tensor":
+    """Mean residual vector after the 18 blocks on a seeded set of descriptor-like features (fp32, torch; the same
+    arithmetic as oracle/lightglue.py, restated here because the product may not import the oracle)."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(seed + 2)
+    n = 192
+    d0 = F.normalize(torch.randn(n, DIM, generator=g), dim=1)
+    d1 = F.normalize(d0 + 0.05 * torch.randn(n, DIM, generator=g), dim=1)
+    k0 = (torch.rand(n, 2, generator=g) - 0.5) * 1.5
+    k1 = k0 - torch.tensor([[0.04, 0.0]])
+
+    def rot(t):
+        a, b = t.unflatten(-1, (-1, 2)).unbind(-1)
+        return torch.stack((-b, a), -1).flatten(-2)
+
+    def enc(k):
+        p = (k @ sd["posenc.Wr.weight"].t()).repeat_interleave(2, -1)
+        return p.cos(), p.sin()
+
+    def heads(t):
+        return t.unflatten(-1, (4, HEAD_DIM)).transpose(0, 1)
+
+    def ffn(p, x, m):
+        h = F.linear(torch.cat([x, m], -1), sd[p + "0.weight"], sd[p + "0.bias"])
+        h = F.gelu(F.layer_norm(h, (2 * DIM,), sd[p + "1.weight"], sd[p + "1.bias"], 1e-5))
+        return x + F.linear(h, sd[p + "3.weight"], sd[p + "3.bias"])
+
+    with torch.no_grad():
+        x, e = [d0, d1], [enc(k0), enc(k1)]
+        for i in range(N_LAYERS):
+            p = f"transformers.{i}.self_attn."
+            for s_ in range(2):
+                qkv = F.linear(x[s_], sd[p + "Wqkv.weight"], sd[p + "Wqkv.bias"]).unflatten(-1, (4, HEAD_DIM, 3)).transpose(0, 1)
+                q, k, v = qkv[..., 0], qkv[..., 1], qkv[..., 2]
+                c, s2 = e[s_]
+                q, k = q * c + rot(q) * s2, k * c + rot(k) * s2
+                ctx = F.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v
+                m = F.linear(ctx.transpose(0, 1).flatten(-2), sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+                x[s_] = ffn(p + "ffn.", x[s_], m)
+            p = f"transformers.{i}.cross_attn."
+            qk = [heads(F.linear(t, sd[p + "to_qk.weight"], sd[p + "to_qk.bias"])) for t in x]
+            vv = [heads(F.linear(t, sd[p + "to_v.weight"], sd[p + "to_v.bias"])) for t in x]
+            sim = qk[0] @ qk[1].transpose(-1, -2) / 8.0
+            m0 = F.softmax(sim, -1) @ vv[1]
+            m1 = F.softmax(sim.transpose(-1, -2), -1) @ vv[0]
+            ms = [F.linear(t.transpose(0, 1).flatten(-2), sd[p + "to_out.weight"], sd[p + "to_out.bias"]) for t in (m0, m1)]
+            x = [ffn(p + "ffn.", x[s_], ms[s_]) for s_ in range(2)]
+        return torch.cat(x).mean(0)
 
 
 def save_state_dict(sd, path: str) -> None:

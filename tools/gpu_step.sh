@@ -19,7 +19,7 @@ print(d["kernel_ms_per_step"]); print("spread", d["value_spread_per_step"], "e2e
 print("live", d.get("live_pipeline")); print("latency", d.get("latency_single_pair")); print("records", d["results"]["gathered_records"])
 PY
 ;;
-ab) echo "== A/B: two-kernel FFN"; SSB_LG_FUSED_FFN=0 timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_unfused.json 2> gpurun_out/bench_${tag}_unfused.err
+ab) echo "== A/B: ${AB:-SSB_LG_ASSIGN_V1=1}"; env ${AB:-SSB_LG_ASSIGN_V1=1} timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_unfused.json 2> gpurun_out/bench_${tag}_unfused.err
 python - "$tag" <<'PY'
 import json, sys
 d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}_unfused.json"))
