@@ -36,6 +36,8 @@ namespace ssb {
 __global__ void stereo_postfilter_kernel(const float* __restrict__ kp_xy, int K, const int* __restrict__ cnt,
                                          const int32_t* __restrict__ matches0, int kp, float min_disp,
                                          float* __restrict__ ur, uint8_t* __restrict__ has_depth) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pair = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
@@ -64,6 +66,8 @@ __global__ void stereo_postfilter_kernel(const float* __restrict__ kp_xy, int K,
 __global__ void tracking_assemble_kernel(const float* __restrict__ kf_xy, const int* __restrict__ kf_count,
                                          const float* __restrict__ kp_xy, const int* __restrict__ kp_count, int K,
                                          float* __restrict__ trk_xy, int* __restrict__ trk_count) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int z = blockIdx.y, p = z >> 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool frame = (z & 1) != 0;
@@ -77,6 +81,8 @@ __global__ void tracking_assemble_kernel(const float* __restrict__ kf_xy, const 
 __global__ void tracking_postfilter_kernel(const int32_t* __restrict__ matches0, int kp, const int* __restrict__ trk_count,
                                            const uint8_t* __restrict__ kf_hd, const uint8_t* __restrict__ hd, int K,
                                            uint8_t* __restrict__ ok) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int p = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
@@ -96,6 +102,8 @@ promote_keyframe_kernel(const uint8_t* __restrict__ mask, const float* __restric
                         void* const* __restrict__ slot_ptrs, int K, float* __restrict__ kf_xy,
                         int* __restrict__ kf_count, uint8_t* __restrict__ kf_hd, __half* __restrict__ kf_desc,
                         size_t kf_desc_stride) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int p = blockIdx.y;
   if (mask[p] == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,10 +245,9 @@ class FrontEnd {
     uint8_t m[64];
     for (int p = 0; p < pairs; ++p) m[p] = mask == nullptr ? 1 : (mask[p] != 0);
     SSB_CUDA_CHECK(cudaMemcpyAsync(promote_mask_, m, pairs, cudaMemcpyHostToDevice, stream_));   // m: see the sync below
-    promote_keyframe_kernel<<<dim3((K_ + 7) / 8, pairs), 256, 0, stream_>>>(
+    SSB_CUDA_CHECK(launch_kernel(promote_keyframe_kernel, dim3(dim3((K_ + 7) / 8, pairs)), dim3(256), 0, stream_, 1, 
         promote_mask_, sp.impl.kp_xy(), sp.impl.kp_count(), hd_, slot_ptrs_, K_, kf_xy_, kf_count_, kf_hd_, kf_desc_,
-        kf_desc_stride_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+        kf_desc_stride_));
     count_launch();
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream_));
     return SSB_OK;
@@ -376,21 +383,18 @@ class FrontEnd {
     SSB_RETURN_IF(sp.impl.run(images_dev, 2 * pairs, h, w, slot_ptrs_, stream_));
     if (extract_only_) return SSB_OK;   // mono frames (BASELINE config C1): the 2 * pairs images are independent
     SSB_RETURN_IF(lg.impl.run(pairs, sp.impl.kp_xy(), K_, sp.impl.kp_count(), slot_ptrs_, stream_));
-    stereo_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
-        sp.impl.kp_xy(), K_, sp.impl.kp_count(), lg.impl.matches_dev(), lg.impl.kp(), min_disp_, ur_, hd_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(stereo_postfilter_kernel, dim3(dim3((K_ + 255) / 256, pairs)), dim3(256), 0, stream_, 1, 
+        sp.impl.kp_xy(), K_, sp.impl.kp_count(), lg.impl.matches_dev(), lg.impl.kp(), min_disp_, ur_, hd_));
     count_launch();
     prof_mark(stream_, "fe.postfilter");
     if (tracking_) {
-      tracking_assemble_kernel<<<dim3((K_ + 255) / 256, 2 * pairs), 256, 0, stream_>>>(
-          kf_xy_, kf_count_, sp.impl.kp_xy(), sp.impl.kp_count(), K_, trk_xy_, trk_count_);
-      SSB_CUDA_CHECK(cudaGetLastError());
+      SSB_CUDA_CHECK(launch_kernel(tracking_assemble_kernel, dim3(dim3((K_ + 255) / 256, 2 * pairs)), dim3(256), 0, stream_, 1, 
+          kf_xy_, kf_count_, sp.impl.kp_xy(), sp.impl.kp_count(), K_, trk_xy_, trk_count_));
       count_launch();
       prof_mark(stream_, "fe.track_assemble");
       SSB_RETURN_IF(lg_trk.impl.run(pairs, trk_xy_, K_, trk_count_, trk_desc_ptrs_, stream_));
-      tracking_postfilter_kernel<<<dim3((K_ + 255) / 256, pairs), 256, 0, stream_>>>(
-          lg_trk.impl.matches_dev(), lg_trk.impl.kp(), trk_count_, kf_hd_, hd_, K_, trk_ok_);
-      SSB_CUDA_CHECK(cudaGetLastError());
+      SSB_CUDA_CHECK(launch_kernel(tracking_postfilter_kernel, dim3(dim3((K_ + 255) / 256, pairs)), dim3(256), 0, stream_, 1, 
+          lg_trk.impl.matches_dev(), lg_trk.impl.kp(), trk_count_, kf_hd_, hd_, K_, trk_ok_));
       count_launch();
       prof_mark(stream_, "fe.track_postfilter");
     }

@@ -230,6 +230,8 @@ flash_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
+  pdl_launch_dependents();
   const uint32_t tS = tmem;        // 128 columns
   const uint32_t tO = tmem + 128;  // 64 columns
   const uint32_t tP = tmem + 192;  // 64 columns = 128 fp16 probabilities per row
@@ -547,7 +549,7 @@ inline int launch_flash_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK
   if (total <= 0) return SSB_OK;
   const int resident = 2 * device_sm_count();
   const int ctas = total < resident ? total : resident;
-  kernel<<<ctas, kFaThreads, kFaSmemBytes, stream>>>(tmQ, tmK, tmV, tmO, p);
+  SSB_CUDA_CHECK(launch_kernel(kernel, dim3(ctas), dim3(kFaThreads), kFaSmemBytes, stream, 1, tmQ, tmK, tmV, tmO, p));
   if (trace.exchange(trace_env ? 2 : 0) == 1) {   // first launch only: dump the phase time stamps of CTA 0 / warp 2
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
     static long long h[64][8];

@@ -10,6 +10,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 namespace ssb {
 
@@ -96,6 +97,18 @@ int device_sm_count();
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the pair pipeline is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_kernel
+// below): its CTAs may become resident - and run their prologue: barrier initialisation, TMEM allocation, tensor-map
+// prefetch - while the previous kernel of the stream is still draining, instead of after the grid-to-grid launch
+// latency (2 - 4 us x ~100 launches per step).  pdl_wait() blocks until the previous kernel has completed and its
+// writes are visible; it must be executed by EVERY CTA before its first global-memory access and before it exits (a
+// grid whose CTAs all left without waiting would "complete" before its predecessor and release ITS successor early).
+// pdl_launch_dependents() lets the next kernel's CTAs be scheduled as soon as resources allow.  Both are no-ops for a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -345,6 +358,38 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 #endif  // __CUDACC__
+
+// Host: launch `kernel` with programmatic stream serialization (see pdl_wait above) unless SSB_PDL=0, optionally as
+// thread-block clusters of `cluster` CTAs.  Returns the launch status.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 unsigned cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // Host: encode TMA tensor maps (driver entry point resolved through the runtime, no libcuda link).
 // `elem_strides` (optional, rank entries): traversal stride per dimension - with stride s the box covers

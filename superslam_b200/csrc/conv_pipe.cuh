@@ -140,6 +140,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -386,9 +388,8 @@ int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams 
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;
-  conv_pipe_kernel<Epi, kFuse1a><<<ctas, kFuse1a ? kPipeThreadsFused : kPipeThreads, smem_bytes, stream>>>(
-      tmA, tmB, p, epi);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(conv_pipe_kernel<Epi, kFuse1a>, dim3(ctas), dim3(kFuse1a ? kPipeThreadsFused : kPipeThreads),
+                               smem_bytes, stream, 1, tmA, tmB, p, epi));
   count_launch();
   prof_mark(stream, p.label);
   return SSB_OK;

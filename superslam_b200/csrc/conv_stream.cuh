@@ -88,6 +88,8 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // weights: one (slab, tap) slice per ring stage, in the order the MMAs consume them
@@ -219,8 +221,8 @@ int launch_conv_stream(const CUtensorMap& tmA, const CUtensorMap& tmB, StreamPar
   if (total <= 0) return SSB_OK;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;
-  conv_stream_kernel<Epi><<<ctas, kStreamThreads, kStreamSmemBytes, stream>>>(tmA, tmB, p, epi);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(conv_stream_kernel<Epi>, dim3(ctas), dim3(kStreamThreads), kStreamSmemBytes, stream, 1, tmA,
+                               tmB, p, epi));
   count_launch();
   prof_mark(stream, p.label);
   return SSB_OK;

@@ -109,6 +109,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
+  pdl_launch_dependents();
 
   // tile -> (image z, first row); tiles that lie beyond the image's keypoint count are skipped by every role alike
   auto decode = [&](int tile, int& z, int& row0) -> bool {
@@ -383,8 +385,8 @@ inline int launch_ffn_fused(const CUtensorMap& a0, const CUtensorMap& a1, const 
   if (total <= 0) return SSB_OK;
   const int sms = device_sm_count();
   const int ctas = total < sms ? total : sms;
-  ffn_fused_kernel<<<ctas, kFfnThreads, kFfnSmemBytes, stream>>>(a0, a1, w1, w2, out, p);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(ffn_fused_kernel, dim3(ctas), dim3(kFfnThreads), kFfnSmemBytes, stream, 1, a0, a1, w1, w2,
+                               out, p));
   count_launch();
   prof_mark(stream, p.label);
   return SSB_OK;

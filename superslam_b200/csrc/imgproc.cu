@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256)
 remap_linear_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, size_t src_pitch,
                        const uint32_t* __restrict__ xy, const uint16_t* __restrict__ frac, int npx,
                        uint8_t* __restrict__ dst, size_t dst_pitch) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;   // group of four pixels
   const int i0 = q * 4;
   if (i0 >= npx) return;
@@ -136,8 +138,7 @@ int Rectifier::remap_device(const uint8_t* src_dev, int count, uint8_t* dst_dev,
   if (dst_pitch == 0) dst_pitch = static_cast<size_t>(npx);
   SSB_CHECK(dst_pitch % 4 == 0, SSB_ERR_INVALID, "destination image pitch must be a multiple of 4 bytes");
   dim3 grid((npx / 4 + 255) / 256, count);
-  remap_linear_u8_kernel<<<grid, 256, 0, stream>>>(src_dev, sh_, sw_, src_pitch, xy_, frac_, npx, dst_dev, dst_pitch);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(remap_linear_u8_kernel, dim3(grid), dim3(256), 0, stream, 1, src_dev, sh_, sw_, src_pitch, xy_, frac_, npx, dst_dev, dst_pitch));
   count_launch();
   prof_mark(stream, "fe.remap");
   return SSB_OK;

@@ -40,6 +40,8 @@ lg_prepare_kernel(const float* __restrict__ kp_xy, int kp_stride, const int* __r
                   void* const* __restrict__ desc_ptrs, const float* __restrict__ wr, float cx, float cy,
                   float scale, int kp, __half* __restrict__ x16, float* __restrict__ x32,
                   float* __restrict__ cs, float* __restrict__ sn) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int kPitch = 258;   // halfs per staged row: 129 words, so a column read by 32 rows is conflict-free
   __shared__ __half stash[32 * kPitch];
   const int z = blockIdx.y;
@@ -105,6 +107,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(128)
 matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, float b, int kp,
                     const int* __restrict__ cnt, float* __restrict__ lz) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int z = blockIdx.y;
   const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= cnt[z]) return;
@@ -123,6 +127,8 @@ matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, 
 __global__ void __launch_bounds__(256)
 lse_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp, const int* __restrict__ cnt,
                 float* __restrict__ lse) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -177,6 +183,8 @@ argmax_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp,
                    const int* __restrict__ cnt, const float* __restrict__ lse,
                    const float* __restrict__ lz, float* __restrict__ max0, int* __restrict__ arg0,
                    int* __restrict__ arg1) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -259,6 +267,8 @@ __device__ __forceinline__ float asg_exp(float x) { return fast_exp2(x * 1.44269
 __global__ void __launch_bounds__(256)
 assign_stats_kernel(const float* __restrict__ sim, int kp, const int* __restrict__ cnt, float2* __restrict__ rowpart,
                     float2* __restrict__ colpart) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float2 cpart[8][kAsgCols];
   const int cb = blockIdx.x, rb = blockIdx.y, pair = blockIdx.z;
   const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
@@ -322,6 +332,8 @@ assign_stats_kernel(const float* __restrict__ sim, int kp, const int* __restrict
 __global__ void __launch_bounds__(256)
 assign_merge_lse_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, int kp,
                         const int* __restrict__ cnt, float* __restrict__ lse) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int side = blockIdx.y, pair = blockIdx.z;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int n = cnt[2 * pair + side], other = cnt[2 * pair + (side ^ 1)];
@@ -356,6 +368,8 @@ __device__ __forceinline__ void asg_better(float& bv, int& bi, float v, int i) {
 __global__ void __launch_bounds__(256)
 assign_argmax_kernel(const float* __restrict__ sim, int kp, const int* __restrict__ cnt, const float* __restrict__ lse,
                      const float* __restrict__ lz, AsgBest* __restrict__ rowbest, AsgBest* __restrict__ colbest) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ AsgBest cpart[8][kAsgCols];
   const int cb = blockIdx.x, rb = blockIdx.y, pair = blockIdx.z;
   const int n0 = cnt[2 * pair], n1 = cnt[2 * pair + 1];
@@ -421,6 +435,8 @@ __global__ void __launch_bounds__(256)
 assign_merge_best_kernel(const AsgBest* __restrict__ rowbest, const AsgBest* __restrict__ colbest, int kp,
                          const int* __restrict__ cnt, float* __restrict__ max0, int* __restrict__ arg0,
                          int* __restrict__ arg1) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int side = blockIdx.y, pair = blockIdx.z;
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int n = cnt[2 * pair + side], other = cnt[2 * pair + (side ^ 1)];
@@ -448,6 +464,8 @@ __global__ void mutual_filter_kernel(const float* __restrict__ max0, const int* 
                                      const int* __restrict__ arg1, const int* __restrict__ cnt, int kp,
                                      float threshold, int32_t* __restrict__ matches0,
                                      float* __restrict__ mscores0) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int pair = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kp) return;
@@ -1194,9 +1212,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   {
     const float scale = static_cast<float>(std::max(img_w_, img_h_)) / 2.0f;
     const float cx = img_w_ / 2.0f, cy = img_h_ / 2.0f;
-    lg_prepare_kernel<<<dim3(KP / 32, P2), 256, 0, stream>>>(kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
-                                                            w_->wr, cx, cy, scale, KP, x16_, x32_, cs_, sn_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(lg_prepare_kernel, dim3(dim3(KP / 32, P2)), dim3(256), 0, stream, 1, kp_xy_dev, kp_stride, cnt, desc_ptrs_dev,
+                                                            w_->wr, cx, cy, scale, KP, x16_, x32_, cs_, sn_));
     count_launch();
     prof_mark(stream, "lg.prepare");
   }
@@ -1296,8 +1313,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     EpiSplit e{w_->final_proj.bias, ts_mda_, ts_mdb_};
     SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }
-  matchability_kernel<<<dim3(KP / 128, P2), 128, 0, stream>>>(x32_, w_->match_w, w_->match_b, KP, cnt, lz_);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(matchability_kernel, dim3(dim3(KP / 128, P2)), dim3(128), 0, stream, 1, x32_, w_->match_w, w_->match_b, KP, cnt, lz_));
   count_launch();
   prof_mark(stream, "lg.matchability");
   const size_t pass_stride = static_cast<size_t>(pairs_) * KP * KP;   // sim^T follows the capacity-sized sim block
@@ -1325,13 +1341,11 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
       EpiStoreF32 e{ts_simT_, 1.0f};
       SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
     }
-    lse_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(lse_rows_kernel, dim3(dim3(KP / 8, pairs * 2)), dim3(256), 0, stream, 1, s_, pass_stride, KP, cnt, lse_));
     count_launch();
     prof_mark(stream, "lg.lse");
-    argmax_rows_kernel<<<dim3(KP / 8, pairs * 2), 256, 0, stream>>>(s_, pass_stride, KP, cnt, lse_, lz_, max0_,
-                                                                   arg0_, arg1_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(argmax_rows_kernel, dim3(dim3(KP / 8, pairs * 2)), dim3(256), 0, stream, 1, s_, pass_stride, KP, cnt, lse_, lz_, max0_,
+                                                                   arg0_, arg1_));
     count_launch();
     prof_mark(stream, "lg.argmax");
   } else {
@@ -1340,26 +1354,21 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     AsgBest* rowbest = reinterpret_cast<AsgBest*>(colpart + static_cast<size_t>(pairs_) * (KP / kAsgRows) * KP);
     AsgBest* colbest = rowbest + static_cast<size_t>(pairs_) * (KP / kAsgCols) * KP;
     const dim3 tiles2(KP / kAsgCols, KP / kAsgRows, pairs), lines(KP / 256, 2, pairs);
-    assign_stats_kernel<<<tiles2, 256, 0, stream>>>(s_, KP, cnt, rowpart, colpart);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(assign_stats_kernel, dim3(tiles2), dim3(256), 0, stream, 1, s_, KP, cnt, rowpart, colpart));
     count_launch();
     prof_mark(stream, "lg.lse");
-    assign_merge_lse_kernel<<<lines, 256, 0, stream>>>(rowpart, colpart, KP, cnt, lse_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(assign_merge_lse_kernel, dim3(lines), dim3(256), 0, stream, 1, rowpart, colpart, KP, cnt, lse_));
     count_launch();
     prof_mark(stream, "lg.lse_merge");
-    assign_argmax_kernel<<<tiles2, 256, 0, stream>>>(s_, KP, cnt, lse_, lz_, rowbest, colbest);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(assign_argmax_kernel, dim3(tiles2), dim3(256), 0, stream, 1, s_, KP, cnt, lse_, lz_, rowbest, colbest));
     count_launch();
     prof_mark(stream, "lg.argmax");
-    assign_merge_best_kernel<<<lines, 256, 0, stream>>>(rowbest, colbest, KP, cnt, max0_, arg0_, arg1_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(assign_merge_best_kernel, dim3(lines), dim3(256), 0, stream, 1, rowbest, colbest, KP, cnt, max0_, arg0_, arg1_));
     count_launch();
     prof_mark(stream, "lg.argmax_merge");
   }
-  mutual_filter_kernel<<<dim3((KP + 255) / 256, pairs), 256, 0, stream>>>(max0_, arg0_, arg1_, cnt, KP, 0.1f,
-                                                                         matches_, mscores_);
-  SSB_CUDA_CHECK(cudaGetLastError());
+  SSB_CUDA_CHECK(launch_kernel(mutual_filter_kernel, dim3(dim3((KP + 255) / 256, pairs)), dim3(256), 0, stream, 1, max0_, arg0_, arg1_, cnt, KP, 0.1f,
+                                                                         matches_, mscores_));
   count_launch();
   prof_mark(stream, "lg.mutual");
   return SSB_OK;

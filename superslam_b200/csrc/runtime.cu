@@ -2,6 +2,7 @@
 // map encoding through the driver entry point, device checks.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -21,6 +22,11 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("SSB_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+  return on;
+}
 
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

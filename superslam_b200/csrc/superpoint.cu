@@ -80,6 +80,8 @@ void* SlotPool::slot_ptr(int slot) const {
 // oracle/imgproc.py::bgr_to_gray_u8 is pinned against cv2 on all 2^24 colours.  (The 14-bit coefficients
 // 1868 / 9617 / 4899 of OpenCV 2.x/3.x, used here at first, differ by one grey level on 0.24 % of random pixels.)
 __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, size_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const uint8_t* p = bgr + 3 * i;
@@ -277,6 +279,8 @@ __device__ __forceinline__ void window_max4(const float* v, float* out) {
 __global__ void __launch_bounds__(256)
 nms_candidates_kernel(const float* __restrict__ scores, int hs, int ws, int rb, double thr,
                       unsigned long long* __restrict__ cand, int cand_cap, int* __restrict__ cand_count) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int R = kNmsRadius;
   constexpr int IW = kNmsTw + 2 * R, IH = kNmsTh + 2 * R;   // 136 x 40
   __shared__ __align__(16) float in[IH][IW];
@@ -349,6 +353,8 @@ select_topk_kernel(const unsigned long long* __restrict__ cand, int cand_cap,
                    const int* __restrict__ cand_count, int K, int sort_cap, int ws, int hc, int wc,
                    float scale_x, float scale_y, float* __restrict__ kp_xy, float* __restrict__ kp_score,
                    int* __restrict__ kp_cell, int* __restrict__ kp_count) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ unsigned long long skeys[];  // [sort_cap]
   __shared__ unsigned hist[256];
   __shared__ unsigned long long s_prefix;
@@ -452,6 +458,8 @@ select_topk_kernel(const unsigned long long* __restrict__ cand, int cand_cap,
 __global__ void __launch_bounds__(256)
 gather_normalize_kernel(const __half* __restrict__ grid, int cells, const int* __restrict__ kp_cell,
                         const int* __restrict__ kp_count, int K, void* const* __restrict__ desc_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int z = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kp = blockIdx.x * 8 + warp;
@@ -755,6 +763,9 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
   SSB_CUDA_CHECK(cudaSetDevice(device_));
   SSB_RETURN_IF(ensure_shape(batch, h, w));
   const int B = batch;
+  // candidate counters of the NMS: reset here, in front of the first kernel, so that no memset node sits between two
+  // kernels of the chain (every kernel-to-kernel edge stays a programmatic one, common.cuh pdl_wait)
+  SSB_CUDA_CHECK(cudaMemsetAsync(cand_count_, 0, B * sizeof(int), stream));
   // Cin = 128 layers: persistent halo-reuse kernel with streamed weights, 128 output channels per CTA
   auto sconv = [&](const char* label, const CUtensorMap& tmH, const CUtensorMap& tmS, const ConvLayer& L, int H,
                    int W, int pool) -> int {
@@ -806,12 +817,10 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     dim3 g(p.tiles_w * ((hc_ + 7) / 8), 1, B);
     SSB_RETURN_IF(launch_core(tm_ada_, tm_ada_, ldb_.tmB, p, e, g, stream));
   }
-  SSB_CUDA_CHECK(cudaMemsetAsync(cand_count_, 0, B * sizeof(int), stream));
   {
     dim3 g((ws_ + kNmsTw - 1) / kNmsTw, (hs_ + kNmsTh - 1) / kNmsTh, B);
-    nms_candidates_kernel<<<g, 256, 0, stream>>>(scores_, hs_, ws_, remove_borders_, threshold_,
-                                                          cand_, cand_cap_, cand_count_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(nms_candidates_kernel, dim3(g), dim3(256), 0, stream, 1, scores_, hs_, ws_, remove_borders_, threshold_,
+                                                          cand_, cand_cap_, cand_count_));
     count_launch();
     prof_mark(stream, "sp.nms");
   }
@@ -827,17 +836,15 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
       return SSB_OK;
     };
     SSB_DEVICE_CONFIG(&select_topk_kernel, 1, configure());
-    select_topk_kernel<<<B, 1024, smem, stream>>>(cand_, cand_cap_, cand_count_, max_kpts_, sort_cap, ws_,
-                                                  hc_, wc_, sx, sy, kp_xy_, kp_score_, kp_cell_, kp_count_);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(select_topk_kernel, dim3(B), dim3(1024), smem, stream, 1, cand_, cand_cap_, cand_count_, max_kpts_, sort_cap, ws_,
+                                                  hc_, wc_, sx, sy, kp_xy_, kp_score_, kp_cell_, kp_count_));
     count_launch();
     prof_mark(stream, "sp.select");
   }
   if (desc_out != nullptr) {
     dim3 g((max_kpts_ + 7) / 8, B);
-    gather_normalize_kernel<<<g, 256, 0, stream>>>(grid_, hc_ * wc_, kp_cell_, kp_count_, max_kpts_,
-                                                   desc_out);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(gather_normalize_kernel, dim3(g), dim3(256), 0, stream, 1, grid_, hc_ * wc_, kp_cell_, kp_count_, max_kpts_,
+                                                   desc_out));
     count_launch();
     prof_mark(stream, "sp.gather");
   }
@@ -874,8 +881,7 @@ int SuperPoint::extract(const uint8_t* const* images, int batch, int h, int w, i
     SSB_CHECK(ds != nullptr, SSB_ERR_CUDA, "device staging allocation failed");
     SSB_CUDA_CHECK(cudaMemcpyAsync(ds, hs, img_bytes * batch, cudaMemcpyHostToDevice, stream_));
     const size_t n = static_cast<size_t>(batch) * h * w;
-    bgr_to_gray_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream_>>>(ds, img_, n);
-    SSB_CUDA_CHECK(cudaGetLastError());
+    SSB_CUDA_CHECK(launch_kernel(bgr_to_gray_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream_, 1, ds, img_, n));
     count_launch();
     prof_mark(stream_, "sp.bgr2gray");
   }

@@ -242,6 +242,8 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (clustered) cluster_sync_all();   // the peers' barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
+  pdl_launch_dependents();
   // tile walk: all (x, y, z) tiles strided over the CTAs, or - cluster mode - a fixed y per CTA (= its cluster rank)
   const bool fixed_y = p.cluster_y != 0;
   const int ny = fixed_y ? p.grid_y : 1;
@@ -527,12 +529,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     // groups of tiles walked by one cluster: M tiles x batch (a cluster spans the N tiles)
     const long long groups = static_cast<long long>(grid.x) * grid.z;
     ctas = static_cast<int>(groups < max_clusters ? groups : max_clusters) * csize;
-    cfg.gridDim = dim3(static_cast<unsigned>(ctas));
-    SSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, umma_core_kernel<Epi>, a0, a1, b, p, epi));
+    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream,
+                                 static_cast<unsigned>(csize), a0, a1, b, p, epi));
   } else {
-    umma_core_kernel<Epi><<<ctas, kCoreThreads, smem, stream>>>(a0, a1, b, p, epi);
+    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream, 1,
+                                 a0, a1, b, p, epi));
   }
-  SSB_CUDA_CHECK(cudaGetLastError());
   if (tracing) {
     SSB_CUDA_CHECK(cudaStreamSynchronize(stream));
     long long h[32][8];
