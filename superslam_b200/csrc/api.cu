@@ -369,6 +369,7 @@ class FrontEnd {
     }
   }
   int enqueue_eager(const uint8_t* images_dev, int pairs, int h, int w) {
+    PdlScope pdl(2 * pairs);   // programmatic dependent launch for latency-bound (small) calls only
     prof_begin(stream_);
     if (rect_l_ != nullptr) {
       SSB_CHECK(h == rect_l_->src_h() && w == rect_l_->src_w(), SSB_ERR_INVALID,

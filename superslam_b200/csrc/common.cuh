@@ -361,7 +361,17 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // Host: launch `kernel` with programmatic stream serialization (see pdl_wait above) unless SSB_PDL=0, optionally as
 // thread-block clusters of `cluster` CTAs.  Returns the launch status.
+// Measured on B200 (profiles/README.md, round 2): programmatic edges cut the single-pair call by 3 - 13 % (a latency-bound
+// chain of ~100 small launches) but cost ~2 % of the throughput of a 64-pair step, whose kernels each fill the GPU for
+// 50 - 300 us.  So the scope is set by the caller from the batch it is about to enqueue.
 bool pdl_enabled();
+bool pdl_set_scope(bool on);   // for the calling thread; returns the previous setting
+constexpr int kPdlMaxImages = 8;   // PDL for calls on at most this many images
+struct PdlScope {
+  bool old;
+  explicit PdlScope(int images) : old(pdl_set_scope(images <= kPdlMaxImages)) {}
+  ~PdlScope() { pdl_set_scope(old); }
+};
 #ifdef __CUDACC__
 template <class... KArgs, class... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

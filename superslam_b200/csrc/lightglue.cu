@@ -1375,6 +1375,7 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
 }
 
 int LightGlue::match_common(int n0, int n1, int32_t* matches0, float* mscores0) {
+  PdlScope pdl(2);
   SSB_RETURN_IF(run(1, kp_xy_, kp_, kp_count_, desc_ptrs_, stream_));
   int32_t* mh = reinterpret_cast<int32_t*>(host_io_);
   float* sh = host_io_ + kp_;

@@ -23,9 +23,16 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// SSB_PDL=0|1 forces it off / on; otherwise the calling thread's current scope decides (PdlScope, common.cuh)
+static thread_local bool g_pdl_scope = true;
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = std::getenv("SSB_PDL"); return e == nullptr || std::atoi(e) != 0; }();
-  return on;
+  static const int forced = [] { const char* e = std::getenv("SSB_PDL"); return e == nullptr ? -1 : (std::atoi(e) != 0 ? 1 : 0); }();
+  return forced >= 0 ? forced != 0 : g_pdl_scope;
+}
+bool pdl_set_scope(bool on) {
+  const bool old = g_pdl_scope;
+  g_pdl_scope = on;
+  return old;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -902,6 +902,7 @@ int SuperPoint::extract(const uint8_t* const* images, int batch, int h, int w, i
   void** ptrs_dev = desc_ptrs_dev_;
   SSB_CHECK(ptrs_dev != nullptr, SSB_ERR_CUDA, "pointer table allocation failed");
   SSB_CUDA_CHECK(cudaMemcpyAsync(ptrs_dev, ptrs.data(), batch * sizeof(void*), cudaMemcpyHostToDevice, stream_));
+  PdlScope pdl(batch);
   int rs = run(img_, batch, h, w, ptrs_dev, stream_);
   if (rs != SSB_OK) return rs;
   const int K = max_kpts_;

@@ -37,6 +37,14 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 done ;;
+ncufull) # NCU_KERNELS="name:regex ..." one full capture (source counters included) of the 3rd launch matching each regex
+for spec in ${NCU_KERNELS:-attn:flash_attention qkv:EpiQkvRope ffn1:EpiLnGelu}; do
+  name=${spec%%:*}; re=${spec#*:}
+  echo "== ncu --set full: $name ($re)"
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$re --launch-skip 2 --launch-count 1 -f \
+      -o gpurun_out/full_${tag}_$name python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 1 > gpurun_out/ncufull_${tag}_$name.log 2>&1
+  ls -la gpurun_out/full_${tag}_$name.ncu-rep 2>/dev/null | awk '{print $5, $9}'
+done ;;
 ncu) echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 1 > gpurun_out/ncu_$tag.log 2>&1
