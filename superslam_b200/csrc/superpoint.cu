@@ -166,40 +166,39 @@ struct EpiScores {
   float* scores;      // [B][hs][ws]
   int Hc, Wc, hs, ws;
   static constexpr bool kSplit = false;  // the 65-way softmax needs the whole row in one thread
+  // One thread = one cell: 65 logits -> probabilities of the 64 pixels.  exp through ex2.approx on log2(e)-scaled
+  // logits and ONE reciprocal per cell (the first version: 65 expf + 64 IEEE divisions, ~1500 instructions per cell
+  // and 0.2 ms per 128 images for a 0.16 GFLOP product); both stay within an ulp or two of the fp32 softmax, and all
+  // index work downstream (NMS equality, threshold, top-K) is done on THIS map.
   __device__ void operator()(EpiCtx& c, bool) const {
     float v[80];
     tmem_ld_32x32(c.tmem_row, v);
     tmem_ld_32x32(c.tmem_row + 32, v + 32);
     tmem_ld_32x16(c.tmem_row + 64, v + 64);
     tmem_ld_wait();
+    constexpr float kLog2e = 1.4426950408889634f;
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 65; ++j) {
-      v[j] += __ldg(bias + j);
+      v[j] = (v[j] + __ldg(bias + j)) * kLog2e;
       m = fmaxf(m, v[j]);
     }
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < 65; ++j) {
-      v[j] = expf(v[j] - m);
-      sum += v[j];
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v[j] - m));
+      v[j] = e;
+      sum += e;
     }
+    const float inv = 1.0f / sum;
     if (c.py < Hc && c.px < Wc) {
       float* base = scores + (static_cast<size_t>(c.z) * hs + c.py * 8) * ws + c.px * 8;
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        float4 a, b;
-        a.x = v[8 * r + 0] / sum;
-        a.y = v[8 * r + 1] / sum;
-        a.z = v[8 * r + 2] / sum;
-        a.w = v[8 * r + 3] / sum;
-        b.x = v[8 * r + 4] / sum;
-        b.y = v[8 * r + 5] / sum;
-        b.z = v[8 * r + 6] / sum;
-        b.w = v[8 * r + 7] / sum;
         float4* dst = reinterpret_cast<float4*>(base + static_cast<size_t>(r) * ws);
-        dst[0] = a;
-        dst[1] = b;
+        dst[0] = make_float4(v[8 * r + 0] * inv, v[8 * r + 1] * inv, v[8 * r + 2] * inv, v[8 * r + 3] * inv);
+        dst[1] = make_float4(v[8 * r + 4] * inv, v[8 * r + 5] * inv, v[8 * r + 6] * inv, v[8 * r + 7] * inv);
       }
     }
   }
@@ -218,10 +217,15 @@ struct EpiDescNorm {
       float v[32];
       tmem_ld_32x32(c.tmem_row + col, v);
       tmem_ld_wait();
+      const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = v[j] + __ldg(bias + col + j);
-        ss = fmaf(x, x, ss);
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        const float x0 = v[4 * j] + bb.x, x1 = v[4 * j + 1] + bb.y, x2 = v[4 * j + 2] + bb.z, x3 = v[4 * j + 3] + bb.w;
+        ss = fmaf(x0, x0, ss);      // same summation order as before (ascending columns)
+        ss = fmaf(x1, x1, ss);
+        ss = fmaf(x2, x2, ss);
+        ss = fmaf(x3, x3, ss);
       }
     }
     ss = epi_pair_sum(c, ss);  // the two column halves of the row live in different warps
@@ -234,11 +238,15 @@ struct EpiDescNorm {
         float v[32];
         tmem_ld_32x32(c.tmem_row + col, v);
         tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          const float4 ba = __ldg(b4 + 2 * j), bb = __ldg(b4 + 2 * j + 1);
           float x[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) x[t] = (v[8 * j + t] + __ldg(bias + col + 8 * j + t)) * inv;
+          x[0] = (v[8 * j + 0] + ba.x) * inv, x[1] = (v[8 * j + 1] + ba.y) * inv;
+          x[2] = (v[8 * j + 2] + ba.z) * inv, x[3] = (v[8 * j + 3] + ba.w) * inv;
+          x[4] = (v[8 * j + 4] + bb.x) * inv, x[5] = (v[8 * j + 5] + bb.y) * inv;
+          x[6] = (v[8 * j + 6] + bb.z) * inv, x[7] = (v[8 * j + 7] + bb.w) * inv;
           uint4 o;
           o.x = pack_half2(x[0], x[1]);
           o.y = pack_half2(x[2], x[3]);
