@@ -20,6 +20,7 @@
 #include <string>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "umma_core.cuh"
 
 namespace ssb {
@@ -1268,6 +1269,11 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     fp.scale_log2 = scale * 1.4426950408889634f;
     fp.ctx = ctx_;
     fp.kp = KP;
+    // second version (two query tiles per CTA, a thread per row: attention2.cuh); SSB_FA_V1=1 selects the first
+    static const bool v1 = [] { const char* e = std::getenv("SSB_FA_V1"); return e != nullptr && std::atoi(e) != 0; }();
+    if (!v1)
+      return launch_flash_attention2(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, P2, stream,
+                                     key_xor ? "lg.attn_cross" : "lg.attn_self");
     return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, stream,
                                   key_xor ? "lg.attn_cross" : "lg.attn_self");
   };

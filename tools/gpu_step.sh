@@ -41,7 +41,7 @@ ncufull) # NCU_KERNELS="name:regex ..." one full capture (source counters includ
 for spec in ${NCU_KERNELS:-attn:flash_attention qkv:EpiQkvRope ffn1:EpiLnGelu}; do
   name=${spec%%:*}; re=${spec#*:}
   echo "== ncu --set full: $name ($re)"
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$re --launch-skip 2 --launch-count 1 -f \
+  timeout 600 ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:$re --launch-skip 2 --launch-count 1 -f \
       -o gpurun_out/full_${tag}_$name python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 1 > gpurun_out/ncufull_${tag}_$name.log 2>&1
   ls -la gpurun_out/full_${tag}_$name.ncu-rep 2>/dev/null | awk '{print $5, $9}'
 done ;;
