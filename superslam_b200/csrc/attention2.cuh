@@ -9,26 +9,29 @@
 // Here
 //   * a thread owns a whole query row (128 logits per key block): no exchange, no pair barrier, row max and row sum are
 //     thread-local;
-//   * the reference of the exponentials is the running one (exact maximum of the tile's first key block, kept until a
-//     row sum shows that a later block exceeded it by more than 2^8 - then the block is redone against its exact
-//     maximum and O, l are rescaled): the common block reads S once, 32 columns at a time, with ~64 live registers;
-//   * the two tiles of a CTA share every K / V block (half the TMA traffic and barrier traffic per tile) and one
-//     producer and one MMA warp; while one warp group computes exponentials the tensor core works for the other
-//     (S(j+1) of a tile is issued as soon as its P(j) is written, before P(j) V(j)).
+//   * the reference of the exponentials is the running one (exact maximum of the tile's first key block, kept until the
+//     sum of a 32-key chunk shows that a logit exceeded it by more than 2^8 - then the reference is raised and what has
+//     been produced so far - this chunk's values in registers, the chunks of P already in tensor memory, l and O - is
+//     rescaled, so S is never read twice): the common block reads S once, 32 columns at a time, ~64 live registers;
+//   * the two tiles of a CTA share every K / V block (half the TMA traffic per tile) and the producer warp; each tile has
+//     its OWN MMA-issuer warp, a plain sequential loop: S(j+1) is issued the moment the tile's softmax warps have pulled
+//     the last column of S(j) out of tensor memory (s_free) - i.e. under the last quarter of softmax(j) - and P(j) V(j)
+//     when P(j) is written.  (With one issuer for both tiles, blocked on one tile's barrier while the other tile's was
+//     ready, the softmax warps spent 22 % of their time waiting for S: profiles/ncu_attention2_r02.txt.)
 // TMEM (512 columns, one CTA per SM): S0 | S1 (128 each, fp32 logits), P0 | P1 (64 each: 128 fp16 probabilities per row,
 // the A operand of P V), O0 | O1 (64 each).  Shared memory: Q 2 x 32 KB (double-buffered per unit), K and V rings
 // (2 x 16 KB each), 2 x 16 KB output staging.
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax of tile 0,
-// 6..9 = softmax of tile 1 (TMEM lane quadrant = warp % 4).
+// Warp roles (352 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer of tile 0, 2..5 = softmax of tile 0,
+// 6..9 = softmax of tile 1 (TMEM lane quadrant = warp % 4), 10 = MMA issuer of tile 1.
 #pragma once
 
 #include "attention.cuh"
 
 namespace ssb {
 
-constexpr int kFa2Threads = 320;
-constexpr uint32_t kFa2KS = 2, kFa2VS = 2;   // K / V ring depths
-constexpr int kFa2SmemBytes = 2 * 32768 /*Q*/ + kFa2KS * 16384 + kFa2VS * 16384 + 2 * 16384 /*O staging*/ + 256 /*barriers*/ +
+constexpr int kFa2Threads = 352;
+constexpr uint32_t kFa2KS = 3, kFa2VS = 3;   // K / V ring depths (the two tiles' issuers may drift apart by that many blocks)
+constexpr int kFa2SmemBytes = 2 * 32768 /*Q*/ + kFa2KS * 16384 + kFa2VS * 16384 + 2 * 16384 /*O staging*/ + 512 /*barriers*/ +
                               1024 /*align*/;
 
 // One unit of work: query rows q0 .. q0 + 255 of (image, head) z, i.e. tile 0 and (if it has rows) tile 1.
@@ -63,15 +66,16 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* sO = sV + kFa2VS * 16384;                    // [2 tiles][4 quadrants][32 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * 16384);
   uint64_t* q_full = bars;          // [2]
-  uint64_t* q_empty = bars + 2;     // [2]
-  uint64_t* k_full = bars + 4;      // [KS]
-  uint64_t* k_empty = bars + 6;
-  uint64_t* v_full = bars + 8;      // [VS]
-  uint64_t* v_empty = bars + 10;
-  uint64_t* s_full = bars + 12;     // [2 tiles]  MMA -> softmax: S is in tensor memory
-  uint64_t* p_full = bars + 14;     // [2 tiles]  softmax -> MMA: P is written (and S has been read): 4 warps
-  uint64_t* pv_done = bars + 16;    // [2 tiles]  MMA -> softmax: P V has retired (P and O may be touched)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* q_empty = bars + 2;     // [2]   both issuers
+  uint64_t* k_full = bars + 4;      // [KS <= 4]
+  uint64_t* k_empty = bars + 8;     //        both issuers
+  uint64_t* v_full = bars + 12;     // [VS <= 4]
+  uint64_t* v_empty = bars + 16;    //        both issuers
+  uint64_t* s_full = bars + 20;     // [2 tiles]  issuer -> softmax: S is in tensor memory
+  uint64_t* p_full = bars + 22;     // [2 tiles]  softmax -> issuer: P is written: 4 warps
+  uint64_t* pv_done = bars + 24;    // [2 tiles]  issuer -> softmax: P V has retired (P and O may be touched)
+  uint64_t* s_free = bars + 26;     // [2 tiles]  softmax -> issuer: S has been read out of tensor memory: 4 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_pairs = (p.q_tiles + 1) >> 1;
@@ -83,16 +87,19 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 2);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 2);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&q_empty[i], 2);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
   }
@@ -143,107 +150,86 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer (whole warp in uniform control flow, one elected lane issues) ----
+  } else if (warp == 1 || warp == 10) {
+    // ---- MMA issuer of tile wg (whole warp in uniform control flow, one elected lane issues).  It walks EVERY key block
+    // of the CTA in order - also those of units whose tile wg has no rows, for which it only hands the K / V / Q buffers
+    // back - so that each *_empty barrier always sees exactly two arrivals per phase.
+    const int wg = warp == 1 ? 0 : 1;
     const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
     const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
     const uint32_t qbase = smem_u32(sQ), kbase = smem_u32(sK), vbase = smem_u32(sV);
-    // S of tile `wg` for the global key block `b`, with Q from unit buffer `qb`
-    auto issue_s = [&](int wg, uint32_t qb, uint32_t b) {
+    const uint32_t tS = tmem + wg * 128, tP = tmem + 256 + wg * 64, tO = tmem + 384 + wg * 64;
+    auto issue_s = [&](uint32_t qb, uint32_t g) {          // S for the CTA's key block g, Q from unit buffer qb
       const uint64_t qdesc = make_smem_desc_k_sw128(qbase + qb * 32768 + wg * 16384, 1024);
-      const uint64_t kdesc = make_smem_desc_k_sw128(kbase + (b % kFa2KS) * 16384, 1024);
+      const uint64_t kdesc = make_smem_desc_k_sw128(kbase + (g % kFa2KS) * 16384, 1024);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem + wg * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[wg]);
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int wg, uint32_t b, bool first) {
-      const uint32_t sv = b % kFa2VS;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {   // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
-          const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
-          umma_f16_ts(tmem + 384 + wg * 64, tmem + 256 + wg * 64 + 8 * k, vdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
-        }
-        umma_commit(&pv_done[wg]);
-      }
-      __syncwarp();
-    };
-    auto wait_k = [&](uint32_t b) {
-      mbar_wait(&k_full[b % kFa2KS], (b / kFa2KS) & 1u);
+    auto wait_kq = [&](uint32_t g, bool first, uint32_t u) {
+      mbar_wait(&k_full[g % kFa2KS], (g / kFa2KS) & 1u);
+      if (first) mbar_wait(&q_full[u & 1u], (u >> 1) & 1u);
       tc_fence_after();
     };
-    auto release_k = [&](uint32_t b) {   // after the last S that reads K block b has been issued
-      if (elect_one()) umma_commit(&k_empty[b % kFa2KS]);
-      __syncwarp();
-    };
-    uint32_t u = 0, kb = 0, c[2] = {0, 0};
+    uint32_t u = 0, g = 0, c = 0;   // unit index, key block index of the CTA, key blocks of this tile
+    bool s_issued = false;          // S of block g has been issued ahead (at the end of block g - 1)
     Fa2Unit cur, nxt;
     int unit = next_unit(blockIdx.x, cur);
-    if (unit < total) {
-      mbar_wait(&q_full[0], 0);
-      tc_fence_after();
-      wait_k(0);
-      issue_s(0, 0, 0);
-      if (cur.t1) issue_s(1, 0, 0);
-      release_k(0);
-      if (cur.nblk == 1) {
-        if (elect_one()) umma_commit(&q_empty[0]);
-        __syncwarp();
-      }
-    }
     while (unit < total) {
       const int nunit = next_unit(unit + stride, nxt);
-      const bool has_next = nunit < total;
-      const uint32_t qb = u & 1u, nqb = qb ^ 1u;
-      for (int j = 0; j < cur.nblk; ++j, ++kb) {
-        const bool more = j + 1 < cur.nblk;
-        const bool s_next = more || has_next;             // some S reads K block kb + 1
-        if (s_next) {
-          wait_k(kb + 1);
-          if (!more) {                                    // first block of the next unit: its Q must have landed
-            mbar_wait(&q_full[nqb], ((u + 1) >> 1) & 1u);
-            tc_fence_after();
+      const bool active = wg == 0 || cur.t1;
+      const uint32_t qb = u & 1u;
+      for (int j = 0; j < cur.nblk; ++j, ++g) {
+        const bool last = j + 1 == cur.nblk;
+        const uint32_t sk = g % kFa2KS, sv = g % kFa2VS;
+        if (!active) {   // hand the buffers back in order (after they were filled: the phases must not run ahead)
+          wait_kq(g, j == 0, u);
+          mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
+          if (lane == 0) {
+            mbar_arrive(&k_empty[sk]);
+            mbar_arrive(&v_empty[sv]);
+            if (last) mbar_arrive(&q_empty[qb]);
           }
+          __syncwarp();
+          s_issued = false;
+          continue;
         }
-        mbar_wait(&v_full[kb % kFa2VS], (kb / kFa2VS) & 1u);
-        tc_fence_after();
-        // ---- tile 0: P(kb) is written (and S(kb) read) -> next S, then P V
-        mbar_wait(&p_full[0], c[0] & 1u);
-        tc_fence_after();
-        if (more) issue_s(0, qb, kb + 1);
-        else if (has_next) issue_s(0, nqb, kb + 1);
-        issue_pv(0, kb, j == 0);
-        ++c[0];
-        // ---- tile 1
-        if (cur.t1) {
-          mbar_wait(&p_full[1], c[1] & 1u);
-          tc_fence_after();
+        if (!s_issued) {   // first block of the CTA, or the tile was idle during the previous unit
+          wait_kq(g, j == 0, u);
+          issue_s(qb, g);
         }
-        if (more) {
-          if (cur.t1) issue_s(1, qb, kb + 1);
-        } else if (has_next && nxt.t1) {
-          issue_s(1, nqb, kb + 1);                        // S1's buffer is free: every P1 written so far has been waited for
+        if (elect_one()) {   // K block g (and, with its last block, the unit's Q) is free once the S just issued retires
+          umma_commit(&k_empty[sk]);
+          if (last) umma_commit(&q_empty[qb]);
         }
-        if (cur.t1) {
-          issue_pv(1, kb, j == 0);
-          ++c[1];
-        }
-        if (s_next) release_k(kb + 1);
-        if (elect_one()) umma_commit(&v_empty[kb % kFa2VS]);
         __syncwarp();
-        // Q buffers: the unit's last S (block nblk - 1) has just been issued when j == nblk - 2; a next unit of one
-        // block has had its only S issued when !more
-        if (j + 2 == cur.nblk) {
-          if (elect_one()) umma_commit(&q_empty[qb]);
-          __syncwarp();
+        // S(g + 1) as soon as S(g) has been read: the block follows directly and belongs to a unit with rows for this tile
+        const bool next_here = !last || (nunit < total && (wg == 0 || nxt.t1));
+        mbar_wait(&s_free[wg], c & 1u);
+        tc_fence_after();
+        s_issued = false;
+        if (next_here) {
+          wait_kq(g + 1, last, u + 1);
+          issue_s(last ? (qb ^ 1u) : qb, g + 1);
+          s_issued = true;
         }
-        if (!more && has_next && nxt.nblk == 1) {
-          if (elect_one()) umma_commit(&q_empty[nqb]);
-          __syncwarp();
+        mbar_wait(&p_full[wg], c & 1u);
+        mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
+            const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
+            umma_f16_ts(tO, tP + 8 * k, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&pv_done[wg]);
+          umma_commit(&v_empty[sv]);
         }
+        __syncwarp();
+        ++c;
       }
       unit = nunit;
       cur = nxt;
@@ -270,8 +256,7 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(&s_full[wg], c & 1u);
         tc_fence_after();
         const int kvalid = t.nk - j * kFaBlockKeys;   // valid keys in this block (>= 1; < 128 only in an image's last block)
-        // exact row maximum of the block (raw logits; the positive scale is applied once)
-        auto block_max = [&]() -> float {
+        if (j == 0) {   // reference of the tile: exact row maximum of its first key block (raw logits x scale)
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
             if (kvalid < 32 * (i + 1)) {
@@ -282,66 +267,93 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], v[e]);
           });
-          return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
-        };
-        if (j == 0) m_used = block_max();
-        float lsum = 0.f;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
+          m_used = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+        }
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+        float before = 0.f;   // sum of the block's probabilities up to the previous chunk
+        tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
+          if (i == 3) {   // the last columns of S are in registers: the issuer may overwrite S with the next block's
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[wg]);
+          }
+          if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (32 * i + e >= kvalid) v[e] = -INFINITY;
+          }
           const float2 nm2 = make_float2(-m_used, -m_used);
-          float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
-          tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
-            if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
+          float2 ev[16];
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (32 * i + e >= kvalid) v[e] = -INFINITY;
+          for (int k = 0; k < 16; ++k) {
+            float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
+            if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+              e = exp2_poly2(e);     // FMA pipe instead of the MUFU
+            } else {
+              e.x = fast_exp2(e.x);
+              e.y = fast_exp2(e.y);
             }
-            uint32_t w[16];
+            if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
+            ev[k] = e;
+          }
+          if (i == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
+            mbar_wait(&pv_done[wg], (c - 1) & 1u);
+            tc_fence_after();
+          }
+          // A logit more than 2^8 above the reference shows in the chunk's sum (32 probabilities <= 256 otherwise; fp16
+          // holds 65504).  Rare: raise the reference by the excess and rescale everything produced against the old one -
+          // this chunk (still fp32), the chunks of P already written, the sums, and (not in a tile's first block) l and O.
+          const float now = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+          const bool need = !(now - before <= 256.0f);
+          if (__any_sync(0xffffffffu, need)) {
+            float big = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
-              if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
-                e = exp2_poly2(e);     // FMA pipe instead of the MUFU
-              } else {
-                e.x = fast_exp2(e.x);
-                e.y = fast_exp2(e.y);
-              }
-              if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
-              w[k] = pack_half2(e.x, e.y);
-            }
-            if (i == 0 && attempt == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
-              mbar_wait(&pv_done[wg], (c - 1) & 1u);
-              tc_fence_after();
-            }
-            tmem_st_32x16_u32(tP + 16 * i, w);
-          });
-          lsum = (ls0.x + ls0.y) + (ls1.x + ls1.y);
-          // An element above the reference by more than 2^8 shows in the row sum (<= 128 otherwise ... 256 with every
-          // element at +1).  Rare: redo the block against its exact maximum and rescale l and O.
-          const bool need = attempt == 0 && !(lsum <= 256.0f);
-          if (!__any_sync(0xffffffffu, need)) break;
-          const float bm = block_max();
-          const float m_new = need ? fmaxf(bm, m_used) : m_used;
-          const float alpha = need ? fast_exp2(m_used - m_new) : 1.0f;
-          m_used = m_new;
-          l *= alpha;
-          if (j > 0) {
+            for (int k = 0; k < 16; ++k) big = fmaxf(big, fmaxf(ev[k].x, ev[k].y));
+            // excess in whole powers of two: alpha = 2^-d with 2^d >= big / 2 (NaN / inf logits: alpha = 2^-126, no trap)
+            const int d = need ? min(max(static_cast<int>((__float_as_uint(big) >> 23) & 0xffu) - 127, 0), 126) : 0;
+            const float alpha = __uint_as_float(static_cast<uint32_t>(127 - d) << 23);
+            m_used += static_cast<float>(d);
+            const float2 a2 = make_float2(alpha, alpha);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) ev[k] = ffma2(ev[k], a2, make_float2(0.f, 0.f));
+            ls0 = ffma2(ls0, a2, make_float2(0.f, 0.f));
+            ls1 = ffma2(ls1, a2, make_float2(0.f, 0.f));
+            l *= alpha;
 #pragma unroll 1
-            for (int h = 0; h < 4; ++h) {
-              float o[16];
-              tmem_ld_32x16(tO + h * 16, o);
+            for (int h = 0; h < i; ++h) {   // P chunks 0 .. i-1: 16 cells of two fp16 each
+              uint32_t cells[16];
+              tmem_ld_32x16(tP + 16 * h, reinterpret_cast<float*>(cells));
               tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 16; ++e) o[e] *= alpha;
-              tmem_st_32x16(tO + h * 16, o);
+              for (int k = 0; k < 16; ++k) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cells[k]));
+                cells[k] = pack_half2(f.x * alpha, f.y * alpha);
+              }
+              tmem_st_32x16_u32(tP + 16 * h, cells);
+            }
+            if (j > 0) {
+#pragma unroll 1
+              for (int h = 0; h < 4; ++h) {
+                float o[16];
+                tmem_ld_32x16(tO + h * 16, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o[e] *= alpha;
+                tmem_st_32x16(tO + h * 16, o);
+              }
             }
           }
-        }
-        l += lsum;
+          before = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) w[k] = pack_half2(ev[k].x, ev[k].y);
+          tmem_st_32x16_u32(tP + 16 * i, w);
+        });
+        l += before;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[wg]);   // one arrival per warp; also tells the MMA warp that S has been read
+        if (lane == 0) mbar_arrive(&p_full[wg]);   // one arrival per warp
       }
       // ---- tile epilogue: O / l -> fp16 context rows (this warp's 32 rows through its staging slab, one TMA store)
       mbar_wait(&pv_done[wg], (c - 1) & 1u);
@@ -357,13 +369,13 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_ld_32x32(tO + h * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int gq = 0; gq < 4; ++gq) {
             uint4 wv;
-            wv.x = valid ? pack_half2(o[8 * g + 0] * inv, o[8 * g + 1] * inv) : 0u;
-            wv.y = valid ? pack_half2(o[8 * g + 2] * inv, o[8 * g + 3] * inv) : 0u;
-            wv.z = valid ? pack_half2(o[8 * g + 4] * inv, o[8 * g + 5] * inv) : 0u;
-            wv.w = valid ? pack_half2(o[8 * g + 6] * inv, o[8 * g + 7] * inv) : 0u;
-            *reinterpret_cast<uint4*>(slab + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = wv;
+            wv.x = valid ? pack_half2(o[8 * gq + 0] * inv, o[8 * gq + 1] * inv) : 0u;
+            wv.y = valid ? pack_half2(o[8 * gq + 2] * inv, o[8 * gq + 3] * inv) : 0u;
+            wv.z = valid ? pack_half2(o[8 * gq + 4] * inv, o[8 * gq + 5] * inv) : 0u;
+            wv.w = valid ? pack_half2(o[8 * gq + 6] * inv, o[8 * gq + 7] * inv) : 0u;
+            *reinterpret_cast<uint4*>(slab + lane * 128 + (((h * 4 + gq) ^ (lane & 7)) << 4)) = wv;
           }
         }
         fence_proxy_async_smem();
