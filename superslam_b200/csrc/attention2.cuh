@@ -9,15 +9,15 @@
 // Here
 //   * a thread owns a whole query row (128 logits per key block): no exchange, no pair barrier, row max and row sum are
 //     thread-local;
-//   * the reference of the exponentials is the running one (exact maximum of the tile's first key block, kept until the
-//     sum of a 32-key chunk shows that a logit exceeded it by more than 2^8 - then the reference is raised and what has
-//     been produced so far - this chunk's values in registers, the chunks of P already in tensor memory, l and O - is
-//     rescaled, so S is never read twice): the common block reads S once, 32 columns at a time, ~64 live registers;
+//   * the reference of the exponentials is the running one (exact maximum of the tile's first key block, kept until a
+//     row sum shows that a later block exceeded it by more than 2^8 - then the block is redone against its exact
+//     maximum and O, l are rescaled): the common block reads S once, 32 columns at a time, with ~64 live registers;
 //   * the two tiles of a CTA share every K / V block (half the TMA traffic per tile) and the producer warp; each tile has
-//     its OWN MMA-issuer warp, a plain sequential loop: S(j+1) is issued the moment the tile's softmax warps have pulled
-//     the last column of S(j) out of tensor memory (s_free) - i.e. under the last quarter of softmax(j) - and P(j) V(j)
-//     when P(j) is written.  (With one issuer for both tiles, blocked on one tile's barrier while the other tile's was
-//     ready, the softmax warps spent 22 % of their time waiting for S: profiles/ncu_attention2_r02.txt.)
+//     its OWN MMA-issuer warp, a plain sequential loop (S(j+1) as soon as P(j) is written, then P(j) V(j)), so a tile
+//     never waits because the single issuer is blocked on the other tile's barrier.
+//     (Tried and measured slower, 2.30 vs 2.00 ms per 9 launches: releasing S to the issuer after its last read, which
+//     needs the reference check per 32-key chunk instead of per block - the S wait of the softmax warps fell from 17 %
+//     to 8 % of the samples, but the extra instructions of the inner loop cost more than that.)
 // TMEM (512 columns, one CTA per SM): S0 | S1 (128 each, fp32 logits), P0 | P1 (64 each: 128 fp16 probabilities per row,
 // the A operand of P V), O0 | O1 (64 each).  Shared memory: Q 2 x 32 KB (double-buffered per unit), K and V rings
 // (2 x 16 KB each), 2 x 16 KB output staging.
@@ -74,7 +74,6 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* s_full = bars + 20;     // [2 tiles]  issuer -> softmax: S is in tensor memory
   uint64_t* p_full = bars + 22;     // [2 tiles]  softmax -> issuer: P is written: 4 warps
   uint64_t* pv_done = bars + 24;    // [2 tiles]  issuer -> softmax: P V has retired (P and O may be touched)
-  uint64_t* s_free = bars + 26;     // [2 tiles]  softmax -> issuer: S has been read out of tensor memory: 4 warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,7 +98,6 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
   }
@@ -206,19 +204,18 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (last) umma_commit(&q_empty[qb]);
         }
         __syncwarp();
-        // S(g + 1) as soon as S(g) has been read: the block follows directly and belongs to a unit with rows for this tile
+        // P(g) is written, so S(g) has been read: S(g + 1) first (the softmax warps wait for it), then P(g) V(g).  The
+        // next block must follow directly and belong to a unit with rows for this tile.
         const bool next_here = !last || (nunit < total && (wg == 0 || nxt.t1));
-        mbar_wait(&s_free[wg], c & 1u);
+        if (next_here) wait_kq(g + 1, last, u + 1);
+        mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
+        mbar_wait(&p_full[wg], c & 1u);
         tc_fence_after();
         s_issued = false;
         if (next_here) {
-          wait_kq(g + 1, last, u + 1);
           issue_s(last ? (qb ^ 1u) : qb, g + 1);
           s_issued = true;
         }
-        mbar_wait(&p_full[wg], c & 1u);
-        mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
-        tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {   // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
@@ -256,7 +253,8 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(&s_full[wg], c & 1u);
         tc_fence_after();
         const int kvalid = t.nk - j * kFaBlockKeys;   // valid keys in this block (>= 1; < 128 only in an image's last block)
-        if (j == 0) {   // reference of the tile: exact row maximum of its first key block (raw logits x scale)
+        // exact row maximum of the block (raw logits; the positive scale is applied once)
+        auto block_max = [&]() -> float {
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
             if (kvalid < 32 * (i + 1)) {
@@ -267,93 +265,66 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], v[e]);
           });
-          m_used = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
-        }
-        float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
-        float before = 0.f;   // sum of the block's probabilities up to the previous chunk
-        tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
-          if (i == 3) {   // the last columns of S are in registers: the issuer may overwrite S with the next block's
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[wg]);
-          }
-          if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (32 * i + e >= kvalid) v[e] = -INFINITY;
-          }
-          const float2 nm2 = make_float2(-m_used, -m_used);
-          float2 ev[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
-            if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
-              e = exp2_poly2(e);     // FMA pipe instead of the MUFU
-            } else {
-              e.x = fast_exp2(e.x);
-              e.y = fast_exp2(e.y);
-            }
-            if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
-            ev[k] = e;
-          }
-          if (i == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
-            mbar_wait(&pv_done[wg], (c - 1) & 1u);
-            tc_fence_after();
-          }
-          // A logit more than 2^8 above the reference shows in the chunk's sum (32 probabilities <= 256 otherwise; fp16
-          // holds 65504).  Rare: raise the reference by the excess and rescale everything produced against the old one -
-          // this chunk (still fp32), the chunks of P already written, the sums, and (not in a tile's first block) l and O.
-          const float now = (ls0.x + ls0.y) + (ls1.x + ls1.y);
-          const bool need = !(now - before <= 256.0f);
-          if (__any_sync(0xffffffffu, need)) {
-            float big = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) big = fmaxf(big, fmaxf(ev[k].x, ev[k].y));
-            // excess in whole powers of two: alpha = 2^-d with 2^d >= big / 2 (NaN / inf logits: alpha = 2^-126, no trap)
-            const int d = need ? min(max(static_cast<int>((__float_as_uint(big) >> 23) & 0xffu) - 127, 0), 126) : 0;
-            const float alpha = __uint_as_float(static_cast<uint32_t>(127 - d) << 23);
-            m_used += static_cast<float>(d);
-            const float2 a2 = make_float2(alpha, alpha);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) ev[k] = ffma2(ev[k], a2, make_float2(0.f, 0.f));
-            ls0 = ffma2(ls0, a2, make_float2(0.f, 0.f));
-            ls1 = ffma2(ls1, a2, make_float2(0.f, 0.f));
-            l *= alpha;
+          return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+        };
+        if (j == 0) m_used = block_max();
+        float lsum = 0.f;
 #pragma unroll 1
-            for (int h = 0; h < i; ++h) {   // P chunks 0 .. i-1: 16 cells of two fp16 each
-              uint32_t cells[16];
-              tmem_ld_32x16(tP + 16 * h, reinterpret_cast<float*>(cells));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          const float2 nm2 = make_float2(-m_used, -m_used);
+          float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+          tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
+            if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (32 * i + e >= kvalid) v[e] = -INFINITY;
+            }
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
+              if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+                e = exp2_poly2(e);     // FMA pipe instead of the MUFU
+              } else {
+                e.x = fast_exp2(e.x);
+                e.y = fast_exp2(e.y);
+              }
+              if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
+              w[k] = pack_half2(e.x, e.y);
+            }
+            if (i == 0 && attempt == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
+              mbar_wait(&pv_done[wg], (c - 1) & 1u);
+              tc_fence_after();
+            }
+            tmem_st_32x16_u32(tP + 16 * i, w);
+          });
+          lsum = (ls0.x + ls0.y) + (ls1.x + ls1.y);
+          // An element above the reference by more than 2^8 shows in the row sum (<= 128 otherwise ... 256 with every
+          // element at +1).  Rare: redo the block against its exact maximum and rescale l and O.
+          const bool need = attempt == 0 && !(lsum <= 256.0f);
+          if (!__any_sync(0xffffffffu, need)) break;
+          const float bm = block_max();
+          const float m_new = need ? fmaxf(bm, m_used) : m_used;
+          const float alpha = need ? fast_exp2(m_used - m_new) : 1.0f;
+          m_used = m_new;
+          l *= alpha;
+          if (j > 0) {
+#pragma unroll 1
+            for (int h = 0; h < 4; ++h) {
+              float o[16];
+              tmem_ld_32x16(tO + h * 16, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cells[k]));
-                cells[k] = pack_half2(f.x * alpha, f.y * alpha);
-              }
-              tmem_st_32x16_u32(tP + 16 * h, cells);
-            }
-            if (j > 0) {
-#pragma unroll 1
-              for (int h = 0; h < 4; ++h) {
-                float o[16];
-                tmem_ld_32x16(tO + h * 16, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) o[e] *= alpha;
-                tmem_st_32x16(tO + h * 16, o);
-              }
+              for (int e = 0; e < 16; ++e) o[e] *= alpha;
+              tmem_st_32x16(tO + h * 16, o);
             }
           }
-          before = (ls0.x + ls0.y) + (ls1.x + ls1.y);
-          uint32_t w[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) w[k] = pack_half2(ev[k].x, ev[k].y);
-          tmem_st_32x16_u32(tP + 16 * i, w);
-        });
-        l += before;
+        }
+        l += lsum;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[wg]);   // one arrival per warp
+        if (lane == 0) mbar_arrive(&p_full[wg]);   // one arrival per warp; also tells the MMA warp that S has been read
       }
       // ---- tile epilogue: O / l -> fp16 context rows (this warp's 32 rows through its staging slab, one TMA store)
       mbar_wait(&pv_done[wg], (c - 1) & 1u);
@@ -369,13 +340,13 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_ld_32x32(tO + h * 32, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
+          for (int g = 0; g < 4; ++g) {
             uint4 wv;
-            wv.x = valid ? pack_half2(o[8 * gq + 0] * inv, o[8 * gq + 1] * inv) : 0u;
-            wv.y = valid ? pack_half2(o[8 * gq + 2] * inv, o[8 * gq + 3] * inv) : 0u;
-            wv.z = valid ? pack_half2(o[8 * gq + 4] * inv, o[8 * gq + 5] * inv) : 0u;
-            wv.w = valid ? pack_half2(o[8 * gq + 6] * inv, o[8 * gq + 7] * inv) : 0u;
-            *reinterpret_cast<uint4*>(slab + lane * 128 + (((h * 4 + gq) ^ (lane & 7)) << 4)) = wv;
+            wv.x = valid ? pack_half2(o[8 * g + 0] * inv, o[8 * g + 1] * inv) : 0u;
+            wv.y = valid ? pack_half2(o[8 * g + 2] * inv, o[8 * g + 3] * inv) : 0u;
+            wv.z = valid ? pack_half2(o[8 * g + 4] * inv, o[8 * g + 5] * inv) : 0u;
+            wv.w = valid ? pack_half2(o[8 * g + 6] * inv, o[8 * g + 7] * inv) : 0u;
+            *reinterpret_cast<uint4*>(slab + lane * 128 + (((h * 4 + g) ^ (lane & 7)) << 4)) = wv;
           }
         }
         fence_proxy_async_smem();

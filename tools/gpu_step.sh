@@ -19,13 +19,15 @@ print(d["kernel_ms_per_step"]); print("spread", d["value_spread_per_step"], "e2e
 print("live", d.get("live_pipeline")); print("latency", d.get("latency_single_pair")); print("records", d["results"]["gathered_records"])
 PY
 ;;
-ab) echo "== A/B: ${AB:-SSB_LG_ASSIGN_V1=1}"; env ${AB:-SSB_LG_ASSIGN_V1=1} timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_unfused.json 2> gpurun_out/bench_${tag}_unfused.err
-python - "$tag" <<'PY'
+ab) # ABS="ENV=1 ENV2=x ..." (default: SSB_LG_ASSIGN_V1=1): one short bench per entry with that environment assignment
+for ab in ${ABS:-SSB_LG_ASSIGN_V1=1}; do
+  echo "== A/B: $ab"; env $ab timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_ab.json 2> gpurun_out/bench_${tag}_ab.err
+  python - "$tag" <<'PY'
 import json, sys
-d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}_unfused.json"))
-print("unfused value", round(d["value"], 1), d["clocks"]); print(d["kernel_ms_per_step"])
+d = json.load(open(f"gpurun_out/bench_{sys.argv[1]}_ab.json"))
+print("   value", round(d["value"], 1), d["clocks"]["sm_mhz"], "MHz;", {k: v for k, v in list(d["kernel_ms_per_step"].items())[:6]})
 PY
-;;
+done ;;
 configs) for c in C1 C3 C4 C5; do echo "== bench --config $c"; timeout 600 python bench.py --config $c --steps 5 --no-cpu-baseline > gpurun_out/bench_${tag}_$c.json 2> gpurun_out/bench_${tag}_$c.err; tail -2 gpurun_out/bench_${tag}_$c.err
 python - "$tag" "$c" <<'PY'
 import json, sys
