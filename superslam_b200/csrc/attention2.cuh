@@ -9,29 +9,29 @@
 // Here
 //   * a thread owns a whole query row (128 logits per key block): no exchange, no pair barrier, row max and row sum are
 //     thread-local;
-//   * the reference of the exponentials is the running one (exact maximum of the tile's first key block, kept until a
-//     row sum shows that a later block exceeded it by more than 2^8 - then the block is redone against its exact
-//     maximum and O, l are rescaled): the common block reads S once, 32 columns at a time, with ~64 live registers;
-//   * the two tiles of a CTA share every K / V block (half the TMA traffic per tile) and the producer warp; each tile has
-//     its OWN MMA-issuer warp, a plain sequential loop (S(j+1) as soon as P(j) is written, then P(j) V(j)), so a tile
-//     never waits because the single issuer is blocked on the other tile's barrier.
-//     (Tried and measured slower, 2.30 vs 2.00 ms per 9 launches: releasing S to the issuer after its last read, which
-//     needs the reference check per 32-key chunk instead of per block - the S wait of the softmax warps fell from 17 %
-//     to 8 % of the samples, but the extra instructions of the inner loop cost more than that.)
+//   * S is read twice per block, 32 columns at a time with ~64 live registers: a max pass (the exact row maximum of the
+//     block; the reference of the exponentials is only raised - and l, O rescaled - when it grows by more than 2^8) and
+//     the exponential pass, whose last tcgen05.ld hands S back to the MMA warp (s_free): S(j+1) is computed under the
+//     last quarter of softmax(j);
+//   * the two tiles of a CTA share every K / V block (half the TMA traffic and barrier traffic per tile) and one
+//     producer and one MMA warp; while one warp group computes exponentials the tensor core works for the other.
+//   Measured on the way (profiles/README.md): a lazy reference without the max pass (block redone when a row sum betrays
+//   an overflow) must keep S until P is written - its softmax warps waited 17 % of the time for the next S; checking per
+//   32-key chunk instead, or a second issuer warp, cost more instructions / issue slots than they won.
 // TMEM (512 columns, one CTA per SM): S0 | S1 (128 each, fp32 logits), P0 | P1 (64 each: 128 fp16 probabilities per row,
 // the A operand of P V), O0 | O1 (64 each).  Shared memory: Q 2 x 32 KB (double-buffered per unit), K and V rings
 // (2 x 16 KB each), 2 x 16 KB output staging.
-// Warp roles (352 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer of tile 0, 2..5 = softmax of tile 0,
-// 6..9 = softmax of tile 1 (TMEM lane quadrant = warp % 4), 10 = MMA issuer of tile 1.
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = softmax of tile 0,
+// 6..9 = softmax of tile 1 (TMEM lane quadrant = warp % 4).
 #pragma once
 
 #include "attention.cuh"
 
 namespace ssb {
 
-constexpr int kFa2Threads = 352;
-constexpr uint32_t kFa2KS = 3, kFa2VS = 3;   // K / V ring depths (the two tiles' issuers may drift apart by that many blocks)
-constexpr int kFa2SmemBytes = 2 * 32768 /*Q*/ + kFa2KS * 16384 + kFa2VS * 16384 + 2 * 16384 /*O staging*/ + 512 /*barriers*/ +
+constexpr int kFa2Threads = 320;
+constexpr uint32_t kFa2KS = 2, kFa2VS = 2;   // K / V ring depths
+constexpr int kFa2SmemBytes = 2 * 32768 /*Q*/ + kFa2KS * 16384 + kFa2VS * 16384 + 2 * 16384 /*O staging*/ + 256 /*barriers*/ +
                               1024 /*align*/;
 
 // One unit of work: query rows q0 .. q0 + 255 of (image, head) z, i.e. tile 0 and (if it has rows) tile 1.
@@ -66,15 +66,16 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* sO = sV + kFa2VS * 16384;                    // [2 tiles][4 quadrants][32 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * 16384);
   uint64_t* q_full = bars;          // [2]
-  uint64_t* q_empty = bars + 2;     // [2]   both issuers
-  uint64_t* k_full = bars + 4;      // [KS <= 4]
-  uint64_t* k_empty = bars + 8;     //        both issuers
-  uint64_t* v_full = bars + 12;     // [VS <= 4]
-  uint64_t* v_empty = bars + 16;    //        both issuers
-  uint64_t* s_full = bars + 20;     // [2 tiles]  issuer -> softmax: S is in tensor memory
-  uint64_t* p_full = bars + 22;     // [2 tiles]  softmax -> issuer: P is written: 4 warps
-  uint64_t* pv_done = bars + 24;    // [2 tiles]  issuer -> softmax: P V has retired (P and O may be touched)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* q_empty = bars + 2;     // [2]
+  uint64_t* k_full = bars + 4;      // [KS]
+  uint64_t* k_empty = bars + 6;
+  uint64_t* v_full = bars + 8;      // [VS]
+  uint64_t* v_empty = bars + 10;
+  uint64_t* s_full = bars + 12;     // [2 tiles]  MMA -> softmax: S is in tensor memory
+  uint64_t* p_full = bars + 14;     // [2 tiles]  softmax -> MMA: P is written (and S has been read): 4 warps
+  uint64_t* pv_done = bars + 16;    // [2 tiles]  MMA -> softmax: P V has retired (P and O may be touched)
+  uint64_t* s_free = bars + 18;     // [2 tiles]  softmax -> MMA: the last column of S is in registers: 4 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_pairs = (p.q_tiles + 1) >> 1;
@@ -86,18 +87,17 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 2);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 2);
-    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 2);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_mbar_init();
   }
@@ -148,85 +148,111 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp == 1 || warp == 10) {
-    // ---- MMA issuer of tile wg (whole warp in uniform control flow, one elected lane issues).  It walks EVERY key block
-    // of the CTA in order - also those of units whose tile wg has no rows, for which it only hands the K / V / Q buffers
-    // back - so that each *_empty barrier always sees exactly two arrivals per phase.
-    const int wg = warp == 1 ? 0 : 1;
+  } else if (warp == 1) {
+    // ---- MMA issuer (whole warp in uniform control flow, one elected lane issues) ----
     const uint32_t idesc_s = make_idesc_f16(128);          // S: N = 128 keys
     const uint32_t idesc_o = make_idesc_f16(64, 0, 1);     // O: N = 64, B (= V) is MN-major
     const uint32_t qbase = smem_u32(sQ), kbase = smem_u32(sK), vbase = smem_u32(sV);
-    const uint32_t tS = tmem + wg * 128, tP = tmem + 256 + wg * 64, tO = tmem + 384 + wg * 64;
-    auto issue_s = [&](uint32_t qb, uint32_t g) {          // S for the CTA's key block g, Q from unit buffer qb
+    // S of tile `wg` for the global key block `b`, with Q from unit buffer `qb`
+    auto issue_s = [&](int wg, uint32_t qb, uint32_t b) {
       const uint64_t qdesc = make_smem_desc_k_sw128(qbase + qb * 32768 + wg * 16384, 1024);
-      const uint64_t kdesc = make_smem_desc_k_sw128(kbase + (g % kFa2KS) * 16384, 1024);
+      const uint64_t kdesc = make_smem_desc_k_sw128(kbase + (b % kFa2KS) * 16384, 1024);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + wg * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[wg]);
       }
       __syncwarp();
     };
-    auto wait_kq = [&](uint32_t g, bool first, uint32_t u) {
-      mbar_wait(&k_full[g % kFa2KS], (g / kFa2KS) & 1u);
-      if (first) mbar_wait(&q_full[u & 1u], (u >> 1) & 1u);
+    auto issue_pv = [&](int wg, uint32_t b, bool first) {
+      const uint32_t sv = b % kFa2VS;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
+          const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
+          umma_f16_ts(tmem + 384 + wg * 64, tmem + 256 + wg * 64 + 8 * k, vdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[wg]);
+      }
+      __syncwarp();
+    };
+    auto wait_k = [&](uint32_t b) {
+      mbar_wait(&k_full[b % kFa2KS], (b / kFa2KS) & 1u);
       tc_fence_after();
     };
-    uint32_t u = 0, g = 0, c = 0;   // unit index, key block index of the CTA, key blocks of this tile
-    bool s_issued = false;          // S of block g has been issued ahead (at the end of block g - 1)
+    auto release_k = [&](uint32_t b) {   // after the last S that reads K block b has been issued
+      if (elect_one()) umma_commit(&k_empty[b % kFa2KS]);
+      __syncwarp();
+    };
+    uint32_t u = 0, kb = 0, c[2] = {0, 0};
     Fa2Unit cur, nxt;
     int unit = next_unit(blockIdx.x, cur);
+    if (unit < total) {
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      wait_k(0);
+      issue_s(0, 0, 0);
+      if (cur.t1) issue_s(1, 0, 0);
+      release_k(0);
+      if (cur.nblk == 1) {
+        if (elect_one()) umma_commit(&q_empty[0]);
+        __syncwarp();
+      }
+    }
     while (unit < total) {
       const int nunit = next_unit(unit + stride, nxt);
-      const bool active = wg == 0 || cur.t1;
-      const uint32_t qb = u & 1u;
-      for (int j = 0; j < cur.nblk; ++j, ++g) {
-        const bool last = j + 1 == cur.nblk;
-        const uint32_t sk = g % kFa2KS, sv = g % kFa2VS;
-        if (!active) {   // hand the buffers back in order (after they were filled: the phases must not run ahead)
-          wait_kq(g, j == 0, u);
-          mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
-          if (lane == 0) {
-            mbar_arrive(&k_empty[sk]);
-            mbar_arrive(&v_empty[sv]);
-            if (last) mbar_arrive(&q_empty[qb]);
+      const bool has_next = nunit < total;
+      const uint32_t qb = u & 1u, nqb = qb ^ 1u;
+      for (int j = 0; j < cur.nblk; ++j, ++kb) {
+        const bool more = j + 1 < cur.nblk;
+        const bool s_next = more || has_next;             // some S reads K block kb + 1
+        if (s_next) {
+          wait_k(kb + 1);
+          if (!more) {                                    // first block of the next unit: its Q must have landed
+            mbar_wait(&q_full[nqb], ((u + 1) >> 1) & 1u);
+            tc_fence_after();
           }
-          __syncwarp();
-          s_issued = false;
-          continue;
         }
-        if (!s_issued) {   // first block of the CTA, or the tile was idle during the previous unit
-          wait_kq(g, j == 0, u);
-          issue_s(qb, g);
-        }
-        if (elect_one()) {   // K block g (and, with its last block, the unit's Q) is free once the S just issued retires
-          umma_commit(&k_empty[sk]);
-          if (last) umma_commit(&q_empty[qb]);
-        }
-        __syncwarp();
-        // P(g) is written, so S(g) has been read: S(g + 1) first (the softmax warps wait for it), then P(g) V(g).  The
-        // next block must follow directly and belong to a unit with rows for this tile.
-        const bool next_here = !last || (nunit < total && (wg == 0 || nxt.t1));
-        if (next_here) wait_kq(g + 1, last, u + 1);
-        mbar_wait(&v_full[sv], (g / kFa2VS) & 1u);
-        mbar_wait(&p_full[wg], c & 1u);
+        mbar_wait(&v_full[kb % kFa2VS], (kb / kFa2VS) & 1u);
         tc_fence_after();
-        s_issued = false;
-        if (next_here) {
-          issue_s(last ? (qb ^ 1u) : qb, g + 1);
-          s_issued = true;
+        // per tile: S(kb + 1) as soon as the softmax warps hold the last column of S(kb) (s_free: under the last quarter
+        // of softmax(kb)), P(kb) V(kb) when P(kb) is written.  Tile 0 first: its warps run about half a block ahead.
+        mbar_wait(&s_free[0], c[0] & 1u);
+        tc_fence_after();
+        if (more) issue_s(0, qb, kb + 1);
+        else if (has_next) issue_s(0, nqb, kb + 1);
+        mbar_wait(&p_full[0], c[0] & 1u);
+        tc_fence_after();
+        issue_pv(0, kb, j == 0);
+        ++c[0];
+        if (cur.t1) {
+          mbar_wait(&s_free[1], c[1] & 1u);
+          tc_fence_after();
         }
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {   // B: 16 key rows = 2048 B.  A: 16 keys of P = 8 TMEM columns.
-            const uint64_t vdesc = make_smem_desc_mn_sw128(vbase + sv * 16384 + k * 2048, 1024, 1024);
-            umma_f16_ts(tO, tP + 8 * k, vdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&pv_done[wg]);
-          umma_commit(&v_empty[sv]);
+        if (more) {
+          if (cur.t1) issue_s(1, qb, kb + 1);
+        } else if (has_next && nxt.t1) {
+          issue_s(1, nqb, kb + 1);                        // S1's buffer is free: every S1 issued so far has been read
         }
+        if (cur.t1) {
+          mbar_wait(&p_full[1], c[1] & 1u);
+          tc_fence_after();
+          issue_pv(1, kb, j == 0);
+          ++c[1];
+        }
+        if (s_next) release_k(kb + 1);
+        if (elect_one()) umma_commit(&v_empty[kb % kFa2VS]);
         __syncwarp();
-        ++c;
+        // Q buffers: the unit's last S (block nblk - 1) has just been issued when j == nblk - 2; a next unit of one
+        // block has had its only S issued when !more
+        if (j + 2 == cur.nblk) {
+          if (elect_one()) umma_commit(&q_empty[qb]);
+          __syncwarp();
+        }
+        if (!more && has_next && nxt.nblk == 1) {
+          if (elect_one()) umma_commit(&q_empty[nqb]);
+          __syncwarp();
+        }
       }
       unit = nunit;
       cur = nxt;
@@ -267,59 +293,64 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           });
           return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
         };
-        if (j == 0) m_used = block_max();
-        float lsum = 0.f;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
-          const float2 nm2 = make_float2(-m_used, -m_used);
-          float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
-          tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
-            if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
+        // Reference of the exponentials: the running maximum, refreshed only when a block exceeds it by more than 2^8
+        // (P <= 256 in fp16, exact after the final division by l); then l and O are rescaled.  The maximum is exact per
+        // block, so no block is ever redone and S can go back to the MMA warp after its last read.
+        const float bm = block_max();
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m_used = bm;
+        } else if (bm > m_used + 8.0f) {
+          alpha = fast_exp2(m_used - bm);
+          m_used = bm;
+          need = true;
+        }
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
+        tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
+          if (i == 3) {   // S is in registers: the MMA warp may overwrite it with the next block's logits
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[wg]);
+          }
+          if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (32 * i + e >= kvalid) v[e] = -INFINITY;
+            for (int e = 0; e < 32; ++e)
+              if (32 * i + e >= kvalid) v[e] = -INFINITY;
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
+            if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
+              e = exp2_poly2(e);     // FMA pipe instead of the MUFU
+            } else {
+              e.x = fast_exp2(e.x);
+              e.y = fast_exp2(e.y);
             }
-            uint32_t w[16];
+            if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
+            w[k] = pack_half2(e.x, e.y);
+          }
+          if (i == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
+            mbar_wait(&pv_done[wg], (c - 1) & 1u);
+            tc_fence_after();
+            if (__any_sync(0xffffffffu, need)) {   // rare: the running maximum grew by more than 2^8
+              l *= alpha;
+#pragma unroll 1
+              for (int h = 0; h < 4; ++h) {
+                float o[16];
+                tmem_ld_32x16(tO + h * 16, o);
+                tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
-              if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
-                e = exp2_poly2(e);     // FMA pipe instead of the MUFU
-              } else {
-                e.x = fast_exp2(e.x);
-                e.y = fast_exp2(e.y);
+                for (int e = 0; e < 16; ++e) o[e] *= alpha;
+                tmem_st_32x16(tO + h * 16, o);
               }
-              if (k & 1) ls1 = fadd2(ls1, e); else ls0 = fadd2(ls0, e);
-              w[k] = pack_half2(e.x, e.y);
-            }
-            if (i == 0 && attempt == 0 && c > 0) {   // P and O are still in use by the previous P V until pv_done fires
-              mbar_wait(&pv_done[wg], (c - 1) & 1u);
-              tc_fence_after();
-            }
-            tmem_st_32x16_u32(tP + 16 * i, w);
-          });
-          lsum = (ls0.x + ls0.y) + (ls1.x + ls1.y);
-          // An element above the reference by more than 2^8 shows in the row sum (<= 128 otherwise ... 256 with every
-          // element at +1).  Rare: redo the block against its exact maximum and rescale l and O.
-          const bool need = attempt == 0 && !(lsum <= 256.0f);
-          if (!__any_sync(0xffffffffu, need)) break;
-          const float bm = block_max();
-          const float m_new = need ? fmaxf(bm, m_used) : m_used;
-          const float alpha = need ? fast_exp2(m_used - m_new) : 1.0f;
-          m_used = m_new;
-          l *= alpha;
-          if (j > 0) {
-#pragma unroll 1
-            for (int h = 0; h < 4; ++h) {
-              float o[16];
-              tmem_ld_32x16(tO + h * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 16; ++e) o[e] *= alpha;
-              tmem_st_32x16(tO + h * 16, o);
             }
           }
-        }
+          tmem_st_32x16_u32(tP + 16 * i, w);
+        });
+        const float lsum = (ls0.x + ls0.y) + (ls1.x + ls1.y);
         l += lsum;
         tmem_st_wait();
         tc_fence_before();

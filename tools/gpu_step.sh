@@ -39,6 +39,10 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 done ;;
+trace) # TRACES="lg.ffn1 lg.qkv ...": per-tile time stamps of CTA 0 (MMA warp / epilogue warp) of the first launch with that label
+for lb in ${TRACES:-lg.ffn1 lg.qkv lg.ffn2}; do
+  echo "== core trace $lb"; SSB_CORE_TRACE=$lb timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 1 --warmup 1 2>&1 >/dev/null | grep -A14 "core trace" | head -16
+done ;;
 ncufull) # NCU_KERNELS="name:regex ..." one full capture (source counters included) of the 3rd launch matching each regex
 for spec in ${NCU_KERNELS:-attn:flash_attention qkv:EpiQkvRope ffn1:EpiLnGelu}; do
   name=${spec%%:*}; re=${spec#*:}
