@@ -279,24 +279,30 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_wait(&s_full[wg], c & 1u);
         tc_fence_after();
         const int kvalid = t.nk - j * kFaBlockKeys;   // valid keys in this block (>= 1; < 128 only in an image's last block)
+        // The 128 logits of the row are read ONCE into registers and S goes back to the MMA warp at once: S(j+1) is
+        // computed under the whole softmax(j).  (The two-pass version read S twice, 32 columns at a time: its max pass
+        // was bound by the tcgen05.ld latency - 19 % of the softmax warps' time - and they waited another 12 % for S.)
+        float s[128];
+        tmem_ld_32x32(tS, s);
+        tmem_ld_32x32(tS + 32, s + 32);
+        tmem_ld_32x32(tS + 64, s + 64);
+        tmem_ld_32x32(tS + 96, s + 96);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[wg]);
+        if (kvalid < kFaBlockKeys) {   // warp-uniform, last block of an image only: keys beyond the count -> exp2(-inf) = 0
+#pragma unroll
+          for (int e = 0; e < 128; ++e)
+            if (e >= kvalid) s[e] = -INFINITY;
+        }
         // exact row maximum of the block (raw logits; the positive scale is applied once)
-        auto block_max = [&]() -> float {
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
-            if (kvalid < 32 * (i + 1)) {
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (32 * i + e >= kvalid) v[e] = -INFINITY;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], v[e]);
-          });
-          return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
-        };
+        for (int e = 0; e < 128; ++e) mx[e & 3] = fmaxf(mx[e & 3], s[e]);
+        const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
         // Reference of the exponentials: the running maximum, refreshed only when a block exceeds it by more than 2^8
-        // (P <= 256 in fp16, exact after the final division by l); then l and O are rescaled.  The maximum is exact per
-        // block, so no block is ever redone and S can go back to the MMA warp after its last read.
-        const float bm = block_max();
+        // (P <= 256 in fp16, exact after the final division by l); then l and O are rescaled.
         float alpha = 1.0f;
         bool need = false;
         if (j == 0) {
@@ -308,21 +314,12 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
         const float2 nm2 = make_float2(-m_used, -m_used);
         float2 ls0 = make_float2(0.f, 0.f), ls1 = make_float2(0.f, 0.f);
-        tmem_chunks_pipelined<4>(tS, [&](int i, float* v) {
-          if (i == 3) {   // S is in registers: the MMA warp may overwrite it with the next block's logits
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[wg]);
-          }
-          if (kvalid < 32 * (i + 1)) {   // warp-uniform: keys beyond the count -> exp2(-inf) = 0
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (32 * i + e >= kvalid) v[e] = -INFINITY;
-          }
+        for (int i = 0; i < 4; ++i) {
           uint32_t w[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            float2 e = ffma2(make_float2(v[2 * k], v[2 * k + 1]), sc2, nm2);
+            float2 e = ffma2(make_float2(s[32 * i + 2 * k], s[32 * i + 2 * k + 1]), sc2, nm2);
             if (kPolyEvery > 0 && (k % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) {
               e = exp2_poly2(e);     // FMA pipe instead of the MUFU
             } else {
@@ -349,7 +346,7 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
           }
           tmem_st_32x16_u32(tP + 16 * i, w);
-        });
+        }
         const float lsum = (ls0.x + ls0.y) + (ls1.x + ls1.y);
         l += lsum;
         tmem_st_wait();

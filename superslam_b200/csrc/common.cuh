@@ -149,14 +149,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box.  The bound is wall
+// time (4 s on %globaltimer, checked every 1024 polls) - a try_wait may itself sleep for a system-dependent time, so
+// a poll count says little - and the message names the barrier (shared-memory address) and the phase waited for.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("ssb: mbarrier wait timed out (block %d,%d,%d thread %d, barrier smem+%#x, parity %u)\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("ssb: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
+    if ((++spins & 1023u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout(smem_u32(bar), parity);
     }
   }
 }
@@ -310,6 +323,86 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- CTA pairs (cta_group::2) --------------------------------------------------------------------
+// Two CTAs of a cluster (ranks 0 and 1, the two SMs of a TPC) execute ONE tcgen05.mma stream issued by the leader
+// (rank 0): M = 256, each CTA supplies its own 128 rows of A and N/2 rows of B from the same shared-memory offsets and
+// receives its 128 rows x N columns in its own tensor memory - every CTA reads half of B, which is what moves the
+// shared-memory-operand-bound N = 64 convolutions (conventions checked on hardware: tools/umma2_probe.cu).  Every tcgen05
+// instruction of such a kernel carries cta_group::2; tensor memory is allocated by the same warp of both CTAs.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed.
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+// Instruction descriptor of a pair MMA: fp16 A/B, fp32 accumulate, M = 256 (128 rows per CTA), N = n (n/2 rows of B per CTA).
+__device__ __forceinline__ uint32_t make_idesc2_f16(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+// Arrive - with release semantics at cluster scope - on the barrier at the same offset in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_map(smem_u32(bar), rank)) : "memory");
+}
+// Wait that also acquires what other CTAs of the cluster released before arriving.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if ((++spins & 1023u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) mbar_timeout(smem_u32(bar), parity);
+    }
+  }
+}
+// TMA load of a CTA pair: the box lands in THIS CTA's shared memory, the bytes are counted on the LEADER's barrier
+// (the shared::cluster address of rank 0's copy of it).
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_map(smem_u32(bar), 0)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_map(smem_u32(bar), 0)), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
 }
 
 // ---- descriptors -------------------------------------------------------------------------------

@@ -66,7 +66,13 @@ struct PipeParams {
   int img_h, img_w;
 };
 
-template <class Epi, bool kFuse1a>
+// kPair: CTA pairs (cta_group::2, see common.cuh).  The two CTAs of a cluster walk neighbouring tiles in lockstep; the
+// leader's MMA warp issues M = 256 MMAs for both (each CTA: its own halo as A, 32 of the 64 output channels as B, its own
+// 128 pixels x 64 channels in its tensor memory).  The N = 64 MMAs of these layers are bound by shared-memory operand
+// reads (4 KB of A + 2 KB of B per 32-cycle MMA against 128 B/clk); a pair reads 4 + 1 KB per CTA.  Barriers the issuer
+// waits on (halo_full, tmem_empty, a1_full, w_full) live in the leader and count both CTAs' arrivals; barriers the MMAs
+// complete (halo_empty, tmem_full, c1_full) are signalled in both CTAs by one multicast commit.  Needs n_slices == 1.
+template <class Epi, bool kFuse1a, bool kPair>
 __global__ void __launch_bounds__(kFuse1a ? kPipeThreadsFused : kPipeThreads, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const PipeParams p, const __grid_constant__ Epi epi) {
@@ -95,41 +101,55 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t kC1Col = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slice = blockIdx.x % p.n_slices;
-  const int first = blockIdx.x / p.n_slices;
-  const int stride = gridDim.x / p.n_slices;
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the pair's MMAs)
+  const int slice = kPair ? 0 : blockIdx.x % p.n_slices;
+  // tile walk: `tl` runs over the leader's tiles (identical in both CTAs of a pair, so that they stay in lockstep); this
+  // CTA's tile is tl + rank, clamped to the last one (an odd total: the peer recomputes that tile, same values)
+  const int first = kPair ? static_cast<int>(blockIdx.x) - rank : blockIdx.x / p.n_slices;
+  const int stride = kPair ? static_cast<int>(gridDim.x) : gridDim.x / p.n_slices;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int total = tiles_per_img * p.batch;
+  auto my_tile = [&](int tl) { return kPair ? min(tl + rank, total - 1) : tl; };
+  constexpr uint32_t kArrivals = kPair ? 2u : 1u;   // CTAs arriving on the leader's barriers
+  constexpr int kWTapBytes = kPair ? 4096 : 8192;   // one tap of this CTA's weights: 32 or 64 output channels x 64
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     mbar_init(w_full, 1);
     for (int b = 0; b < kHaloBufs; ++b) {
-      mbar_init(&halo_full[b], kFuse1a ? 8 : 1);   // one arrival per producer warp
+      mbar_init(&halo_full[b], kFuse1a ? 8 * kArrivals : 1);   // one arrival per producer warp (of both CTAs)
       mbar_init(&halo_empty[b], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], kPipeEpiWarps);    // one arrival per epilogue warp
-      mbar_init(&a1_full[b], 8);
+      mbar_init(&tmem_empty[b], kPipeEpiWarps * kArrivals);    // one arrival per epilogue warp
+      mbar_init(&a1_full[b], 8 * kArrivals);
     }
     mbar_init(c1_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc2(tmem_slot, kTmemCols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (kFuse1a) {
     // conv1a B operand [n = 64][k = 16]: k < 9 tap weights * 16/255, k = 9 the bias, rest 0; hi + lo fp16
-    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
-      const int n = i >> 4, k = i & 15;
+    // (pair: this CTA's 32 output channels, rows 0..31)
+    constexpr int kRows = kPair ? 32 : 64;
+    for (int i = threadIdx.x; i < kRows * 16; i += blockDim.x) {
+      const int r = i >> 4, k = i & 15;
+      const int n = rank * kRows + r;
       const float v = k < 9 ? p.w1a[k * 64 + n] * (16.0f / 255.0f) : (k == 9 ? p.b1a[n] : 0.f);
       const __half hi = __float2half_rn(v);
       const __half lo = __float2half_rn(v - __half2float(hi));
-      *reinterpret_cast<__half*>(s_w1 + plain16_offset(n, k)) = hi;
-      *reinterpret_cast<__half*>(s_w1 + 2048 + plain16_offset(n, k)) = lo;
+      *reinterpret_cast<__half*>(s_w1 + plain16_offset(r, k)) = hi;
+      *reinterpret_cast<__half*>(s_w1 + 2048 + plain16_offset(r, k)) = lo;
     }
     // im2col rows 324..383 of both operands stay zero for the whole kernel
     for (int i = threadIdx.x; i < 2 * kPipeA1Bytes / 16; i += blockDim.x)
@@ -138,6 +158,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the leader's barriers exist before the peer arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
@@ -145,33 +166,54 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, kPipeWeightBytes);
-      for (int tap = 0; tap < 9; ++tap)
-        tma_load_3d(s_w + tap * 8192, &tmB, w_full, 0, tap * p.cout_rows + slice * 64, 0);
+      if (kPair) {   // both CTAs' halves are counted on the leader's barrier
+        if (rank == 0) mbar_arrive_expect_tx(w_full, 2 * 9 * kWTapBytes);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_3d_pair(s_w + tap * kWTapBytes, &tmB, w_full, 0, tap * p.cout_rows + rank * 32, 0);
+      } else {
+        mbar_arrive_expect_tx(w_full, kPipeWeightBytes);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_3d(s_w + tap * 8192, &tmB, w_full, 0, tap * p.cout_rows + slice * 64, 0);
+      }
       if (!kFuse1a) {
         int seq = 0;
-        for (int t = first; t < total; t += stride, ++seq) {
+        for (int tl = first; tl < total; tl += stride, ++seq) {
+          const int t = my_tile(tl);
           const int hb = seq % kHaloBufs;
           const int z = t / tiles_per_img, r = t % tiles_per_img;
           const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
           mbar_wait(&halo_empty[hb], (static_cast<uint32_t>(seq / kHaloBufs) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&halo_full[hb], 18 * 18 * 128);
-          tma_load_4d(s_halo + hb * kPipeHaloBytes, &tmA, &halo_full[hb], 0, w0 - 1, h0 - 1, z);
+          if (kPair) {
+            if (rank == 0) mbar_arrive_expect_tx(&halo_full[hb], 2 * 18 * 18 * 128);
+            tma_load_4d_pair(s_halo + hb * kPipeHaloBytes, &tmA, &halo_full[hb], 0, w0 - 1, h0 - 1, z);
+          } else {
+            mbar_arrive_expect_tx(&halo_full[hb], 18 * 18 * 128);
+            tma_load_4d(s_halo + hb * kPipeHaloBytes, &tmA, &halo_full[hb], 0, w0 - 1, h0 - 1, z);
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // The whole warp walks the tile loop and computes descriptors in warp-uniform control flow, so they live
     // in uniform registers and each tcgen05.mma is one instruction for the elected lane.  (Inside an
     // `if (lane == 0)` region the operands are vector registers and every MMA becomes an
     // ELECT / R2UR x3 / branch "waterfall" of ~100 cycles - three times the 32 cycles an N = 64 MMA takes.)
-    const uint32_t idesc = make_idesc_f16(64);
+    const uint32_t idesc = kPair ? make_idesc2_f16(64) : make_idesc_f16(64);
     const uint32_t w_base = smem_u32(s_w), halo_base = smem_u32(s_halo);
     const uint32_t a1_base = smem_u32(s_a1), w1_base = smem_u32(s_w1);
-    mbar_wait(w_full, 0);
+    auto wait = [&](uint64_t* bar, uint32_t parity) {   // barriers the peer arrives on need the cluster-scope acquire
+      if (kPair) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+    };
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+      if (kPair) umma2_f16(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (kPair) umma2_commit(bar); else umma_commit(bar);
+    };
+    wait(w_full, 0);
     // fused: conv1a of tile `seq1` = 3 M-tiles x (hi + lo) MMAs with K = 16 into TMEM columns kC1Col..
     auto issue_conv1a = [&](int seq1) {
-      mbar_wait(&a1_full[seq1 & 1], static_cast<uint32_t>(seq1 >> 1) & 1u);
+      wait(&a1_full[seq1 & 1], static_cast<uint32_t>(seq1 >> 1) & 1u);
       tc_fence_after();
       const uint32_t a1 = a1_base + (seq1 & 1) * kPipeA1Bytes;
       const uint64_t bhi = make_smem_desc_k_plain16(w1_base), blo = make_smem_desc_k_plain16(w1_base + 2048);
@@ -179,10 +221,10 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
           const uint64_t ad = make_smem_desc_k_plain16(a1 + m * 4096);
-          umma_f16(tmem_base + kC1Col + m * 64, ad, bhi, idesc, 0u);
-          umma_f16(tmem_base + kC1Col + m * 64, ad, blo, idesc, 1u);
+          mma(tmem_base + kC1Col + m * 64, ad, bhi, 0u);
+          mma(tmem_base + kC1Col + m * 64, ad, blo, 1u);
         }
-        umma_commit(c1_full);
+        commit(c1_full);
       }
       __syncwarp();
     };
@@ -192,12 +234,12 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int b = seq & 1;
       const int hb = seq % kHaloBufs;
       const uint32_t use = static_cast<uint32_t>(seq >> 1) & 1u;
-      mbar_wait(&halo_full[hb], static_cast<uint32_t>(seq / kHaloBufs) & 1u);
+      wait(&halo_full[hb], static_cast<uint32_t>(seq / kHaloBufs) & 1u);
       tc_fence_after();
       // fused: the converters are done with the conv1a product of this tile (halo_full), so the next
       // tile's conv1a goes first; its conversion then overlaps this tile's 72 conv1b MMAs
       if (kFuse1a && t + stride < total) issue_conv1a(seq + 1);
-      mbar_wait(&tmem_empty[b], use ^ 1u);
+      wait(&tmem_empty[b], use ^ 1u);
       tc_fence_after();
       const uint32_t hbase = halo_base + hb * kPipeHaloBytes;
       const uint32_t d0 = tmem_base + b * 128;
@@ -205,20 +247,22 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap % 3;
-          const uint64_t bdesc = make_smem_desc_k_sw128(w_base + tap * 8192, 1024);
+          const uint64_t bdesc = make_smem_desc_k_sw128(w_base + tap * kWTapBytes, 1024);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const uint64_t adesc = make_smem_desc_k_sw128(hbase + ((kh * 18 + kw) + sub * 8) * 128, 18 * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(d0 + sub * 64, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+              mma(d0 + sub * 64, adesc + 2 * k, bdesc + 2 * k, (tap | k) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&halo_empty[hb]);
-        umma_commit(&tmem_full[b]);
+        commit(&halo_empty[hb]);
+        commit(&tmem_full[b]);
       }
       __syncwarp();
     }
+  } else if (warp == 1) {
+    // pair: the peer's MMA warp has nothing to issue
   } else if (warp < 2 + kPipeEpiWarps) {
     // eight epilogue warps: warp w reads TMEM lanes 32*(w%4)..+31 (hardware rule) of sub-tile (w-2)/4.
     // (With four warps - one per scheduler - the dependent chain TMEM load -> bias/ReLU -> pooling
@@ -239,7 +283,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.stage_cur = c.stage;
     c.stage_bufs = kStageBufs;
     c.stage_sel = 0;
-    for (int t = first; t < total; t += stride, ++seq) {
+    for (int tl = first; tl < total; tl += stride, ++seq) {
+      const int t = my_tile(tl);
       const int b = seq & 1;
       const int z = t / tiles_per_img, r = t % tiles_per_img;
       const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
@@ -252,7 +297,9 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       epi(c, true);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[b]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
+      }
     }
     stage_drain(c);
   } else if (kFuse1a) {
@@ -297,37 +344,42 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *reinterpret_cast<uint4*>(dst + 128) = hi;
       }
     };
+    // arrivals the issuer waits for go to the leader's barrier (pair) or this CTA's
+    auto arrive = [&](uint64_t* bar) {
+      if (kPair) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
+    };
     int seq = 0;
     if (first < total) {
       __half pre[2];
-      load_patch(first, pre);
+      load_patch(my_tile(first), pre);
       store_patch(s_patch, pre);
       asm volatile("bar.sync 3, 256;" ::: "memory");
       build_a1(s_patch, s_a1);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a1_full[0]);
+      if (lane == 0) arrive(&a1_full[0]);
       if (first + stride < total) {
-        load_patch(first + stride, pre);
+        load_patch(my_tile(first + stride), pre);
         store_patch(s_patch + kPipePatchElems, pre);
       }
       asm volatile("bar.sync 3, 256;" ::: "memory");
     }
-    for (int t = first; t < total; t += stride, ++seq) {
+    for (int tl = first; tl < total; tl += stride, ++seq) {
+      const int t = my_tile(tl);
       const int hb = seq & 1;
       const int r = t % tiles_per_img;
       const int w0 = (r % p.tiles_w) * 16, h0 = (r / p.tiles_w) * 16;
-      const int tn = t + stride, tnn = t + 2 * stride;
+      const int tn = tl + stride, tnn = tl + 2 * stride;   // the leader's next tiles: the loop bounds of both CTAs
       // software pipeline: the global loads of the patch two tiles ahead are in flight during this iteration
       __half pre[2];
-      if (tnn < total) load_patch(tnn, pre);
+      if (tnn < total) load_patch(my_tile(tnn), pre);
       // (1) im2col operand of the NEXT tile (its buffer was last read by conv1a of tile seq-1, whose
       //     completion this warp observed through c1_full one iteration ago)
       if (tn < total) {
         build_a1(s_patch + ((seq + 1) & 1) * kPipePatchElems, s_a1 + ((seq + 1) & 1) * kPipeA1Bytes);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a1_full[(seq + 1) & 1]);
+        if (lane == 0) arrive(&a1_full[(seq + 1) & 1]);
       }
       // (2) this tile's conv1a product -> ReLU -> fp16 halo (zero outside the image = conv1b's padding)
       mbar_wait(c1_full, static_cast<uint32_t>(seq) & 1u);
@@ -361,7 +413,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&halo_full[hb]);
+      if (lane == 0) arrive(&halo_full[hb]);
       // (3) publish the prefetched patch (tile seq+2) into the buffer tile seq used (read in iteration seq-1)
       if (tnn < total) store_patch(s_patch + hb * kPipePatchElems, pre);
       asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -369,27 +421,69 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (kPair) {
+    cluster_sync_all();   // the peer's tensor memory and barriers stay alive until the leader's last MMA has retired
+    if (warp == 1) tmem_dealloc2(tmem_base, kTmemCols);
+  } else {
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
-template <class Epi, bool kFuse1a>
+// kPair: tmB must be the weight map with 32-row boxes (one CTA's half of a tap); needs n_slices == 1.
+template <class Epi, bool kFuse1a, bool kPair = false>
 int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams p, const Epi& epi, int W, int H,
                      int batch, cudaStream_t stream) {
   p.tiles_w = (W + 15) / 16;
   p.tiles_h = (H + 15) / 16;
   p.batch = batch;
+  if (kPair && p.n_slices != 1) {
+    set_last_error("launch_conv_pipe: CTA pairs need a single 64-channel slice");
+    return SSB_ERR_INVALID;
+  }
   constexpr int smem_bytes = kFuse1a ? kPipeSmemBytes : kPipeSmemBytesTma;
   auto configure = [&]() -> int {
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem_bytes));
     return SSB_OK;
   };
-  SSB_DEVICE_CONFIG((&conv_pipe_kernel<Epi, kFuse1a>), 1, configure());
+  SSB_DEVICE_CONFIG((&conv_pipe_kernel<Epi, kFuse1a, kPair>), 1, configure());
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;
-  SSB_CUDA_CHECK(launch_kernel(conv_pipe_kernel<Epi, kFuse1a>, dim3(ctas), dim3(kFuse1a ? kPipeThreadsFused : kPipeThreads),
-                               smem_bytes, stream, 1, tmA, tmB, p, epi));
+  if (kPair) {
+    // whole pairs, and no more than can be co-resident (cached per device like the function attribute)
+    static char occupancy_key;
+    const int sms = device_sm_count();   // (takes the registry lock itself: not inside begin / end)
+    int* slot = device_config_begin(&occupancy_key);
+    if (*slot == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+      cfg.blockDim = dim3(kFuse1a ? kPipeThreadsFused : kPipeThreads);
+      cfg.dynamicSmemBytes = smem_bytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, conv_pipe_kernel<Epi, kFuse1a, kPair>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sms / 2;
+      }
+      *slot = n;
+      if (std::getenv("SSB_DEBUG") != nullptr)
+        std::fprintf(stderr, "ssb: conv_pipe pair mode (%s): %d co-resident CTA pairs on %d SMs\n", p.label, n, sms);
+    }
+    const int max_pairs = *slot;
+    device_config_end();
+    const int want = (ctas + 1) / 2;
+    ctas = 2 * (want < max_pairs ? want : max_pairs);
+  }
+  SSB_CUDA_CHECK(launch_kernel(conv_pipe_kernel<Epi, kFuse1a, kPair>, dim3(ctas),
+                               dim3(kFuse1a ? kPipeThreadsFused : kPipeThreads), smem_bytes, stream, kPair ? 2 : 1, tmA, tmB, p,
+                               epi));
   count_launch();
   prof_mark(stream, p.label);
   return SSB_OK;

@@ -580,6 +580,8 @@ int SuperPoint::load_layer(const WeightArchive& ar, const char* name, int cin, i
   SSB_RETURN_IF(encode_tmap_f16(&L->tmB, L->w, 3, dims, strides, box));
   uint32_t box64[3] = {64, 64, 1};   // one 64-output-channel slice of one tap (conv_pipe.cuh)
   SSB_RETURN_IF(encode_tmap_f16(&L->tmB64, L->w, 3, dims, strides, box64));
+  uint32_t box32[3] = {64, 32, 1};   // half a slice: one CTA of a pair (conv_pipe.cuh, kPair)
+  SSB_RETURN_IF(encode_tmap_f16(&L->tmB32, L->w, 3, dims, strides, box32));
   uint32_t box128[3] = {64, static_cast<uint32_t>(pad >= 128 ? 128 : pad), 1};   // conv_stream.cuh
   return encode_tmap_f16(&L->tmB128, L->w, 3, dims, strides, box128);
 }
@@ -800,6 +802,13 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     p.img_h = h;
     p.img_w = w;
     EpiConvRelu e{L.bias, tmS, pool, 8};
+    // Cout = 64: CTA pairs (cta_group::2), each CTA reads half of the weights per MMA.  SSB_SP_PAIR=0 selects the
+    // one-CTA kernels for A/B measurements.
+    static const bool pair = [] { const char* e = std::getenv("SSB_SP_PAIR"); return e != nullptr && std::atoi(e) != 0; }();
+    if (pair && p.n_slices == 1) {
+      if (fuse1a) return launch_conv_pipe<EpiConvRelu, true, true>(L.tmB32, L.tmB32, p, e, W, H, B, stream);
+      return launch_conv_pipe<EpiConvRelu, false, true>(tmH, L.tmB32, p, e, W, H, B, stream);
+    }
     if (fuse1a) return launch_conv_pipe<EpiConvRelu, true>(L.tmB64, L.tmB64, p, e, W, H, B, stream);
     return launch_conv_pipe<EpiConvRelu, false>(tmH, L.tmB64, p, e, W, H, B, stream);
   };

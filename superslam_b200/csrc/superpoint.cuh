@@ -46,6 +46,7 @@ struct ConvLayer {
   __half* w = nullptr;   // [taps*taps][cout_pad][cin] fp16 (K-major rows for the B operand)
   float* bias = nullptr; // [cout_pad]
   CUtensorMap tmB;
+  CUtensorMap tmB32;     // same matrix, 32-row boxes (one CTA of a pair)
   CUtensorMap tmB64;     // same matrix, 64-row boxes
   CUtensorMap tmB128;    // same matrix, 128-row boxes (conv_stream.cuh)
 };

@@ -38,7 +38,7 @@ def main():
         e = launches.setdefault(k, {"name": r[col["Kernel Name"]]})
         e[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", ""))
     seq = list(launches.values())
-    starts = [i for i, e in enumerate(seq) if "conv_pipe_kernel" in e["name"] and ", 1>" in e["name"]]
+    starts = [i for i, e in enumerate(seq) if "conv_pipe_kernel<ssb::EpiConvRelu, 1" in e["name"]]   # the fused first layer
     if block >= len(starts):
         raise SystemExit(f"only {len(starts)} steps in the list")
     a = starts[block]
