@@ -365,6 +365,13 @@ __device__ __forceinline__ uint32_t make_idesc2_f16(uint32_t n) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_map(smem_u32(bar), rank)) : "memory");
 }
+// The same without cluster-scope release (default semantics: release at CTA scope): for arrivals that publish nothing the
+// remote waiter reads through the generic proxy - "this CTA has finished reading its tensor memory", or operands that
+// this SM's own tensor core reads from this CTA's shared memory after the writer's fence.proxy.async.  (The cluster-scope
+// release costs every arriving thread a MEMBAR: the top stall of the first pair kernel.)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_map(smem_u32(bar), rank)) : "memory");
+}
 // Wait that also acquires what other CTAs of the cluster released before arriving.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0, ok = 0;

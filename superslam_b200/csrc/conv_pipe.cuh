@@ -97,6 +97,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* a1_full = bars + 11;     // [2] fused: im2col operand built (8 warp arrivals)
   uint64_t* c1_full = bars + 13;     // fused: conv1a product in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  volatile uint32_t* wbase_slot = tmem_slot + 1;   // shared-memory address of the weights, re-read per tile (see the MMA warp)
   constexpr uint32_t kTmemCols = kFuse1a ? 512 : 256;   // conv1b accumulators 2 x 128, conv1a product 3 x 64
   constexpr uint32_t kC1Col = 256;
 
@@ -128,6 +129,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(c1_full, 1);
     fence_mbar_init();
+    *wbase_slot = smem_u32(s_w);
   }
   if (warp == 1) {
     if (kPair) {
@@ -243,17 +245,26 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t hbase = halo_base + hb * kPipeHaloBytes;
       const uint32_t d0 = tmem_base + b * 128;
+      // The two base descriptors are formed HERE, in warp-uniform code, and every operand of the 72 MMAs is base +
+      // compile-time constant (the start-address field counts 16-byte units; halo and weights sit below 256 KB, so the
+      // sum never carries out of its 14 bits).  Formed inside the elected region they were vector-register values:
+      // 88 R2UR + spills per tile, the issuing thread spent 70 % of its time in this loop and delivered an MMA every
+      // ~45 cycles - no faster than the tensor pipe drains them (48), so every hiccup at a tile boundary cost tensor time.
+      // The weights never move, so the compiler hoists their 36 descriptors out of the tile loop - into VECTOR registers
+      // (there are not enough uniform ones), and every MMA then starts with two R2UR.  Reading the address back from
+      // shared memory per tile makes it loop-variant: one R2UR per tile, the 36 descriptors are uniform adds.
+      const uint64_t a_base = make_smem_desc_k_sw128(hbase, 18 * 128);
+      const uint64_t b_base = make_smem_desc_k_sw128(*wbase_slot, 1024);
       if (elect_one()) {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int kh = tap / 3, kw = tap % 3;
-          const uint64_t bdesc = make_smem_desc_k_sw128(w_base + tap * kWTapBytes, 1024);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            const uint64_t adesc = make_smem_desc_k_sw128(hbase + ((kh * 18 + kw) + sub * 8) * 128, 18 * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              mma(d0 + sub * 64, adesc + 2 * k, bdesc + 2 * k, (tap | k) != 0 ? 1u : 0u);
+              mma(d0 + sub * 64, a_base + static_cast<uint64_t>((((kh * 18 + kw) + sub * 8) * 128) >> 4) + 2 * k,
+                  b_base + static_cast<uint64_t>((tap * kWTapBytes) >> 4) + 2 * k, (tap | k) != 0 ? 1u : 0u);
           }
         }
         commit(&halo_empty[hb]);
@@ -298,7 +309,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
+        if (kPair) mbar_arrive_remote(&tmem_empty[b], 0); else mbar_arrive(&tmem_empty[b]);
       }
     }
     stage_drain(c);
@@ -346,7 +357,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     // arrivals the issuer waits for go to the leader's barrier (pair) or this CTA's
     auto arrive = [&](uint64_t* bar) {
-      if (kPair) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
+      if (kPair) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
     };
     int seq = 0;
     if (first < total) {

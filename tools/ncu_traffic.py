@@ -12,6 +12,7 @@ by position and reports, per label, launches, mean duration and DRAM bytes per i
 (LightGlue) - the unit bench.py multiplies by its own batch for roofline.traffic.
 """
 import csv
+import re
 import json
 import sys
 from collections import OrderedDict
@@ -38,7 +39,7 @@ def main():
         e = launches.setdefault(k, {"name": r[col["Kernel Name"]]})
         e[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", ""))
     seq = list(launches.values())
-    starts = [i for i, e in enumerate(seq) if "conv_pipe_kernel<ssb::EpiConvRelu, 1" in e["name"]]   # the fused first layer
+    starts = [i for i, e in enumerate(seq) if re.search(r"conv_pipe_kernel<ssb::EpiConvRelu, (\(bool\))?1", e["name"])]   # the fused first layer
     if block >= len(starts):
         raise SystemExit(f"only {len(starts)} steps in the list")
     a = starts[block]
