@@ -72,7 +72,9 @@ struct PipeParams {
 // reads (4 KB of A + 2 KB of B per 32-cycle MMA against 128 B/clk); a pair reads 4 + 1 KB per CTA.  Barriers the issuer
 // waits on (halo_full, tmem_empty, a1_full, w_full) live in the leader and count both CTAs' arrivals; barriers the MMAs
 // complete (halo_empty, tmem_full, c1_full) are signalled in both CTAs by one multicast commit.  Needs n_slices == 1.
-template <class Epi, bool kFuse1a, bool kPair>
+// kN = 128 (pairs only, not fused): all 128 output channels of conv3a in one MMA stream - each CTA holds 64 of them, the
+// N = 128 MMAs are math-bound (64 cycles against 48 of operand reads) and the halo is loaded once instead of once per slice.
+template <class Epi, bool kFuse1a, bool kPair, int kN = 64>
 __global__ void __launch_bounds__(kFuse1a ? kPipeThreadsFused : kPipeThreads, 1)
 conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const PipeParams p, const __grid_constant__ Epi epi) {
@@ -98,7 +100,8 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* c1_full = bars + 13;     // fused: conv1a product in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   volatile uint32_t* wbase_slot = tmem_slot + 1;   // shared-memory address of the weights, re-read per tile (see the MMA warp)
-  constexpr uint32_t kTmemCols = kFuse1a ? 512 : 256;   // conv1b accumulators 2 x 128, conv1a product 3 x 64
+  static_assert(kN == 64 || (kN == 128 && kPair && !kFuse1a), "128 output channels: CTA pairs, TMA-fed variant only");
+  constexpr uint32_t kTmemCols = (kFuse1a || kN == 128) ? 512 : 256;   // accumulators 2 x (2 x kN), conv1a product 3 x 64
   constexpr uint32_t kC1Col = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,7 +115,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int total = tiles_per_img * p.batch;
   auto my_tile = [&](int tl) { return kPair ? min(tl + rank, total - 1) : tl; };
   constexpr uint32_t kArrivals = kPair ? 2u : 1u;   // CTAs arriving on the leader's barriers
-  constexpr int kWTapBytes = kPair ? 4096 : 8192;   // one tap of this CTA's weights: 32 or 64 output channels x 64
+  constexpr int kWTapBytes = kPair ? kN * 64 : 8192;   // one tap of this CTA's weights: kN / 2 (pair) or 64 output channels x 64
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -171,7 +174,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kPair) {   // both CTAs' halves are counted on the leader's barrier
         if (rank == 0) mbar_arrive_expect_tx(w_full, 2 * 9 * kWTapBytes);
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_3d_pair(s_w + tap * kWTapBytes, &tmB, w_full, 0, tap * p.cout_rows + rank * 32, 0);
+          tma_load_3d_pair(s_w + tap * kWTapBytes, &tmB, w_full, 0, tap * p.cout_rows + rank * (kN / 2), 0);
       } else {
         mbar_arrive_expect_tx(w_full, kPipeWeightBytes);
         for (int tap = 0; tap < 9; ++tap)
@@ -200,7 +203,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // in uniform registers and each tcgen05.mma is one instruction for the elected lane.  (Inside an
     // `if (lane == 0)` region the operands are vector registers and every MMA becomes an
     // ELECT / R2UR x3 / branch "waterfall" of ~100 cycles - three times the 32 cycles an N = 64 MMA takes.)
-    const uint32_t idesc = kPair ? make_idesc2_f16(64) : make_idesc_f16(64);
+    const uint32_t idesc = kPair ? make_idesc2_f16(kN) : make_idesc_f16(64);
     const uint32_t w_base = smem_u32(s_w), halo_base = smem_u32(s_halo);
     const uint32_t a1_base = smem_u32(s_a1), w1_base = smem_u32(s_w1);
     auto wait = [&](uint64_t* bar, uint32_t parity) {   // barriers the peer arrives on need the cluster-scope acquire
@@ -244,7 +247,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       wait(&tmem_empty[b], use ^ 1u);
       tc_fence_after();
       const uint32_t hbase = halo_base + hb * kPipeHaloBytes;
-      const uint32_t d0 = tmem_base + b * 128;
+      const uint32_t d0 = tmem_base + b * (2 * kN);
       // The two base descriptors are formed HERE, in warp-uniform code, and every operand of the 72 MMAs is base +
       // compile-time constant (the start-address field counts 16-byte units; halo and weights sit below 256 KB, so the
       // sum never carries out of its 14 bits).  Formed inside the elected region they were vector-register values:
@@ -263,7 +266,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              mma(d0 + sub * 64, a_base + static_cast<uint64_t>((((kh * 18 + kw) + sub * 8) * 128) >> 4) + 2 * k,
+              mma(d0 + sub * kN, a_base + static_cast<uint64_t>((((kh * 18 + kw) + sub * 8) * 128) >> 4) + 2 * k,
                   b_base + static_cast<uint64_t>((tap * kWTapBytes) >> 4) + 2 * k, (tap | k) != 0 ? 1u : 0u);
           }
         }
@@ -287,7 +290,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     c.n0 = slice * 64;
     c.m_valid = 0x7fffffff;
     c.col_begin = 0;
-    c.col_end = 64;
+    c.col_end = kN;
     c.half = 0;
     c.xchg = nullptr;
     c.stage = s_stage + (warp - 2) * (kStageBufs * 4096);
@@ -304,7 +307,7 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       c.z = z;
       c.py = h0 + (c.row >> 3);
       c.px = w0 + sub * 8 + (c.row & 7);
-      c.tmem_row = tmem_base + b * 128 + sub * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      c.tmem_row = tmem_base + b * (2 * kN) + sub * kN + (static_cast<uint32_t>(q * 32) << 16);
       epi(c, true);
       tc_fence_before();
       __syncwarp();
@@ -440,24 +443,27 @@ conv_pipe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// kPair: tmB must be the weight map with 32-row boxes (one CTA's half of a tap); needs n_slices == 1.
-template <class Epi, bool kFuse1a, bool kPair = false>
+// kPair: tmB must be the weight map with kN / 2-row boxes (one CTA's half of a tap); needs n_slices == kN / 64.
+template <class Epi, bool kFuse1a, bool kPair = false, int kN = 64>
 int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams p, const Epi& epi, int W, int H,
                      int batch, cudaStream_t stream) {
   p.tiles_w = (W + 15) / 16;
   p.tiles_h = (H + 15) / 16;
   p.batch = batch;
-  if (kPair && p.n_slices != 1) {
-    set_last_error("launch_conv_pipe: CTA pairs need a single 64-channel slice");
-    return SSB_ERR_INVALID;
+  if (kPair) {
+    if (p.n_slices != kN / 64) {
+      set_last_error("launch_conv_pipe: CTA pairs serve all %d output channels of the layer", kN);
+      return SSB_ERR_INVALID;
+    }
+    p.n_slices = 1;
   }
   constexpr int smem_bytes = kFuse1a ? kPipeSmemBytes : kPipeSmemBytesTma;
   auto configure = [&]() -> int {
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(conv_pipe_kernel<Epi, kFuse1a, kPair, kN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem_bytes));
     return SSB_OK;
   };
-  SSB_DEVICE_CONFIG((&conv_pipe_kernel<Epi, kFuse1a, kPair>), 1, configure());
+  SSB_DEVICE_CONFIG((&conv_pipe_kernel<Epi, kFuse1a, kPair, kN>), 1, configure());
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * batch;
   int ctas = device_sm_count() / p.n_slices * p.n_slices;
   if (total * p.n_slices < ctas) ctas = static_cast<int>(total) * p.n_slices;
@@ -479,7 +485,7 @@ int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams 
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, conv_pipe_kernel<Epi, kFuse1a, kPair>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, conv_pipe_kernel<Epi, kFuse1a, kPair, kN>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = sms / 2;
       }
@@ -492,7 +498,7 @@ int launch_conv_pipe(const CUtensorMap& tmA, const CUtensorMap& tmB, PipeParams 
     const int want = (ctas + 1) / 2;
     ctas = 2 * (want < max_pairs ? want : max_pairs);
   }
-  SSB_CUDA_CHECK(launch_kernel(conv_pipe_kernel<Epi, kFuse1a, kPair>, dim3(ctas),
+  SSB_CUDA_CHECK(launch_kernel(conv_pipe_kernel<Epi, kFuse1a, kPair, kN>, dim3(ctas),
                                dim3(kFuse1a ? kPipeThreadsFused : kPipeThreads), smem_bytes, stream, kPair ? 2 : 1, tmA, tmB, p,
                                epi));
   count_launch();

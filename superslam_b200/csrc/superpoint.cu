@@ -805,6 +805,8 @@ int SuperPoint::run(const uint8_t* images_dev, int batch, int h, int w, void* co
     // Cout = 64: CTA pairs (cta_group::2), each CTA reads half of the weights per MMA (conv1a+1b 2.88 -> 2.73 ms,
     // conv2a / conv2b 0.64 -> 0.57 ms per 128 images).  SSB_SP_PAIR=0 selects the one-CTA kernels for A/B measurements.
     static const bool pair = [] { const char* e = std::getenv("SSB_SP_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
+    if (pair && p.n_slices == 2 && !fuse1a)   // conv3a: 128 output channels, 64 per CTA of a pair
+      return launch_conv_pipe<EpiConvRelu, false, true, 128>(tmH, L.tmB64, p, e, W, H, B, stream);
     if (pair && p.n_slices == 1) {
       if (fuse1a) return launch_conv_pipe<EpiConvRelu, true, true>(L.tmB32, L.tmB32, p, e, W, H, B, stream);
       return launch_conv_pipe<EpiConvRelu, false, true>(tmH, L.tmB32, p, e, W, H, B, stream);
