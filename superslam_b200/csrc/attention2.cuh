@@ -31,24 +31,27 @@ namespace ssb {
 
 constexpr int kFa2Threads = 320;
 constexpr uint32_t kFa2KS = 2, kFa2VS = 2;   // K / V ring depths
+constexpr int kFa2MaxImages = 256;   // keypoint counts cached in shared memory (more images: read from global memory)
 constexpr int kFa2SmemBytes = 2 * 32768 /*Q*/ + kFa2KS * 16384 + kFa2VS * 16384 + 2 * 16384 /*O staging*/ + 256 /*barriers*/ +
-                              1024 /*align*/;
+                              kFa2MaxImages * 4 /*counts*/ + 1024 /*align*/;
 
 // One unit of work: query rows q0 .. q0 + 255 of (image, head) z, i.e. tile 0 and (if it has rows) tile 1.
 struct Fa2Unit {
   int z, img, head, q0, nq, nk, zk, nblk;
   bool t1;
 };
-__device__ __forceinline__ bool fa2_decode(const FaParams& p, int unit, Fa2Unit& t) {
+// `cnt`: the keypoint counts - the kernel's shared-memory copy (every role decodes every unit; from global memory each
+// decode is a dependent L2 round trip in front of the unit's first barrier wait)
+__device__ __forceinline__ bool fa2_decode(const FaParams& p, const int* cnt, int unit, Fa2Unit& t) {
   const int q_pairs = (p.q_tiles + 1) >> 1;
   t.z = unit / q_pairs;
   t.q0 = (unit - t.z * q_pairs) * 256;
   t.img = t.z / p.heads;
   t.head = t.z - t.img * p.heads;
-  t.nq = p.cnt[t.img];
+  t.nq = cnt[t.img];
   if (t.q0 >= t.nq) return false;
   t.t1 = t.q0 + 128 < t.nq;
-  t.nk = p.cnt[t.img ^ p.key_xor];
+  t.nk = cnt[t.img ^ p.key_xor];
   t.zk = (t.img ^ p.key_xor) * p.heads + t.head;
   t.nblk = (t.nk + kFaBlockKeys - 1) / kFaBlockKeys;
   return true;
@@ -76,6 +79,7 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* pv_done = bars + 16;    // [2 tiles]  MMA -> softmax: P V has retired (P and O may be touched)
   uint64_t* s_free = bars + 18;     // [2 tiles]  softmax -> MMA: the last column of S is in registers: 4 warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  int* s_cnt = reinterpret_cast<int*>(bars + 32);   // [kFa2MaxImages]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_pairs = (p.q_tiles + 1) >> 1;
@@ -111,11 +115,18 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t tmem = *tmem_slot;
   pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
   pdl_launch_dependents();
+  const int images = p.zcount / p.heads;
+  const int* cnt = p.cnt;
+  if (images <= kFa2MaxImages) {
+    for (int i = threadIdx.x; i < images; i += blockDim.x) s_cnt[i] = p.cnt[i];
+    __syncthreads();
+    cnt = s_cnt;
+  }
 
   // next valid unit at or after `unit`
   auto next_unit = [&](int unit, Fa2Unit& t) -> int {
     for (; unit < total; unit += stride)
-      if (fa2_decode(p, unit, t) && t.nblk > 0) return unit;
+      if (fa2_decode(p, cnt, unit, t) && t.nblk > 0) return unit;
     return total;
   };
 

@@ -1264,6 +1264,9 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     p.m_valid = dev_count(cnt);
     return p;
   };
+  // Plain linears as CTA pairs (umma_core.cuh, CoreParams::b_rows): two neighbouring row tiles share one MMA stream and
+  // each CTA stages half of the weight rows.  SSB_LG_PAIR=0 selects the one-CTA kernels for A/B measurements.
+  static const bool lg_pair = [] { const char* e = std::getenv("SSB_LG_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
   // SSB_LG_FUSED_FFN=1: one kernel per FFN (ffn_fused.cuh), the 512-wide hidden activation stays in tensor memory.
   // Correct (same tests), but measured SLOWER than the two kernels below (4.18 vs 3.66 ms per 18 FFNs at 64 pairs):
   // acc1 fills all 512 TMEM columns, so nothing can be double-buffered and LayerNorm+GELU (E1) and the HBM-bound
@@ -1287,7 +1290,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     {
       CoreParams p = lin("lg.ffn2", 8, 0, 256);
       EpiResidual e{F.fc2.bias, x32_, ts_x16_, KP};
-      SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
+      if (lg_pair) SSB_RETURN_IF((launch_core<EpiResidual, true>(tm_h1_, tm_h1_, F.fc2.tmB128, p, e, dim3(tiles, 1, P2), stream)));
+      else SSB_RETURN_IF(launch_core(tm_h1_, tm_h1_, F.fc2.tmB, p, e, dim3(tiles, 1, P2), stream));
     }
     return SSB_OK;
   };
@@ -1319,7 +1323,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     {
       CoreParams p = lin("lg.qkv", 4, 0, 256);
       EpiQkvRope e{L.qkv.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 1};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
+      if (lg_pair) SSB_RETURN_IF((launch_core<EpiQkvRope, true>(tm_x16_, tm_x16_, L.qkv.tmB128, p, e, dim3(tiles, 3, P2), stream)));
+      else SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv.tmB, p, e, dim3(tiles, 3, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_k3_, 0, 1.0f));
     if (!w_->fold_out) {
@@ -1333,7 +1338,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     {
       CoreParams p = lin("lg.qkv_cross", 4, 0, 256);
       EpiQkvRope e{L.qkv_c.bias, cs_, sn_, ts_q_, ts_k_, ts_v_, KP, 0};
-      SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
+      if (lg_pair) SSB_RETURN_IF((launch_core<EpiQkvRope, true>(tm_x16_, tm_x16_, L.qkv_c.tmB128, p, e, dim3(tiles, 2, P2), stream)));
+      else SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, L.qkv_c.tmB, p, e, dim3(tiles, 2, P2), stream));
     }
     SSB_RETURN_IF(attention(tm_q3_, 1, 0.125f));
     if (!w_->fold_out) {
@@ -1348,7 +1354,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   {
     CoreParams p = lin("lg.final_proj", 4, 0, 256);
     EpiSplit e{w_->final_proj.bias, ts_mda_, ts_mdb_};
-    SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
+    if (lg_pair) SSB_RETURN_IF((launch_core<EpiSplit, true>(tm_x16_, tm_x16_, w_->final_proj.tmB128, p, e, dim3(tiles, 1, P2), stream)));
+    else SSB_RETURN_IF(launch_core(tm_x16_, tm_x16_, w_->final_proj.tmB, p, e, dim3(tiles, 1, P2), stream));
   }
   SSB_CUDA_CHECK(launch_kernel(matchability_kernel, dim3(dim3(KP / 128, P2)), dim3(128), 0, stream, 1, x32_, w_->match_w, w_->match_b, KP, cnt, lz_));
   count_launch();

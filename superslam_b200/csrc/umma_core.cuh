@@ -74,6 +74,13 @@ struct CoreParams {
   // statistics (LayerNorm over all N tiles) can exchange per-row partials through distributed shared
   // memory (EpiCtx::peer_*).  Used with grid_y == 2.
   int cluster_y;
+  // Pair mode (launch_core<Epi, true>): the two CTAs of a cluster take neighbouring M tiles (x even / odd) of the same
+  // (y, z) and run ONE cta_group::2 MMA stream issued by the leader - each CTA stages its own 128 rows of A and HALF of
+  // the B rows (b_rows = block_n / 2; the B tensor map must have boxes of that many rows).  A [128 x 64] x [256 x 64]
+  // K chunk costs 48 KB of TMA writes plus 48 KB of operand reads against 512 cycles of math at 128 B/clk of shared
+  // memory: the linears were shared-memory bound; a pair moves 32 + 32 KB per CTA.  Linear layers only (taps = 1,
+  // tile_h = 1, an even number of M tiles, one N part).
+  int b_rows;          // rows of B this CTA stages per K chunk (block_n, or block_n / 2 in pair mode)
   long long* trace;    // diagnostic (SSB_CORE_TRACE=<label>): CTA 0 time-stamps its first 32 tiles, [tile][8]
   const char* label;   // host-only: kernel name for the event profiler
 };
@@ -185,16 +192,17 @@ __device__ __forceinline__ float epi_pair_sum(const EpiCtx& c, float v) {
   return t;
 }
 
-__host__ __device__ inline int core_stage_bytes(int block_n) { return kATileBytes + block_n * 128; }
+__host__ __device__ inline int core_stage_bytes(int b_rows) { return kATileBytes + b_rows * 128; }
 
 constexpr int kCoreStagingBytes = 8 * 4096;   // one 4 KiB TMA-store staging buffer per epilogue warp (x stage_bufs)
 
+constexpr int kCoreCountSlots = 256;   // device-side extents cached per batch index z (see the kernel prologue)
 inline int core_smem_bytes(int block_n, int stages, int stage_bufs) {
   return stages * core_stage_bytes(block_n) + stage_bufs * kCoreStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*xchg*/ +
-         2048 /*peer slots*/;
+         2048 /*peer slots*/ + 3 * kCoreCountSlots * 4 /*extents*/;
 }
 
-template <class Epi>
+template <class Epi, bool kPair = false>
 __global__ void __launch_bounds__(kCoreThreads, 1)
 umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const CoreParams p, const __grid_constant__ Epi epi) {
@@ -202,7 +210,7 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // round the base up to 1 KiB with pointer arithmetic on the __shared__ array itself, so the compiler keeps
   // the shared address space (LDS/STS instead of generic LD/ST with 64-bit address math)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = core_stage_bytes(p.block_n);
+  const int stage_bytes = core_stage_bytes(p.b_rows);
   uint8_t* ring = smem;
   uint8_t* staging = ring + p.stages * stage_bytes;    // 8 x 4 KiB, 1024-aligned (all sizes are multiples of 1 KiB)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + p.stage_bufs * kCoreStagingBytes);
@@ -213,9 +221,11 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* xchg = reinterpret_cast<float*>(staging + p.stage_bufs * kCoreStagingBytes + 256);
   float* peer_slots = xchg + 256;                        // [2][128][2]
   uint64_t* peer_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [2]
+  int* s_ext = reinterpret_cast<int*>(peer_slots + 512);   // [3][kCoreCountSlots]: m_valid, n_valid, k_valid per z
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;   // pair mode: 0 = leader (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -227,51 +237,72 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], kCoreEpiThreads / 32);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[b], (kCoreEpiThreads / 32) * (kPair ? 2 : 1));   // one arrival per epilogue warp (of both CTAs)
       mbar_init(&peer_bar[b], 1);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc2(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  const bool clustered = p.cluster_y != 0;
+  const bool clustered = kPair || p.cluster_y != 0;
   if (clustered) cluster_sync_all();   // the peers' barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                // the previous kernel's results (PDL: everything above ran under its tail)
   pdl_launch_dependents();
+  // The device-side extents (keypoint counts) of every batch index are read ONCE into shared memory.  Looked up in
+  // global memory by decode(), each tile cost every role one to three dependent L2 round trips before it could
+  // start: the tile trace showed 1 000 - 1 700 cycles between the end of one epilogue and the start of the next in
+  // kernels whose epilogue sets the pace (qkv, ffn1).
+  const bool ext_cached = p.grid_z <= kCoreCountSlots;
+  if (ext_cached) {
+    for (int i = threadIdx.x; i < p.grid_z; i += blockDim.x) {
+      s_ext[i] = p.m_valid.get(i);
+      s_ext[kCoreCountSlots + i] = p.n_valid.get(i);
+      s_ext[2 * kCoreCountSlots + i] = p.k_valid.get(i);
+    }
+    __syncthreads();
+  }
   // tile walk: all (x, y, z) tiles strided over the CTAs, or - cluster mode - a fixed y per CTA (= its cluster rank)
+  // pair mode: the tile index runs over PAIRS of M tiles (both CTAs walk the same sequence); this CTA's tile is
+  // x = 2 * (pair index) + rank, and a pair is skipped as a whole when the leader's tile lies outside the extents
   const bool fixed_y = p.cluster_y != 0;
-  const int ny = fixed_y ? p.grid_y : 1;
+  const int ny = kPair ? 2 : (fixed_y ? p.grid_y : 1);
   const int y_fixed = static_cast<int>(blockIdx.x) % ny;
   const int first = static_cast<int>(blockIdx.x) / ny;
   const int stride = static_cast<int>(gridDim.x) / ny;
-  const int gx = p.grid_x;
+  const int gx = kPair ? p.grid_x / 2 : p.grid_x;
   const int total = fixed_y ? gx * p.grid_z : gx * p.grid_y * p.grid_z;
 
   // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
   auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
-    const int x = tile % gx;
+    const int x = kPair ? 2 * (tile % gx) + rank : tile % gx;
     const int y = fixed_y ? y_fixed : (tile / gx) % p.grid_y;
     z = fixed_y ? tile / gx : tile / (gx * p.grid_y);
     w0 = (x % p.tiles_w) * p.tile_w;
     h0 = (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
-    m_valid = p.m_valid.get(z);
-    if (p.m_valid.ptr != nullptr && w0 >= m_valid) return false;
-    if (p.n_valid.ptr != nullptr && n0 >= p.n_valid.get(z)) return false;
+    m_valid = ext_cached ? s_ext[z] : p.m_valid.get(z);
+    if (p.m_valid.ptr != nullptr && (kPair ? w0 - rank * p.tile_w : w0) >= m_valid) return false;
+    if (p.n_valid.ptr != nullptr && n0 >= (ext_cached ? s_ext[kCoreCountSlots + z] : p.n_valid.get(z))) return false;
     kc0 = p.kc0;
-    if (p.k_valid.ptr != nullptr) kc0 = min(kc0, (p.k_valid.get(z) + kChunkK - 1) / kChunkK);
+    if (p.k_valid.ptr != nullptr)
+      kc0 = min(kc0, ((ext_cached ? s_ext[2 * kCoreCountSlots + z] : p.k_valid.get(z)) + kChunkK - 1) / kChunkK);
     return true;
   };
 
   if (warp == 0) {
     // producer: whole warp in uniform control flow, one elected lane issues the TMA loads (see warp 1)
-    const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+    const uint32_t tx_bytes = static_cast<uint32_t>(kPair ? 2 * stage_bytes : stage_bytes);   // pair: both CTAs' boxes
     int it = 0;
     for (int tile = first; tile < total; tile += stride) {
       int z, w0, h0, n0, m_valid, kc0;
@@ -296,15 +327,21 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // matrices keep their layout when kc0 is clipped by k_valid.
             const int bcol = (c < kc0 ? c : p.kc0 + (c - kc0)) * kChunkK;
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-              if (c < kc0) {
-                tma_load_4d(sa, &tmA0, &full_bar[s], c * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
+              if (kPair) {   // the bytes of both CTAs are counted on the leader's barrier
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                tma_load_4d_pair(sa, c < kc0 ? &tmA0 : &tmA1, &full_bar[s], (c < kc0 ? c : c - kc0) * kChunkK, w0, h0, az);
+                tma_load_3d_pair(sb, &tmB, &full_bar[s], bcol, n0 + rank * p.b_rows, bz);
               } else {
-                tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
-              }
-              for (int part = 0; part < p.n_parts; ++part) {
-                tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
-                            tap * p.b_tap_rows + n0 + part * p.n_part, bz);
+                mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                if (c < kc0) {
+                  tma_load_4d(sa, &tmA0, &full_bar[s], c * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
+                } else {
+                  tma_load_4d(sa, &tmA1, &full_bar[s], (c - kc0) * kChunkK, w0 + tw - p.pad, h0 + th - p.pad, az);
+                }
+                for (int part = 0; part < p.n_parts; ++part) {
+                  tma_load_3d(sb + part * p.n_part * 128, &tmB, &full_bar[s], bcol,
+                              tap * p.b_tap_rows + n0 + part * p.n_part, bz);
+                }
               }
             }
             __syncwarp();
@@ -312,11 +349,14 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // Whole-warp, warp-uniform loop; one elected lane issues.  Keeping descriptor arithmetic out of a
     // divergent `if (lane == 0)` region lets it live in uniform registers, so a tcgen05.mma is a single
     // instruction instead of an ELECT / R2UR / branch sequence of ~100 cycles.
-    const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.n_part));
+    const uint32_t idesc = kPair ? make_idesc2_f16(static_cast<uint32_t>(p.n_part)) : make_idesc_f16(static_cast<uint32_t>(p.n_part));
+    auto wait = [&](uint64_t* bar, uint32_t parity) {   // barriers the peer's agents complete: cluster-scope acquire
+      if (kPair) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+    };
     const uint32_t ring_base = smem_u32(ring);
     int it = 0, seq = 0;
     for (int tile = first; tile < total; tile += stride) {
@@ -327,14 +367,14 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
       const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && seq < 32;
       if (tr) p.trace[seq * 8 + 0] = clock64();
-      mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+      wait(&tmem_empty[buf], (use & 1u) ^ 1u);   // epilogue has drained this accumulator
       tc_fence_after();
       if (tr) p.trace[seq * 8 + 1] = clock64();
       const uint32_t d_tmem = tmem_base + buf * p.buf_stride;
       for (int kk = 0; kk < num_k; ++kk, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = static_cast<uint32_t>(it / p.stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+        wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = ring_base + s * stage_bytes;
         const uint32_t sb = sa + kATileBytes;
@@ -346,18 +386,23 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k) {
               // +32 bytes per K=16 slice inside the 128B swizzle row -> +2 in the (addr>>4) field
-              umma_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
+              if (kPair) umma2_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem + part * p.n_part, adesc + 2 * k, bdesc + 2 * k, idesc, (kk | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[s]);
+          if (kPair) umma2_commit(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&tmem_full[buf]);
+      if (elect_one()) {
+        if (kPair) umma2_commit(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);
+      }
       __syncwarp();
       if (tr) p.trace[seq * 8 + 2] = clock64();
       ++seq;
     }
+  } else if (warp == 1) {
+    // pair mode: the peer's MMA warp has nothing to issue
   } else {
     const int ew = warp - 2;          // 0..7
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
@@ -411,7 +456,9 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_remote(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]);
+      }
       if (tr) p.trace[seq * 8 + 5] = clock64();
       ++seq;
     }
@@ -421,7 +468,10 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (clustered) cluster_sync_all();   // a peer may still be writing this CTA's exchange slots / operand stages
-  if (warp == 1) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == 1) {
+    if (kPair) tmem_dealloc2(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
 }
 
 // ---- host launcher --------------------------------------------------------------------------------
@@ -433,7 +483,8 @@ inline int core_tmem_cols(int cols) {
 
 // `grid` is the logical tile space (x = M tiles, y = N tiles, z = batch); the launch itself uses one
 // persistent CTA per SM.
-template <class Epi>
+// kPair: CTA pairs (CoreParams::b_rows): `b` must be the B map with block_n / 2-row boxes.
+template <class Epi, bool kPair = false>
 int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, CoreParams p,
                 const Epi& epi, dim3 grid, cudaStream_t stream) {
   if (p.block_n % 16 != 0 || p.block_n > 512 || p.tile_w * p.tile_h != kTileM) {
@@ -442,6 +493,13 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   }
   p.n_parts = (p.block_n + 255) / 256;
   p.n_part = p.block_n / p.n_parts;
+  p.b_rows = kPair ? p.block_n / 2 : p.block_n;
+  if (kPair && (p.taps_h * p.taps_w != 1 || p.tile_h != 1 || grid.x % 2 != 0 || p.n_parts != 1 || p.cluster_y != 0 ||
+                p.block_n % 32 != 0)) {
+    set_last_error("launch_core: pair mode needs a linear layer with an even number of M tiles (block_n=%d grid.x=%u)", p.block_n,
+                   grid.x);
+    return SSB_ERR_INVALID;
+  }
   if (p.n_part % 16 != 0 || (Epi::kSplit && (p.block_n / 2) % 32 != 0)) {
     set_last_error("launch_core: block_n %d not splittable for this epilogue", p.block_n);
     return SSB_ERR_INVALID;
@@ -456,7 +514,7 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   if (p.stages <= 0) {
     // 222 KiB budget: ring as deep as fits next to a double-buffered staging area, at least 2 stages;
     // very wide tiles (block_n 512) fall back to single-buffered staging
-    const int sb = core_stage_bytes(p.block_n);
+    const int sb = core_stage_bytes(p.b_rows);
     int st = (222 * 1024 - 2 * kCoreStagingBytes - 4096) / sb;
     if (st < 2) {
       p.stage_bufs = 1;
@@ -464,12 +522,12 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     }
     p.stages = st > 6 ? 6 : (st < 2 ? 2 : st);
   }
-  const int smem = core_smem_bytes(p.block_n, p.stages, p.stage_bufs);
+  const int smem = core_smem_bytes(p.b_rows, p.stages, p.stage_bufs);
   auto configure = [&]() -> int {   // per device and template instantiation (common.cuh)
-    SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SSB_CUDA_CHECK(cudaFuncSetAttribute(umma_core_kernel<Epi, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return SSB_OK;
   };
-  SSB_DEVICE_CONFIG((&umma_core_kernel<Epi>), smem, configure());
+  SSB_DEVICE_CONFIG((&umma_core_kernel<Epi, kPair>), smem, configure());
   const long long total = static_cast<long long>(grid.x) * grid.y * grid.z;
   if (total <= 0) return SSB_OK;
   // diagnostic: SSB_CORE_TRACE=<label> dumps CTA 0's per-tile time stamps of the first launch with that label
@@ -489,8 +547,8 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
     }
   }
   int ctas = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-  if (p.cluster_y) {
-    if (grid.y != 2) {
+  if (p.cluster_y || kPair) {
+    if (!kPair && grid.y != 2) {
       set_last_error("launch_core: cluster mode needs exactly two N tiles");
       return SSB_ERR_INVALID;
     }
@@ -517,7 +575,7 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
       int* slot = device_config_begin(&occupancy_key);
       if ((*slot >> 12) != smem) {
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi>, &cfg) != cudaSuccess || n <= 0) {
+        if (cudaOccupancyMaxActiveClusters(&n, umma_core_kernel<Epi, kPair>, &cfg) != cudaSuccess || n <= 0) {
           cudaGetLastError();
           n = sms / csize;
         }
@@ -526,13 +584,14 @@ int launch_core(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
       max_clusters = *slot & 0xfff;
       device_config_end();
     }
-    // groups of tiles walked by one cluster: M tiles x batch (a cluster spans the N tiles)
-    const long long groups = static_cast<long long>(grid.x) * grid.z;
+    // groups of tiles walked by one cluster: M tiles x batch (a cluster spans the N tiles); pair mode: pairs of M
+    // tiles x N tiles x batch
+    const long long groups = kPair ? static_cast<long long>(grid.x / 2) * grid.y * grid.z : static_cast<long long>(grid.x) * grid.z;
     ctas = static_cast<int>(groups < max_clusters ? groups : max_clusters) * csize;
-    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream,
+    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi, kPair>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream,
                                  static_cast<unsigned>(csize), a0, a1, b, p, epi));
   } else {
-    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream, 1,
+    SSB_CUDA_CHECK(launch_kernel(umma_core_kernel<Epi, kPair>, dim3(static_cast<unsigned>(ctas)), dim3(kCoreThreads), smem, stream, 1,
                                  a0, a1, b, p, epi));
   }
   if (tracing) {
