@@ -283,13 +283,45 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int gx = kPair ? p.grid_x / 2 : p.grid_x;
   const int total = fixed_y ? gx * p.grid_z : gx * p.grid_y * p.grid_z;
 
-  // Decode a tile index; returns false for tiles that lie entirely outside the device-side extents.
-  auto decode = [&](int tile, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
-    const int x = kPair ? 2 * (tile % gx) + rank : tile % gx;
-    const int y = fixed_y ? y_fixed : (tile / gx) % p.grid_y;
-    z = fixed_y ? tile / gx : tile / (gx * p.grid_y);
-    w0 = (x % p.tiles_w) * p.tile_w;
-    h0 = (x / p.tiles_w) * p.tile_h;
+  // The walk keeps (x, y, z) of the current tile and advances them by the decomposed stride: decoding the linear index
+  // took five integer divisions by run-time values per tile and role (plus two for the pixel of a row) - some 800 cycles
+  // in front of every epilogue, in kernels whose epilogue sets the pace.
+  struct Walk {
+    int tile, x, y, z;
+  };
+  const int gy_eff = fixed_y ? 1 : p.grid_y;
+  const int walk_sx = stride % gx, walk_sy = (stride / gx) % gy_eff, walk_sz = (stride / gx) / gy_eff;
+  auto walk_begin = [&]() {
+    Walk w;
+    w.tile = first;
+    w.x = first % gx;
+    w.y = (first / gx) % gy_eff;
+    w.z = (first / gx) / gy_eff;
+    return w;
+  };
+  auto walk_next = [&](Walk& w) {
+    w.tile += stride;
+    w.x += walk_sx;
+    w.y += walk_sy;
+    w.z += walk_sz;
+    if (w.x >= gx) {
+      w.x -= gx;
+      ++w.y;
+    }
+    if (w.y >= gy_eff) {
+      w.y -= gy_eff;
+      ++w.z;
+    }
+  };
+  const bool linear_rows = p.tiles_w == p.grid_x;   // linear layers: one row of M tiles per batch index
+
+  // Decode a tile; returns false for tiles that lie entirely outside the device-side extents.
+  auto decode = [&](const Walk& wk, int& z, int& w0, int& h0, int& n0, int& m_valid, int& kc0) -> bool {
+    const int x = kPair ? 2 * wk.x + rank : wk.x;
+    const int y = fixed_y ? y_fixed : wk.y;
+    z = wk.z;
+    w0 = linear_rows ? x * p.tile_w : (x % p.tiles_w) * p.tile_w;
+    h0 = linear_rows ? 0 : (x / p.tiles_w) * p.tile_h;
     n0 = y * p.block_n;
     m_valid = ext_cached ? s_ext[z] : p.m_valid.get(z);
     if (p.m_valid.ptr != nullptr && (kPair ? w0 - rank * p.tile_w : w0) >= m_valid) return false;
@@ -304,9 +336,9 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     // producer: whole warp in uniform control flow, one elected lane issues the TMA loads (see warp 1)
     const uint32_t tx_bytes = static_cast<uint32_t>(kPair ? 2 * stage_bytes : stage_bytes);   // pair: both CTAs' boxes
     int it = 0;
-    for (int tile = first; tile < total; tile += stride) {
+    for (Walk wk = walk_begin(); wk.tile < total; walk_next(wk)) {
       int z, w0, h0, n0, m_valid, kc0;
-      if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
+      if (!decode(wk, z, w0, h0, n0, m_valid, kc0)) continue;
       const int kc = kc0 + p.kc1;
       const int az = z * p.a_z_mul + p.a_z_add;
       const int bz = (z ^ p.b_z_xor) * p.b_z_mul + p.b_z_add;
@@ -359,9 +391,9 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     };
     const uint32_t ring_base = smem_u32(ring);
     int it = 0, seq = 0;
-    for (int tile = first; tile < total; tile += stride) {
+    for (Walk wk = walk_begin(); wk.tile < total; walk_next(wk)) {
       int z, w0, h0, n0, m_valid, kc0;
-      if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
+      if (!decode(wk, z, w0, h0, n0, m_valid, kc0)) continue;
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
       const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
@@ -413,16 +445,17 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     c.stage_cur = c.stage;
     c.stage_bufs = p.stage_bufs;
     c.stage_sel = 0;
-    for (int tile = first; tile < total; tile += stride) {
+    const int row_w = (q * 32 + lane) % p.tile_w, row_h = (q * 32 + lane) / p.tile_w;   // pixel of this thread's row in a tile
+    for (Walk wk = walk_begin(); wk.tile < total; walk_next(wk)) {
       int z, w0, h0, n0, m_valid, kc0;
-      if (!decode(tile, z, w0, h0, n0, m_valid, kc0)) continue;
+      if (!decode(wk, z, w0, h0, n0, m_valid, kc0)) continue;
       const int num_k = p.taps_h * p.taps_w * (kc0 + p.kc1);
       const int buf = p.tmem_bufs == 2 ? (seq & 1) : 0;
       const uint32_t use = static_cast<uint32_t>(p.tmem_bufs == 2 ? (seq >> 1) : seq);
       c.row = q * 32 + lane;
       c.lane = lane;
-      c.px = w0 + (c.row % p.tile_w);
-      c.py = h0 + (c.row / p.tile_w);
+      c.px = w0 + row_w;
+      c.py = h0 + row_h;
       c.z = z;
       c.n0 = n0;
       c.m_valid = m_valid;
