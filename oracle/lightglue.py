@@ -126,6 +126,55 @@ def _cross_block(w, i, x0, x1):
     return x0, x1
 
 
+# ---- fixed-precision restatement: the same model with every tensor the CUDA path keeps in fp16 rounded
+# to fp16 where that path rounds it - GEMM operands (weights, the fp16 copy of the residual stream, q / k / v, the
+# attention probabilities, the context, the FFN hidden activation) - and fp32 everywhere else (accumulation, softmax
+# statistics, LayerNorm, the residual master, the assignment).  out_proj / to_out are folded into ffn.0 in fp64 and rounded
+# once, as lightglue.cu does at weight load.  It is NOT bit-exact with the GPU (summation order inside the tensor cores,
+# the polynomial exponentials), so index agreement with it is reported as a flip rate, not asserted as equality.
+def _r16(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
+def _ffn16(w, p, x16, ctx16, wo, bo):
+    w1, b1 = w[p + "0.weight"].double(), w[p + "0.bias"].double()
+    w1a, w1b = w1[:, :DIM], w1[:, DIM:]
+    wf = torch.cat([w1a, w1b @ wo.double()], 1).float()
+    bf = (b1 + w1b @ bo.double()).float()
+    h = F.linear(torch.cat([x16, ctx16], -1), _r16(wf), bf)
+    h = F.layer_norm(h, (h.shape[-1],), w[p + "1.weight"], w[p + "1.bias"], 1e-5)
+    return F.linear(_r16(F.gelu(h)), _r16(w[p + "3.weight"]), w[p + "3.bias"])
+
+
+def _attend16(q16, k16, v16, scale):
+    s = torch.einsum("hid,hjd->hij", q16, k16) * scale
+    e = torch.exp(s - s.max(-1, keepdim=True).values)
+    ctx = torch.einsum("hij,hjd->hid", _r16(e), v16) / e.sum(-1, keepdim=True)
+    return _r16(ctx.transpose(0, 1).flatten(-2))
+
+
+def _self_block16(w, i, x, enc):
+    p = f"transformers.{i}.self_attn."
+    x16 = _r16(x)
+    qkv = F.linear(x16, _r16(w[p + "Wqkv.weight"]), w[p + "Wqkv.bias"]).unflatten(-1, (N_HEADS, HEAD_DIM, 3)).transpose(0, 1)
+    q, k, v = _r16(_rope(enc, qkv[..., 0])), _r16(_rope(enc, qkv[..., 1])), _r16(qkv[..., 2])
+    ctx16 = _attend16(q, k, v, HEAD_DIM ** -0.5)
+    return x + _ffn16(w, p + "ffn.", x16, ctx16, w[p + "out_proj.weight"], w[p + "out_proj.bias"])
+
+
+def _cross_block16(w, i, x0, x1):
+    p = f"transformers.{i}.cross_attn."
+    heads = lambda t: t.unflatten(-1, (N_HEADS, HEAD_DIM)).transpose(0, 1)
+    x016, x116 = _r16(x0), _r16(x1)
+    wqk, wv = _r16(w[p + "to_qk.weight"]), _r16(w[p + "to_v.weight"])
+    qk0, qk1 = _r16(heads(F.linear(x016, wqk, w[p + "to_qk.bias"]))), _r16(heads(F.linear(x116, wqk, w[p + "to_qk.bias"])))
+    v0, v1 = _r16(heads(F.linear(x016, wv, w[p + "to_v.bias"]))), _r16(heads(F.linear(x116, wv, w[p + "to_v.bias"])))
+    c0 = _attend16(qk0, qk1, v1, HEAD_DIM ** -0.5)
+    c1 = _attend16(qk1, qk0, v0, HEAD_DIM ** -0.5)
+    wo, bo = w[p + "to_out.weight"], w[p + "to_out.bias"]
+    return x0 + _ffn16(w, p + "ffn.", x016, c0, wo, bo), x1 + _ffn16(w, p + "ffn.", x116, c1, wo, bo)
+
+
 def log_assignment(w, i, x0, x1, return_sim=False):
     """MatchAssignment + sigmoid_log_double_softmax, inner [N,M] block only (the dustbin row/column
     never enters filter_matches)."""
@@ -153,9 +202,10 @@ def filter_matches(scores, th=FILTER_THRESHOLD):
     return torch.where(valid0, m0, torch.full_like(m0, -1)).to(torch.int32), ms0
 
 
-def match(w, kpts0, desc0, kpts1, desc1, return_intermediates=False):
+def match(w, kpts0, desc0, kpts1, desc1, return_intermediates=False, fp16_storage=False):
     """kpts*: [N,2] f32 already normalised; desc*: [N,256] (fp16 values are widened to f32, as the
-    engine's fp16 input binding would be).  Returns (matches0 int32 [N0], mscores0 f32 [N0])."""
+    engine's fp16 input binding would be).  Returns (matches0 int32 [N0], mscores0 f32 [N0]).
+    fp16_storage: the fixed-precision restatement above (fp16 where the CUDA path stores fp16)."""
     w = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(v)) for k, v in w.items()}
     k0 = torch.from_numpy(np.asarray(kpts0, np.float32))
     k1 = torch.from_numpy(np.asarray(kpts1, np.float32))
@@ -165,11 +215,11 @@ def match(w, kpts0, desc0, kpts1, desc1, return_intermediates=False):
     with torch.no_grad():
         e0, e1 = _posenc(w, k0), _posenc(w, k1)
         for i in range(N_LAYERS):
-            x0 = _self_block(w, i, x0, e0)
-            x1 = _self_block(w, i, x1, e1)
+            x0 = _self_block16(w, i, x0, e0) if fp16_storage else _self_block(w, i, x0, e0)
+            x1 = _self_block16(w, i, x1, e1) if fp16_storage else _self_block(w, i, x1, e1)
             if return_intermediates:
                 inter[f"self{i}"] = (x0.numpy().copy(), x1.numpy().copy())
-            x0, x1 = _cross_block(w, i, x0, x1)
+            x0, x1 = _cross_block16(w, i, x0, x1) if fp16_storage else _cross_block(w, i, x0, x1)
             if return_intermediates:
                 inter[f"cross{i}"] = (x0.numpy().copy(), x1.numpy().copy())
         scores, sim = log_assignment(w, N_LAYERS - 1, x0, x1, return_sim=True)

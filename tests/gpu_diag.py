@@ -141,6 +141,15 @@ def main():
     for r in rep["rows"]:
         print(f"   i {r['i']:4d} oracle {r['oracle']:4d} gpu {r['other']:4d} {r['kind']:8s} row_gap {r['row_gap']:.4g} "
               f"col_gap {r['col_gap']:.4g} thr_gap {r['thr_gap']:.4g}")
+    # the flip rate against the fixed-precision restatement (fp16 where the CUDA path stores fp16)
+    fm0, fms0, finter = olg.match(sd, k0, d0, k1, d1, return_intermediates=True, fp16_storage=True)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity
+    G = parity.gpu_assignment_scores(lg.debug_read, kp, n0, n1)
+    print(f"lg vs fp16-storage oracle: matches0 differ {(m.matches0 != fm0).sum()} of {n0} (fp16 oracle vs fp32 oracle: "
+          f"{(fm0 != om0).sum()}); score error GPU-fp16oracle {olg.competitive_score_error(finter['scores'], G):.4g}, "
+          f"GPU-fp32oracle {olg.competitive_score_error(inter['scores'], G):.4g}, fp16oracle-fp32oracle "
+          f"{olg.competitive_score_error(inter['scores'], finter['scores']):.4g}")
 
 
 if __name__ == "__main__":

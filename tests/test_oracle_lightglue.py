@@ -97,6 +97,21 @@ def test_ragged_counts_and_single_keypoint(lg_weights):
     assert m0.shape == (1,)
 
 
+def test_fp16_storage_restatement_stays_close_to_the_fp32_model(lg_weights):
+    """the fixed-precision restatement (fp16 where the CUDA path stores fp16) is the model the GPU's flip
+    rate is reported against (tests/gpu_diag.py).  Its scores stay within the tolerance the GPU tests allow
+    (tests/parity.py: 1e-3 of the logit scale) and its matches differ from the fp32 model's at near-ties only."""
+    k0, d0, k1, d1 = _inputs(160, 144, seed=5)
+    m0, ms0, it = olg.match(lg_weights, k0, d0, k1, d1, return_intermediates=True)
+    f0, fs0, fit = olg.match(lg_weights, k0, d0, k1, d1, return_intermediates=True, fp16_storage=True)
+    err = olg.competitive_score_error(it["scores"], fit["scores"])
+    scale = max(1.0, float(np.abs(it["sim"]).max()))
+    assert 0.0 < err <= 1e-3 * scale          # rounds something, and not more than the GPU is allowed to
+    rep = olg.disagreement_report(it["scores"], m0, ms0, f0, fs0)
+    assert not olg.explained_by_score_error(rep, err)
+    assert (m0 >= 0).sum() > 40
+
+
 def test_normalize_keypoints_uses_yaml_size():
     xy = np.array([[0, 0], [1241, 376], [620.5, 188]], np.float32)
     out = olg.normalize_keypoints(xy, 1241, 376)
