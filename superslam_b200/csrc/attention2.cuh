@@ -421,14 +421,15 @@ inline int launch_flash_attention2(const CUtensorMap& tmQ, const CUtensorMap& tm
                                    const CUtensorMap& tmO, FaParams p, int q_tiles, int z, int images, cudaStream_t stream,
                                    const char* label) {
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, FaParams);
-  // one pair of exponentials in SSB_FA_POLY on the FMA pipe (default 4; measured per 9 self-attention launches at 64
-  // pairs with S held in registers: 0 -> 2.04 ms, 2 -> 2.09, 3 -> 2.04, 4 -> 1.98)
-  static const int poly = [] { const char* e = std::getenv("SSB_FA_POLY"); return e ? std::atoi(e) : 4; }();
+  // one pair of exponentials in SSB_FA_POLY on the FMA pipe (default 3; measured per 9 self-attention launches at 64
+  // pairs with S held in registers: 0 -> 2.04 ms, 2 -> 2.09, 3 -> 2.04, 4 -> 1.98.  4 is within noise of 3 and moved the
+  // score error of the trained-like test to 1.08e-3 of the logit scale, over the 1e-3 the parity tests allow.)
+  static const int poly = [] { const char* e = std::getenv("SSB_FA_POLY"); return e ? std::atoi(e) : 3; }();
   Kernel kernel;
   if (poly == 0) kernel = flash_attention2_kernel<0>;
   else if (poly == 2) kernel = flash_attention2_kernel<2>;
-  else if (poly == 3) kernel = flash_attention2_kernel<3>;
-  else kernel = flash_attention2_kernel<4>;
+  else if (poly == 4) kernel = flash_attention2_kernel<4>;
+  else kernel = flash_attention2_kernel<3>;
   auto configure = [&]() -> int {
     SSB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFa2SmemBytes));
     return SSB_OK;
