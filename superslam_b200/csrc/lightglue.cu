@@ -1266,7 +1266,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   };
   // Plain linears as CTA pairs (umma_core.cuh, CoreParams::b_rows): two neighbouring row tiles share one MMA stream and
   // each CTA stages half of the weight rows.  SSB_LG_PAIR=0 selects the one-CTA kernels for A/B measurements.
-  static const bool lg_pair = [] { const char* e = std::getenv("SSB_LG_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
+  // (A single pair per call is latency-bound - 16 row tiles - and the cluster launch and its two cluster barriers cost
+  // more than the pair saves: LightGlue match p50 1.19 vs 1.12 ms.  Pair kernels from two pairs per call on.)
+  static const bool lg_pair_env = [] { const char* e = std::getenv("SSB_LG_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
+  const bool lg_pair = lg_pair_env && pairs >= 2;
   // SSB_LG_FUSED_FFN=1: one kernel per FFN (ffn_fused.cuh), the 512-wide hidden activation stays in tensor memory.
   // Correct (same tests), but measured SLOWER than the two kernels below (4.18 vs 3.66 ms per 18 FFNs at 64 pairs):
   // acc1 fills all 512 TMEM columns, so nothing can be double-buffered and LayerNorm+GELU (E1) and the HBM-bound
