@@ -707,6 +707,10 @@ def main():
                                           "batch; not measured in this run)",
                         "avg_launch_ms": avg_ms, "share_of_step": ms / total_prof_ms, "peak_source": peak_src,
                         "algorithmic_gflop_per_launch": gf}
+                if dom == "sp.conv1ab":   # what keeps this kernel off the tensor roof (profiles/README.md, round 2)
+                    roof["limiter"] = ("shared-memory port: an N = 64 tcgen05.mma reads 4 KB of A + 2 KB of B per 32 cycles "
+                                       "of math = 48 cycles at 128 B/clk (measured 48.0; CTA pairs 43.0, "
+                                       "tools/umma2_probe.cu), plus halo / im2col / staging traffic on the same port")
             else:
                 roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": peak_gbs,
                         "unit": "GB/s", "frac": None, "traffic": None, "avg_launch_ms": avg_ms,
