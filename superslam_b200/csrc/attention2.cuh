@@ -117,7 +117,7 @@ flash_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   pdl_launch_dependents();
   const int images = p.zcount / p.heads;
   const int* cnt = p.cnt;
-  if (images <= kFa2MaxImages) {
+  if (images <= kFa2MaxImages && total > 2 * stride) {   // only when a CTA walks several units (see umma_core.cuh)
     for (int i = threadIdx.x; i < images; i += blockDim.x) s_cnt[i] = p.cnt[i];
     __syncthreads();
     cnt = s_cnt;

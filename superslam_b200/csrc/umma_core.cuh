@@ -263,7 +263,10 @@ umma_core_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // global memory by decode(), each tile cost every role one to three dependent L2 round trips before it could
   // start: the tile trace showed 1 000 - 1 700 cycles between the end of one epilogue and the start of the next in
   // kernels whose epilogue sets the pace (qkv, ffn1).
-  const bool ext_cached = p.grid_z <= kCoreCountSlots;
+  // (Only when a CTA walks several tiles: a latency-bound call - one tile per CTA at most - is better off with the one
+  // dependent load than with a block-wide copy and barrier behind the dependency wait of every kernel.)
+  const long long all_tiles = static_cast<long long>(p.grid_x) * p.grid_y * p.grid_z;
+  const bool ext_cached = p.grid_z <= kCoreCountSlots && all_tiles > 2LL * static_cast<long long>(gridDim.x);
   if (ext_cached) {
     for (int i = threadIdx.x; i < p.grid_z; i += blockDim.x) {
       s_ext[i] = p.m_valid.get(i);
