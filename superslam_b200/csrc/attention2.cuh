@@ -1,6 +1,6 @@
 // Fused attention, second version: TWO 128-query tiles per CTA, one softmax warp group per tile, one thread per query row.
 //
-// What the first version (attention.cuh: one tile per CTA, two co-resident CTAs per SM, two threads per row) spends per
+// What the first version (round 1: one tile per CTA, two co-resident CTAs per SM, two threads per row) spent per
 // 128 x 128 key block and CTA, from the ncu source counters (profiles/ncu_attention_r02.txt): 4 670 warp instructions, of
 // which only ~2 050 are the softmax itself (MUFU, FFMA2 / FADD2, F2FP, FMNMX3) - the rest is per-block overhead: the
 // max exchange between the two threads of a row (shared memory + a named barrier), barrier polling by four producer / MMA

@@ -121,140 +121,6 @@ matchability_kernel(const float* __restrict__ x32, const float* __restrict__ w, 
   lz[static_cast<size_t>(z) * kp + row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
 }
 
-// Row log-sum-exp of sim (pass 0: z = pair, rows of image 2z over columns of image 2z+1; pass 1 on
-// sim^T gives the column log-sum-exp).  blockIdx.y = pair*2 + pass.  One warp per row, 16-byte loads with all
-// of a row's loads of one sweep in flight together (one 4-byte load per iteration left the warp waiting on
-// memory latency 32 times per row); the second sweep hits L1.
-__global__ void __launch_bounds__(256)
-lse_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp, const int* __restrict__ cnt,
-                float* __restrict__ lse) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  const int nr = cnt[2 * pair + pass], nc = cnt[2 * pair + (pass ^ 1)];
-  if (row >= nr) return;
-  const float* s = sim + pass * pass_stride + (static_cast<size_t>(pair) * kp + row) * kp;
-  float m = -INFINITY;
-  for (int j0 = 0; j0 < nc; j0 += 512) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      v[u] = j < nc ? *reinterpret_cast<const float4*>(s + j) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      m = fmaxf(m, v[u].x);                      // j < nc here whenever the load happened
-      if (j + 1 < nc) m = fmaxf(m, v[u].y);
-      if (j + 2 < nc) m = fmaxf(m, v[u].z);
-      if (j + 3 < nc) m = fmaxf(m, v[u].w);
-    }
-  }
-  m = warp_max(m);
-  float sum = 0.f;
-  for (int j0 = 0; j0 < nc; j0 += 512) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      v[u] = j < nc ? *reinterpret_cast<const float4*>(s + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      if (j < nc) sum += expf(v[u].x - m);
-      if (j + 1 < nc) sum += expf(v[u].y - m);
-      if (j + 2 < nc) sum += expf(v[u].z - m);
-      if (j + 3 < nc) sum += expf(v[u].w - m);
-    }
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) lse[(static_cast<size_t>(2 * pair + pass)) * kp + row] = m + logf(sum);
-}
-
-// Row arg-max of the assignment scores
-//   score(i,j) = ((sim - lse_row0[i]) + (sim - lse_col1[j])) + (lz0[i] + lz1[j])
-// evaluated with the same association on sim (pass 0, gives matches0 candidates and their score) and
-// on sim^T (pass 1, gives the column arg-max), so both passes see bit-identical values.
-__global__ void __launch_bounds__(256)
-argmax_rows_kernel(const float* __restrict__ sim, size_t pass_stride, int kp,
-                   const int* __restrict__ cnt, const float* __restrict__ lse,
-                   const float* __restrict__ lz, float* __restrict__ max0, int* __restrict__ arg0,
-                   int* __restrict__ arg1) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int pair = blockIdx.y >> 1, pass = blockIdx.y & 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  const int nr = cnt[2 * pair + pass], nc = cnt[2 * pair + (pass ^ 1)];
-  if (row >= nr) return;
-  const float* s = sim + pass * pass_stride + (static_cast<size_t>(pair) * kp + row) * kp;
-  const float* lse0 = lse + static_cast<size_t>(2 * pair) * kp;
-  const float* lse1 = lse0 + kp;
-  const float* lz0 = lz + static_cast<size_t>(2 * pair) * kp;
-  const float* lz1 = lz0 + kp;
-  // the row's own terms are constants of the sweep; the column terms are read 16 bytes at a time
-  const float* lse_c = pass == 0 ? lse1 : lse0;
-  const float* lz_c = pass == 0 ? lz1 : lz0;
-  const float lse_r = pass == 0 ? lse0[row] : lse1[row];
-  const float lz_r = pass == 0 ? lz0[row] : lz1[row];
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int j0 = 0; j0 < nc; j0 += 256) {
-    float4 v[2], lc[2], zc[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      if (j < nc) {
-        v[u] = *reinterpret_cast<const float4*>(s + j);
-        lc[u] = *reinterpret_cast<const float4*>(lse_c + j);
-        zc[u] = *reinterpret_cast<const float4*>(lz_c + j);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = j0 + u * 128 + lane * 4;
-      if (j < nc) {
-        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        const float ll[4] = {lc[u].x, lc[u].y, lc[u].z, lc[u].w};
-        const float zz[4] = {zc[u].x, zc[u].y, zc[u].z, zc[u].w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (j + k < nc) {
-            // image-0 terms first, image-1 terms second, exactly as in the formula above
-            const float val = pass == 0 ? ((vv[k] - lse_r) + (vv[k] - ll[k])) + (lz_r + zz[k])
-                                        : ((vv[k] - ll[k]) + (vv[k] - lse_r)) + (zz[k] + lz_r);
-            if (val > best) {
-              best = val;
-              bi = j + k;
-            }
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-    if (ob > best || (ob == best && oi < bi)) {
-      best = ob;
-      bi = oi;
-    }
-  }
-  if (lane == 0) {
-    if (pass == 0) {
-      max0[static_cast<size_t>(pair) * kp + row] = best;
-      arg0[static_cast<size_t>(pair) * kp + row] = bi;
-    } else {
-      arg1[static_cast<size_t>(pair) * kp + row] = bi;
-    }
-  }
-}
-
 // ---- assignment statistics from ONE copy of sim ---------------------------------------------------
 // The double log-softmax needs the row AND the column log-sum-exp of sim, the filter the row AND the column arg-max of
 // the scores.  Instead of a second GEMM that writes sim^T (so that both become coalesced row passes: 2 x 4 MB written
@@ -647,58 +513,8 @@ struct EpiBias16 {
 // (65536 elements per tile), hence two TMEM passes instead of three, vector loads of the per-column
 // parameters and a 12-instruction GELU.
 
-// Exact (erf) GELU on packed fp16 pairs:  gelu(y) = relu(y) - 0.5|y| * E(|y|),  E(s) = erfc(s / sqrt 2) =
-// 2^(-s * P6(s)) with P6 a degree-6 minimax fit of -log2(erfc(s / sqrt 2)) / s on [0, 4 sqrt 2] (4e-7 in
-// fp32; beyond the clamp E < 2e-8).  The epilogue of this GEMM is instruction-bound (65536 elements per
-// 128-row tile), so the LayerNorm runs in fp32 and the GELU - whose result is stored as fp16 anyway - in
-// half2: eleven instructions per PAIR.  Against the exactly rounded result the fp16 evaluation has an rms
-// error of 3.1e-4 on N(0, 1.5) inputs, the rounding to fp16 alone 2.1e-4.
-__device__ __forceinline__ __half2 gelu_erf_h2(__half2 y) {
-  const __half2 a = __habs2(y);
-  const __half2 t = __hmin2(a, __float2half2_rn(5.6568542f));
-  __half2 p = __float2half2_rn(-8.85259948e-06f);
-  p = __hfma2(p, t, __float2half2_rn(5.76901113e-05f));
-  p = __hfma2(p, t, __float2half2_rn(4.06791425e-04f));
-  p = __hfma2(p, t, __float2half2_rn(-7.36236150e-03f));
-  p = __hfma2(p, t, __float2half2_rn(5.26655323e-02f));
-  p = __hfma2(p, t, __float2half2_rn(4.59164890e-01f));
-  p = __hfma2(p, t, __float2half2_rn(1.15110875e+00f));
-  const __half2 e = h2exp2(__hmul2(__hneg2(t), p));
-  return __hfma2(__hmul2(a, __float2half2_rn(-0.5f)), e, __hmax2(y, __float2half2_rn(0.f)));
-}
-
-// The same on kN packed pairs at once, written stage by stage: a Horner chain is six dependent HFMA2 (4-5 cycles
-// each), and with two epilogue warps per scheduler nothing else hides that latency - ptxas kept the chains of
-// the one-pair version back to back ("wait" was the top stall of this kernel).  Eight independent chains
-// interleaved issue one instruction per cycle.
-template <int kN>
-__device__ __forceinline__ void gelu_erf_h2_batch(__half2 (&y)[kN]) {
-  __half2 t[kN], p[kN];
-#pragma unroll
-  for (int i = 0; i < kN; ++i) t[i] = __hmin2(__habs2(y[i]), __float2half2_rn(5.6568542f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(__float2half2_rn(-8.85259948e-06f), t[i], __float2half2_rn(5.76901113e-05f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(4.06791425e-04f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(-7.36236150e-03f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(5.26655323e-02f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(4.59164890e-01f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hfma2(p[i], t[i], __float2half2_rn(1.15110875e+00f));
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = __hmul2(__hneg2(t[i]), p[i]);
-#pragma unroll
-  for (int i = 0; i < kN; ++i) p[i] = h2exp2(p[i]);
-#pragma unroll
-  for (int i = 0; i < kN; ++i)
-    y[i] = __hfma2(__hmul2(__habs2(y[i]), __float2half2_rn(-0.5f)), p[i], __hmax2(y[i], __float2half2_rn(0.f)));
-}
-
-// Second formulation, 9 instructions per PAIR instead of ~20 (the epilogue of ffn1 is instruction-bound: 13 of its
-// instructions per element were this function):  gelu(y) = 0.5 y (1 + erf(y / sqrt 2))  with
+// Exact (erf) GELU on packed fp16 pairs, 9 instructions per PAIR (the epilogue of ffn1 is instruction-bound; the first
+// formulation - a degree-6 fit of -log2(erfc) and an exponential - took ~20):  gelu(y) = 0.5 y (1 + erf(y / sqrt 2))  with
 //   erf(y / sqrt 2) = tanh(y (c1 + c3 y^2 + c5 y^4)),   |y| <= 6   (least-squares fit: max error of gelu 3.0e-5,
 // a seventh of the fp16 rounding of the result; the textbook tanh form with two coefficients is off by 4.7e-4)
 // and ONE packed MUFU op per pair (tanh.approx.f16x2).  Beyond |y| = 6 the argument is clamped: tanh(u(6)) = 1 - 1e-10.
@@ -727,10 +543,6 @@ __device__ __forceinline__ void gelu_h2_batch(__half2 (&y)[kN]) {
     y[i] = __hfma2(h, p[i], h);
   }
 }
-
-}  // namespace ssb
-#include "ffn_fused.cuh"   // uses gelu_erf_h2_batch above
-namespace ssb {
 
 struct EpiLnGelu {
   const float* bias;
@@ -1167,7 +979,7 @@ int LightGlue::alloc_workspace() {
   A(q_, Z * KP * kLgHeadDim * 2);
   A(k_, Z * KP * kLgHeadDim * 2);
   A(v_, Z * KP * kLgHeadDim * 2);
-  A(s_, P2 * KP * KP * 4);  // sim per pair (the second half: sim^T of the first assignment version, SSB_LG_ASSIGN_V1)
+  A(s_, static_cast<size_t>(pairs_) * KP * KP * 4);  // sim per pair
   // per-tile partials of the assignment sweeps: row (kp/128 column blocks) + column (kp/64 row blocks) entries of
   // 8 bytes, once for the log-sum-exp and once for the arg-max
   A(asg_part_, 2 * static_cast<size_t>(pairs_) * (KP / kAsgCols + KP / kAsgRows) * KP * 8);
@@ -1201,14 +1013,11 @@ int LightGlue::alloc_workspace() {
   SSB_RETURN_IF(tm_rows3(&ts_q_, q_, 64, kp_, z, 32));
   SSB_RETURN_IF(tm_rows3(&ts_k_, k_, 64, kp_, z, 32));
   SSB_RETURN_IF(tm_rows3(&ts_v_, v_, 64, kp_, z, 32));
-  // fp32 sim / sim^T [P][kp][kp] seen as fp16 [P][kp][2 kp] (EpiStoreF32)
+  // fp32 sim [P][kp][kp] seen as fp16 [P][kp][2 kp] (EpiStoreF32)
   SSB_RETURN_IF(tm_rows3(&ts_sim_, s_, 2 * kp_, kp_, pairs_, 32));
-  SSB_RETURN_IF(tm_rows3(&ts_simT_, s_ + static_cast<size_t>(pairs_) * KP * KP, 2 * kp_, kp_, pairs_, 32));
   SSB_RETURN_IF(tm_rows3(&ts_mda_, mda_, 768, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows3(&ts_mdb_, mdb_, 768, kp_, p2, 32));
   SSB_RETURN_IF(tm_rows4(&tm_mda_a_, mda_, 768, kp_, p2));
-  SSB_RETURN_IF(tm_rows4(&tm_mdb_a_, mdb_, 768, kp_, p2));
-  SSB_RETURN_IF(tm_rows3(&tm_mda_b_, mda_, 768, kp_, p2, 256));
   SSB_RETURN_IF(tm_rows3(&tm_mdb_b_, mdb_, 768, kp_, p2, 256));
   return SSB_OK;
 }
@@ -1270,19 +1079,10 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   // more than the pair saves: LightGlue match p50 1.19 vs 1.12 ms.  Pair kernels from two pairs per call on.)
   static const bool lg_pair_env = [] { const char* e = std::getenv("SSB_LG_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
   const bool lg_pair = lg_pair_env && pairs >= 2;
-  // SSB_LG_FUSED_FFN=1: one kernel per FFN (ffn_fused.cuh), the 512-wide hidden activation stays in tensor memory.
-  // Correct (same tests), but measured SLOWER than the two kernels below (4.18 vs 3.66 ms per 18 FFNs at 64 pairs):
-  // acc1 fills all 512 TMEM columns, so nothing can be double-buffered and LayerNorm+GELU (E1) and the HBM-bound
-  // residual update (E2) - each longer than the tile's MMAs - run exposed instead of under the next tile's MMAs.
-  static const bool fused_ffn = [] { const char* e = std::getenv("SSB_LG_FUSED_FFN"); return e != nullptr && std::atoi(e) != 0; }();
+  // (A one-kernel FFN that keeps the 512-wide hidden activation in tensor memory was built and measured SLOWER than the
+  // two kernels below - 4.18 vs 3.66 ms per 18 FFNs at 64 pairs: its accumulator fills all 512 TMEM columns, so nothing
+  // can be double-buffered and LayerNorm+GELU and the HBM-bound residual update run exposed.  profiles/README.md.)
   auto ffn = [&](const LgBlockFfn& F) -> int {
-    if (fused_ffn) {
-      FfnParams fp;
-      fp.b1 = F.fc1.bias, fp.ln_g = F.ln_g, fp.ln_b = F.ln_b, fp.b2 = F.fc2.bias;
-      fp.x32 = x32_, fp.cnt = cnt, fp.kp = KP, fp.tiles_per_img = tiles, fp.images = P2;
-      fp.label = "lg.ffn";
-      return launch_ffn_fused(tm_x16_, w_->fold_out ? tm_ctx_ : tm_msg_, F.fc1.tmB, F.fc2.tmB, ts_x16_, fp, stream);
-    }
     {
       CoreParams p = lin("lg.ffn1", 4, 4, 256);
       p.cluster_y = 1;   // the two 256-column halves of a row tile run on a CTA pair (LayerNorm over 512)
@@ -1307,13 +1107,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     fp.scale_log2 = scale * 1.4426950408889634f;
     fp.ctx = ctx_;
     fp.kp = KP;
-    // second version (two query tiles per CTA, a thread per row: attention2.cuh); SSB_FA_V1=1 selects the first
-    static const bool v1 = [] { const char* e = std::getenv("SSB_FA_V1"); return e != nullptr && std::atoi(e) != 0; }();
-    if (!v1)
-      return launch_flash_attention2(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, P2, stream,
-                                     key_xor ? "lg.attn_cross" : "lg.attn_self");
-    return launch_flash_attention(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, stream,
-                                  key_xor ? "lg.attn_cross" : "lg.attn_self");
+    return launch_flash_attention2(tm_q_a_, tmKeys, tm_v3_, ts_ctx_, fp, tiles, Z, P2, stream,
+                                   key_xor ? "lg.attn_cross" : "lg.attn_self");
   };
 
   // test hook: SSB_LG_STOP_AFTER=n returns after n half-blocks (self = odd, cross = even) so the
@@ -1363,7 +1158,6 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
   SSB_CUDA_CHECK(launch_kernel(matchability_kernel, dim3(dim3(KP / 128, P2)), dim3(128), 0, stream, 1, x32_, w_->match_w, w_->match_b, KP, cnt, lz_));
   count_launch();
   prof_mark(stream, "lg.matchability");
-  const size_t pass_stride = static_cast<size_t>(pairs_) * KP * KP;   // sim^T follows the capacity-sized sim block
   {
     CoreParams p = lin("lg.sim", 12, 0, 256);  // sim[pair] = A-form(img 2p) x B-form(img 2p+1)
     p.a_z_mul = 2;
@@ -1374,28 +1168,8 @@ int LightGlue::run(int pairs, const float* kp_xy_dev, int kp_stride, const int* 
     EpiStoreF32 e{ts_sim_, 1.0f};
     SSB_RETURN_IF(launch_core(tm_mda_a_, tm_mda_a_, tm_mdb_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
   }
-  // row / column statistics and arg-max from the one copy of sim (assign_*_kernel above).  SSB_LG_ASSIGN_V1=1 selects
-  // the first version (second GEMM for sim^T + two row passes over both) for A/B measurements.
-  static const bool assign_v1 = [] { const char* e = std::getenv("SSB_LG_ASSIGN_V1"); return e != nullptr && std::atoi(e) != 0; }();
-  if (assign_v1) {
-    {
-      CoreParams p = lin("lg.simT", 12, 0, 256);  // sim^T[pair] = B-form(img 2p+1) x A-form(img 2p): same products
-      p.a_z_mul = 2;
-      p.a_z_add = 1;
-      p.b_z_mul = 2;
-      p.m_valid = dev_count(cnt, 1, 0, 2, 1);
-      p.n_valid = dev_count(cnt, 1, 0, 2, 0);
-      EpiStoreF32 e{ts_simT_, 1.0f};
-      SSB_RETURN_IF(launch_core(tm_mdb_a_, tm_mdb_a_, tm_mda_b_, p, e, dim3(tiles, KP / 256, pairs), stream));
-    }
-    SSB_CUDA_CHECK(launch_kernel(lse_rows_kernel, dim3(dim3(KP / 8, pairs * 2)), dim3(256), 0, stream, 1, s_, pass_stride, KP, cnt, lse_));
-    count_launch();
-    prof_mark(stream, "lg.lse");
-    SSB_CUDA_CHECK(launch_kernel(argmax_rows_kernel, dim3(dim3(KP / 8, pairs * 2)), dim3(256), 0, stream, 1, s_, pass_stride, KP, cnt, lse_, lz_, max0_,
-                                                                   arg0_, arg1_));
-    count_launch();
-    prof_mark(stream, "lg.argmax");
-  } else {
+  // row / column statistics and arg-max from the one copy of sim (assign_*_kernel above)
+  {
     float2* rowpart = reinterpret_cast<float2*>(asg_part_);
     float2* colpart = rowpart + static_cast<size_t>(pairs_) * (KP / kAsgCols) * KP;
     AsgBest* rowbest = reinterpret_cast<AsgBest*>(colpart + static_cast<size_t>(pairs_) * (KP / kAsgRows) * KP);

@@ -105,7 +105,7 @@ class LightGlue {
   __half* x16_ = nullptr;       // [2P][kp][256] fp16 copy (GEMM operand)
   __half *q_ = nullptr, *k_ = nullptr;  // [2P*4][kp][64]
   __half* v_ = nullptr;         // [2P*4][kp][64]
-  float* s_ = nullptr;          // [2P][kp][kp] assignment similarity sim (/ sim^T, first version only) (fp32)
+  float* s_ = nullptr;          // [P][kp][kp] assignment similarity sim (fp32)
   uint8_t* asg_part_ = nullptr; // per-tile partials of the two assignment sweeps (lightglue.cu assign_*_kernel)
   __half *ctx_ = nullptr, *msg_ = nullptr;  // [2P][kp][256]
   __half* h1_ = nullptr;        // [2P][kp][512]
@@ -120,8 +120,8 @@ class LightGlue {
   size_t host_io_bytes_ = 0;
 
   CUtensorMap tm_x16_, tm_msg_, tm_ctx_, tm_h1_, tm_q_a_, tm_q3_, tm_k3_, tm_v3_, tm_mda_a_,
-      tm_mdb_b_, tm_mdb_a_, tm_mda_b_;
-  CUtensorMap ts_x16_, ts_msg_, ts_ctx_, ts_sim_, ts_simT_, ts_h1_, ts_q_, ts_k_, ts_v_, ts_mda_, ts_mdb_;  // TMA-store maps
+      tm_mdb_b_;
+  CUtensorMap ts_x16_, ts_msg_, ts_ctx_, ts_sim_, ts_h1_, ts_q_, ts_k_, ts_v_, ts_mda_, ts_mdb_;  // TMA-store maps
 };
 
 }  // namespace ssb

@@ -1,5 +1,5 @@
 // The tensor-core engine behind every dense contraction that is not a halo-reuse convolution
-// (conv_halo.cuh) or attention (attention.cuh):
+// (conv_pipe.cuh, conv_stream.cuh) or attention (attention2.cuh):
 //   D[128 x BLOCK_N] (fp32, TMEM) = sum over k-steps  A_step[128 x 64] * B_step[BLOCK_N x 64]^T
 // issued as tcgen05.mma (kind::f16, M=128) by one thread, operands staged by TMA into a multi-stage
 // 128B-swizzled shared-memory ring, accumulator read back with tcgen05.ld by eight epilogue warps.

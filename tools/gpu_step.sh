@@ -19,8 +19,8 @@ print(d["kernel_ms_per_step"]); print("spread", d["value_spread_per_step"], "e2e
 print("live", d.get("live_pipeline")); print("latency", d.get("latency_single_pair")); print("records", d["results"]["gathered_records"])
 PY
 ;;
-ab) # ABS="ENV=1 ENV2=x ..." (default: SSB_LG_ASSIGN_V1=1): one short bench per entry with that environment assignment
-for ab in ${ABS:-SSB_LG_ASSIGN_V1=1}; do
+ab) # ABS="ENV=1 ENV2=x ..." (default: SSB_LG_PAIR=0): one short bench per entry with that environment assignment
+for ab in ${ABS:-SSB_LG_PAIR=0}; do
   echo "== A/B: $ab"; env $ab timeout 300 python bench.py --no-cpu-baseline --no-extras --steps 10 > gpurun_out/bench_${tag}_ab.json 2> gpurun_out/bench_${tag}_ab.err
   python - "$tag" <<'PY'
 import json, sys
