@@ -22,11 +22,28 @@ def test_traffic_table_matches_the_committed_launch_list():
     assert exp["sp.conv1ab"]["per"] == "image" and exp["lg.ffn2"]["per"] == "pair"
 
 
+def test_round2_traffic_table_matches_its_launch_list():
+    """The table bench.py quotes `roofline.traffic` from (profiles/ncu_traffic_r02.json) is what tools/ncu_traffic.py
+    derives from the committed launch list of the final build (kernel names carry the pair / N template arguments)."""
+    csv = os.path.join(ROOT, "profiles", "launches_r02_v5_p64.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), csv, "64"],
+                         capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    exp = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
+    got.pop("_comment"), exp.pop("_comment")
+    assert got == exp
+    assert sum(v["launches"] for v in exp.values()) == 94
+    assert max(exp.items(), key=lambda kv: kv[1]["share_of_step"])[0] == "sp.conv1ab"
+    # the Cout = 64 convolutions are the CTA-pair kernels, conv3a the N = 128 pair
+    assert "1, 1, 64>" in exp["sp.conv1ab"]["kernel"] and "0, 1, 128>" in exp["sp.conv3a"]["kernel"]
+
+
 def test_bench_lines_are_valid_json_with_the_contract_keys():
     prof = os.path.join(ROOT, "profiles")
     need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"}
-    for name in ("bench_r01_v15_p64.json", "bench_r01_v15_n2.json"):
+    for name in ("bench_r01_v15_p64.json", "bench_r01_v15_n2.json", "bench_r02_v6_p64.json", "bench_r02_v4_n2.json",
+                 "bench_r02_v6_n8.json", "bench_r02_v4_C3.json", "bench_r02_v4_C5.json"):
         d = json.load(open(os.path.join(prof, name)))
         assert need <= set(d), (name, need - set(d))
         assert d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
