@@ -1,9 +1,10 @@
 // Persistent, warp-specialised 3x3 convolution for the Cin = 64 layers of the SuperPoint trunk
 // (conv1a+conv1b fused, conv2a, conv2b, conv3a): 72 % of the network's FLOPs.
 //
-// One CTA per SM keeps the 9 x [64 x 64] fp16 weights of its 64-output-channel slice RESIDENT in shared
+// One CTA per SM - by default one CTA PAIR per TPC (kPair below: tcgen05.mma.cta_group::2, each CTA keeps half of the
+// output channels' weights) - keeps the 9 x [64 x 64] fp16 weights of its 64-output-channel slice RESIDENT in shared
 // memory (73 KB, loaded once by TMA) and walks 16 x 16 pixel tiles.  Per tile:
-//   halo   (16+2) x (16+2) pixels x 64 ch: either TMA box loads (zero-filled padding, three buffers) or -
+//   halo   (16+2) x (16+2) pixels x 64 ch: either TMA box loads (zero-filled padding, two buffers) or -
 //          fused first layer - produced on chip from the u8 image, so conv1a's activation never exists in
 //          HBM: conv1a (3x3, Cin = 1) is itself a tensor-core product  [384 halo px x 16] x [16 x 64]  with
 //          K = 9 taps + a ones column that carries the bias; the weights are split hi + lo (two fp16) so the
@@ -11,11 +12,14 @@
 //          core matrices), read the product back from TMEM, apply ReLU / the image border and write the
 //          fp16 halo in the 128B-swizzled layout the conv1b MMAs read;
 //   MMA    9 taps x 2 sub-tiles x 4 K-slices of tcgen05.mma (M = 128 = 16 rows x 8 px, N = 64); each tap
-//          reads the halo in place through a descriptor shifted by whole pixels (see conv_halo.cuh);
+//          reads the halo in place through a descriptor shifted by whole pixels (the 128B swizzle works on
+//          absolute shared-memory address bits: tools/umma_probe.cu mode 0);
 //   TMEM   2 x (2 x 64) accumulator columns: the epilogue of tile t (bias, ReLU, optional 2x2 max-pool,
 //          fp16, staged TMA store) overlaps the halo production and the MMAs of tile t+1.
 // Warp roles: 0 = TMA (weights once, halo boxes), 1 = TMEM alloc + MMA issue, 2..9 = epilogue,
 // 10..17 = conv1a im2col builders / TMEM->halo converters (fused variant only).
+// What bounds these kernels is the shared-memory port (profiles/README.md, round 2): an N = 64 MMA reads 6 KB of
+// operands per 32 cycles of math = 48 cycles at 128 B/clk; halo, im2col and staging traffic shares the port.
 #pragma once
 
 #include "common.cuh"
