@@ -1,7 +1,8 @@
 // LightGlue on sm_100a.  Every dense contraction (QKV / out / FFN / final projections, Q*K^T, P*V,
 // the assignment similarity) runs on tcgen05 through umma_core.cuh; rotary embedding, LayerNorm+GELU,
 // the residual update and the hi/lo split of the final projection are fused into the TMEM epilogues.
-// Softmax, log-sum-exp, arg-max and the mutual check are warp-per-row SIMT kernels (HBM/L2 bound).
+// Attention (softmax included) is one fused kernel (attention2.cuh); the double log-softmax and the arg-max of the
+// assignment are tile sweeps over the one copy of sim, the mutual check a per-keypoint SIMT kernel (HBM/L2 bound).
 //
 // Model (cvg/LightGlue lightglue.py, restated in oracle/lightglue.py):
 //   posenc   cos/sin(Wr * kpt) repeat-interleaved to 64, rotary on q,k of self-attention only

@@ -9,7 +9,8 @@
 // and a linear layer is the degenerate 1x1 case with (w = row, h = 0).  Up to two A sources are
 // supported so that concat([x, msg]) never has to be materialised.
 //
-// Persistent: one CTA per SM walks the (x, y, z) tile space; the accumulator is double-buffered in
+// Persistent: one CTA per SM (pair mode, CoreParams::b_rows: one CTA pair per TPC sharing a cta_group::2 MMA
+// stream) walks the (x, y, z) tile space; the accumulator is double-buffered in
 // TMEM (2 x BLOCK_N columns) so the epilogue of tile t overlaps the TMA loads and MMAs of tile t+1.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue; warp w may only touch TMEM lanes 32*(w%4)..+31, so two warps share each lane
