@@ -38,6 +38,24 @@ def test_round2_traffic_table_matches_its_launch_list():
     assert "1, 1, 64>" in exp["sp.conv1ab"]["kernel"] and "0, 1, 128>" in exp["sp.conv3a"]["kernel"]
 
 
+def test_roofline_model_reproduces_the_committed_table():
+    """profiles/roofline_r02.md (which roof binds each kernel: tensor / HBM / shared memory / MUFU) is what
+    tools/roofline_model.py derives from the committed bench line, and the statements the docs make hold in it."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "roofline_model.py")], capture_output=True, text=True,
+                         check=True).stdout
+    assert out == open(os.path.join(ROOT, "profiles", "roofline_r02.md")).read()
+    rows = {}
+    for ln in out.splitlines():
+        c = [x.strip() for x in ln.split("|")]
+        if len(c) > 9 and c[1] and c[1] not in ("kernel", "---"):
+            rows[c[1]] = (c[8], float(c[9]))
+    assert rows["sp.conv1ab"][0] == "shared memory" and rows["sp.conv2a"][0] == "shared memory"
+    assert rows["lg.ffn2"][0] == "HBM" and rows["lg.attn_self"][0] == "MUFU" and rows["sp.conv3b"][0] == "tensor"
+    # no kernel runs faster than its binding roof allows (conv3a: a 0.24 ms kernel, above the SUSTAINED tensor figure)
+    assert all(f <= 1.0 for k, (r, f) in rows.items() if k != "sp.conv3a"), rows
+    assert rows["sp.conv3a"][1] <= 1644.4 / 1380.6
+
+
 def test_bench_lines_are_valid_json_with_the_contract_keys():
     prof = os.path.join(ROOT, "profiles")
     need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
