@@ -6,8 +6,8 @@
 For every kernel of one 64-pair step the script states the ALGORITHMIC work per launch in four currencies - tensor-core
 FLOPs (2 * MAC), HBM bytes (every tensor read once and written once), shared-memory bytes (what the kernel's structure
 moves through the 128 B/clk port of an SM: TMA writes, tcgen05.mma operand reads, staging stores and their TMA-store
-reads) and exponentials - turns each into a time at the measured peaks (MEASURED_PEAKS.json: sustained bf16 TFLOP/s and
-copy GB/s; the shared-memory port and the MUFU at the SM clock the bench line reports), and puts the measured launch
+reads) and exponentials - turns each into a time at the measured peaks (the sustained bf16 TFLOP/s and copy GB/s the bench line was
+scored against; the shared-memory port and the MUFU at the SM clock the bench line reports), and puts the measured launch
 time (bench.py, CUDA events) next to the largest of them.  No GPU needed: it only reads committed files.
 
 The per-tile shared-memory byte counts are the ones derived in profiles/README.md (round 2) and csrc/conv_pipe.cuh /
@@ -95,9 +95,10 @@ def kernels():
 def main():
     bench = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "bench_r02_v6_p64.json")
     d = json.load(open(bench))
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    tf = peaks.get("bf16_tflops_sustained", 1380.6)
-    gbs = peaks.get("hbm_gbs", 6538.0)
+    # the peaks the bench line itself was scored against (MEASURED_PEAKS.json of the box that produced it)
+    tf = float(d["roofline"]["peak"]) if d["roofline"].get("unit") == "TFLOP/s" else 1380.6
+    hk = next(iter(d.get("hbm_kernels", {}).values()), None)
+    gbs = round(hk["gb_per_s"] / hk["frac_of_peak"]) if hk else 6538.0
     mhz = d["clocks"]["sm_mhz"] or 1750.0
     smem_gbs = SMS * SMEM_B_PER_CLK * mhz * 1e6 / 1e9
     mufu_per_s = SMS * MUFU_PER_CLK * mhz * 1e6
